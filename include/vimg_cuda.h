@@ -1,0 +1,299 @@
+/*
+ * vimg_cuda.h -- C ABI of the B200 `cuda` render device for v-img.
+ *
+ * This is the drop-in boundary for the reference's render hot path.  The
+ * reference (atom501/v-img) has no plugin/FFI layer; the seam is the C++ call
+ *
+ *     scene_integrator(const integrator_data&, BVH&, prims, lights, F)
+ *         -> std::vector<glm::vec3>                  include/integrators.h:36-153
+ *     trace_pixel(..., x, y) -> glm::vec3            include/integrators.h:181-220
+ *
+ * made from src/main.cpp:219-248 / :271-292 after the (unchanged) scene
+ * loaders and host BVH builders have run.  A `cuda` device replaces exactly
+ * that call: the host adapter flattens the already-built scene objects into
+ * the POD `vimg_scene_desc` below (plain pointers + sizes, reference data
+ * layouts, no C++ or torch types), uploads it once with vimg_scene_create()
+ * and renders with vimg_render().  INTEGRATION.md shows the adapter TU.
+ *
+ * Conventions
+ *   - all functions return 0 (VIMG_OK) on success, a negative vimg_status
+ *     otherwise; vimg_last_error() gives a thread-local message.  Nothing
+ *     throws across the ABI.  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails with VIMG_ERR_NO_DEVICE.
+ *   - the caller keeps ownership of every host array in the descriptor;
+ *     vimg_scene_create() deep-copies to the device(s).
+ *   - one render at a time per vimg_scene (thread-compatible, like the
+ *     reference's scene containers, src/main.cpp:116-120).
+ *   - output images are W*H*3 floats, linear radiance averaged over spp,
+ *     row 0 = TOP of the image: index = x + (H-1-y)*W
+ *     (include/integrators.h:113).
+ */
+#ifndef VIMG_CUDA_H
+#define VIMG_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIMG_ABI_VERSION 1
+
+typedef enum vimg_status {
+  VIMG_OK = 0,
+  VIMG_ERR_INVALID_ARGUMENT = -1,
+  VIMG_ERR_NO_DEVICE = -2,
+  VIMG_ERR_CUDA = -3,
+  VIMG_ERR_OUT_OF_MEMORY = -4,
+  VIMG_ERR_IO = -5,
+  VIMG_ERR_UNSUPPORTED = -6
+} vimg_status;
+
+/* integrator names follow src/scene_loading/json_scene.cpp:213-223 and
+ * enum class integrator_func (include/integrators.h:24). */
+typedef enum vimg_integrator {
+  VIMG_INTEGRATOR_S_NORMAL = 0,
+  VIMG_INTEGRATOR_G_NORMAL = 1,
+  VIMG_INTEGRATOR_MATERIAL = 2,
+  VIMG_INTEGRATOR_MIS = 3
+} vimg_integrator;
+
+/* ---- camera: TLCam private state (include/tl_camera.h:11-18) ------------ */
+typedef struct vimg_camera {
+  float cam_to_world[16]; /* glm::mat4, column-major (m[col][row])          */
+  float p_size[2];        /* image-plane size from the TLCam ctor            */
+  int32_t resolution[2];  /* width, height                                   */
+  float vfov_deg;         /* vertical fov, degrees                           */
+  float aperture_radius;  /* 0 => pinhole                                    */
+  float focal_dist;
+} vimg_camera;
+
+/* ---- BVH: the reference's flattened layout (include/bvh.h:22-28,51-57) -- */
+typedef struct vimg_bvh {
+  const uint32_t* nodes;       /* n_nodes x {first_index, obj_count}; leaf iff obj_count != 0 */
+  uint64_t n_nodes;
+  const float* bb_mins_maxes;  /* n_bb_slots x 3 floats; root min/max at slots 0/2; the pair of
+                                  children (c, c+1) at slots 2c+2..2c+5 = Lmin,Rmin,Lmax,Rmax */
+  uint64_t n_bb_slots;
+  const uint64_t* obj_indices; /* leaf primitive permutation (std::vector<size_t>)            */
+  uint64_t n_obj_indices;
+  uint32_t max_depth;
+} vimg_bvh;
+
+/* ---- primitives: list_objects order == primitive index ------------------ */
+typedef enum vimg_prim_type { VIMG_PRIM_TRIANGLE = 0, VIMG_PRIM_SPHERE = 1 } vimg_prim_type;
+
+typedef struct vimg_prim {
+  uint32_t type; /* vimg_prim_type                                          */
+  uint32_t a;    /* triangle: mesh index          | sphere: sphere index     */
+  uint32_t b;    /* triangle: tri_index in mesh   | sphere: unused           */
+} vimg_prim;
+
+typedef struct vimg_sphere {   /* include/geometry/sphere.h:28-31 */
+  float center[3];
+  float radius;
+  uint32_t material;
+} vimg_sphere;
+
+#define VIMG_NO_UV 255u        /* MeshConsts::no_uv, include/geometry/mesh.h:10-12 */
+
+typedef struct vimg_mesh {     /* include/geometry/mesh.h:14-57 */
+  const uint32_t* indices;     /* n_tris x 3                                */
+  uint64_t n_tris;
+  const float* vertices;       /* n_verts x 3                               */
+  uint64_t n_verts;
+  const float* normals;        /* n_verts x 3 or NULL (Mesh::normals empty)  */
+  const float* const* texcoords; /* n_uv_sets arrays of n_verts x 2         */
+  uint32_t n_uv_sets;
+  uint8_t color_tex_uv;        /* index into texcoords or VIMG_NO_UV         */
+  uint8_t normal_tex_uv;
+  uint8_t metallic_roughness_tex_uv;
+  uint8_t pad_;
+  uint32_t material;
+} vimg_mesh;
+
+/* ---- textures ----------------------------------------------------------- */
+typedef enum vimg_wrap { /* TextureWrappingMode, include/texture/texture_common.h:7 */
+  VIMG_WRAP_CLAMP_TO_EDGE = 0,
+  VIMG_WRAP_MIRRORED_REPEAT = 1,
+  VIMG_WRAP_REPEAT = 2
+} vimg_wrap;
+
+typedef enum vimg_texture_type {
+  VIMG_TEX_CONST = 0,   /* ConstColor    include/texture/texture_RGB.h:45-57 */
+  VIMG_TEX_CHECKER = 1, /* Checkerboard  include/texture/texture_RGB.h:59-81 */
+  VIMG_TEX_IMAGE = 2    /* ImageTexture  include/texture/texture_RGB.h:83-150 */
+} vimg_texture_type;
+
+typedef struct vimg_texture {
+  uint32_t type;
+  float col_a[3];        /* const: albedo | checker: col_a                   */
+  float col_b[3];        /* checker: col_b                                   */
+  uint32_t width;        /* checker: width | image: level-0 width            */
+  uint32_t height;
+  uint32_t n_levels;     /* image: mipmap.size()                             */
+  uint32_t wrap_u, wrap_v;
+  const float* const* levels; /* image: n_levels arrays, level l is
+                                 max(W>>l,1) x max(H>>l,1) x 3 floats, row 0 = top */
+} vimg_texture;
+
+typedef struct vimg_texture_rg { /* TextureRG include/texture/texture_RG.h:10-57 */
+  uint32_t width, height;
+  uint32_t wrap_u, wrap_v;
+  const float* data;     /* width*height x 2 floats                          */
+} vimg_texture_rg;
+
+/* ---- materials ---------------------------------------------------------- */
+typedef enum vimg_material_type {
+  VIMG_MAT_LAMBERTIAN = 0,    /* src/material/lambertian.cpp                  */
+  VIMG_MAT_DIFFUSE_LIGHT = 1, /* include/material/diffuse_light.h             */
+  VIMG_MAT_DIELECTRIC = 2,    /* src/material/dielectric.cpp                  */
+  VIMG_MAT_PRINCIPLED = 3,    /* include/material/principled.h                */
+  VIMG_MAT_BASE = 4           /* Material base defaults, material.h:25-72     */
+} vimg_material_type;
+
+#define VIMG_NO_TEXTURE (-1)
+
+typedef struct vimg_material {
+  uint32_t type;
+  int32_t texture;       /* TextureRGB* -> index into textures, or -1        */
+  int32_t texture_rg;    /* Principled::metallic_roughness or -1             */
+  int32_t normal_map;    /* Material::normal_map (image texture index) or -1 */
+  float emit[3];         /* DiffuseLight::emit                               */
+  float ior;             /* Dielectric::ior                                  */
+  /* Principled (include/material/principled.h:25-40) */
+  float metallic_roughness_factor[2];
+  float specular_transmission;
+  float subsurface;
+  float specular;
+  float specular_tint;
+  float anisotropic;
+  float sheen;
+  float sheen_tint;
+  float clearcoat;
+  float clearcoat_gloss;
+  float eta;
+} vimg_material;
+
+/* ---- lights and background ---------------------------------------------- */
+#define VIMG_LIGHT_BACKGROUND (-1) /* Emitter::is_background(), emitters.h:25 */
+
+typedef enum vimg_background_type {
+  VIMG_BG_CONST = 0,  /* ConstBackground include/background.h:25-65          */
+  VIMG_BG_ENVMAP = 1  /* EnvMap          include/background.h:68-179         */
+} vimg_background_type;
+
+typedef struct vimg_background {
+  uint32_t type;
+  float color[3];          /* ConstBackground::col                           */
+  int32_t image;           /* EnvMap::image -> index into textures           */
+  float world_to_env[16];  /* column-major                                   */
+  float env_to_world[16];
+  float radiance_scale;
+  uint32_t cdf_width;      /* ArraySampling2D::width / height                */
+  uint32_t cdf_height;
+  const float* row_cdf;    /* cdf_height + 1 floats  (row_probabilities.cdf) */
+  const float* col_cdfs;   /* cdf_height x (cdf_width + 1) floats            */
+} vimg_background;
+
+/* ---- the whole scene ---------------------------------------------------- */
+typedef struct vimg_scene_desc {
+  uint32_t abi_version;    /* VIMG_ABI_VERSION */
+  vimg_camera camera;
+  vimg_bvh bvh;
+  const vimg_prim* prims;           uint64_t n_prims;
+  const vimg_sphere* spheres;       uint32_t n_spheres;
+  const vimg_mesh* meshes;          uint32_t n_meshes;
+  const vimg_material* materials;   uint32_t n_materials;
+  const vimg_texture* textures;     uint32_t n_textures;
+  const vimg_texture_rg* textures_rg; uint32_t n_textures_rg;
+  const int32_t* lights;            uint32_t n_lights; /* list_lights order: prim index or
+                                                          VIMG_LIGHT_BACKGROUND */
+  vimg_background background;
+} vimg_scene_desc;
+
+/* ---- render call -------------------------------------------------------- */
+typedef enum vimg_partition {
+  VIMG_PARTITION_TILE = 0 /* interleaved 8x8 tiles: tile i -> rank i % n_ranks
+                             (mirrors include/integrators.h:57-65,101)       */
+} vimg_partition;
+
+typedef struct vimg_render_params {
+  uint32_t integrator;   /* vimg_integrator                                  */
+  uint32_t samples;      /* spp (integrator_data::samples)                   */
+  uint32_t depth;        /* integrator_data::depth; UINT32_MAX for "depth": -1 */
+  uint32_t rank;         /* this process renders tiles rank, rank+n_ranks, ... */
+  uint32_t n_ranks;      /* 0 or 1 => whole frame                            */
+  uint32_t flags;        /* VIMG_FLAG_*                                      */
+} vimg_render_params;
+
+#define VIMG_FLAG_COUNTERS 1u /* also gather traversal counters (slower)     */
+
+typedef struct vimg_render_stats {
+  uint64_t rays_closest;   /* BVH::hit<optional<HitInfo>> calls               */
+  uint64_t rays_shadow;    /* BVH::occlude calls                              */
+  uint64_t inner_nodes;    /* inner nodes popped   (VIMG_FLAG_COUNTERS only)  */
+  uint64_t leaf_nodes;     /* leaves popped        (VIMG_FLAG_COUNTERS only)  */
+  uint64_t tri_tests;      /* triangle tests       (VIMG_FLAG_COUNTERS only)  */
+  uint64_t sphere_tests;   /* sphere tests         (VIMG_FLAG_COUNTERS only)  */
+  uint64_t nan_samples;    /* samples with a NaN channel (integrators.h:128)  */
+  uint64_t samples;        /* pixel samples taken by this rank                */
+  double kernel_ms;        /* device time of the render kernel(s), CUDA events */
+  double total_ms;         /* kernel + D2H of the frame                       */
+  uint32_t kernel_launches;
+} vimg_render_stats;
+
+typedef struct vimg_scene vimg_scene; /* opaque device-resident scene */
+
+/* number of CUDA devices visible (0 if none / no driver).  Never fails. */
+int vimg_cuda_device_count(void);
+
+/* thread-local message of the last failing call ("" if none). */
+const char* vimg_last_error(void);
+
+/* deep-copy `desc` to device `device_id` and build the GPU layout. */
+int vimg_scene_create(const vimg_scene_desc* desc, int device_id, vimg_scene** out_scene);
+void vimg_scene_destroy(vimg_scene* scene);
+
+/* bytes of device memory the scene occupies (BVH + geometry + textures). */
+uint64_t vimg_scene_device_bytes(const vimg_scene* scene);
+
+/* Replaces scene_integrator<F>() (include/integrators.h:36-153).
+ * out_rgb: HOST buffer of W*H*3 floats (row 0 = top).  With n_ranks > 1 only
+ * this rank's tiles are written, every other pixel is 0 (so a sum over ranks,
+ * e.g. an NCCL reduce, assembles the frame exactly).  The call includes the
+ * device->host copy of the frame. */
+int vimg_render(vimg_scene* scene, const vimg_render_params* params, float* out_rgb,
+                vimg_render_stats* stats /* nullable */);
+
+/* Same, but the frame stays in device memory (for NCCL / peer stores and for
+ * timing without the D2H copy).  *out_dev_rgb is owned by the scene and valid
+ * until the next render or vimg_scene_destroy().  `stream` is a cudaStream_t
+ * (NULL = default stream); the call returns after the stream is synchronised. */
+int vimg_render_device(vimg_scene* scene, const vimg_render_params* params,
+                       float** out_dev_rgb, void* stream, vimg_render_stats* stats);
+
+/* Replaces trace_pixel<F>() (include/integrators.h:181-220): one pixel, image
+ * coordinates as in the reference's -d "x y" (y = 0 is the bottom row). */
+int vimg_trace_pixel(vimg_scene* scene, const vimg_render_params* params, int x, int y,
+                     float out_rgb[3]);
+
+/* Parity hook: primitive index of the closest hit of every camera ray
+ * (-1 = miss), for all `samples` samples of every pixel, using the same
+ * per-pixel RNG stream and R2 jitter as the normal integrators.
+ * out_prim_id: HOST buffer of W*H*samples int32, index = image_index*samples + s.
+ * out_t (nullable): same shape, the hit distance ray.maxT (inf on miss). */
+int vimg_trace_ids(vimg_scene* scene, uint32_t samples, int32_t* out_prim_id, float* out_t);
+
+/* ---- scene blob I/O (flattened scene cache; used for test fixtures) ------ */
+/* serialise a descriptor to a single relocatable file and back.  A loaded
+ * scene owns its arrays; free with vimg_scene_desc_free(). */
+int vimg_scene_desc_save(const vimg_scene_desc* desc, const char* path);
+int vimg_scene_desc_load(const char* path, vimg_scene_desc** out_desc);
+void vimg_scene_desc_free(vimg_scene_desc* desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIMG_CUDA_H */

@@ -1,0 +1,378 @@
+// ref_driver.cpp -- ORACLE / TEST INFRASTRUCTURE.  Not part of the product path.
+//
+// Links the UNMODIFIED reference sources (compiled where they lie under
+// /root/reference by oracle/Makefile) behind a small C API so that tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// can (1) load a scene with the reference's own loaders and BVH builders,
+// (2) render it with the reference's own scene_integrator<F>()
+// (include/integrators.h:36-153), (3) dump bit-exact parity targets (primary
+// hit primitive ids) and (4) hand out the scene flattened through the product's
+// adapter (v-img_b200/adapter/vimg_adapter.cpp).
+//
+// Built in three flavours (oracle/Makefile):
+//   parity : no -march, -ffp-contract=off  -> scalar slab path (bvh.h:118-126),
+//            exact 1/dir, no FMA contraction.  THE bit-exact oracle.
+//   perf   : -O3 -march=native, as the reference's CMake does (CMakeLists.txt:55-57)
+//            -> AVX2 sibling-pair path.  THE timing baseline.
+//   count  : parity flags + a build-time instrumented bvh.h (thread-local ray /
+//            node / primitive-test counters) for the roofline cross-check.
+#include <background.h>
+#include <bvh.h>
+#include <geometry/mesh.h>
+#include <geometry/sphere.h>
+#include <geometry/triangle.h>
+#include <integrators.h>
+#include <material/principled.h>
+#include <scene_loading/json_scene.h>
+#include <texture/texture_RG.h>
+#include <texture/texture_RGB.h>
+
+#include <chrono>
+#include <cstring>
+#include <numeric>
+#include <thread>
+
+#include "../v-img_b200/adapter/vimg_adapter.h"
+
+#ifdef VREF_COUNTERS
+// declared by oracle/count_hook.h, bumped by the build-time instrumented bvh.h
+// (oracle/Makefile, count flavour)
+std::atomic<uint64_t> vref_counters_g[6];
+#endif
+
+namespace {
+
+struct RefScene {
+  integrator_data settings;
+  std::vector<std::unique_ptr<Material>> mat_list;
+  std::vector<std::unique_ptr<Surface>> list_objects;
+  std::vector<Emitter*> list_lights;
+  std::vector<std::unique_ptr<Mesh>> list_meshes;
+  std::vector<std::unique_ptr<TextureRGB>> texture_list;
+  std::vector<std::unique_ptr<TextureRG>> textureRG_list;
+  BVH bvh;
+  std::unique_ptr<VimgFlatScene> flat;
+  double bvh_build_s = 0;
+};
+
+// src/main.cpp:26-36 (setup_for_bvh) + :181-204, restated because main.cpp is
+// not part of the oracle build.
+void build_bvh(RefScene& sc, int bvh_type) {
+  std::vector<AABB> bboxes;
+  std::vector<glm::vec3> centers;
+  bboxes.reserve(sc.list_objects.size());
+  centers.reserve(sc.list_objects.size());
+  for (auto const& obj : sc.list_objects) {
+    AABB box = obj->bounds();
+    bboxes.push_back(box);
+    centers.push_back((box.bboxes[1] + box.bboxes[0]) * 0.5f);
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  if (bvh_type == 1) {
+    std::vector<size_t> temp_indices(bboxes.size());
+    std::iota(temp_indices.begin(), temp_indices.end(), 0);
+    sc.bvh = BVH::build_sweep_bvh(bboxes, centers, temp_indices, 8);
+  } else {
+    sc.bvh = BVH::build_bin_bvh(bboxes, centers, 16);
+  }
+  sc.bvh_build_s =
+      std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+typedef glm::vec3 (*integrator_fn)(Ray&, std::vector<size_t>&, const BVH&,
+                                   const std::vector<std::unique_ptr<Surface>>&,
+                                   const GroupOfEmitters&, pcg32_random_t&, uint32_t, Background*);
+
+integrator_fn pick(int integrator) {
+  switch (integrator) {
+    case 0: return shading_normal_integrator;
+    case 1: return geometric_normal_integrator;
+    case 2: return material_integrator;
+    default: return mis_integrator;
+  }
+}
+
+// ---- synthetic scene of SURVEY.md section 8(d) (configs C4 / C5), built through the reference's
+// own C++ classes: height-field mesh + mip-mapped image texture + normal map + HDR env map + DOF.
+float height_fn(float x, float z) {
+  return 0.6f * std::sin(3.f * x) * std::cos(2.f * z)
+         + 0.15f * std::sin(17.f * x + 1.f) * std::sin(13.f * z)
+         + 0.03f * std::sin(71.f * x) * std::cos(67.f * z);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vref_flavour() {
+#if defined(VREF_COUNTERS)
+  return 2;
+#elif defined(__AVX2__)
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+int vref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+void* vref_scene_from_json(const char* path, int bvh_type) {
+  auto sc = std::make_unique<RefScene>();
+  bool ok = set_scene_from_json(path, sc->settings, sc->list_objects, sc->mat_list,
+                                sc->list_lights, sc->list_meshes, sc->textureRG_list,
+                                sc->texture_list);
+  if (!ok) return nullptr;
+  sc->settings.num_threads = -1;
+  build_bvh(*sc, bvh_type);
+  return sc.release();
+}
+
+// G x G quads; tex_size^2 colour texture (mips) and normal map; env_w x env_h env map.
+// with_rg != 0 adds a square metallic-roughness TextureRG (a30) for coverage.
+void* vref_scene_synthetic(int G, int width, int height, int tex_size, int env_w, int env_h,
+                           uint32_t spp, uint32_t depth, int bvh_type, int with_rg,
+                           float aperture_radius) {
+  auto sc = std::make_unique<RefScene>();
+  const int V = G + 1;
+  std::vector<glm::vec3> vertices(size_t(V) * V), normals(size_t(V) * V);
+  std::vector<glm::vec2> uvs(size_t(V) * V);
+  const float eps = 1e-3f;
+  for (int j = 0; j < V; ++j)
+    for (int i = 0; i < V; ++i) {
+      float x = -5.f + 10.f * float(i) / float(G);
+      float z = -5.f + 10.f * float(j) / float(G);
+      size_t a = size_t(j) * V + i;
+      vertices[a] = glm::vec3(x, height_fn(x, z), z);
+      float dx = (height_fn(x + eps, z) - height_fn(x - eps, z)) / (2.f * eps);
+      float dz = (height_fn(x, z + eps) - height_fn(x, z - eps)) / (2.f * eps);
+      normals[a] = glm::normalize(glm::vec3(-dx, 1.f, -dz));
+      uvs[a] = glm::vec2(8.f * float(i) / float(G), 8.f * float(j) / float(G));
+    }
+  std::vector<std::array<uint32_t, 3>> indices;
+  indices.reserve(size_t(G) * G * 2);
+  for (int j = 0; j < G; ++j)
+    for (int i = 0; i < G; ++i) {
+      uint32_t a = uint32_t(j) * V + i, b = a + 1, c = a + V, d = c + 1;
+      indices.push_back({a, c, b});
+      indices.push_back({b, c, d});
+    }
+
+  // colour texture with mips (mip-generating ctor, src/image_texture.cpp:60-130)
+  std::vector<glm::vec3> img(size_t(tex_size) * tex_size);
+  for (int y = 0; y < tex_size; ++y)
+    for (int x = 0; x < tex_size; ++x) {
+      float u = float(x) / float(tex_size), v = float(y) / float(tex_size);
+      float c = 0.5f + 0.5f * std::sin(40.f * u) * std::sin(40.f * v);
+      img[size_t(y) * tex_size + x] = glm::vec3(0.2f + 0.6f * c, 0.3f + 0.3f * u, 0.2f + 0.5f * v);
+    }
+  sc->texture_list.push_back(std::make_unique<ImageTexture>(
+      img, tex_size, tex_size, TextureWrappingMode::Repeat, TextureWrappingMode::Repeat));
+  TextureRGB* col_tex = sc->texture_list.back().get();
+
+  // single-level normal map
+  std::vector<glm::vec3> nimg(size_t(tex_size) * tex_size);
+  for (int y = 0; y < tex_size; ++y)
+    for (int x = 0; x < tex_size; ++x) {
+      float u = float(x) / float(tex_size), v = float(y) / float(tex_size);
+      nimg[size_t(y) * tex_size + x]
+          = glm::normalize(glm::vec3(0.3f * std::cos(200.f * u), 0.3f * std::cos(200.f * v), 1.f));
+    }
+  std::vector<std::vector<glm::vec3>> nlevels{nimg};
+  sc->texture_list.push_back(std::make_unique<ImageTexture>(
+      nlevels, tex_size, tex_size, TextureWrappingMode::Repeat, TextureWrappingMode::Repeat));
+  ImageTexture* normal_map = static_cast<ImageTexture*>(sc->texture_list.back().get());
+
+  TextureRG* rg = nullptr;
+  if (with_rg) {
+    const int R = 64;
+    std::vector<glm::vec2> rgimg(size_t(R) * R);
+    for (int y = 0; y < R; ++y)
+      for (int x = 0; x < R; ++x)
+        rgimg[size_t(y) * R + x] = glm::vec2(0.5f + 0.5f * std::sin(0.37f * x) * std::cos(0.21f * y),
+                                             0.6f + 0.4f * std::cos(0.11f * (x + y)));
+    sc->textureRG_list.push_back(std::make_unique<TextureRG>(
+        R, R, rgimg, TextureWrappingMode::MirroredRepeat, TextureWrappingMode::Repeat));
+    rg = sc->textureRG_list.back().get();
+  }
+
+  sc->mat_list.push_back(std::make_unique<Principled>(
+      col_tex, rg, glm::vec2(0.2f, 0.4f), /*spec_trans*/ 0.f, /*subsurface*/ 0.f,
+      /*specular*/ 0.5f, /*spec_tint*/ 0.f, /*anisotropic*/ 0.f, /*sheen*/ 0.f,
+      /*sheen_tint*/ 0.5f, /*clearcoat*/ 0.3f, /*clearcoat_gloss*/ 0.8f, /*eta*/ 1.5f, normal_map));
+  Material* mat = sc->mat_list.back().get();
+
+  std::vector<std::vector<glm::vec2>> uvsets{uvs};
+  sc->list_meshes.push_back(std::make_unique<Mesh>(indices, vertices, normals, uvsets, mat,
+                                                   /*color uv*/ 0, /*normal uv*/ 0,
+                                                   with_rg ? 0 : MeshConsts::no_uv));
+  std::vector<Emitter*> no_lights;
+  add_tri_list_to_scene(sc->list_objects, sc->list_meshes.back().get(), no_lights);
+
+  // env map (lat-long, clamp, identity transforms)
+  std::vector<glm::vec3> env(size_t(env_w) * env_h);
+  for (int y = 0; y < env_h; ++y)
+    for (int x = 0; x < env_w; ++x) {
+      float u = (float(x) + 0.5f) / float(env_w), v = (float(y) + 0.5f) / float(env_h);
+      glm::vec3 sky = glm::vec3(0.5f, 0.7f, 1.0f) * (0.3f + 0.7f * (1.f - v));
+      float du = u - 0.3f, dv = v - 0.25f;
+      glm::vec3 sun = glm::vec3(1.f, 0.9f, 0.7f) * (400.f * std::exp(-4000.f * (du * du + dv * dv)));
+      env[size_t(y) * env_w + x] = sky + sun;
+    }
+  ImageTexture env_img(env, env_w, env_h, TextureWrappingMode::ClampToEdge,
+                       TextureWrappingMode::ClampToEdge);
+  sc->settings.background
+      = std::make_unique<EnvMap>(env_img, glm::mat4(1.0f), glm::mat4(1.0f), 1.0f);
+  sc->list_lights.push_back(sc->settings.background.get());
+
+  sc->settings.func = integrator_func::mis;
+  sc->settings.resolution = glm::ivec2(width, height);
+  sc->settings.samples = spp;
+  sc->settings.depth = depth;
+  sc->settings.camera = TLCam(camToWorld(glm::vec3(0, 3.5f, 9), glm::vec3(0, 0, 0), glm::vec3(0, 1, 0)),
+                              glm::ivec2(width, height), 40.f, aperture_radius, 9.5f);
+  sc->settings.num_threads = -1;
+  build_bvh(*sc, bvh_type);
+  return sc.release();
+}
+
+void vref_scene_free(void* h) { delete static_cast<RefScene*>(h); }
+
+// info[0..7] = width, height, spp, depth, integrator, n_prims, n_nodes, max_depth
+void vref_scene_info(void* h, uint64_t info[8], double* bvh_build_s) {
+  auto* sc = static_cast<RefScene*>(h);
+  info[0] = sc->settings.resolution[0];
+  info[1] = sc->settings.resolution[1];
+  info[2] = sc->settings.samples;
+  info[3] = sc->settings.depth;
+  info[4] = (uint64_t)sc->settings.func;
+  info[5] = sc->list_objects.size();
+  info[6] = sc->bvh.nodes.size();
+  info[7] = sc->bvh.max_depth;
+  if (bvh_build_s) *bvh_build_s = sc->bvh_build_s;
+}
+
+// Change a setting the JSON format cannot express (background colour is parsed
+// and ignored, json_scene.cpp:202-206; aperture is fixed to 0, :179).
+void vref_scene_set_const_background(void* h, float r, float g, float b, int as_light) {
+  auto* sc = static_cast<RefScene*>(h);
+  sc->settings.background = std::make_unique<ConstBackground>(glm::vec3(r, g, b));
+  // drop any previous background light, then optionally add the new one
+  std::vector<Emitter*> kept;
+  for (Emitter* e : sc->list_lights)
+    if (!e->is_background()) kept.push_back(e);
+  sc->list_lights = kept;
+  if (as_light) sc->list_lights.push_back(sc->settings.background.get());
+  sc->flat.reset();
+}
+
+void vref_scene_set_camera_dof(void* h, float aperture_radius, float focal_dist) {
+  auto* sc = static_cast<RefScene*>(h);
+  sc->settings.camera.aperture_radius = aperture_radius;  // -fno-access-control
+  sc->settings.camera.focal_dist = focal_dist;
+  sc->flat.reset();
+}
+
+// The scene flattened by the product's adapter; owned by the RefScene handle.
+const vimg_scene_desc* vref_scene_desc(void* h) {
+  auto* sc = static_cast<RefScene*>(h);
+  try {
+    if (!sc->flat)
+      sc->flat = vimg_flatten_scene(sc->settings, sc->bvh, sc->list_objects, sc->list_lights);
+  } catch (const std::exception& e) {
+    fmt::println("vref_scene_desc: {}", e.what());
+    return nullptr;
+  }
+  return &sc->flat->desc;
+}
+
+// Render with the reference's own scene_integrator.  spp == 0 / depth == 0 keep the
+// scene-file values.  Returns seconds spent inside scene_integrator (the span
+// src/main.cpp:211,300-302 prints as "image rendering").
+double vref_render(void* h, int integrator, uint32_t spp, uint32_t depth, int threads,
+                   float* out_rgb) {
+  auto* sc = static_cast<RefScene*>(h);
+  integrator_data& s = sc->settings;
+  uint32_t keep_spp = s.samples, keep_depth = s.depth;
+  if (spp) s.samples = spp;
+  if (depth) s.depth = depth;
+  s.num_threads = (int16_t)threads;
+  GroupOfEmitters lights(sc->list_lights);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<glm::vec3> img
+      = scene_integrator(s, sc->bvh, sc->list_objects, lights, pick(integrator));
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  s.samples = keep_spp;
+  s.depth = keep_depth;
+  if (out_rgb) std::memcpy(out_rgb, img.data(), img.size() * sizeof(glm::vec3));
+  return sec;
+}
+
+// trace_pixel (include/integrators.h:181-220)
+void vref_trace_pixel(void* h, int integrator, uint32_t spp, uint32_t depth, int x, int y,
+                      float out_rgb[3]) {
+  auto* sc = static_cast<RefScene*>(h);
+  integrator_data& s = sc->settings;
+  uint32_t keep_spp = s.samples, keep_depth = s.depth;
+  if (spp) s.samples = spp;
+  if (depth) s.depth = depth;
+  GroupOfEmitters lights(sc->list_lights);
+  glm::vec3 c = trace_pixel(s, sc->bvh, sc->list_objects, lights, pick(integrator), x, y);
+  s.samples = keep_spp;
+  s.depth = keep_depth;
+  out_rgb[0] = c.x;
+  out_rgb[1] = c.y;
+  out_rgb[2] = c.z;
+}
+
+// Primary-hit primitive ids for every sample of every pixel, through the reference's own
+// camera, RNG, R2 sequence and BVH::hit (the loop of include/integrators.h:109-127 with the
+// integrator call replaced by the closest-hit query).  index = image_index * spp + s.
+void vref_trace_ids(void* h, uint32_t spp, int32_t* out_ids, float* out_t) {
+  auto* sc = static_cast<RefScene*>(h);
+  const integrator_data& rd = sc->settings;
+  const size_t W = rd.resolution[0], H = rd.resolution[1];
+  std::unordered_map<const Emitter*, int32_t> to_prim;
+  for (size_t i = 0; i < sc->list_objects.size(); ++i)
+    to_prim[dynamic_cast<const Emitter*>(sc->list_objects[i].get())] = (int32_t)i;
+
+#pragma omp parallel
+  {
+    std::vector<size_t> stack;
+    stack.reserve(sc->bvh.max_depth + 2);
+    pcg32_random_t st;
+#pragma omp for schedule(dynamic, 4)
+    for (long long yy = 0; yy < (long long)H; ++yy) {
+      size_t y = (size_t)yy;
+      for (size_t x = 0; x < W; ++x) {
+        size_t image_index = x + ((H - 1 - y) * W);
+        size_t image_seq_start = x + y;
+        pcg32_srandom_r(&st, image_index, 0);
+        for (size_t s = 0; s < spp; ++s) {
+          glm::vec2 off = random_x_y_r2(image_seq_start + s);
+          Ray ray = rd.camera.generate_ray(x + off.x, y + off.y, rand_float(st), rand_float(st));
+          auto hit = sc->bvh.hit<std::optional<HitInfo>>(ray, stack, sc->list_objects);
+          int32_t id = -1;
+          if (hit.has_value()) id = to_prim.at(hit.value().obj);
+          out_ids[image_index * spp + s] = id;
+          if (out_t) out_t[image_index * spp + s] = ray.maxT;
+        }
+      }
+    }
+  }
+}
+
+// counters[0..5] = rays_closest, rays_shadow, inner nodes popped, leaves popped, primitive
+// tests, (unused) since the last reset (count flavour only; zeros otherwise).
+void vref_counters(uint64_t out[6], int reset) {
+#ifdef VREF_COUNTERS
+  for (int i = 0; i < 6; ++i) {
+    out[i] = vref_counters_g[i].load();
+    if (reset) vref_counters_g[i].store(0);
+  }
+#else
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  (void)reset;
+#endif
+}
+
+}  // extern "C"

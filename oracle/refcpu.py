@@ -1,0 +1,158 @@
+"""ctypes binding of the compiled reference renderer (oracle/_ref/libvimg_ref_*.so).
+
+ORACLE / TEST INFRASTRUCTURE -- only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module.  The
+product path (v-img_b200/) never does.
+
+The shared objects are built from the unmodified reference sources by
+oracle/Makefile (see oracle/ref_driver.cpp for the C API).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FLAVOURS = ("parity", "perf", "count")
+INTEGRATORS = {"s_normal": 0, "g_normal": 1, "material": 2, "mis": 3}
+
+
+def lib_path(flavour):
+    return os.path.join(_HERE, "_ref", f"libvimg_ref_{flavour}.so")
+
+
+def available(flavour="parity"):
+    return os.path.exists(lib_path(flavour))
+
+
+_libs = {}
+
+
+def _load(flavour):
+    if flavour in _libs:
+        return _libs[flavour]
+    lib = C.CDLL(lib_path(flavour))
+    lib.vref_scene_from_json.restype = C.c_void_p
+    lib.vref_scene_from_json.argtypes = [C.c_char_p, C.c_int]
+    lib.vref_scene_synthetic.restype = C.c_void_p
+    lib.vref_scene_synthetic.argtypes = [C.c_int] * 6 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                                         C.c_float]
+    lib.vref_scene_free.argtypes = [C.c_void_p]
+    lib.vref_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    lib.vref_scene_set_const_background.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                                    C.c_int]
+    lib.vref_scene_set_camera_dof.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    lib.vref_scene_desc.restype = C.c_void_p
+    lib.vref_scene_desc.argtypes = [C.c_void_p]
+    lib.vref_render.restype = C.c_double
+    lib.vref_render.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    lib.vref_trace_pixel.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                     C.c_void_p]
+    lib.vref_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.vref_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    lib.vref_flavour.restype = C.c_int
+    lib.vref_hardware_threads.restype = C.c_int
+    _libs[flavour] = lib
+    return lib
+
+
+class RefScene:
+    """A scene loaded and BVH-built by the reference's own host code."""
+
+    def __init__(self, handle, flavour):
+        if not handle:
+            raise RuntimeError("reference failed to load the scene")
+        self._h = handle
+        self.flavour = flavour
+        self._lib = _load(flavour)
+        info = (C.c_uint64 * 8)()
+        bs = C.c_double()
+        self._lib.vref_scene_info(self._h, info, C.byref(bs))
+        (self.width, self.height, self.spp, self.depth, self.integrator, self.n_prims,
+         self.n_nodes, self.max_depth) = [int(v) for v in info]
+        self.bvh_build_s = bs.value
+
+    @classmethod
+    def from_json(cls, path, bvh="binned", flavour="parity"):
+        lib = _load(flavour)
+        return cls(lib.vref_scene_from_json(os.fsencode(path), 1 if bvh == "sweep" else 0), flavour)
+
+    @classmethod
+    def synthetic(cls, G, width, height, tex_size=2048, env_w=2048, env_h=1024, spp=512, depth=64,
+                  bvh="sweep", with_rg=False, aperture=0.02, flavour="parity"):
+        lib = _load(flavour)
+        h = lib.vref_scene_synthetic(G, width, height, tex_size, env_w, env_h, spp, depth,
+                                     1 if bvh == "sweep" else 0, int(with_rg), aperture)
+        return cls(h, flavour)
+
+    def close(self):
+        if self._h:
+            self._lib.vref_scene_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_const_background(self, rgb, as_light=True):
+        self._lib.vref_scene_set_const_background(self._h, *[float(c) for c in rgb], int(as_light))
+
+    def set_camera_dof(self, aperture, focal_dist):
+        self._lib.vref_scene_set_camera_dof(self._h, aperture, focal_dist)
+
+    def desc_ptr(self):
+        """Address of the vimg_scene_desc flattened by the product's adapter (owned by self)."""
+        p = self._lib.vref_scene_desc(self._h)
+        if not p:
+            raise RuntimeError("adapter could not flatten the scene")
+        return p
+
+    def render(self, integrator, spp=0, depth=0, threads=0):
+        """-> (image float32 [H, W, 3] row 0 = top, seconds inside scene_integrator)."""
+        out = np.empty((self.height, self.width, 3), np.float32)
+        sec = self._lib.vref_render(self._h, INTEGRATORS[integrator], spp, depth, threads,
+                                    out.ctypes.data)
+        return out, sec
+
+    def trace_pixel(self, integrator, x, y, spp=0, depth=0):
+        out = np.empty(3, np.float32)
+        self._lib.vref_trace_pixel(self._h, INTEGRATORS[integrator], spp, depth, x, y,
+                                   out.ctypes.data)
+        return out
+
+    def trace_ids(self, spp):
+        """-> (ids int32 [H*W, spp], t float32 [H*W, spp]); row index = image_index."""
+        ids = np.empty((self.height * self.width, spp), np.int32)
+        t = np.empty((self.height * self.width, spp), np.float32)
+        self._lib.vref_trace_ids(self._h, spp, ids.ctypes.data, t.ctypes.data)
+        return ids, t
+
+    def counters(self, reset=True):
+        out = (C.c_uint64 * 6)()
+        self._lib.vref_counters(out, int(reset))
+        return dict(zip(("rays_closest", "rays_shadow", "inner_nodes", "leaf_nodes", "prim_tests",
+                         "unused"), [int(v) for v in out]))
+
+
+def hardware_threads(flavour="perf"):
+    return _load(flavour).vref_hardware_threads()
+
+
+SURVEY_FNV_BASIS = 1469598103934665603  # SURVEY.md's hashes used this (typo'd) offset basis
+
+
+def fnv1a64(arr, basis=0xCBF29CE484222325):
+    """FNV-1a-64 over the raw bytes of an array (sequential; use on small arrays only)."""
+    hv = int(basis)
+    for b in np.ascontiguousarray(arr).view(np.uint8).ravel().tobytes():
+        hv = ((hv ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return f"{hv:016x}"
+
+
+def digest(arr):
+    """64-bit BLAKE2b of the raw bytes of an array: the hash tests/golden/manifest.json records."""
+    import hashlib
+    return hashlib.blake2b(np.ascontiguousarray(arr).view(np.uint8).ravel().tobytes(),
+                           digest_size=8).hexdigest()

@@ -1,0 +1,12 @@
+"""v-img_b200 -- B200-native `cuda` render device for the v-img path tracer.
+
+The product is libvimg_cuda.so (hand-written CUDA for sm_100a behind the C ABI of
+include/vimg_cuda.h).  This package is the thin Python host side: it loads the
+library with ctypes and mirrors the reference's render entry points
+(scene_integrator / trace_pixel, include/integrators.h:36-220) by name.
+
+There is NO CPU fallback: importing works anywhere, but every compute call
+raises VimgError when the CUDA extension or a CUDA device is missing.
+"""
+from .renderer import (INTEGRATORS, Scene, VimgError, device_count, lib_path,  # noqa: F401
+                       load_library)

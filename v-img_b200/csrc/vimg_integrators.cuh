@@ -1,0 +1,467 @@
+// vimg_integrators.cuh -- emitters, background and the four integrators.
+#pragma once
+#include "vimg_disney.cuh"
+
+namespace vimg {
+
+// ----------------------------------------------------- material dispatch ----
+VD bool mat_sample(const DScene& sc, const vimg_material& m, V3 wi, const HitInfo& hit, Pcg32& rng,
+                   bool regularize, ScatterInfo& out) {
+  switch (m.type) {
+    case VIMG_MAT_LAMBERTIAN: return lambertian_sample(wi, hit, rng, out);
+    case VIMG_MAT_DIELECTRIC: return dielectric_sample(m, wi, hit, rng, out);
+    case VIMG_MAT_PRINCIPLED: return principled_sample(sc, m, wi, hit, rng, regularize, out);
+    default: return false;  // DiffuseLight / base: std::nullopt (material.h:37-40)
+  }
+}
+
+// eval_pdf_pair; base default (0, 1) also covers Dielectric and DiffuseLight (material.h:56-60)
+VD void mat_eval_pdf_pair(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, const HitInfo& hit,
+                          RayCone cone, bool regularize, V3& eval, float& pdf) {
+  switch (m.type) {
+    case VIMG_MAT_LAMBERTIAN: lambertian_eval_pdf(sc, m, wi, wo, hit, cone, eval, pdf); return;
+    case VIMG_MAT_PRINCIPLED: principled_eval_pdf(sc, m, wi, wo, hit, cone, regularize, eval, pdf); return;
+    default:
+      eval = mk3(0.f);
+      pdf = 1.0f;
+  }
+}
+
+// eval_div_pdf; base default 0 (material.h:51-54)
+VD V3 mat_eval_div_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, const HitInfo& hit,
+                       RayCone cone, bool regularize) {
+  switch (m.type) {
+    case VIMG_MAT_LAMBERTIAN: return col_at_ray_hit(sc, m.texture, wi, cone, hit);
+    case VIMG_MAT_DIELECTRIC: return mk3(1.f);
+    case VIMG_MAT_PRINCIPLED: {
+      V3 e;
+      float p;
+      principled_eval_pdf(sc, m, wi, wo, hit, cone, regularize, e, p);
+      return e / p;
+    }
+    default: return mk3(0.f);
+  }
+}
+
+// ------------------------------------------------------------ background ----
+VD V3 xform_dir(const float* m, V3 d) {
+  V4 r = mat4_mul(m, mk4(d.x, d.y, d.z, 0.0f));
+  return mk3(r.x, r.y, r.z);
+}
+
+VD void envmap_uv(const DScene& sc, V3 in_dir, float& u, float& v) {
+  V3 dir = normalize(xform_dir(sc.bg.world_to_env, in_dir));
+  u = (float)((1.f + (double)m_atan2f(-dir.x, dir.z) * VIMG_INV_PI_D) * 0.5f);
+  v = (float)((double)m_acosf(dir.y) * VIMG_INV_PI_D);
+}
+
+// ConstBackground / EnvMap::background_emit (background.h:34-36, 88-108)
+VD V3 background_emit(const DScene& sc, V3 in_dir, RayCone cone) {
+  if (sc.bg.type == VIMG_BG_CONST) return mk3(sc.bg.color[0], sc.bg.color[1], sc.bg.color[2]);
+  float u, v;
+  envmap_uv(sc, in_dir, u, v);
+  const DTexture& img = sc.textures[sc.bg.image];
+  // std::log2(double): |spread| * (height / pi)
+  float lambda = (float)log2((double)fabsf(cone.spread_angle) * ((double)img.height / VIMG_PI_D));
+  lambda = is_nan(lambda) ? 0.f : lambda;
+  return col_mipmap_interpolate(sc, img, lambda - 2.f, mk2(u, v)) * sc.bg.radiance_scale;
+}
+
+// background_pdf (background.h:56, 141-169)
+VD float background_pdf(const DScene& sc, V3 in_dir) {
+  if (sc.bg.type == VIMG_BG_CONST) return (float)(1.f / (4 * VIMG_PI_D));
+  float u, v;
+  envmap_uv(sc, in_dir, u, v);
+  const uint32_t W = sc.bg.cdf_w, H = sc.bg.cdf_h;
+  const DTexture& img = sc.textures[sc.bg.image];
+  int pixel_u = (int)(u * img.width);
+  int pixel_v = (int)(v * img.height);
+  int column_index = std_clampi(pixel_u, 0, (int)img.width - 1);
+  int row_index = std_clampi(pixel_v, 0, (int)img.height - 1);
+  float pdf_y = sc.bg.row_cdf[row_index + 1] - sc.bg.row_cdf[row_index];
+  const float* row = sc.bg.col_cdfs + (size_t)row_index * (W + 1);
+  float pdf_x = row[column_index + 1] - row[column_index];
+  float sin_elevation = (float)sin(VIMG_PI_D * (double)v);
+  (void)H;
+  return (float)((double)(pdf_y * pdf_x * img.width * img.height)
+                 / (2.f * VIMG_PI_D * VIMG_PI_D * (double)sin_elevation));
+}
+
+// ------------------------------------------------------------------ lights ----
+// Triangle::sample (triangle.cpp:178-233)
+VD V3 triangle_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32& rng, EmitterInfo& info) {
+  const vimg_prim pr = sc.prims[prim];
+  const DMesh& mesh = sc.meshes[pr.a];
+  const uint32_t* idx = sc.tri_indices + 3 * ((size_t)mesh.tri_base + pr.b);
+  const uint32_t i0 = idx[0] + mesh.vert_base, i1 = idx[1] + mesh.vert_base, i2 = idx[2] + mesh.vert_base;
+  V3 p0 = load3(sc.vertices, i0), p1 = load3(sc.vertices, i1), p2 = load3(sc.vertices, i2);
+  const V3 edge1 = p1 - p0, edge2 = p2 - p0;
+  V3 tri_normal = normalize(cross(edge1, edge2));
+  V3 n0, n1, n2;
+  if (mesh.has_normals) {
+    n0 = load3(sc.normals, i0);
+    n1 = load3(sc.normals, i1);
+    n2 = load3(sc.normals, i2);
+  } else {
+    n0 = n1 = n2 = tri_normal;
+  }
+  float rand1 = rand_float(rng);
+  float rand2 = rand_float(rng);
+  float u, v;
+  if (rand1 < rand2) {
+    u = rand1 / 2.f;
+    v = rand2 - u;
+  } else {
+    v = rand2 / 2.f;
+    u = rand1 - v;
+  }
+  float w = 1.f - u - v;
+  const V3 hit_p = p0 * u + p1 * v + p2 * w;
+  V3 hit_n = normalize(u * n0 + v * n1 + w * n2);
+  V3 dir_vec = hit_p - look_from;
+  float dist2 = length2(dir_vec);
+  dir_vec = normalize(dir_vec);
+  float area = length(cross(edge2, edge1)) / 2.0f;
+  float pdf = 1.f / area;
+  float cosine = fabsf(dot(hit_n, -dir_vec));
+  float G = cosine / dist2;
+  info.wi = dir_vec;
+  info.pdf = pdf;
+  info.dist = sqrtf(dist2);
+  info.G = G;
+  return mat_emitted(sc.materials[mesh.material], info.wi, hit_n);
+}
+
+// Triangle::surf_pdf (triangle.cpp:235-248)
+VD float triangle_surf_pdf(const DScene& sc, uint32_t prim) {
+  const vimg_prim pr = sc.prims[prim];
+  const DMesh& mesh = sc.meshes[pr.a];
+  const uint32_t* idx = sc.tri_indices + 3 * ((size_t)mesh.tri_base + pr.b);
+  V3 p0 = load3(sc.vertices, idx[0] + mesh.vert_base), p1 = load3(sc.vertices, idx[1] + mesh.vert_base),
+     p2 = load3(sc.vertices, idx[2] + mesh.vert_base);
+  V3 edge1 = p1 - p0, edge2 = p2 - p0;
+  float area = length(cross(edge2, edge1)) / 2.0f;
+  return 1.f / area;
+}
+
+// Sphere::sample (sphere.cpp:58-118)
+VD V3 sphere_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32& rng, EmitterInfo& info) {
+  const vimg_sphere& s = sc.spheres[sc.prims[prim].a];
+  const V3 center = mk3(s.center[0], s.center[1], s.center[2]);
+  const float radius = s.radius;
+  float rand1 = rand_float(rng);
+  float rand2 = rand_float(rng);
+  V3 shading_normal;
+  if (length2(look_from - center) <= radius * radius) {
+    V3 point_on_unit_sphere = sample_sphere(rand1, rand2);
+    V3 point_on_sphere = (point_on_unit_sphere * radius) + center;
+    V3 vec_from_lf_to_pos = point_on_sphere - look_from;
+    shading_normal = point_on_unit_sphere;
+    const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+    V3 dir_to_surf = normalize(vec_from_lf_to_pos);
+    float dist2 = length2(vec_from_lf_to_pos);
+    float cosine = fabsf(dot(shading_normal, -dir_to_surf));
+    float G = cosine / dist2;
+    info.wi = dir_to_surf;
+    info.pdf = 1.f / sphere_sa;
+    info.dist = sqrtf(dist2);
+    info.G = G;
+  } else {
+    // unqualified sqrt() on a float => double
+    float cos_theta_max
+        = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
+    V3 dir_center_to_lf = normalize(look_from - center);
+    ONB onb = init_onb(dir_center_to_lf);
+    V3 sample_z_dir = sample_sphere_cap(rand1, rand2, cos_theta_max);
+    V3 sampled_point = normalize(xform_with_onb(onb, sample_z_dir)) * radius + center;
+    float dist2 = length2(sampled_point - look_from);
+    shading_normal = normalize(sampled_point - center);
+    V3 sampled_dir = normalize(sampled_point - look_from);
+    float cosine = fabsf(dot(shading_normal, -sampled_dir));
+    float G = cosine / dist2;
+    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+    info.wi = sampled_dir;
+    info.pdf = pdf_solid_angle * G;
+    info.dist = sqrtf(dist2);
+    info.G = G;
+  }
+  return mat_emitted(sc.materials[s.material], info.wi, shading_normal);
+}
+
+// Sphere::surf_pdf (sphere.cpp:120-139)
+VD float sphere_surf_pdf(const DScene& sc, uint32_t prim, V3 look_from, V3 point_on_light, V3 dir) {
+  const vimg_sphere& s = sc.spheres[sc.prims[prim].a];
+  const V3 center = mk3(s.center[0], s.center[1], s.center[2]);
+  const float radius = s.radius;
+  if (length2(look_from - center) <= radius * radius) {
+    const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+    return 1.f / sphere_sa;
+  }
+  float cos_theta_max = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
+  float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+  V3 shading_normal = normalize(point_on_light - center);
+  float cosine = fabsf(dot(shading_normal, -dir));
+  float dist2 = length2(point_on_light - look_from);
+  return pdf_solid_angle * cosine / dist2;
+}
+
+// ConstBackground::sample (background.h:37-49) / EnvMap::sample (background.h:110-139)
+VD V3 background_light_sample(const DScene& sc, Pcg32& rng, EmitterInfo& info) {
+  float r1 = rand_float(rng);
+  float r2 = rand_float(rng);
+  if (sc.bg.type == VIMG_BG_CONST) {
+    info.wi = sample_sphere(r1, r2);
+    info.pdf = (float)(1.f / (4 * VIMG_PI_D));
+    info.dist = CUDART_INF_F;
+    info.G = 1.f;
+    return mk3(sc.bg.color[0], sc.bg.color[1], sc.bg.color[2]);
+  }
+  // ArraySampling2D::sample (sampling.h:205-222)
+  const uint32_t W = sc.bg.cdf_w, H = sc.bg.cdf_h;
+  uint32_t row_index, column_index;
+  float dv, du;
+  sample_cdf_1d(sc.bg.row_cdf, H + 1, r1, row_index, dv);
+  const float* row = sc.bg.col_cdfs + (size_t)row_index * (W + 1);
+  sample_cdf_1d(row, W + 1, r2, column_index, du);
+  const float u_env = ((float)column_index + du) / W;
+  const float v_env = ((float)row_index + dv) / H;
+  float pdf_y = sc.bg.row_cdf[row_index + 1] - sc.bg.row_cdf[row_index];
+  float pdf_x = row[column_index + 1] - row[column_index];
+  float choose_sample_pdf = pdf_y * pdf_x;
+
+  const DTexture& img = sc.textures[sc.bg.image];
+  float elevation = (float)((double)v_env * VIMG_PI_D);
+  float y = (float)cos((double)v_env * VIMG_PI_D);  // std::cos(double)
+  const float azimuth = (float)((double)(u_env * 2.f) * VIMG_PI_D);
+  float x = m_sinf(azimuth) * m_sinf(elevation);
+  float z = -1 * m_cosf(azimuth) * m_sinf(elevation);
+  V3 wi = normalize(xform_dir(sc.bg.env_to_world, mk3(x, y, z)));
+  float sin_elevation = m_sinf(elevation);
+  float pdf = (float)((double)(choose_sample_pdf * img.width * img.height)
+                      / (2.f * VIMG_PI_D * VIMG_PI_D * (double)sin_elevation));
+  info.wi = wi;
+  info.pdf = pdf;
+  info.dist = CUDART_INF_F;
+  info.G = 1.f;
+  return col_at_uv_mipmap(sc, img, 0, mk2(u_env, v_env)) * sc.bg.radiance_scale;
+}
+
+// GroupOfEmitters::sample (emitters.h:39-56)
+VD V3 lights_sample(const DScene& sc, V3 look_from, Pcg32& rng, EmitterInfo& info) {
+  float rnd = rand_float(rng);
+  float sx = rnd * sc.n_lights;
+  const int index_obj = std_clampi((int)sx, 0, (int)sc.n_lights - 1);
+  const float prob_obj = 1.f / sc.n_lights;
+  const int32_t light = sc.lights[index_obj];
+  V3 col;
+  if (light == VIMG_LIGHT_BACKGROUND)
+    col = background_light_sample(sc, rng, info);
+  else if (sc.prims[light].type == VIMG_PRIM_SPHERE)
+    col = sphere_light_sample(sc, (uint32_t)light, look_from, rng, info);
+  else
+    col = triangle_light_sample(sc, (uint32_t)light, look_from, rng, info);
+  info.pdf *= prob_obj;
+  return col;
+}
+
+VD float emitter_surf_pdf(const DScene& sc, int32_t prim, V3 look_from, V3 look_at, V3 dir) {
+  if (sc.prims[prim].type == VIMG_PRIM_SPHERE)
+    return sphere_surf_pdf(sc, (uint32_t)prim, look_from, look_at, dir);
+  return triangle_surf_pdf(sc, (uint32_t)prim);
+}
+
+// -------------------------------------------------------------- integrators ----
+struct PathCounters {
+  uint32_t rays_closest, rays_shadow;
+  TravCounters trav;
+};
+
+// shading_normal_integrator / geometric_normal_integrator (normals.cpp:4-46)
+template <bool GEOMETRIC, bool COUNT>
+VD V3 normal_integrator(const DScene& sc, Ray& ray, PathCounters& pc) {
+  HitInfo hit;
+  pc.rays_closest++;
+  if (scene_hit<COUNT>(sc, ray, hit, &pc.trav)) {
+    V3 n = GEOMETRIC ? hit.hit_n_g : hit.hit_n_s;
+    return (n + 1.0f) / 2.0f;
+  }
+  V3 unit_dir = normalize(ray.dir);
+  float a = (float)(0.5 * ((double)unit_dir.y + 1.0));  // double arithmetic (normals.cpp:19)
+  return (1.0f - a) * mk3(1.0f, 1.0f, 1.0f) + a * mk3(0.5f, 0.7f, 1.0f);
+}
+
+VD bool russian_roulette(Pcg32& rng, float eta_scale, V3& throughput) {
+  float rnd = (float)pcg32_random(rng) / (float)0xFFFFFFFFu;  // raw draw, can equal 1.0
+  V3 rr = (1.f / eta_scale) * throughput;
+  float max_val = std_min(std_max(std_max(rr.x, rr.y), rr.z), 0.95f);
+  if (rnd > max_val) return false;
+  throughput = throughput / max_val;
+  return true;
+}
+
+// material_integrator (mat_integrator.cpp:4-85)
+template <bool COUNT>
+VD V3 material_integrator(const DScene& sc, const Ray& input_ray, Pcg32& rng, uint32_t depth,
+                          PathCounters& pc) {
+  Ray test_ray = input_ray;
+  V3 throughput = mk3(1.0f);
+  bool non_specular_bounce = false;
+  float eta_scale = 1;
+  for (uint32_t d = 0; d < depth; d++) {
+    HitInfo hit;
+    pc.rays_closest++;
+    if (!scene_hit<COUNT>(sc, test_ray, hit, &pc.trav))
+      return throughput * background_emit(sc, test_ray.dir, test_ray.cone);
+    const vimg_material& mat = sc.materials[hit.mat];
+    V3 emitted_col = mat_emitted(mat, test_ray.dir, hit.hit_n_s);
+    ScatterInfo sr;
+    if (!mat_sample(sc, mat, test_ray.dir, hit, rng, non_specular_bounce, sr))
+      return throughput * emitted_col;
+    if (!sr.is_specular) non_specular_bounce = true;
+    float hit_dist = length(test_ray.o - hit.hit_p);
+    float surface_spread_angle = spread_angle_from_curvature(
+        hit.mean_curvature, test_ray.cone.cone_width, test_ray.dir, hit.hit_n_s);
+    if (sr.eta != 0.f) {
+      eta_scale /= (sr.eta * sr.eta);
+      test_ray.cone = propagate_refract_cone(test_ray.cone, test_ray.dir, surface_spread_angle,
+                                             sr.eta, sr.wo);
+    } else {
+      test_ray.cone = propagate_reflect_cone(test_ray.cone, surface_spread_angle * 2.f, hit_dist);
+    }
+    throughput = throughput
+                 * (emitted_col
+                    + mat_eval_div_pdf(sc, mat, test_ray.dir, sr.wo, hit, test_ray.cone,
+                                       non_specular_bounce));
+    if (d > 5) {
+      if (!russian_roulette(rng, eta_scale, throughput)) break;
+    }
+    RayCone cone = test_ray.cone;
+    test_ray.o = hit.hit_p;
+    test_ray.dir = sr.wo;
+    test_ray.minT = 0.0001f;
+    test_ray.maxT = CUDART_INF_F;
+    test_ray.cone = cone;
+  }
+  return mk3(0.0f);
+}
+
+VD float balance_heuristic(float pdf1, float pdf2) { return pdf1 / (pdf1 + pdf2); }
+
+VD float geometric_term(V3 look_from, V3 point_on_surface, V3 surface_normal) {
+  V3 dir_from_surf = look_from - point_on_surface;
+  float distance2 = length2(dir_from_surf);
+  dir_from_surf = normalize(dir_from_surf);
+  float cosine = fabsf(dot(surface_normal, dir_from_surf));
+  return cosine / distance2;
+}
+
+// mis_integrator (mis_integrator.cpp:18-189)
+template <bool COUNT>
+VD V3 mis_integrator(const DScene& sc, const Ray& input_ray, Pcg32& rng, uint32_t depth,
+                     PathCounters& pc) {
+  Ray test_ray = input_ray;
+  V3 bounce_result = mk3(0.0f);
+  V3 throughput = mk3(1.0f);
+  bool non_specular_bounce = false;
+  float eta_scale = 1;
+
+  HitInfo hit;
+  pc.rays_closest++;
+  if (!scene_hit<COUNT>(sc, test_ray, hit, &pc.trav))
+    return background_emit(sc, test_ray.dir, test_ray.cone);
+  if (mat_is_emissive(sc.materials[hit.mat]))
+    return mat_emitted(sc.materials[hit.mat], test_ray.dir, hit.hit_n_s);
+
+  for (uint32_t d = 0; d < depth; d++) {
+    const vimg_material& mat = sc.materials[hit.mat];
+    bool delta = mat_is_delta(mat);
+    float hit_dist = length(test_ray.o - hit.hit_p);
+    float surface_spread_angle = spread_angle_from_curvature(
+        hit.mean_curvature, test_ray.cone.cone_width, test_ray.dir, hit.hit_n_s);
+
+    if (!delta) {
+      EmitterInfo li;
+      V3 light_col = lights_sample(sc, hit.hit_p, rng, li);
+      if (li.pdf != 0.f) {
+        Ray shadow_ray;
+        shadow_ray.o = hit.hit_p;
+        shadow_ray.dir = li.wi;
+        shadow_ray.minT = 0.0001f;
+        shadow_ray.maxT = li.dist - 0.0001f;
+        PreHit ph;
+        pc.rays_shadow++;
+        bool occluded = bvh_traverse<true, COUNT>(sc, shadow_ray, ph, &pc.trav);
+        if (!occluded) {
+          V3 mat_eval;
+          float mat_pdf;
+          mat_eval_pdf_pair(sc, mat, test_ray.dir, li.wi, hit,
+                            propagate_reflect_cone(test_ray.cone, surface_spread_angle * 2.f, hit_dist),
+                            non_specular_bounce, mat_eval, mat_pdf);
+          if (mat_pdf != 0 && !is_nan(mat_pdf)) {
+            float G = li.G;
+            float mis_weight = balance_heuristic(li.pdf, mat_pdf * G);
+            bounce_result = bounce_result + throughput * mat_eval * mis_weight * G * light_col / li.pdf;
+          }
+        }
+      }
+    }
+
+    ScatterInfo sm;
+    if (!mat_sample(sc, mat, test_ray.dir, hit, rng, non_specular_bounce, sm)) return bounce_result;
+    if (!sm.is_specular) non_specular_bounce = true;
+    if (sm.eta != 0.f) {
+      eta_scale /= (sm.eta * sm.eta);
+      test_ray.cone = propagate_refract_cone(test_ray.cone, test_ray.dir, surface_spread_angle,
+                                             sm.eta, sm.wo);
+    } else {
+      test_ray.cone = propagate_reflect_cone(test_ray.cone, surface_spread_angle * 2.f, hit_dist);
+    }
+    V3 mat_sample_eval;
+    float mat_sample_pdf;
+    mat_eval_pdf_pair(sc, mat, test_ray.dir, sm.wo, hit, test_ray.cone, non_specular_bounce,
+                      mat_sample_eval, mat_sample_pdf);
+    if (is_nan(mat_sample_pdf)) return bounce_result;
+    throughput = throughput * (mat_sample_eval / mat_sample_pdf);
+
+    Ray direct_light_ray;
+    direct_light_ray.o = hit.hit_p;
+    direct_light_ray.dir = sm.wo;
+    direct_light_ray.minT = 0.0001f;
+    direct_light_ray.maxT = CUDART_INF_F;
+    direct_light_ray.cone = test_ray.cone;
+    HitInfo next;
+    pc.rays_closest++;
+    if (scene_hit<COUNT>(sc, direct_light_ray, next, &pc.trav)) {
+      const vimg_material& nmat = sc.materials[next.mat];
+      if (mat_is_emissive(nmat)) {
+        V3 emit = mat_emitted(nmat, direct_light_ray.dir, next.hit_n_s);
+        if (mat_sample_pdf != 0) {
+          float light_pdf = emitter_surf_pdf(sc, next.prim, hit.hit_p, next.hit_p, sm.wo) / sc.n_lights;
+          float G = geometric_term(hit.hit_p, next.hit_p, next.hit_n_g);
+          float mis_weight = balance_heuristic(mat_sample_pdf * G, light_pdf);
+          bounce_result = bounce_result + throughput * mis_weight * emit;
+        } else {
+          bounce_result = bounce_result + throughput * emit;
+        }
+        return bounce_result;
+      }
+      if (d > 5) {
+        if (!russian_roulette(rng, eta_scale, throughput)) break;
+      }
+      hit = next;
+      test_ray = direct_light_ray;
+    } else {
+      if (mat_sample_pdf != 0 && sc.bg.emissive) {
+        float light_pdf = background_pdf(sc, direct_light_ray.dir) / sc.n_lights;
+        float mis_weight = balance_heuristic(mat_sample_pdf, light_pdf);
+        bounce_result = bounce_result
+                        + throughput * mis_weight
+                              * background_emit(sc, direct_light_ray.dir, direct_light_ray.cone);
+      }
+      return bounce_result;
+    }
+  }
+  return bounce_result;
+}
+
+}  // namespace vimg

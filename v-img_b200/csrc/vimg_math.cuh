@@ -1,0 +1,120 @@
+// vimg_math.cuh -- arithmetic with the reference's exact semantics.
+//
+// Bit-exact parity with the reference's scalar path
+// fixes the ORDER of every float operation.  This header restates, for the
+// device, the glm 1.0.1 scalar expressions the reference's hot path uses and
+// the libstdc++ definitions of std::min/max/clamp/lerp.  The translation unit
+// must be compiled with -fmad=false: the only fused multiply-adds are the
+// explicit fmaf() calls where the reference calls std::fma
+// (include/geometry/triangle.h:11-15, disney_common.h:40).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define VD __device__ __forceinline__
+
+namespace vimg {
+
+struct V2 { float x, y; };
+struct V3 { float x, y, z; };
+struct V4 { float x, y, z, w; };
+
+VD V2 mk2(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+VD V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+VD V3 mk3(float s) { return mk3(s, s, s); }
+VD V4 mk4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+// component-wise, like glm's vec operators
+VD V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+VD V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+VD V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+VD V3 operator/(V3 a, V3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+VD V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+VD V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+VD V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+VD V3 operator+(V3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+VD V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+VD V2 operator+(V2 a, V2 b) { return mk2(a.x + b.x, a.y + b.y); }
+VD V2 operator-(V2 a, V2 b) { return mk2(a.x - b.x, a.y - b.y); }
+VD V2 operator*(V2 a, V2 b) { return mk2(a.x * b.x, a.y * b.y); }
+VD V2 operator*(V2 a, float s) { return mk2(a.x * s, a.y * s); }
+VD V2 operator*(float s, V2 a) { return mk2(s * a.x, s * a.y); }
+VD V2 operator-(V2 a) { return mk2(-a.x, -a.y); }
+VD V4 operator+(V4 a, V4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+VD V4 operator*(V4 a, float s) { return mk4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// glm::dot -- compute_dot<vec3>: tmp = a*b; (tmp.x + tmp.y) + tmp.z
+VD float dot(V3 a, V3 b) {
+  float tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z;
+  return tx + ty + tz;
+}
+VD float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+VD float length2(V3 v) { return dot(v, v); }
+VD float length(V3 v) { return sqrtf(dot(v, v)); }
+// glm::normalize = v * inversesqrt(dot(v,v)), inversesqrt = 1 / sqrt
+VD V3 normalize(V3 v) { return v * (1.0f / sqrtf(dot(v, v))); }
+VD V2 normalize(V2 v) { return v * (1.0f / sqrtf(dot(v, v))); }
+VD V3 cross(V3 a, V3 b) {
+  return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+// glm::min(a,b) = (b < a) ? b : a ; glm::max(a,b) = (a < b) ? b : a
+VD float glm_min(float a, float b) { return (b < a) ? b : a; }
+VD float glm_max(float a, float b) { return (a < b) ? b : a; }
+// std::min / std::max / std::clamp (libstdc++)
+VD float std_min(float a, float b) { return (b < a) ? b : a; }
+VD float std_max(float a, float b) { return (a < b) ? b : a; }
+VD float std_clamp(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+VD int std_clampi(int v, int lo, int hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+// glm::mix(x, y, a) = x * (1 - a) + y * a
+VD V3 mix(V3 x, V3 y, float a) { return x * (1.0f - a) + y * a; }
+VD V2 mix(V2 x, V2 y, float a) { return x * (1.0f - a) + y * a; }
+// std::lerp(float) as libstdc++ implements it (<cmath> __lerp)
+VD float std_lerp(float a, float b, float t) {
+  if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;
+  if (t == 1) return b;
+  const float x = a + t * (b - a);
+  return (t > 1) == (b > a) ? (b < x ? x : b) : (b > x ? x : b);
+}
+
+// glm mat4 (column-major, m[col*4+row]) times vec4:
+//   (m0*v0 + m1*v1) + (m2*v2 + m3*v3)       type_mat4x4.inl operator*(mat, vec)
+VD V4 mat4_mul(const float* m, V4 v) {
+  V4 m0 = mk4(m[0], m[1], m[2], m[3]), m1 = mk4(m[4], m[5], m[6], m[7]);
+  V4 m2 = mk4(m[8], m[9], m[10], m[11]), m3 = mk4(m[12], m[13], m[14], m[15]);
+  V4 add0 = m0 * v.x + m1 * v.y;
+  V4 add1 = m2 * v.z + m3 * v.w;
+  return add0 + add1;
+}
+
+// ---- libm ------------------------------------------------------------------
+// The reference calls glibc.  Its float functions sinf/cosf/logf/log2f/powf are
+// correctly rounded in all but rare cases, CUDA's float versions are 1-2 ulp.
+// These only feed tolerance-checked paths (material/mis); evaluating them in
+// double and rounding once reproduces glibc's result almost always, which
+// keeps GPU and CPU paths on the same RNG trajectory for longer.  Double
+// expressions of the reference call the double functions directly.
+#ifndef VIMG_FAST_LIBM
+VD float m_sinf(float x) { return (float)sin((double)x); }
+VD float m_cosf(float x) { return (float)cos((double)x); }
+VD float m_logf(float x) { return (float)log((double)x); }
+VD float m_log2f(float x) { return (float)log2((double)x); }
+VD float m_acosf(float x) { return (float)acos((double)x); }
+VD float m_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+#else
+VD float m_sinf(float x) { return sinf(x); }
+VD float m_cosf(float x) { return cosf(x); }
+VD float m_logf(float x) { return logf(x); }
+VD float m_log2f(float x) { return log2f(x); }
+VD float m_acosf(float x) { return acosf(x); }
+VD float m_atan2f(float y, float x) { return atan2f(y, x); }
+#endif
+
+#define VIMG_PI_D 3.141592653589793238462643383279502884  /* std::numbers::pi   */
+#define VIMG_INV_PI_D 0.318309886183790671537767526745028724 /* std::numbers::inv_pi */
+#define VIMG_INV_PI_F 0.318309886183790671537767526745028724f /* inv_pi_v<float>  */
+
+VD bool is_inf(float x) { return fabsf(x) == CUDART_INF_F; }
+VD bool is_nan(float x) { return x != x; }
+
+}  // namespace vimg

@@ -1,0 +1,157 @@
+// vimg_types.cuh -- device-resident scene layout (HBM) and per-ray state.
+//
+// Layout decisions (DESIGN.md "Data layout in HBM"):
+//  * BVH: one 64-byte, 64-byte-aligned record per INNER node = the reference's
+//    sibling-pair slots [Lmin,Rmin,Lmax,Rmax] (include/bvh.h:171-176, 48 B) +
+//    both children's {first_index,obj_count} (include/bvh.h:22-28).  One pop =
+//    4 x LDG.128 of one record; no separate node fetch, no dependent second load.
+//    Node numbering, child order and leaf order are the reference's, unchanged,
+//    so traversal visits boxes and primitives in the reference's order (bit-exact
+//    ids need that).
+//  * Leaf primitives: 48-byte records pre-gathered in obj_indices order (the
+//    reference chases obj_indices -> Surface* -> Mesh -> indices -> vertices).
+//  * Shading data (normals, uvs, materials, textures) stays in SoA pools that are
+//    read once per hit, not per traversal step.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/vimg_cuda.h"
+#include "vimg_math.cuh"
+
+namespace vimg {
+
+struct __align__(16) DPairNode {
+  float lmin[3], rmin[3], lmax[3], rmax[3];
+  uint32_t l_first, l_count, r_first, r_count;
+};
+static_assert(sizeof(DPairNode) == 64, "pair record must be 64 bytes");
+
+#define VIMG_LEAF_SPHERE 1u
+#define VIMG_LEAF_DEGENERATE 2u /* length2(cross(e2,e1)) == 0 (triangle.h:92) */
+
+struct __align__(16) DLeafPrim {
+  float a[9];        // triangle: p0,p1,p2 | sphere: center.xyz, radius
+  uint32_t prim_id;  // index in list_objects
+  uint32_t flags;
+  uint32_t pad_;
+};
+static_assert(sizeof(DLeafPrim) == 48, "leaf record must be 48 bytes");
+
+struct DMesh {
+  uint32_t vert_base;    // into vertices / normals pools
+  uint32_t tri_base;     // into tri_indices pool (per triangle, 3 x u32 local indices)
+  uint32_t has_normals;
+  int32_t uv_color;      // float2 offset of the uv set into the uv pool, or -1
+  int32_t uv_normal;
+  int32_t uv_mr;
+  uint32_t material;
+};
+
+struct DTexture {
+  uint32_t type;
+  float col_a[3], col_b[3];
+  uint32_t width, height, n_levels, wrap_u, wrap_v;
+  uint32_t level_off[16];  // texel (float3) offset of each mip level in the texel pool
+};
+
+struct DTextureRG {
+  uint32_t width, height, wrap_u, wrap_v;
+  uint32_t off;  // float2 offset into the rg pool
+};
+
+struct DCamera {
+  float m[16];
+  float p_size[2];
+  int32_t res[2];
+  float aperture_radius, focal_dist;
+  float cone_spread;  // raycone_for_primary_ray(): constant per camera (ray.h:44-48)
+};
+
+struct DBackground {
+  uint32_t type;
+  float color[3];
+  int32_t image;
+  float world_to_env[16], env_to_world[16];
+  float radiance_scale;
+  uint32_t cdf_w, cdf_h;
+  const float* row_cdf;
+  const float* col_cdfs;
+  uint32_t emissive;  // Background::is_emissive()
+};
+
+struct DCounters {  // matches the tail of vimg_render_stats
+  unsigned long long rays_closest, rays_shadow, inner_nodes, leaf_nodes, tri_tests, sphere_tests,
+      nan_samples, samples;
+};
+
+struct DScene {
+  DCamera cam;
+  // BVH
+  const DPairNode* pairs;  // (n_nodes - 1) / 2 records, record of children (c, c+1) at (c-1)/2
+  const DLeafPrim* leaf_prims;
+  float root_min[3], root_max[3];
+  uint32_t root_first, root_count;  // nodes[0]
+  uint32_t n_nodes;
+  uint32_t stack_cap;
+  // primitives / geometry pools
+  const vimg_prim* prims;
+  const vimg_sphere* spheres;
+  const DMesh* meshes;
+  const uint32_t* tri_indices;
+  const float* vertices;  // xyz
+  const float* normals;   // xyz
+  const float* uvs;       // uv
+  // shading
+  const vimg_material* materials;
+  const DTexture* textures;
+  const float* texels;  // rgb
+  const DTextureRG* textures_rg;
+  const float* rg_texels;
+  const int32_t* lights;
+  uint32_t n_lights;
+  DBackground bg;
+};
+
+struct RayCone {
+  float cone_width, spread_angle;
+};
+
+// Ray of include/ray.h:16-42
+struct Ray {
+  V3 dir, o;
+  float minT, maxT;
+  RayCone cone;
+};
+
+struct ONB {
+  V3 u, v, w;
+};
+
+// HitInfo of include/hit_utils.h:61-74; `mat`/`obj` pointers become indices
+struct HitInfo {
+  uint32_t mat;
+  int32_t prim;
+  V3 hit_p, hit_n_s, hit_n_g;
+  V2 uv, mr_uv;
+  ONB frame;
+  float primitive_area, tex_coord_area, mean_curvature;
+};
+
+// ForHitInfo of include/hit_utils.h:76-82 (prim pointer -> leaf record index)
+struct PreHit {
+  float e0, e1, e2, inv_det;
+  int32_t leaf_slot;  // index into leaf_prims, -1 = no hit
+};
+
+struct EmitterInfo {
+  V3 wi;
+  float pdf, dist, G;
+};
+
+struct ScatterInfo {
+  V3 wo;
+  float eta;
+  bool is_specular;
+};
+
+}  // namespace vimg

@@ -1,0 +1,209 @@
+"""ctypes host binding of libvimg_cuda.so (see include/vimg_cuda.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# integrator names of the reference's scene files (src/scene_loading/json_scene.cpp:213-223)
+INTEGRATORS = {"s_normal": 0, "g_normal": 1, "material": 2, "mis": 3}
+UINT32_MAX = 0xFFFFFFFF  # "depth": -1 in a scene file (json_scene.cpp:186,193)
+FLAG_COUNTERS = 1
+
+
+class VimgError(RuntimeError):
+    pass
+
+
+class _Camera(C.Structure):
+    _fields_ = [("cam_to_world", C.c_float * 16), ("p_size", C.c_float * 2),
+                ("resolution", C.c_int32 * 2), ("vfov_deg", C.c_float),
+                ("aperture_radius", C.c_float), ("focal_dist", C.c_float)]
+
+
+class _DescHead(C.Structure):  # leading members of vimg_scene_desc
+    _fields_ = [("abi_version", C.c_uint32), ("camera", _Camera)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("integrator", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32),
+                ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("inner_nodes", C.c_uint64), ("leaf_nodes", C.c_uint64),
+                ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
+                ("nan_samples", C.c_uint64), ("samples", C.c_uint64),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("kernel_launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
+           "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
+           "vimg_trace_ids", "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
+
+
+def lib_path():
+    return os.path.join(_HERE, "libvimg_cuda.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libvimg_cuda.so; raises VimgError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise VimgError(f"{path} is missing: build it with `make -C v-img_b200/csrc` "
+                        "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    lib = C.CDLL(path)
+    lib.vimg_cuda_device_count.restype = C.c_int
+    lib.vimg_last_error.restype = C.c_char_p
+    lib.vimg_scene_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.vimg_scene_destroy.argtypes = [C.c_void_p]
+    lib.vimg_scene_device_bytes.restype = C.c_uint64
+    lib.vimg_scene_device_bytes.argtypes = [C.c_void_p]
+    lib.vimg_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p,
+                                C.POINTER(RenderStats)]
+    lib.vimg_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(C.c_void_p),
+                                       C.c_void_p, C.POINTER(RenderStats)]
+    lib.vimg_trace_pixel.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_int, C.c_int,
+                                     C.c_void_p]
+    lib.vimg_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.vimg_scene_desc_save.argtypes = [C.c_void_p, C.c_char_p]
+    lib.vimg_scene_desc_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.vimg_scene_desc_free.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def device_count():
+    return load_library().vimg_cuda_device_count()
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise VimgError(f"{what} failed ({rc}): {lib.vimg_last_error().decode()}")
+
+
+def save_desc(desc_ptr, path):
+    lib = load_library()
+    rc = lib.vimg_scene_desc_save(desc_ptr, os.fsencode(path))
+    if rc != 0:
+        raise VimgError(f"vimg_scene_desc_save({path}) failed ({rc})")
+
+
+class Scene:
+    """A scene resident in the HBM of one GPU.
+
+    Build it from a flattened-scene file (`Scene.load`) or from the address of a
+    `vimg_scene_desc` produced by the reference-side adapter (`Scene.from_desc`).
+    """
+
+    def __init__(self, desc_ptr, device=0, _owned_desc=None):
+        self._lib = load_library()
+        self._owned_desc = _owned_desc
+        self._h = None
+        head = _DescHead.from_address(desc_ptr)
+        self.width, self.height = int(head.camera.resolution[0]), int(head.camera.resolution[1])
+        self.device = device
+        h = C.c_void_p()
+        _check(self._lib, self._lib.vimg_scene_create(desc_ptr, device, C.byref(h)),
+               "vimg_scene_create")
+        self._h = h
+
+    @classmethod
+    def load(cls, path, device=0):
+        lib = load_library()
+        d = C.c_void_p()
+        rc = lib.vimg_scene_desc_load(os.fsencode(path), C.byref(d))
+        if rc != 0:
+            raise VimgError(f"vimg_scene_desc_load({path}) failed ({rc})")
+        try:
+            return cls(d.value, device)
+        finally:
+            lib.vimg_scene_desc_free(d)  # vimg_scene_create deep-copied everything
+
+    @classmethod
+    def from_desc(cls, desc_ptr, device=0):
+        return cls(desc_ptr, device)
+
+    def close(self):
+        if self._h:
+            self._lib.vimg_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self):
+        return int(self._lib.vimg_scene_device_bytes(self._h))
+
+    def _params(self, func, samples, depth, rank, n_ranks, counters):
+        return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks,
+                            FLAG_COUNTERS if counters else 0)
+
+    def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None):
+        """Mirror of scene_integrator<F>() (include/integrators.h:36-153).
+
+        Returns (image float32 [H, W, 3] in HOST memory, row 0 = top; stats dict).
+        `out` may be a (pinned) float32 array to receive the frame.
+        """
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.float32)
+        assert out.dtype == np.float32 and out.size == self.height * self.width * 3
+        st = RenderStats()
+        p = self._params(func, samples, depth, rank, n_ranks, counters)
+        _check(self._lib, self._lib.vimg_render(self._h, C.byref(p), out.ctypes.data, C.byref(st)),
+               "vimg_render")
+        return out, st.as_dict()
+
+    def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None):
+        """Render and leave the frame in HBM.  Returns (device pointer, stats dict)."""
+        st = RenderStats()
+        p = self._params(func, samples, depth, rank, n_ranks, counters)
+        dev = C.c_void_p()
+        _check(self._lib, self._lib.vimg_render_device(self._h, C.byref(p), C.byref(dev), stream,
+                                                       C.byref(st)), "vimg_render_device")
+        return dev.value, st.as_dict()
+
+    def frame_tensor(self, dev_ptr):
+        """Wrap the device frame as a torch tensor [H, W, 3] without copying (for NCCL)."""
+        import torch
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (self.height, self.width, 3), "typestr": "<f4",
+                                      "data": (dev_ptr, False), "version": 3}
+        return torch.as_tensor(h, device=f"cuda:{self.device}")
+
+    def trace_pixel(self, func, x, y, samples, depth):
+        """Mirror of trace_pixel<F>() (include/integrators.h:181-220); y = 0 is the bottom row."""
+        out = np.empty(3, np.float32)
+        p = self._params(func, samples, depth, 0, 1, False)
+        _check(self._lib, self._lib.vimg_trace_pixel(self._h, C.byref(p), x, y, out.ctypes.data),
+               "vimg_trace_pixel")
+        return out
+
+    def trace_ids(self, samples, want_t=True):
+        """Primary-hit primitive ids, int32 [H*W, samples] (-1 = miss), and hit distances."""
+        ids = np.empty((self.height * self.width, samples), np.int32)
+        t = np.empty((self.height * self.width, samples), np.float32) if want_t else None
+        _check(self._lib, self._lib.vimg_trace_ids(self._h, samples, ids.ctypes.data,
+                                                   t.ctypes.data if want_t else None),
+               "vimg_trace_ids")
+        return ids, t
