@@ -22,6 +22,9 @@
 #include <geometry/sphere.h>
 #include <geometry/triangle.h>
 #include <integrators.h>
+#include <material/dielectric.h>
+#include <material/diffuse_light.h>
+#include <material/lambertian.h>
 #include <material/principled.h>
 #include <scene_loading/json_scene.h>
 #include <texture/texture_RG.h>
@@ -232,6 +235,128 @@ void* vref_scene_synthetic(int G, int width, int height, int tex_size, int env_w
                               glm::ivec2(width, height), 40.f, aperture_radius, 9.5f);
   sc->settings.num_threads = -1;
   build_bvh(*sc, bvh_type);
+  return sc.release();
+}
+
+// Rebuild the reference's own scene objects from a flattened descriptor (the inverse of the
+// adapter).  /root/reference and its scene files do not exist on the GPU box; the golden
+// .vscene files do, so this is how the compiled reference renders C1-C3 there (cpu_baseline,
+// --impl reference) and how tests prove that a .vscene carries the complete scene.  The BVH
+// is taken from the descriptor, not rebuilt.
+void* vref_scene_from_desc(const vimg_scene_desc* d, uint32_t spp, uint32_t depth, int integrator) {
+  auto sc = std::make_unique<RefScene>();
+  auto wrap = [](uint32_t w) {
+    return w == VIMG_WRAP_CLAMP_TO_EDGE ? TextureWrappingMode::ClampToEdge
+           : w == VIMG_WRAP_MIRRORED_REPEAT ? TextureWrappingMode::MirroredRepeat
+                                            : TextureWrappingMode::Repeat;
+  };
+  auto v3 = [](const float* p) { return glm::vec3(p[0], p[1], p[2]); };
+  auto m4 = [](const float* p) {
+    glm::mat4 m;
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r) m[c][r] = p[c * 4 + r];
+    return m;
+  };
+  auto image_from = [&](const vimg_texture& t) {
+    std::vector<std::vector<glm::vec3>> levels(t.n_levels);
+    for (uint32_t l = 0; l < t.n_levels; ++l) {
+      size_t w = std::max(t.width >> l, 1u), h = std::max(t.height >> l, 1u);
+      levels[l].resize(w * h);
+      std::memcpy(levels[l].data(), t.levels[l], w * h * 12);
+    }
+    return ImageTexture(levels, t.width, t.height, wrap(t.wrap_u), wrap(t.wrap_v));
+  };
+  for (uint32_t i = 0; i < d->n_textures; ++i) {
+    const vimg_texture& t = d->textures[i];
+    if (t.type == VIMG_TEX_CONST)
+      sc->texture_list.push_back(std::make_unique<ConstColor>(v3(t.col_a)));
+    else if (t.type == VIMG_TEX_CHECKER)
+      sc->texture_list.push_back(std::make_unique<Checkerboard>(t.width, t.height, v3(t.col_a), v3(t.col_b)));
+    else
+      sc->texture_list.push_back(std::make_unique<ImageTexture>(image_from(t)));
+  }
+  for (uint32_t i = 0; i < d->n_textures_rg; ++i) {
+    const vimg_texture_rg& t = d->textures_rg[i];
+    std::vector<glm::vec2> data(size_t(t.width) * t.height);
+    std::memcpy(data.data(), t.data, data.size() * 8);
+    sc->textureRG_list.push_back(std::make_unique<TextureRG>(t.width, t.height, data, wrap(t.wrap_u), wrap(t.wrap_v)));
+  }
+  auto tex = [&](int32_t id) -> TextureRGB* { return id < 0 ? nullptr : sc->texture_list[id].get(); };
+  for (uint32_t i = 0; i < d->n_materials; ++i) {
+    const vimg_material& m = d->materials[i];
+    ImageTexture* nmap = m.normal_map < 0 ? nullptr : static_cast<ImageTexture*>(tex(m.normal_map));
+    switch (m.type) {
+      case VIMG_MAT_LAMBERTIAN: sc->mat_list.push_back(std::make_unique<Lambertian>(tex(m.texture))); break;
+      case VIMG_MAT_DIFFUSE_LIGHT: sc->mat_list.push_back(std::make_unique<DiffuseLight>(v3(m.emit))); break;
+      case VIMG_MAT_DIELECTRIC: sc->mat_list.push_back(std::make_unique<Dielectric>(m.ior)); break;
+      case VIMG_MAT_PRINCIPLED:
+        sc->mat_list.push_back(std::make_unique<Principled>(
+            tex(m.texture), m.texture_rg < 0 ? nullptr : sc->textureRG_list[m.texture_rg].get(),
+            glm::vec2(m.metallic_roughness_factor[0], m.metallic_roughness_factor[1]),
+            m.specular_transmission, m.subsurface, m.specular, m.specular_tint, m.anisotropic,
+            m.sheen, m.sheen_tint, m.clearcoat, m.clearcoat_gloss, m.eta, nmap));
+        break;
+      default: sc->mat_list.push_back(std::make_unique<Material>()); break;
+    }
+    sc->mat_list.back()->normal_map = nmap;
+  }
+  for (uint32_t i = 0; i < d->n_meshes; ++i) {
+    const vimg_mesh& m = d->meshes[i];
+    std::vector<std::array<uint32_t, 3>> indices(m.n_tris);
+    std::memcpy(indices.data(), m.indices, m.n_tris * 12);
+    std::vector<glm::vec3> vertices(m.n_verts), normals;
+    std::memcpy(vertices.data(), m.vertices, m.n_verts * 12);
+    if (m.normals) {
+      normals.resize(m.n_verts);
+      std::memcpy(normals.data(), m.normals, m.n_verts * 12);
+    }
+    std::vector<std::vector<glm::vec2>> uvsets(m.n_uv_sets);
+    for (uint32_t k = 0; k < m.n_uv_sets; ++k) {
+      uvsets[k].resize(m.n_verts);
+      std::memcpy(uvsets[k].data(), m.texcoords[k], m.n_verts * 8);
+    }
+    sc->list_meshes.push_back(std::make_unique<Mesh>(indices, vertices, normals, uvsets,
+                                                     sc->mat_list[m.material].get(), m.color_tex_uv,
+                                                     m.normal_tex_uv, m.metallic_roughness_tex_uv));
+  }
+  for (uint64_t i = 0; i < d->n_prims; ++i) {
+    const vimg_prim& p = d->prims[i];
+    if (p.type == VIMG_PRIM_SPHERE) {
+      const vimg_sphere& s = d->spheres[p.a];
+      sc->list_objects.push_back(std::make_unique<Sphere>(v3(s.center), s.radius, sc->mat_list[s.material].get()));
+    } else {
+      sc->list_objects.push_back(std::make_unique<Triangle>(sc->list_meshes[p.a].get(), p.b));
+    }
+  }
+  const vimg_background& bg = d->background;
+  if (bg.type == VIMG_BG_ENVMAP) {
+    ImageTexture img = image_from(d->textures[bg.image]);
+    sc->settings.background = std::make_unique<EnvMap>(img, m4(bg.world_to_env), m4(bg.env_to_world), bg.radiance_scale);
+  } else {
+    sc->settings.background = std::make_unique<ConstBackground>(v3(bg.color));
+  }
+  for (uint32_t i = 0; i < d->n_lights; ++i) {
+    if (d->lights[i] == VIMG_LIGHT_BACKGROUND)
+      sc->list_lights.push_back(sc->settings.background.get());
+    else
+      sc->list_lights.push_back(dynamic_cast<Emitter*>(sc->list_objects[d->lights[i]].get()));
+  }
+  const vimg_camera& c = d->camera;
+  sc->settings.camera = TLCam(m4(c.cam_to_world), glm::ivec2(c.resolution[0], c.resolution[1]),
+                              c.vfov_deg, c.aperture_radius, c.focal_dist);
+  sc->settings.camera.p_size[0] = c.p_size[0];  // keep the flattened values (-fno-access-control)
+  sc->settings.camera.p_size[1] = c.p_size[1];
+  sc->settings.resolution = glm::ivec2(c.resolution[0], c.resolution[1]);
+  sc->settings.samples = spp;
+  sc->settings.depth = depth;
+  sc->settings.func = static_cast<integrator_func>(integrator);
+  sc->settings.num_threads = -1;
+  sc->bvh.nodes.resize(d->bvh.n_nodes);
+  std::memcpy(sc->bvh.nodes.data(), d->bvh.nodes, d->bvh.n_nodes * 8);
+  sc->bvh.BB_mins_maxes.resize(d->bvh.n_bb_slots);
+  std::memcpy(sc->bvh.BB_mins_maxes.data(), d->bvh.bb_mins_maxes, d->bvh.n_bb_slots * 12);
+  sc->bvh.obj_indices.assign(d->bvh.obj_indices, d->bvh.obj_indices + d->bvh.n_obj_indices);
+  sc->bvh.max_depth = d->bvh.max_depth;
   return sc.release();
 }
 

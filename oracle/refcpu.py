@@ -37,6 +37,8 @@ def _load(flavour):
     lib.vref_scene_synthetic.restype = C.c_void_p
     lib.vref_scene_synthetic.argtypes = [C.c_int] * 6 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                                          C.c_float]
+    lib.vref_scene_from_desc.restype = C.c_void_p
+    lib.vref_scene_from_desc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
     lib.vref_scene_free.argtypes = [C.c_void_p]
     lib.vref_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     lib.vref_scene_set_const_background.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float,
@@ -84,6 +86,14 @@ class RefScene:
         h = lib.vref_scene_synthetic(G, width, height, tex_size, env_w, env_h, spp, depth,
                                      1 if bvh == "sweep" else 0, int(with_rg), aperture)
         return cls(h, flavour)
+
+    @classmethod
+    def from_desc(cls, desc_ptr, spp, depth, integrator="mis", flavour="parity"):
+        """Rebuild the reference's scene objects from a flattened vimg_scene_desc (e.g. a loaded
+        tests/golden/scenes/*.vscene); the descriptor's BVH is used as is."""
+        lib = _load(flavour)
+        return cls(lib.vref_scene_from_desc(desc_ptr, spp, depth & 0xFFFFFFFF,
+                                            INTEGRATORS[integrator]), flavour)
 
     def close(self):
         if self._h:

@@ -1,0 +1,252 @@
+"""Parity of the CUDA render device (through the C ABI) against the reference.
+
+Bit-exact targets: primary-hit primitive ids, hit distances, s_normal / g_normal images.
+Tolerance targets: material / mis images, relMSE = mean((gpu-ref)^2 / (ref^2 + 1e-2)) on the
+linear float image.  The GPU reproduces the reference's per-pixel RNG stream and draw order,
+so paths only diverge where a libm low-bit difference flips a decision; SURVEY.md section 8(d)(i)
+then asks for relMSE(GPU_N, CPU_N) <= 0.1 * 2 sigma^2 / N with sigma^2 estimated from the
+reference itself (N vs 4N prefix trick).  Each test states the bound it uses.
+"""
+import numpy as np
+import pytest
+
+from helpers import golden_ref, golden_scene_path, rel_mse
+
+pytestmark = pytest.mark.gpu
+
+IDS_SCENES = ["cornell_box_spheres", "cornell_box_spheres_sweep", "glass_in_box", "glass_in_box_sweep",
+              "disney_spheres", "cornell_small", "glass_small", "disney_small", "sphere_light_medium",
+              "sphere_light_small", "cornell_checker", "cornell_dof", "synthetic_small", "synthetic_rg"]
+NORMAL_SCENES = [s for s in IDS_SCENES if s != "glass_in_box_sweep"]
+
+_scenes = {}
+
+
+def scene(vimg, name):
+    if name not in _scenes:
+        _scenes[name] = vimg.Scene.load(golden_scene_path(name))
+    return _scenes[name]
+
+
+@pytest.mark.parametrize("name", IDS_SCENES)
+def test_primary_hit_ids_and_distances_bit_exact(vimg, refcpu, man, name):
+    r = man[name]["ref"]
+    ids, t = scene(vimg, name).trace_ids(r["ids_spp"])
+    ref = golden_ref(name)
+    if "ids" in ref.files:
+        assert np.array_equal(ids, ref["ids"]), f"{int((ids != ref['ids']).sum())} ids differ"
+    assert refcpu.digest(ids) == r["ids_hash"]
+    assert refcpu.digest(t) == r["t_hash"]
+    assert abs(float((ids[:, 0] >= 0).mean()) - r["hit_fraction_sample0"]) == 0
+
+
+@pytest.mark.parametrize("integ", ["s_normal", "g_normal"])
+@pytest.mark.parametrize("name", NORMAL_SCENES)
+def test_normal_integrators_bit_exact(vimg, refcpu, man, name, integ):
+    e = man[name]
+    img, st = scene(vimg, name).scene_integrator(integ, 4, e["depth"])
+    s = e["ref"]["normal_stride"]
+    sub = golden_ref(name)[integ + "_strided"]
+    assert np.array_equal(img[::s, ::s], sub)
+    assert refcpu.digest(img) == e["ref"][integ + "_hash"]
+    assert st["nan_samples"] == 0 and st["samples"] == e["width"] * e["height"] * 4
+    assert st["rays_closest"] == st["samples"] and st["rays_shadow"] == 0
+
+
+def sigma2_from_prefix(ref, lo_key, hi_key, n_lo, n_hi):
+    """per-sample relative variance from relMSE(ref_N, ref_4N): the N samples are a prefix of the 4N"""
+    return rel_mse(ref[lo_key], ref[hi_key]) / (1.0 / n_lo - 1.0 / n_hi)
+
+
+# (scene, key, bound): bound on relMSE(GPU, CPU) at equal spp.
+IMAGE_CASES = [
+    ("cornell_small", "mis_64", "prefix"), ("cornell_small", "mis_256", "prefix"),
+    ("cornell_small", "material_64", 5e-3),
+    ("glass_small", "mis_64", 1e-4), ("glass_small", "material_64", 1e-4),
+    ("disney_small", "mis_64", "prefix"), ("disney_small", "mis_256", "prefix"),
+    ("disney_small", "material_32", 2e-3),
+    ("sphere_light_medium", "mis_64", 1e-4), ("sphere_light_medium", "material_64", 1e-4),
+    ("sphere_light_small", "mis_64", 1e-4), ("sphere_light_small", "material_64", 1e-4),
+    ("cornell_checker", "mis_64", 1e-3), ("cornell_skylight", "mis_64", 1e-3),
+    ("cornell_skylight", "material_64", 5e-3),
+    ("synthetic_small", "mis_64", 1e-4), ("synthetic_small", "material_32", 1e-4),
+    ("synthetic_rg", "mis_64", 1e-4),
+]
+
+
+@pytest.mark.parametrize("name,key,bound", IMAGE_CASES)
+def test_material_and_mis_images_within_tolerance(vimg, man, name, key, bound):
+    v = man[name]["ref"][key]
+    integ = key.rsplit("_", 1)[0]
+    ref = golden_ref(name)
+    img, st = scene(vimg, name).scene_integrator(integ, v["spp"], v["depth"])
+    if bound == "prefix":
+        # 0.1 * 2 sigma^2 / N, sigma^2 from the reference's own 64 vs 256 spp images
+        sigma2 = sigma2_from_prefix(ref, "mis_64", "mis_256", 64, 256)
+        bound = 0.1 * 2.0 * sigma2 / v["spp"]
+    err = rel_mse(img, ref[key])
+    same = float((img == ref[key]).all(-1).mean())
+    print(f"{name}/{key}: relMSE {err:.3e} (bound {bound:.3e}), bit-identical pixels {same:.4f}")
+    assert err <= bound
+    # bias check: per-channel means within 1 % (a pure variance test would miss an energy bug)
+    gm, rm = img.reshape(-1, 3).mean(0), ref[key].reshape(-1, 3).mean(0)
+    assert np.all(np.abs(gm - rm) <= 0.01 * np.maximum(rm, 1e-3))
+    assert st["nan_samples"] == 0
+
+
+@pytest.mark.parametrize("name,key,min_identical", [
+    ("cornell_small", "mis_64", 1.0), ("cornell_small", "material_64", 1.0),
+    ("glass_small", "mis_64", 1.0), ("glass_small", "material_64", 1.0),
+    ("disney_small", "mis_256", 1.0), ("disney_small", "material_32", 1.0),
+    ("sphere_light_small", "mis_64", 1.0), ("sphere_light_medium", "material_64", 1.0),
+    ("cornell_checker", "mis_64", 1.0), ("cornell_skylight", "mis_64", 0.99),
+    ("synthetic_small", "mis_64", 0.85), ("synthetic_rg", "mis_64", 0.85)])
+def test_paths_stay_on_the_reference_rng_trajectory(vimg, man, name, key, min_identical):
+    """With glibc's sinf/cosf restated exactly (vimg_libm.cuh) and the reference's float/double
+    promotions kept, whole images of the Lambertian / glass / Disney scenes come out BIT-IDENTICAL
+    to the CPU reference at equal spp; textured env-map scenes keep > 85 % identical pixels (their
+    log2f / acosf / atan2f calls are not restated bit-exactly)."""
+    v = man[name]["ref"][key]
+    img, _ = scene(vimg, name).scene_integrator(key.rsplit("_", 1)[0], v["spp"], v["depth"])
+    same = float((img == golden_ref(name)[key]).all(-1).mean())
+    assert same >= min_identical, same
+
+
+def test_full_size_c2_against_the_live_reference(vimg, refcpu, man):
+    """BASELINE config C2: ids of all 4 samples and both normal images, full 800x800, compared
+    array-for-array with the compiled reference rendering the same .vscene on this host."""
+    name = "cornell_box_spheres"
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    rs = refcpu.RefScene.from_desc(d.ptr, 4, 64)
+    sc = scene(vimg, name)
+    ids, t = sc.trace_ids(4)
+    rids, rt = rs.trace_ids(4)
+    assert np.array_equal(ids, rids) and np.array_equal(t, rt)
+    for integ in ("s_normal", "g_normal"):
+        g, _ = sc.scene_integrator(integ, 4, 64)
+        r, _ = rs.render(integ, spp=4)
+        assert np.array_equal(g, r)
+
+
+def test_full_size_c3_mis_low_spp_against_the_live_reference(vimg, refcpu, man):
+    """BASELINE config C3 (disney_spheres, 1800x800, depth -1) at 4 spp against the reference."""
+    name = "disney_spheres"
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    rs = refcpu.RefScene.from_desc(d.ptr, 4, 0xFFFFFFFF)
+    g, st = scene(vimg, name).scene_integrator("mis", 4, 0xFFFFFFFF)
+    r, _ = rs.render("mis", spp=4)
+    same = float((g == r).all(-1).mean())
+    err = rel_mse(g, r)
+    print(f"C3 mis 4spp: relMSE {err:.3e}, bit-identical pixels {same:.4f}, rays {st['rays_closest'] + st['rays_shadow']}")
+    assert same == 1.0 and err == 0.0
+
+
+def test_trace_pixel_matches_the_frame(vimg, man):
+    sc = scene(vimg, "disney_small")
+    img, _ = sc.scene_integrator("mis", 16, 0xFFFFFFFF)
+    H = sc.height
+    for x, y in [(0, 0), (100, 50), (224, 99), (37, 3)]:
+        px = sc.trace_pixel("mis", x, y, 16, 0xFFFFFFFF)
+        assert np.array_equal(px, img[H - 1 - y, x])
+
+
+def test_trace_pixel_matches_reference_trace_pixel(vimg, refcpu, man):
+    d = vimg.LoadedDesc(golden_scene_path("glass_small"))
+    rs = refcpu.RefScene.from_desc(d.ptr, 32, 64)
+    sc = scene(vimg, "glass_small")
+    for x, y in [(80, 60), (10, 100), (150, 5)]:
+        assert np.array_equal(sc.trace_pixel("material", x, y, 32, 64),
+                              rs.trace_pixel("material", x, y, spp=32, depth=64))
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_tile_partition_sums_to_the_full_frame(vimg, n_ranks):
+    """tile t -> rank t % n_ranks; unowned pixels are 0, so the sum over ranks (what the NCCL
+    reduce does) must equal the single-GPU frame bit for bit."""
+    sc = scene(vimg, "disney_small")
+    full, st = sc.scene_integrator("mis", 8, 0xFFFFFFFF)
+    acc = np.zeros_like(full)
+    owned = np.zeros(full.shape[:2], np.int32)
+    samples = 0
+    for r in range(n_ranks):
+        part, pst = sc.scene_integrator("mis", 8, 0xFFFFFFFF, rank=r, n_ranks=n_ranks)
+        owned += (part != 0).any(-1)
+        acc += part
+        samples += pst["samples"]
+    assert np.array_equal(acc, full)
+    assert owned.max() <= 1 and samples == st["samples"]
+
+
+def test_traversal_counters_match_the_instrumented_reference(vimg, man):
+    from oracle import refcpu
+    if not refcpu.available("count"):
+        pytest.skip("count flavour not built")
+    for name in ("cornell_small", "synthetic_small"):
+        d = vimg.LoadedDesc(golden_scene_path(name))
+        rs = refcpu.RefScene.from_desc(d.ptr, 4, 64, flavour="count")
+        rs.counters(reset=True)
+        rs.render("s_normal", spp=4, threads=4)
+        c = rs.counters()
+        _, st = scene(vimg, name).scene_integrator("s_normal", 4, 64, counters=True)
+        assert st["rays_closest"] == c["rays_closest"] and st["rays_shadow"] == c["rays_shadow"] == 0
+        assert st["inner_nodes"] == c["inner_nodes"] and st["leaf_nodes"] == c["leaf_nodes"]
+        assert st["tri_tests"] + st["sphere_tests"] == c["prim_tests"]
+
+
+def test_mis_ray_counts_match_the_instrumented_reference(vimg, man):
+    from oracle import refcpu
+    if not refcpu.available("count"):
+        pytest.skip("count flavour not built")
+    d = vimg.LoadedDesc(golden_scene_path("glass_small"))
+    rs = refcpu.RefScene.from_desc(d.ptr, 8, 64, flavour="count")
+    rs.counters(reset=True)
+    rs.render("mis", spp=8, threads=4)
+    c = rs.counters()
+    _, st = scene(vimg, "glass_small").scene_integrator("mis", 8, 64, counters=True)
+    for k in ("rays_closest", "rays_shadow", "inner_nodes", "leaf_nodes"):
+        assert st[k] == c[k], (k, st[k], c[k])
+    assert st["tri_tests"] + st["sphere_tests"] == c["prim_tests"]
+
+
+def test_counters_do_not_change_the_image_and_renders_are_deterministic(vimg):
+    sc = scene(vimg, "synthetic_small")
+    a, _ = sc.scene_integrator("mis", 8, 64)
+    b, _ = sc.scene_integrator("mis", 8, 64, counters=True)
+    c, _ = sc.scene_integrator("mis", 8, 64)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_device_frame_equals_host_frame(vimg):
+    import torch
+    sc = scene(vimg, "cornell_small")
+    host, _ = sc.scene_integrator("material", 8, 64)
+    ptr, st = sc.render_device("material", 8, 64)
+    dev = sc.frame_tensor(ptr)
+    assert dev.is_cuda and tuple(dev.shape) == host.shape
+    assert np.array_equal(dev.cpu().numpy(), host)
+    assert st["kernel_launches"] == 1 and st["kernel_ms"] > 0
+
+
+def test_invalid_render_arguments(vimg):
+    sc = scene(vimg, "cornell_small")
+    with pytest.raises(vimg.VimgError):
+        sc.scene_integrator("mis", 0, 64)
+    with pytest.raises(vimg.VimgError):
+        sc.scene_integrator("mis", 4, 64, rank=3, n_ranks=2)
+    with pytest.raises(vimg.VimgError):
+        sc.trace_pixel("mis", 10_000, 0, 4, 64)
+    nolight = scene(vimg, "synthetic_small")  # env map is the only light: fine
+    nolight.scene_integrator("mis", 1, 4)
+
+
+def test_depth_limit_and_one_sample(vimg, refcpu, man):
+    """depth semantics differ between material and mis (SURVEY.md A.7 xv); check small depths."""
+    d = vimg.LoadedDesc(golden_scene_path("cornell_small"))
+    rs = refcpu.RefScene.from_desc(d.ptr, 1, 1)
+    sc = scene(vimg, "cornell_small")
+    for integ in ("material", "mis"):
+        for depth in (1, 2, 7):
+            g, _ = sc.scene_integrator(integ, 3, depth)
+            r, _ = rs.render(integ, spp=3, depth=depth)
+            same = float((g == r).all(-1).mean())
+            assert same == 1.0, (integ, depth, same)

@@ -12,6 +12,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "vimg_libm.cuh"
+
 #define VD __device__ __forceinline__
 
 namespace vimg {
@@ -88,15 +90,16 @@ VD V4 mat4_mul(const float* m, V4 v) {
 }
 
 // ---- libm ------------------------------------------------------------------
-// The reference calls glibc.  Its float functions sinf/cosf/logf/log2f/powf are
-// correctly rounded in all but rare cases, CUDA's float versions are 1-2 ulp.
-// These only feed tolerance-checked paths (material/mis); evaluating them in
-// double and rounding once reproduces glibc's result almost always, which
-// keeps GPU and CPU paths on the same RNG trajectory for longer.  Double
-// expressions of the reference call the double functions directly.
+// The reference calls glibc.  sinf/cosf decide sampled directions (and, with a
+// thin-lens camera, the primary rays of the bit-exact targets), so they are
+// restated exactly (vimg_libm.cuh).  logf/log2f/acosf/atan2f only feed
+// tolerance-checked quantities (texture LOD, env-map uv); glibc's are
+// correctly rounded in all but rare cases while CUDA's float versions are 1-2
+// ulp, so they are evaluated in double and rounded once.  Double expressions of
+// the reference call the double functions directly.
 #ifndef VIMG_FAST_LIBM
-VD float m_sinf(float x) { return (float)sin((double)x); }
-VD float m_cosf(float x) { return (float)cos((double)x); }
+VD float m_sinf(float x) { return vimg_libm::glibc_sinf(x); }  // bit-exact glibc sinf, |x| < 120
+VD float m_cosf(float x) { return vimg_libm::glibc_cosf(x); }
 VD float m_logf(float x) { return (float)log((double)x); }
 VD float m_log2f(float x) { return (float)log2((double)x); }
 VD float m_acosf(float x) { return (float)acos((double)x); }

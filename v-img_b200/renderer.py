@@ -101,6 +101,29 @@ def save_desc(desc_ptr, path):
         raise VimgError(f"vimg_scene_desc_save({path}) failed ({rc})")
 
 
+class LoadedDesc:
+    """A vimg_scene_desc read from a .vscene file; `.ptr` is its address (host memory)."""
+
+    def __init__(self, path):
+        self._lib = load_library()
+        d = C.c_void_p()
+        rc = self._lib.vimg_scene_desc_load(os.fsencode(path), C.byref(d))
+        if rc != 0:
+            raise VimgError(f"vimg_scene_desc_load({path}) failed ({rc})")
+        self.ptr = d.value
+
+    def close(self):
+        if self.ptr:
+            self._lib.vimg_scene_desc_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """A scene resident in the HBM of one GPU.
 
