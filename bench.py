@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the v-img render hot path on B200 (and the reference beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference]
+                    [--workload disney_spheres] [--spp S]
+
+One "step" = one pass of the hot path over one frame: every pixel of the workload's scene,
+all its samples, through the integrator the scene file names (the reference's
+scene_integrator<F>() call, include/integrators.h:36-153).
+
+Workload (BASELINE.json): configs[2] `scenes/disney_spheres.json` -- 1800x800, 512 spp, `mis`,
+"depth": -1, sweep-SAH BVH -- the scene the north star's ">= 100x" target and the README's only
+published number are quoted on.  The scene comes from tests/golden/scenes/*.vscene (the
+reference-loaded scene + host-built BVH, flattened by the adapter); /root/reference is not read.
+
+metric `Mrays/s`: a ray is one BVH::hit<closest> or BVH::occlude call; rays are
+counted by the kernel itself.  `spp_mpix_per_s` (W*H*spp / s / 1e6) is reported beside it.
+With --gpus N (torchrun, one rank per GPU) the frame's 8x8 tiles are dealt round-robin to the
+ranks and the partial frames are summed with an NCCL reduce to rank 0 inside the timed region
+(strong scaling: the frame is fixed).
+
+`--impl reference` times the compiled, unmodified reference (oracle/_ref, perf flavour = what
+its CMake builds: -O3, AVX2 sibling-pair path) on the host cores, on a bounded sample of the
+same workload (fewer spp; throughput is spp-invariant).  The same measurement is attached to
+the cuda arm's line as `cpu_baseline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import golden_scene_path, load_product, manifest, rel_mse  # noqa: E402
+
+INTEG_NAMES = ["s_normal", "g_normal", "material", "mis"]
+# algorithmic cost model of SURVEY.md section 8(d), in the REFERENCE's data layout
+BYTES = {"inner_nodes": 56, "leaf_nodes": 8, "tri_tests": 56, "sphere_tests": 24}
+FLOPS = {"inner_nodes": 50, "tri_tests": 67, "sphere_tests": 40}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                smax.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def workload_info(name, spp_override):
+    e = manifest()[name]
+    spp = spp_override or e["spp"]
+    return {"name": name, "scene": golden_scene_path(name), "width": e["width"], "height": e["height"],
+            "spp": spp, "depth": e["depth"], "integrator": INTEG_NAMES[e["integrator"]],
+            "n_prims": e["n_prims"], "n_nodes": e["n_nodes"]}
+
+
+def config_of(w, n_gpus, extra=None):
+    c = {"workload": f"{w['name']} {w['width']}x{w['height']} {w['spp']}spp {w['integrator']} "
+                     f"depth={'-1 (RR only)' if w['depth'] == 0xFFFFFFFF else w['depth']}",
+         "scene": os.path.relpath(w["scene"], ROOT), "prims": w["n_prims"], "bvh_nodes": w["n_nodes"],
+         "partition": f"8x8 tiles round-robin over {n_gpus} rank(s)" + (" + NCCL reduce(sum) to rank 0" if n_gpus > 1 else ""),
+         "l2": "flushed between timed steps (256 MiB memset); scene itself is < 8 KiB"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------- reference arm
+def time_reference(w, steps, warmup, budget_s=25.0):
+    """Times the compiled reference (perf flavour) on the host cores.  Returns a dict."""
+    from oracle import refcpu
+    vimg = load_product()  # only for vimg_scene_desc_load (host-side file parsing, no GPU work)
+    if not refcpu.available("perf"):
+        return None
+    d = vimg.LoadedDesc(w["scene"])
+    cores = refcpu.hardware_threads("perf")
+    rs = refcpu.RefScene.from_desc(d.ptr, 1, w["depth"], w["integrator"], flavour="perf")
+    # bounded sample: pick spp so that one step takes ~budget/(steps+warmup) seconds
+    _, t1 = rs.render(w["integrator"], spp=1, threads=cores)  # also warms the thread pool / caches
+    _, t2 = rs.render(w["integrator"], spp=2, threads=cores)
+    per_spp = max(t2 - t1, t2 / 2, 1e-3)
+    spp = int(max(1, min(w["spp"], budget_s / (steps + warmup) / per_spp)))
+    for _ in range(warmup):
+        rs.render(w["integrator"], spp=spp, threads=cores)
+    t_total = 0.0
+    for _ in range(steps):
+        _, sec = rs.render(w["integrator"], spp=spp, threads=cores)
+        t_total += sec
+    samples = w["width"] * w["height"] * spp * steps
+    # rays per sample from the instrumented (count) flavour of the same reference, 2 spp
+    rays_per_sample = None
+    if refcpu.available("count"):
+        rc = refcpu.RefScene.from_desc(d.ptr, 2, w["depth"], w["integrator"], flavour="count")
+        rc.counters(reset=True)
+        rc.render(w["integrator"], spp=2, threads=cores)
+        c = rc.counters()
+        rays_per_sample = (c["rays_closest"] + c["rays_shadow"]) / (w["width"] * w["height"] * 2)
+    return {"seconds": t_total, "steps": steps, "spp": spp, "samples": samples, "cores": cores,
+            "spp_mpix_per_s": samples / t_total / 1e6, "rays_per_sample": rays_per_sample,
+            "mrays_per_s": (samples * rays_per_sample / t_total / 1e6) if rays_per_sample else None}
+
+
+def reference_line(w, args):
+    r = time_reference(w, args.steps, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvimg_ref_perf.so not built"}))
+        return
+    sample = (f"{w['name']} full frame at {r['spp']} spp (of {w['spp']}), {r['steps']} step(s); "
+              f"rays/sample {r['rays_per_sample']:.3f} from the count flavour at 2 spp")
+    line = {"metric": "Mrays/s", "value": r["mrays_per_s"], "unit": "Mrays/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "spp_mpix_per_s": r["spp_mpix_per_s"],
+            "config": config_of(w, 1, {"partition": f"reference scene_integrator, {r['cores']} host threads",
+                                       "l2": "n/a (CPU)"}),
+            "cpu_baseline": {"value": r["mrays_per_s"], "unit": "Mrays/s", "cores": r["cores"],
+                             "kind": "reference", "sample": sample,
+                             "spp_mpix_per_s": r["spp_mpix_per_s"]},
+            "e2e": {"value": r["mrays_per_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- cuda arm
+def cuda_line(w, args):
+    import torch
+    import torch.distributed as dist
+
+    vimg = load_product()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if vimg.device_count() == 0:
+        raise SystemExit("bench.py --impl cuda needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    desc = vimg.LoadedDesc(w["scene"])
+    scene = vimg.Scene(desc.ptr, device=local_rank)
+    integ, spp, depth = w["integrator"], w["spp"], w["depth"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        """kernel(s) on this rank's tiles (+ NCCL reduce to rank 0); frame stays in HBM"""
+        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world)
+        if world > 1:
+            dist.reduce(scene.frame_tensor(ptr), dst=0, op=dist.ReduceOp.SUM)
+        return ptr, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = kernel_ms = 0.0
+    launches = 0
+    ev0.record()
+    for i in range(args.steps):
+        ptr, st = step()
+        rays += st["rays_closest"] + st["rays_shadow"]
+        kernel_ms += st["kernel_ms"]
+        launches += st["kernel_launches"]
+        if i + 1 < args.steps:
+            flush.zero_()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms, rays, launches, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        elapsed_ms, kernel_ms_max = float(tmax[0]), float(tmax[3])
+        rays, launches = float(t[1]), int(t[2])
+    else:
+        kernel_ms_max = kernel_ms
+
+    # ---- end-to-end through the public C-ABI call with HOST buffers (rank-local tiles) ----------
+    # every step: scene upload H2D (vimg_scene_create), render, frame D2H into pinned memory
+    host = torch.empty((w["height"], w["width"], 3), dtype=torch.float32).pin_memory()
+    host_np = host.numpy()
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(e2e_steps):
+        sc2 = vimg.Scene(desc.ptr, device=local_rank)
+        _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np)
+        h2d = sc2.device_bytes
+        sc2.close()
+        e2e_rays += st2["rays_closest"] + st2["rays_shadow"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, e2e_rays], dtype=torch.float64, device=dev)
+    if world > 1:
+        tem = te.clone()
+        dist.all_reduce(tem, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_rays = float(tem[0]), float(te[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the render kernel: counted pass (untimed) gives per-ray algorithmic cost ----
+    c_spp = min(spp, 16)
+    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True)
+    c_rays = cst["rays_closest"] + cst["rays_shadow"]
+    bytes_per_ray = sum(BYTES[k] * cst[k] for k in BYTES) / c_rays
+    flops_per_ray = sum(FLOPS[k] * cst[k] for k in FLOPS) / c_rays
+    rays_per_launch = rays / max(launches, 1)
+    launch_s = kernel_ms_max / 1e3 / max(args.steps, 1)  # one launch per step per rank
+    rays_per_launch_rank = rays_per_launch  # rays of one rank's launch
+    hbm_peak, peak_src = measured_peaks()
+    achieved = bytes_per_ray * rays_per_launch_rank / launch_s / 1e9
+    samples_per_step = w["width"] * w["height"] * spp
+    secs = elapsed_ms / 1e3
+
+    line = {
+        "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "cuda",
+        "spp_mpix_per_s": samples_per_step * args.steps / secs / 1e6,
+        "rays_per_sample": rays / (samples_per_step * args.steps),
+        "config": config_of(w, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": w["width"] * w["height"] * 12,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                "spp_mpix_per_s": samples_per_step * e2e_steps / e2e_s / 1e6,
+                "path": "vimg_scene_create (H2D) + vimg_render into pinned host memory (kernel + D2H)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": f"render_kernel<{integ}>", "launch_ms": 1e3 * launch_s,
+                     "algorithmic_bytes_per_ray": bytes_per_ray,
+                     "algorithmic_flops_per_ray": flops_per_ray,
+                     "rays_per_launch": rays_per_launch_rank,
+                     "fp32_tflops_achieved": flops_per_ray * rays_per_launch_rank / launch_s / 1e12,
+                     "note": "bytes in the reference's layout (56/inner, 8/leaf, 56/tri test, 24/sphere "
+                             "test, SURVEY.md section 8(d)); per-ray averages from a counted pass at "
+                             f"{c_spp} spp, rays from the timed launches"},
+    }
+    if not args.no_cpu and world == 1:
+        r = time_reference(w, 1, 1, budget_s=16.0)
+        if r is not None:
+            line["cpu_baseline"] = {
+                "value": r["mrays_per_s"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+                "spp_mpix_per_s": r["spp_mpix_per_s"],
+                "sample": f"{w['name']} full frame at {r['spp']} spp (of {w['spp']}), compiled reference "
+                          f"(perf flavour, AVX2), rays/sample {r['rays_per_sample']:.3f} (count flavour, 2 spp)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="disney_spheres")
+    ap.add_argument("--spp", type=int, default=0, help="override the scene's spp (invalidates the number)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = workload_info(args.workload, args.spp)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            reference_line(w, args)
+        return
+    cuda_line(w, args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,8 +32,8 @@ VD V3 sample_visible_normals(V3 local_dir_in, float alphax, float alphay, Pcg32&
   float phi = (float)(2 * VIMG_PI_D * rand_x);
   float z = fmaf((1.0f - rand_y), (1.0f + hemi_dir_in.z), -hemi_dir_in.z);
   float sinTheta = sqrtf(std_clamp(1.0f - z * z, 0.0f, 1.0f));
-  float x = (float)((double)sinTheta * cos((double)phi));
-  float y = (float)((double)sinTheta * sin((double)phi));
+  float x = (float)((double)sinTheta * d_cos((double)phi));
+  float y = (float)((double)sinTheta * d_sin((double)phi));
   const V3 hemi_N = mk3(x, y, z) + hemi_dir_in;
   return sign * normalize(mk3(alphax * hemi_N.x, alphay * hemi_N.y, std_max(0.f, hemi_N.z)));
 }
@@ -140,7 +140,7 @@ VD V3 sample_local_h_clearcoat(Pcg32& rng, float alpha) {
   float rand1 = rand_float(rng);
   float rand2 = rand_float(rng);
   float cos_square_elevation
-      = (float)((1.f - pow((double)(alpha * alpha), 1. - (double)rand1)) / (double)(1.f - (alpha * alpha)));
+      = (float)((1.f - d_pow((double)(alpha * alpha), 1. - (double)rand1)) / (double)(1.f - (alpha * alpha)));
   float cos_elevation = sqrtf(cos_square_elevation);
   float sin_elevation = sqrtf(1 - cos_square_elevation);
   float h_azimuth = (float)(2.f * VIMG_PI_D * rand2);

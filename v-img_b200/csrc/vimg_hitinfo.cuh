@@ -55,8 +55,8 @@ VD bool refract_with_TIR2D(V2 ray_dir, V2 normal, float eta, V2& out) {
 
 // rotate2DPlusMinus (ray.h:81-92): unqualified cos/sin => double, narrowed to float
 VD void rotate2DPlusMinus(V2 vec, float angle, V2& plus, V2& minus) {
-  float c = (float)cos((double)angle);
-  float s = (float)sin((double)angle);
+  float c = (float)d_cos((double)angle);
+  float s = (float)d_sin((double)angle);
   float cx = c * vec.x, sy = s * vec.y, sx = s * vec.x, cy = c * vec.y;
   plus = mk2(cx - sy, +sx + cy);
   minus = mk2(cx + sy, -sx + cy);
@@ -186,7 +186,7 @@ VD V3 col_at_ray_hit(const DScene& sc, int32_t tex, V3 ray_in_dir, RayCone cone,
   // unqualified log2(width*height) on an unsigned => double
   float lambda = 0.5f * m_log2f(hit.tex_coord_area / hit.primitive_area);
   lambda += m_log2f(fabsf(cone.cone_width) / fabsf(dot(ray_in_dir, hit.hit_n_g)));
-  lambda = (float)((double)lambda + (double)0.5f * log2((double)(t.width * t.height)));
+  lambda = (float)((double)lambda + (double)0.5f * d_log2((double)(t.width * t.height)));
   if (is_nan(lambda)) lambda = 0.f;
   return col_mipmap_interpolate(sc, t, lambda - 2.f, hit.uv);
 }

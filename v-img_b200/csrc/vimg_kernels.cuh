@@ -49,33 +49,62 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderA
   const bool active = thread_pixel(args, sc.cam, x, y);
   PathCounters pc = {};
   uint32_t nan_samples = 0, n_samples = 0;
-  if (active) {
-    const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
-    const size_t image_index = x + ((size_t)(H - 1 - y) * W);
-    const uint32_t image_seq_start = x + y;
-    Pcg32 rng;
-    pcg32_seed(rng, image_index, 0);
-    V3 acc = mk3(0.0f);
-    for (uint32_t s = 0; s < args.samples; s++) {
-      V2 off = random_x_y_r2(image_seq_start + s);
-      // g++ evaluates the two rand_float arguments right to left: rand2 gets the first draw
-      // (include/integrators.h:122-123)
-      float rand2 = rand_float(rng);
-      float rand1 = rand_float(rng);
-      Ray cam_ray = generate_ray(sc.cam, (float)x + off.x, (float)y + off.y, rand1, rand2);
-      V3 col;
-      if (INTEGRATOR == VIMG_INTEGRATOR_S_NORMAL)
-        col = normal_integrator<false, COUNT>(sc, cam_ray, pc);
-      else if (INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL)
-        col = normal_integrator<true, COUNT>(sc, cam_ray, pc);
-      else if (INTEGRATOR == VIMG_INTEGRATOR_MATERIAL)
-        col = material_integrator<COUNT>(sc, cam_ray, rng, args.depth, pc);
-      else
-        col = mis_integrator<COUNT>(sc, cam_ray, rng, args.depth, pc);
-      if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
-      acc = acc + col;
-      n_samples++;
+  const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
+  const size_t image_index = active ? x + ((size_t)(H - 1 - y) * W) : 0;
+  const uint32_t image_seq_start = x + y;
+  Pcg32 rng;
+  pcg32_seed(rng, image_index, 0);
+  V3 acc = mk3(0.0f);
+
+  // camera ray of sample s (include/integrators.h:119-123); g++ evaluates the two rand_float
+  // arguments right to left, so rand2 gets the first draw
+  auto camera_ray = [&](uint32_t s) {
+    V2 off = random_x_y_r2(image_seq_start + s);
+    float rand2 = rand_float(rng);
+    float rand1 = rand_float(rng);
+    return generate_ray(sc.cam, (float)x + off.x, (float)y + off.y, rand1, rand2);
+  };
+
+  if (INTEGRATOR == VIMG_INTEGRATOR_S_NORMAL || INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL) {
+    if (active) {
+      for (uint32_t s = 0; s < args.samples; s++) {
+        Ray cam_ray = camera_ray(s);
+        V3 col = normal_integrator<INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL, COUNT>(sc, cam_ray, pc);
+        if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
+        acc = acc + col;
+        n_samples++;
+      }
     }
+  } else {
+    // path state machine with regeneration: every iteration advances every live lane by one
+    // bounce; a lane that finishes a sample starts the next one in the following iteration
+    PathState ps;
+    uint32_t s = 0;
+    bool alive = active && args.samples > 0;
+    bool in_path = false;
+    while (__any_sync(0xffffffffu, alive)) {
+      if (alive) {
+        if (!in_path) {
+          path_begin(ps, camera_ray(s));
+          in_path = true;
+        }
+        V3 col;
+        bool done;
+        if (INTEGRATOR == VIMG_INTEGRATOR_MATERIAL)
+          done = material_step<COUNT>(sc, ps, rng, args.depth, pc, col);
+        else
+          done = mis_step<COUNT>(sc, ps, rng, args.depth, pc, col);
+        if (done) {
+          if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
+          acc = acc + col;
+          n_samples++;
+          in_path = false;
+          if (++s == args.samples) alive = false;
+        }
+      }
+    }
+  }
+  if (active) {
     acc = acc / (float)args.samples;
     float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
     o[0] = acc.x;

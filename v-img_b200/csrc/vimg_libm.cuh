@@ -29,6 +29,15 @@
 
 namespace vimg_libm {
 
+// |x| >= 120 fallback; out of line on the device so the (never taken) slow path costs no I-cache
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ static double slow_sin(double x) { return sin(x); }
+__device__ __noinline__ static double slow_cos(double x) { return cos(x); }
+#else
+static inline double slow_sin(double x) { return sin(x); }
+static inline double slow_cos(double x) { return cos(x); }
+#endif
+
 // __sincosf_table[0] of glibc (sysdeps/ieee754/flt-32/s_sincosf_data.c).  Table [1], used
 // for quadrants 2 and 3, is the same with c0..c4 negated; round-to-nearest is symmetric, so
 // the negated polynomial is exactly the negated result and one coefficient set suffices.
@@ -100,7 +109,7 @@ VLM_FN float glibc_sinf(float y) {
     double xr = reduce_fast(x, n);
     return sincos_quadrant(xr, n, n & 1);
   }
-  return (float)sin(x);
+  return (float)slow_sin(x);
 }
 
 VLM_FN float glibc_cosf(float y) {
@@ -115,7 +124,7 @@ VLM_FN float glibc_cosf(float y) {
     double xr = reduce_fast(x, n);
     return sincos_quadrant(xr, n, (n ^ 1) & 1);  // cosf: sinf_poly(x * s, x2, p, n ^ 1), s and p from n
   }
-  return (float)cos(x);
+  return (float)slow_cos(x);
 }
 
 }  // namespace vimg_libm

@@ -97,13 +97,25 @@ VD V4 mat4_mul(const float* m, V4 v) {
 // correctly rounded in all but rare cases while CUDA's float versions are 1-2
 // ulp, so they are evaluated in double and rounded once.  Double expressions of
 // the reference call the double functions directly.
+// CUDA's double-precision library functions expand to hundreds of instructions each when
+// inlined; the render kernels call them from many places, so they live in ONE out-of-line
+// copy each (instruction-cache footprint, see DESIGN.md "Kernel structure").
+#define VNI __device__ __noinline__
+VNI double d_sin(double x) { return sin(x); }
+VNI double d_cos(double x) { return cos(x); }
+VNI double d_log(double x) { return log(x); }
+VNI double d_log2(double x) { return log2(x); }
+VNI double d_pow(double x, double y) { return pow(x, y); }
+VNI double d_acos(double x) { return acos(x); }
+VNI double d_atan2(double y, double x) { return atan2(y, x); }
+
 #ifndef VIMG_FAST_LIBM
 VD float m_sinf(float x) { return vimg_libm::glibc_sinf(x); }  // bit-exact glibc sinf, |x| < 120
 VD float m_cosf(float x) { return vimg_libm::glibc_cosf(x); }
-VD float m_logf(float x) { return (float)log((double)x); }
-VD float m_log2f(float x) { return (float)log2((double)x); }
-VD float m_acosf(float x) { return (float)acos((double)x); }
-VD float m_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+VD float m_logf(float x) { return (float)d_log((double)x); }
+VD float m_log2f(float x) { return (float)d_log2((double)x); }
+VD float m_acosf(float x) { return (float)d_acos((double)x); }
+VD float m_atan2f(float y, float x) { return (float)d_atan2((double)y, (double)x); }
 #else
 VD float m_sinf(float x) { return sinf(x); }
 VD float m_cosf(float x) { return cosf(x); }
