@@ -51,6 +51,8 @@ struct vimg_scene {
   int W = 0, H = 0;
   float* d_frame = nullptr;
   DCounters* d_counters = nullptr;
+  unsigned int* d_next_pixel = nullptr;
+  int wf_blocks[2][2] = {{0, 0}, {0, 0}};  // resident-grid size of wavefront_kernel<integrator, COUNT>
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   template <typename T> int upload(const T* host, size_t n, const T** out) {
@@ -305,16 +307,50 @@ static RenderArgs make_args(const vimg_scene* s, uint32_t samples, uint32_t dept
   return a;
 }
 
+// persistent grid of the wavefront kernel: as many blocks as are resident at once
+template <int INTEGRATOR, bool COUNT>
+static int wavefront_grid(vimg_scene* s, uint32_t n_pixels) {
+  int& cached = s->wf_blocks[INTEGRATOR == VIMG_INTEGRATOR_MIS][COUNT];
+  if (cached == 0) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<INTEGRATOR, COUNT>, WF_SLOTS, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    cached = per_sm > 0 && sms > 0 ? per_sm * sms : 148;
+  }
+  const uint32_t needed = (n_pixels + WF_SLOTS - 1) / WF_SLOTS;
+  return (int)(needed < (uint32_t)cached ? needed : (uint32_t)cached);
+}
+
 template <bool COUNT>
-static void launch_render(const vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st) {
+static void launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st) {
+  if (integrator == VIMG_INTEGRATOR_MATERIAL || integrator == VIMG_INTEGRATOR_MIS) {
+    WfArgs w{};
+    w.samples = a.samples;
+    w.depth = a.depth;
+    w.rank = a.rank;
+    w.n_ranks = a.n_ranks;
+    w.tiles_x = a.tiles_x;
+    w.tiles_y = a.tiles_y;
+    w.single_x = a.single_x;
+    w.single_y = a.single_y;
+    w.n_local_pixels = a.single_x >= 0 ? 1u : a.n_local_tiles * 64u;
+    if (w.n_local_pixels == 0) return;
+    cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
+    if (integrator == VIMG_INTEGRATOR_MIS) {
+      const int g = wavefront_grid<VIMG_INTEGRATOR_MIS, COUNT>(s, w.n_local_pixels);
+      wavefront_kernel<VIMG_INTEGRATOR_MIS, COUNT><<<g, WF_SLOTS, 0, st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
+    } else {
+      const int g = wavefront_grid<VIMG_INTEGRATOR_MATERIAL, COUNT>(s, w.n_local_pixels);
+      wavefront_kernel<VIMG_INTEGRATOR_MATERIAL, COUNT><<<g, WF_SLOTS, 0, st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
+    }
+    return;
+  }
   const uint32_t blocks = a.single_x >= 0 ? 1 : (a.n_local_tiles + 1) / 2;
   if (blocks == 0) return;
-  switch (integrator) {
-    case VIMG_INTEGRATOR_S_NORMAL: render_kernel<VIMG_INTEGRATOR_S_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters); break;
-    case VIMG_INTEGRATOR_G_NORMAL: render_kernel<VIMG_INTEGRATOR_G_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters); break;
-    case VIMG_INTEGRATOR_MATERIAL: render_kernel<VIMG_INTEGRATOR_MATERIAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters); break;
-    default: render_kernel<VIMG_INTEGRATOR_MIS, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters); break;
-  }
+  if (integrator == VIMG_INTEGRATOR_S_NORMAL)
+    render_kernel<VIMG_INTEGRATOR_S_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters);
+  else
+    render_kernel<VIMG_INTEGRATOR_G_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters);
 }
 
 static int check_params(const vimg_scene* s, const vimg_render_params* p) {
@@ -348,6 +384,7 @@ void vimg_scene_destroy(vimg_scene* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->d_frame) cudaFree(s->d_frame);
   if (s->d_counters) cudaFree(s->d_counters);
+  if (s->d_next_pixel) cudaFree(s->d_next_pixel);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -369,6 +406,7 @@ int vimg_scene_create(const vimg_scene_desc* desc, int device_id, vimg_scene** o
   if (rc == VIMG_OK) {
     cudaError_t e = cudaMalloc(&s->d_frame, (size_t)s->W * s->H * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, sizeof(DCounters));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_next_pixel, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) rc = fail(VIMG_ERR_CUDA, std::string("scene buffers: ") + cudaGetErrorString(e));

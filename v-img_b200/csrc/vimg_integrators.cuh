@@ -299,37 +299,6 @@ VD bool russian_roulette(Pcg32& rng, float eta_scale, V3& throughput) {
   return true;
 }
 
-// ------------------------------------------------------------ path state machine ----
-// The reference runs one path per call: material_integrator (mat_integrator.cpp:4-85) and
-// mis_integrator (mis_integrator.cpp:18-189).  On the GPU the same arithmetic is laid out as a
-// per-lane state machine so that the 32 lanes of a warp stay in lock step on the expensive
-// code (one closest-hit traversal, one shadow traversal, one BSDF sample and one inlined BSDF
-// evaluation site per iteration) no matter how long their individual paths are: a lane whose
-// path ends starts its pixel's next sample in the next iteration ("path regeneration").
-// RNG draws, their order and every float operation are those of the reference, so images
-// stay bit-identical; only the interleaving across pixels changes.
-struct PathState {
-  Ray ray;          // ray about to be traced (camera ray, or Ray(hit_p, wo, cone) of the last bounce)
-  HitInfo hit;      // surface the path currently sits on (valid once `first` is false)
-  V3 throughput, L;
-  float eta_scale;
-  float last_pdf;   // mat_sample_pdf of the bounce that produced `ray` (mis)
-  uint32_t d;       // bounce counter of the reference's for-loop
-  bool first;       // `ray` is the camera ray
-  bool non_specular_bounce;
-};
-
-VD void path_begin(PathState& ps, const Ray& cam_ray) {
-  ps.ray = cam_ray;
-  ps.throughput = mk3(1.0f);
-  ps.L = mk3(0.0f);
-  ps.eta_scale = 1;
-  ps.last_pdf = 0.f;
-  ps.d = 0;
-  ps.first = true;
-  ps.non_specular_bounce = false;
-}
-
 VD float balance_heuristic(float pdf1, float pdf2) { return pdf1 / (pdf1 + pdf2); }
 
 VD float geometric_term(V3 look_from, V3 point_on_surface, V3 surface_normal) {
@@ -338,198 +307,6 @@ VD float geometric_term(V3 look_from, V3 point_on_surface, V3 surface_normal) {
   dir_from_surf = normalize(dir_from_surf);
   float cosine = fabsf(dot(surface_normal, dir_from_surf));
   return cosine / distance2;
-}
-
-VD void next_ray(PathState& ps, V3 wo, RayCone cone) {
-  ps.ray.o = ps.hit.hit_p;
-  ps.ray.dir = wo;
-  ps.ray.minT = 0.0001f;
-  ps.ray.maxT = CUDART_INF_F;
-  ps.ray.cone = cone;
-  ps.first = false;
-}
-
-// One iteration of material_integrator's for-loop body (mat_integrator.cpp:16-83).
-// Returns true when the path ended; `result` is then the value the reference returns.
-template <bool COUNT>
-VD bool material_step(const DScene& sc, PathState& ps, Pcg32& rng, uint32_t depth, PathCounters& pc,
-                      V3& result) {
-  if (ps.d >= depth) {  // for (d = 0; d < depth; ...) ran out (also depth == 0): return vec3(0)
-    result = mk3(0.0f);
-    return true;
-  }
-  Ray& test_ray = ps.ray;
-  pc.rays_closest++;
-  if (!scene_hit<COUNT>(sc, test_ray, ps.hit, &pc.trav)) {
-    result = ps.throughput * background_emit(sc, test_ray.dir, test_ray.cone);
-    return true;
-  }
-  const HitInfo& hit = ps.hit;
-  const vimg_material& mat = sc.materials[hit.mat];
-  V3 emitted_col = mat_emitted(mat, test_ray.dir, hit.hit_n_s);
-  ScatterInfo sr;
-  if (!mat_sample(sc, mat, test_ray.dir, hit, rng, ps.non_specular_bounce, sr)) {
-    result = ps.throughput * emitted_col;
-    return true;
-  }
-  if (!sr.is_specular) ps.non_specular_bounce = true;
-  float hit_dist = length(test_ray.o - hit.hit_p);
-  float surface_spread_angle = spread_angle_from_curvature(hit.mean_curvature, test_ray.cone.cone_width,
-                                                           test_ray.dir, hit.hit_n_s);
-  if (sr.eta != 0.f) {
-    ps.eta_scale /= (sr.eta * sr.eta);
-    test_ray.cone = propagate_refract_cone(test_ray.cone, test_ray.dir, surface_spread_angle, sr.eta, sr.wo);
-  } else {
-    test_ray.cone = propagate_reflect_cone(test_ray.cone, surface_spread_angle * 2.f, hit_dist);
-  }
-  ps.throughput = ps.throughput
-                  * (emitted_col
-                     + mat_eval_div_pdf(sc, mat, test_ray.dir, sr.wo, hit, test_ray.cone,
-                                        ps.non_specular_bounce));
-  if (ps.d > 5) {
-    if (!russian_roulette(rng, ps.eta_scale, ps.throughput)) {
-      result = mk3(0.0f);  // `break` leaves the loop: return vec3(0)
-      return true;
-    }
-  }
-  next_ray(ps, sr.wo, test_ray.cone);
-  ps.d++;
-  return false;
-}
-
-// One iteration of the mis state machine: trace ps.ray, resolve what it hit (first-hit rules
-// mis_integrator.cpp:34-42, next-bounce rules :120-186), then run the loop body :45-117 at the new
-// surface (NEE + BSDF sample + both BSDF evaluations) to produce the next ray.
-template <bool COUNT>
-VD bool mis_step(const DScene& sc, PathState& ps, Pcg32& rng, uint32_t depth, PathCounters& pc,
-                 V3& result) {
-  Ray& ray = ps.ray;
-  {
-    HitInfo next;
-    pc.rays_closest++;
-    const bool found = scene_hit<COUNT>(sc, ray, next, &pc.trav);
-    if (!found) {
-      V3 bg = background_emit(sc, ray.dir, ray.cone);
-      if (ps.first) {
-        result = bg;
-      } else {
-        if (ps.last_pdf != 0 && sc.bg.emissive) {
-          float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
-          float mis_weight = balance_heuristic(ps.last_pdf, light_pdf);
-          ps.L = ps.L + ps.throughput * mis_weight * bg;
-        }
-        result = ps.L;
-      }
-      return true;
-    }
-    const vimg_material& nmat = sc.materials[next.mat];
-    if (mat_is_emissive(nmat)) {
-      V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
-      if (ps.first) {
-        result = emit;
-      } else {
-        if (ps.last_pdf != 0) {
-          // ray.o is the previous hit point, ray.dir the sampled direction wo
-          float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
-          float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
-          float mis_weight = balance_heuristic(ps.last_pdf * G, light_pdf);
-          ps.L = ps.L + ps.throughput * mis_weight * emit;
-        } else {
-          ps.L = ps.L + ps.throughput * emit;
-        }
-        result = ps.L;
-      }
-      return true;
-    }
-    if (!ps.first) {
-      if (ps.d > 5) {
-        if (!russian_roulette(rng, ps.eta_scale, ps.throughput)) {
-          result = ps.L;
-          return true;
-        }
-      }
-      ps.d++;  // for (...; d++)
-    }
-    ps.hit = next;
-    if (ps.d >= depth) {  // loop condition d < depth
-      result = ps.L;
-      return true;
-    }
-  }
-
-  // ---- loop body at ps.hit, reached along `ray` (the reference's test_ray) ------------------
-  const HitInfo& hit = ps.hit;
-  const vimg_material& mat = sc.materials[hit.mat];
-  const bool delta = mat_is_delta(mat);
-  float hit_dist = length(ray.o - hit.hit_p);
-  float surface_spread_angle
-      = spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s);
-
-  // light sampling (draws: 1 light pick + 2 emitter), shadow ray
-  bool nee = false;
-  EmitterInfo li;
-  V3 light_col = mk3(0.f);
-  if (!delta) {
-    light_col = lights_sample(sc, hit.hit_p, rng, li);
-    if (li.pdf != 0.f) {
-      Ray shadow_ray;
-      shadow_ray.o = hit.hit_p;
-      shadow_ray.dir = li.wi;
-      shadow_ray.minT = 0.0001f;
-      shadow_ray.maxT = li.dist - 0.0001f;
-      PreHit ph;
-      pc.rays_shadow++;
-      nee = !bvh_traverse<true, COUNT>(sc, shadow_ray, ph, &pc.trav);
-    }
-  }
-  const RayCone nee_cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
-  const bool nee_regularize = ps.non_specular_bounce;
-
-  // BSDF sample (draws happen after the light's, before any evaluation: evaluations draw nothing)
-  ScatterInfo sm;
-  const bool scattered = mat_sample(sc, mat, ray.dir, hit, rng, ps.non_specular_bounce, sm);
-  RayCone cone = ray.cone;
-  if (scattered) {
-    if (!sm.is_specular) ps.non_specular_bounce = true;
-    if (sm.eta != 0.f) {
-      ps.eta_scale /= (sm.eta * sm.eta);
-      cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
-    } else {
-      cone = nee_cone;  // the same propagate_reflect_cone(...) expression (mis_integrator.cpp:100-101)
-    }
-  }
-
-  // the two eval_pdf_pair calls of the loop body share ONE inlined evaluation site:
-  //   k = 0: light direction  (mis_integrator.cpp:68-71), k = 1: sampled direction (:104-106)
-  V3 mat_sample_eval = mk3(0.f);
-  float mat_sample_pdf = 0.f;
-#pragma unroll 1
-  for (int k = 0; k < 2; ++k) {
-    const bool want = k == 0 ? nee : scattered;
-    if (!want) continue;
-    V3 e;
-    float p;
-    mat_eval_pdf_pair(sc, mat, ray.dir, k == 0 ? li.wi : sm.wo, hit, k == 0 ? nee_cone : cone,
-                      k == 0 ? nee_regularize : ps.non_specular_bounce, e, p);
-    if (k == 0) {
-      if (p != 0 && !is_nan(p)) {
-        float G = li.G;
-        float mis_weight = balance_heuristic(li.pdf, p * G);
-        ps.L = ps.L + ps.throughput * e * mis_weight * G * light_col / li.pdf;
-      }
-    } else {
-      mat_sample_eval = e;
-      mat_sample_pdf = p;
-    }
-  }
-  if (!scattered || is_nan(mat_sample_pdf)) {
-    result = ps.L;
-    return true;
-  }
-  ps.throughput = ps.throughput * (mat_sample_eval / mat_sample_pdf);
-  ps.last_pdf = mat_sample_pdf;
-  next_ray(ps, sm.wo, cone);
-  return false;
 }
 
 }  // namespace vimg

@@ -24,6 +24,10 @@ VD void warp_add_counter(unsigned long long* dst, uint32_t v) {
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
+}  // namespace vimg
+#include "vimg_wavefront.cuh"
+namespace vimg {
+
 // maps the calling thread to its pixel; returns false if it has none
 VD bool thread_pixel(const RenderArgs& a, const DCamera& cam, uint32_t& x, uint32_t& y) {
   if (a.single_x >= 0) {
@@ -65,43 +69,15 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderA
     return generate_ray(sc.cam, (float)x + off.x, (float)y + off.y, rand1, rand2);
   };
 
-  if (INTEGRATOR == VIMG_INTEGRATOR_S_NORMAL || INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL) {
-    if (active) {
-      for (uint32_t s = 0; s < args.samples; s++) {
-        Ray cam_ray = camera_ray(s);
-        V3 col = normal_integrator<INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL, COUNT>(sc, cam_ray, pc);
-        if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
-        acc = acc + col;
-        n_samples++;
-      }
-    }
-  } else {
-    // path state machine with regeneration: every iteration advances every live lane by one
-    // bounce; a lane that finishes a sample starts the next one in the following iteration
-    PathState ps;
-    uint32_t s = 0;
-    bool alive = active && args.samples > 0;
-    bool in_path = false;
-    while (__any_sync(0xffffffffu, alive)) {
-      if (alive) {
-        if (!in_path) {
-          path_begin(ps, camera_ray(s));
-          in_path = true;
-        }
-        V3 col;
-        bool done;
-        if (INTEGRATOR == VIMG_INTEGRATOR_MATERIAL)
-          done = material_step<COUNT>(sc, ps, rng, args.depth, pc, col);
-        else
-          done = mis_step<COUNT>(sc, ps, rng, args.depth, pc, col);
-        if (done) {
-          if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
-          acc = acc + col;
-          n_samples++;
-          in_path = false;
-          if (++s == args.samples) alive = false;
-        }
-      }
+  // the normal integrators trace one camera ray per sample; material / mis run in
+  // wavefront_kernel (vimg_wavefront.cuh)
+  if (active) {
+    for (uint32_t s = 0; s < args.samples; s++) {
+      Ray cam_ray = camera_ray(s);
+      V3 col = normal_integrator<INTEGRATOR == VIMG_INTEGRATOR_G_NORMAL, COUNT>(sc, cam_ray, pc);
+      if (is_nan(col.x) || is_nan(col.y) || is_nan(col.z)) nan_samples++;
+      acc = acc + col;
+      n_samples++;
     }
   }
   if (active) {

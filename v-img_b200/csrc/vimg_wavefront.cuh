@@ -1,0 +1,493 @@
+// vimg_wavefront.cuh -- persistent, block-local wavefront path tracer (material / mis).
+//
+// Measured (profiles/r1_*): a one-thread-per-pixel megakernel runs the Disney scene with
+// ~6 of 32 lanes active -- a few lanes in the (long) Principled code serialise against many
+// lanes in the (short) Lambertian code -- and thrashes the instruction cache.  This kernel
+// keeps the reference's per-pixel sequential RNG stream (one path in flight per pixel,
+// include/integrators.h:116-131) but regroups paths between stages:
+//
+//   * a block owns WF_SLOTS path slots whose state lives in SHARED MEMORY (SoA);
+//   * slot stage (thread i works on slot i): pending shadow ray -> finish sample / pull the
+//     next pixel / camera ray -> closest-hit traversal -> resolve (miss, emitter, Russian
+//     roulette, depth) -> classify the hit material;
+//   * block barrier; the live slots were bucketed by material class with warp ballots and
+//     shared-memory counters, so that each warp of the next stage sees ONE material;
+//   * shade stage (thread k works on the k-th slot of the bucketed list): light sampling,
+//     BSDF sampling, both BSDF evaluations, next ray, shadow-ray request;
+//   * block barrier, repeat.  Slots whose pixel is complete pull the next pixel of the frame
+//     from a global counter (tile-major order), so there is no per-block tail.
+//
+// Every float operation and every RNG draw happens in the reference's order for its path
+// (src/integrators/mis_integrator.cpp:18-189, mat_integrator.cpp:4-85), so the images are
+// unchanged bit for bit (tests/test_gpu_parity.py).
+#pragma once
+#include "vimg_integrators.cuh"
+
+namespace vimg {
+
+#ifndef WF_SLOTS
+#define WF_SLOTS 256
+#endif
+
+enum : uint32_t {
+  WF_ALIVE = 1u,       // slot owns a pixel with samples left
+  WF_IN_PATH = 2u,     // a path is in flight (else: needs a camera ray)
+  WF_FIRST = 4u,       // the ray in flight is the camera ray
+  WF_NSB = 8u,         // non_specular_bounce
+  WF_NEE = 16u,        // shadow ray pending (mis)
+  WF_NEE_VALID = 32u,  // ... and its contribution passed the pdf checks
+  WF_END = 64u,        // path ends before the next trace (result: L for mis, nee_c for material)
+};
+
+enum : uint32_t { WF_CLASS_LAMBERT = 0, WF_CLASS_PRINCIPLED = 1, WF_CLASS_DIELECTRIC = 2, WF_NUM_CLASSES = 3, WF_CLASS_NONE = 3 };
+
+struct WfShared {
+  float ray_o[3][WF_SLOTS], ray_d[3][WF_SLOTS], cone_w[WF_SLOTS], cone_s[WF_SLOTS];
+  float thr[3][WF_SLOTS];
+  float eta_scale[WF_SLOTS], last_pdf[WF_SLOTS];
+  unsigned long long rng[WF_SLOTS];
+  uint32_t flags[WF_SLOTS], d[WF_SLOTS];
+  int32_t hit_slot[WF_SLOTS];
+  float hit_t[WF_SLOTS], e0[WF_SLOTS], e1[WF_SLOTS], e2[WF_SLOTS], inv_det[WF_SLOTS];
+  float nee_wi[3][WF_SLOTS], nee_dist[WF_SLOTS], nee_c[3][WF_SLOTS];
+  uint16_t list[WF_NUM_CLASSES][WF_SLOTS];
+  uint32_t class_count[2][WF_NUM_CLASSES];
+};
+
+struct WfArgs {
+  uint32_t samples, depth;
+  uint32_t rank, n_ranks;
+  uint32_t tiles_x, tiles_y;
+  uint32_t n_local_pixels;     // 64 * tiles owned by this rank
+  int32_t single_x, single_y;  // >= 0: trace_pixel mode
+};
+
+VD V3 ld3(const float (*a)[WF_SLOTS], int i) { return mk3(a[0][i], a[1][i], a[2][i]); }
+VD void st3(float (*a)[WF_SLOTS], int i, V3 v) {
+  a[0][i] = v.x;
+  a[1][i] = v.y;
+  a[2][i] = v.z;
+}
+
+// local pixel number (tile-major within this rank's tile list) -> image coordinates
+VD bool wf_pixel_xy(const WfArgs& a, const DCamera& cam, uint32_t p, uint32_t& x, uint32_t& y) {
+  if (a.single_x >= 0) {
+    x = (uint32_t)a.single_x;
+    y = (uint32_t)a.single_y;
+    return true;
+  }
+  const uint32_t tile = a.rank + (p >> 6) * a.n_ranks;
+  const uint32_t tx = tile / a.tiles_y, ty = tile % a.tiles_y;
+  x = tx * 8 + (p & 7);
+  y = ty * 8 + ((p >> 3) & 7);
+  return x < (uint32_t)cam.res[0] && y < (uint32_t)cam.res[1];
+}
+
+VD uint32_t wf_leaf_material(const DScene& sc, int32_t leaf_slot) {
+  const DLeafPrim* lp = sc.leaf_prims + leaf_slot;
+  const vimg_prim pr = sc.prims[lp->prim_id];
+  return (lp->flags & VIMG_LEAF_SPHERE) ? sc.spheres[pr.a].material : sc.meshes[pr.a].material;
+}
+
+VD HitInfo wf_hit_info(const DScene& sc, int32_t leaf_slot, const PreHit& ph, const Ray& ray) {
+  const DLeafPrim lp = sc.leaf_prims[leaf_slot];
+  if (lp.flags & VIMG_LEAF_SPHERE) return sphere_hit_info(sc, lp, ray);
+  return triangle_hit_info(sc, lp, ph);
+}
+
+VD uint32_t wf_material_class(uint32_t mat_type) {
+  switch (mat_type) {
+    case VIMG_MAT_LAMBERTIAN: return WF_CLASS_LAMBERT;
+    case VIMG_MAT_PRINCIPLED: return WF_CLASS_PRINCIPLED;
+    case VIMG_MAT_DIELECTRIC: return WF_CLASS_DIELECTRIC;
+    default: return WF_CLASS_NONE;
+  }
+}
+
+template <int INTEGRATOR, bool COUNT>
+__global__ void __launch_bounds__(WF_SLOTS, 2)
+wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfArgs args,
+                 float* __restrict__ out, DCounters* __restrict__ counters,
+                 unsigned int* __restrict__ next_pixel) {
+  constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
+  __shared__ WfShared sh;
+  const int i = threadIdx.x;
+  const uint32_t lane = i & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
+
+  // slot-private state: only the slot's home thread (thread i) ever touches it
+  V3 acc = mk3(0.f), L = mk3(0.f);
+  uint32_t s = 0, px = 0, py = 0;
+  size_t image_index = 0;
+  bool exhausted = false;  // the frame has no more pixels to hand out
+  PathCounters pc = {};
+  uint32_t nan_samples = 0, n_samples = 0;
+  sh.flags[i] = 0;
+  if (i < (int)WF_NUM_CLASSES) sh.class_count[0][i] = sh.class_count[1][i] = 0;
+  __syncthreads();
+
+  for (uint32_t iter = 0;; ++iter) {
+    uint32_t f = sh.flags[i];
+    uint32_t cls = WF_CLASS_NONE;
+
+    // finish the current sample of this slot's pixel (include/integrators.h:128-137)
+    auto finish = [&](V3 result) {
+      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
+      acc = acc + result;
+      n_samples++;
+      f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
+      if (++s == args.samples) {
+        acc = acc / (float)args.samples;
+        float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+        o[0] = acc.x;
+        o[1] = acc.y;
+        o[2] = acc.z;
+        f &= ~WF_ALIVE;
+      }
+    };
+
+    // ================= slot stage (thread i <-> slot i) =================
+    // A. shadow ray requested by the last shade stage (mis_integrator.cpp:59-78)
+    if (MIS && (f & WF_NEE)) {
+      Ray sr;
+      sr.o = ld3(sh.ray_o, i);  // the shade stage left hit_p here
+      sr.dir = ld3(sh.nee_wi, i);
+      sr.minT = 0.0001f;
+      sr.maxT = sh.nee_dist[i] - 0.0001f;
+      PreHit ph;
+      pc.rays_shadow++;
+      const bool occluded = bvh_traverse<true, COUNT>(sc, sr, ph, &pc.trav);
+      if (!occluded && (f & WF_NEE_VALID)) L = L + ld3(sh.nee_c, i);
+      f &= ~(WF_NEE | WF_NEE_VALID);
+    }
+    if (f & WF_END) finish(MIS ? L : ld3(sh.nee_c, i));
+
+    // B. pull the next pixel of the frame, start the next sample
+    {
+      const bool want = !(f & WF_ALIVE) && !exhausted;
+      const uint32_t m = __ballot_sync(0xffffffffu, want);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(next_pixel, (unsigned int)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (want) {
+          const uint32_t p = base + __popc(m & lane_lt);
+          if (p >= args.n_local_pixels) {
+            exhausted = true;
+          } else if (wf_pixel_xy(args, sc.cam, p, px, py) && args.samples > 0) {
+            image_index = px + ((size_t)(H - 1 - py) * W);
+            Pcg32 r;
+            pcg32_seed(r, image_index, 0);
+            sh.rng[i] = r.state;
+            acc = mk3(0.f);
+            s = 0;
+            f = WF_ALIVE;
+          }
+        }
+      }
+    }
+    if ((f & WF_ALIVE) && !(f & WF_IN_PATH)) {
+      // camera ray (include/integrators.h:119-123); rand2 gets the first draw
+      Pcg32 r;
+      r.state = sh.rng[i];
+      r.inc = 1;
+      V2 off = random_x_y_r2(px + py + s);
+      float rand2 = rand_float(r);
+      float rand1 = rand_float(r);
+      Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
+      sh.rng[i] = r.state;
+      st3(sh.ray_o, i, cam.o);
+      st3(sh.ray_d, i, cam.dir);
+      sh.cone_w[i] = cam.cone.cone_width;
+      sh.cone_s[i] = cam.cone.spread_angle;
+      st3(sh.thr, i, mk3(1.0f));
+      sh.eta_scale[i] = 1;
+      sh.last_pdf[i] = 0.f;
+      sh.d[i] = 0;
+      L = mk3(0.0f);
+      f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
+    }
+
+    // C. closest-hit traversal + D. resolve
+    if (f & WF_IN_PATH) {
+      const uint32_t d = sh.d[i];
+      if (!MIS && d >= args.depth) {
+        finish(mk3(0.0f));  // material: for (d = 0; d < depth; ...) ran out -> vec3(0)
+      } else {
+        Ray ray;
+        ray.o = ld3(sh.ray_o, i);
+        ray.dir = ld3(sh.ray_d, i);
+        ray.minT = 0.0001f;
+        ray.maxT = CUDART_INF_F;
+        ray.cone.cone_width = sh.cone_w[i];
+        ray.cone.spread_angle = sh.cone_s[i];
+        PreHit ph;
+        pc.rays_closest++;
+        const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav);
+        const V3 thr = ld3(sh.thr, i);
+        if (!found) {
+          V3 bg = background_emit(sc, ray.dir, ray.cone);
+          if (!MIS) {
+            finish(thr * bg);
+          } else if (f & WF_FIRST) {
+            finish(bg);
+          } else {
+            const float last_pdf = sh.last_pdf[i];
+            if (last_pdf != 0 && sc.bg.emissive) {
+              float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
+              float mis_weight = balance_heuristic(last_pdf, light_pdf);
+              L = L + thr * mis_weight * bg;
+            }
+            finish(L);
+          }
+        } else {
+          const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
+          cls = wf_material_class(nmat.type);
+          if (MIS) {
+            if (mat_is_emissive(nmat)) {
+              cls = WF_CLASS_NONE;
+              const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+              V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
+              if (f & WF_FIRST) {
+                finish(emit);
+              } else {
+                const float last_pdf = sh.last_pdf[i];
+                if (last_pdf != 0) {
+                  // ray.o is the previous hit point, ray.dir the sampled direction
+                  float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
+                  float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
+                  float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
+                  L = L + thr * mis_weight * emit;
+                } else {
+                  L = L + thr * emit;
+                }
+                finish(L);
+              }
+            } else {
+              bool go_on = true;
+              uint32_t dn = d;
+              if (!(f & WF_FIRST)) {
+                if (d > 5) {
+                  Pcg32 r;
+                  r.state = sh.rng[i];
+                  r.inc = 1;
+                  V3 t = thr;
+                  go_on = russian_roulette(r, sh.eta_scale[i], t);
+                  sh.rng[i] = r.state;
+                  if (go_on) st3(sh.thr, i, t);
+                }
+                dn = d + 1;
+              }
+              if (!go_on || dn >= args.depth || cls == WF_CLASS_NONE) {
+                // RR break / loop condition d < depth / base Material (delta, sample_mat -> nullopt)
+                cls = WF_CLASS_NONE;
+                finish(L);
+              } else {
+                sh.d[i] = dn;
+              }
+            }
+          } else if (cls == WF_CLASS_NONE) {
+            // material integrator on DiffuseLight / base Material: sample_mat -> nullopt,
+            // return throughput * emitted (mat_integrator.cpp:21-81)
+            V3 emitted_col = mk3(0.f);
+            if (mat_is_emissive(nmat)) {
+              const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+              emitted_col = mat_emitted(nmat, ray.dir, next.hit_n_s);
+            }
+            finish(thr * emitted_col);
+          }
+          if (cls != WF_CLASS_NONE) {
+            sh.hit_slot[i] = ph.leaf_slot;
+            sh.hit_t[i] = ray.maxT;
+            sh.e0[i] = ph.e0;
+            sh.e1[i] = ph.e1;
+            sh.e2[i] = ph.e2;
+            sh.inv_det[i] = ph.inv_det;
+            f &= ~WF_FIRST;
+          }
+        }
+      }
+    }
+    sh.flags[i] = f;
+
+    // bucket the slots that need shading by material class (one list per class)
+    uint32_t* counts = sh.class_count[iter & 1];
+#pragma unroll
+    for (uint32_t c = 0; c < WF_NUM_CLASSES; ++c) {
+      const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&counts[c], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (cls == c) sh.list[c][base + __popc(m & lane_lt)] = (uint16_t)i;
+      }
+    }
+    // barrier 1: lists complete; also the block-wide "anything left to do" vote
+    const int live = __syncthreads_or((f & WF_ALIVE) != 0 || !exhausted);
+    if (!live) break;
+    if (i < (int)WF_NUM_CLASSES) sh.class_count[(iter + 1) & 1][i] = 0;  // next iteration's counters
+
+    // ================= shade stage (thread k <-> k-th bucketed slot) =================
+    {
+      const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
+      int j = -1;
+      // Principled first (longest), then Lambertian, then Dielectric: whole warps share a class
+      uint32_t k = (uint32_t)i;
+      if (k < n1) {
+        j = sh.list[WF_CLASS_PRINCIPLED][k];
+      } else if ((k -= n1) < n0) {
+        j = sh.list[WF_CLASS_LAMBERT][k];
+      } else if ((k -= n0) < n2) {
+        j = sh.list[WF_CLASS_DIELECTRIC][k];
+      }
+      if (j >= 0) {
+        uint32_t fj = sh.flags[j];
+        Ray ray;
+        ray.o = ld3(sh.ray_o, j);
+        ray.dir = ld3(sh.ray_d, j);
+        ray.minT = 0.0001f;
+        ray.maxT = sh.hit_t[j];
+        ray.cone.cone_width = sh.cone_w[j];
+        ray.cone.spread_angle = sh.cone_s[j];
+        PreHit ph;
+        ph.leaf_slot = sh.hit_slot[j];
+        ph.e0 = sh.e0[j];
+        ph.e1 = sh.e1[j];
+        ph.e2 = sh.e2[j];
+        ph.inv_det = sh.inv_det[j];
+        const HitInfo hit = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+        const vimg_material& mat = sc.materials[hit.mat];
+        Pcg32 rng;
+        rng.state = sh.rng[j];
+        rng.inc = 1;
+        V3 thr = ld3(sh.thr, j);
+        bool nsb = (fj & WF_NSB) != 0;
+        float hit_dist = length(ray.o - hit.hit_p);
+        float surface_spread_angle
+            = spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s);
+
+        if (MIS) {
+          // ---- mis_integrator.cpp:45-117 at `hit` ----
+          bool nee = false, nee_valid = false;
+          EmitterInfo li;
+          V3 light_col = mk3(0.f);
+          if (!mat_is_delta(mat)) {
+            light_col = lights_sample(sc, hit.hit_p, rng, li);
+            nee = li.pdf != 0.f;
+          }
+          const RayCone nee_cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+          const bool nee_regularize = nsb;
+          ScatterInfo sm;
+          const bool scattered = mat_sample(sc, mat, ray.dir, hit, rng, nsb, sm);
+          RayCone cone = ray.cone;
+          float eta_scale = sh.eta_scale[j];
+          if (scattered) {
+            if (!sm.is_specular) nsb = true;
+            if (sm.eta != 0.f) {
+              eta_scale /= (sm.eta * sm.eta);
+              cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
+            } else {
+              cone = nee_cone;
+            }
+          }
+          // ONE inlined eval_pdf_pair site serves both calls of the loop body:
+          //   q = 0 light direction (mis_integrator.cpp:68-71), q = 1 sampled direction (:104-106)
+          V3 contrib = mk3(0.f), mat_sample_eval = mk3(0.f);
+          float mat_sample_pdf = 0.f;
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            if (!(q == 0 ? nee : scattered)) continue;
+            V3 e;
+            float p;
+            mat_eval_pdf_pair(sc, mat, ray.dir, q == 0 ? li.wi : sm.wo, hit, q == 0 ? nee_cone : cone,
+                              q == 0 ? nee_regularize : nsb, e, p);
+            if (q == 0) {
+              if (p != 0 && !is_nan(p)) {
+                float G = li.G;
+                float mis_weight = balance_heuristic(li.pdf, p * G);
+                contrib = thr * e * mis_weight * G * light_col / li.pdf;
+                nee_valid = true;
+              }
+            } else {
+              mat_sample_eval = e;
+              mat_sample_pdf = p;
+            }
+          }
+          fj &= ~(WF_NSB | WF_NEE | WF_NEE_VALID | WF_END);
+          if (nsb) fj |= WF_NSB;
+          if (nee) {
+            fj |= WF_NEE | (nee_valid ? WF_NEE_VALID : 0u);
+            st3(sh.nee_wi, j, li.wi);
+            sh.nee_dist[j] = li.dist;
+            st3(sh.nee_c, j, contrib);
+          }
+          st3(sh.ray_o, j, hit.hit_p);  // origin of the shadow ray and of the next ray
+          if (!scattered || is_nan(mat_sample_pdf)) {
+            fj |= WF_END;  // return bounce_result (after the pending shadow ray)
+          } else {
+            thr = thr * (mat_sample_eval / mat_sample_pdf);
+            st3(sh.thr, j, thr);
+            sh.last_pdf[j] = mat_sample_pdf;
+            sh.eta_scale[j] = eta_scale;
+            st3(sh.ray_d, j, sm.wo);
+            sh.cone_w[j] = cone.cone_width;
+            sh.cone_s[j] = cone.spread_angle;
+          }
+        } else {
+          // ---- material_integrator, mat_integrator.cpp:21-83 at `hit` ----
+          V3 emitted_col = mat_emitted(mat, ray.dir, hit.hit_n_s);
+          ScatterInfo sr;
+          fj &= ~(WF_NSB | WF_END);
+          if (!mat_sample(sc, mat, ray.dir, hit, rng, nsb, sr)) {
+            st3(sh.nee_c, j, thr * emitted_col);
+            fj |= WF_END;
+          } else {
+            if (!sr.is_specular) nsb = true;
+            RayCone cone;
+            float eta_scale = sh.eta_scale[j];
+            if (sr.eta != 0.f) {
+              eta_scale /= (sr.eta * sr.eta);
+              cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo);
+            } else {
+              cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+            }
+            thr = thr * (emitted_col + mat_eval_div_pdf(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
+            const uint32_t d = sh.d[j];
+            bool go_on = true;
+            if (d > 5) go_on = russian_roulette(rng, eta_scale, thr);
+            if (!go_on) {
+              st3(sh.nee_c, j, mk3(0.0f));  // `break`: return vec3(0)
+              fj |= WF_END;
+            } else {
+              st3(sh.thr, j, thr);
+              sh.eta_scale[j] = eta_scale;
+              st3(sh.ray_o, j, hit.hit_p);
+              st3(sh.ray_d, j, sr.wo);
+              sh.cone_w[j] = cone.cone_width;
+              sh.cone_s[j] = cone.spread_angle;
+              sh.d[j] = d + 1;
+            }
+          }
+          if (nsb) fj |= WF_NSB;
+        }
+        sh.rng[j] = rng.state;
+        sh.flags[j] = fj;
+      }
+    }
+    __syncthreads();  // barrier 2: shade results visible to the slots' home threads
+  }
+
+  warp_add_counter(&counters->rays_closest, pc.rays_closest);
+  warp_add_counter(&counters->rays_shadow, pc.rays_shadow);
+  warp_add_counter(&counters->nan_samples, nan_samples);
+  warp_add_counter(&counters->samples, n_samples);
+  if (COUNT) {
+    warp_add_counter(&counters->inner_nodes, pc.trav.inner);
+    warp_add_counter(&counters->leaf_nodes, pc.trav.leaf);
+    warp_add_counter(&counters->tri_tests, pc.trav.tri);
+    warp_add_counter(&counters->sphere_tests, pc.trav.sph);
+  }
+}
+
+}  // namespace vimg
