@@ -313,7 +313,10 @@ static int wavefront_grid(vimg_scene* s, uint32_t n_pixels) {
   int& cached = s->wf_blocks[INTEGRATOR == VIMG_INTEGRATOR_MIS][COUNT];
   if (cached == 0) {
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<INTEGRATOR, COUNT>, WF_SLOTS, 0);
+    cudaFuncSetAttribute(wavefront_kernel<INTEGRATOR, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(WfShared));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wavefront_kernel<INTEGRATOR, COUNT>, WF_THREADS,
+                                                  sizeof(WfShared));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     cached = per_sm > 0 && sms > 0 ? per_sm * sms : 148;
   }
@@ -338,10 +341,10 @@ static void launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrato
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
     if (integrator == VIMG_INTEGRATOR_MIS) {
       const int g = wavefront_grid<VIMG_INTEGRATOR_MIS, COUNT>(s, w.n_local_pixels);
-      wavefront_kernel<VIMG_INTEGRATOR_MIS, COUNT><<<g, WF_SLOTS, 0, st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
+      wavefront_kernel<VIMG_INTEGRATOR_MIS, COUNT><<<g, WF_THREADS, sizeof(WfShared), st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
     } else {
       const int g = wavefront_grid<VIMG_INTEGRATOR_MATERIAL, COUNT>(s, w.n_local_pixels);
-      wavefront_kernel<VIMG_INTEGRATOR_MATERIAL, COUNT><<<g, WF_SLOTS, 0, st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
+      wavefront_kernel<VIMG_INTEGRATOR_MATERIAL, COUNT><<<g, WF_THREADS, sizeof(WfShared), st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
     }
     return;
   }

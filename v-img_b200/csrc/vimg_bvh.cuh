@@ -113,10 +113,14 @@ VD bool tri_hit(const float* a, uint32_t flags, Ray& ray, const RayPre& pre, Pre
   if (flags & VIMG_LEAF_DEGENERATE) return false;  // length2(cross(e2,e1)) == 0, precomputed
   V3 p0 = mk3(a[0], a[1], a[2]), p1 = mk3(a[3], a[4], a[5]), p2 = mk3(a[6], a[7], a[8]);
   V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
-  // permute
-  float p0x = comp(p0t, pre.kx), p0y = comp(p0t, pre.ky), p0z = comp(p0t, pre.kz);
-  float p1x = comp(p1t, pre.kx), p1y = comp(p1t, pre.ky), p1z = comp(p1t, pre.kz);
-  float p2x = comp(p2t, pre.kx), p2y = comp(p2t, pre.ky), p2z = comp(p2t, pre.kz);
+  // permute: (kx, ky, kz) is a cyclic rotation -- kz = 2: (x,y,z), kz = 0: (y,z,x), kz = 1: (z,x,y)
+  const bool z0 = pre.kz == 0, z1 = pre.kz == 1;
+  float p0x = z0 ? p0t.y : (z1 ? p0t.z : p0t.x), p0y = z0 ? p0t.z : (z1 ? p0t.x : p0t.y),
+        p0z = z0 ? p0t.x : (z1 ? p0t.y : p0t.z);
+  float p1x = z0 ? p1t.y : (z1 ? p1t.z : p1t.x), p1y = z0 ? p1t.z : (z1 ? p1t.x : p1t.y),
+        p1z = z0 ? p1t.x : (z1 ? p1t.y : p1t.z);
+  float p2x = z0 ? p2t.y : (z1 ? p2t.z : p2t.x), p2y = z0 ? p2t.z : (z1 ? p2t.x : p2t.y),
+        p2z = z0 ? p2t.x : (z1 ? p2t.y : p2t.z);
   // shear
   p0x += pre.Sx * p0z;
   p0y += pre.Sy * p0z;
@@ -217,16 +221,49 @@ VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt) 
   float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
   if (is_inf(root_hit)) return false;
 
+  // "while-while" traversal: every lane first descends through inner nodes until it holds a
+  // leaf (or runs dry), then the warp tests leaf primitives together.  Per ray the sequence of
+  // box tests, pushes and primitive tests is exactly the reference's push-then-pop order:
+  // instead of pushing the child that would be popped next, it is kept in `cur`.
   uint2 stack[VIMG_STACK_MAX];
   int sp = 0;
-  stack[sp++] = make_uint2(sc.root_first, sc.root_count);
-
-  while (sp > 0) {
-    const uint2 node = stack[--sp];
-    if (node.y != 0) {  // leaf
+  uint2 cur = make_uint2(sc.root_first, sc.root_count);
+  bool have = true;
+  while (have) {
+    while (have && cur.y == 0) {  // inner: test both children of the pair record
+      if (COUNT) cnt->inner++;
+      const float4* rec = reinterpret_cast<const float4*>(sc.pairs + ((cur.x - 1u) >> 1));
+      const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rec + 3));
+      const float lmin[3] = {q0.x, q0.y, q0.z}, rmin[3] = {q0.w, q1.x, q1.y};
+      const float lmax[3] = {q1.z, q1.w, q2.x}, rmax[3] = {q2.y, q2.z, q2.w};
+      const float bb_hit1 = slab(lmin, lmax, ray, pre);
+      const float bb_hit2 = slab(rmin, rmax, ray, pre);
+      uint2 first_child = make_uint2(q3.x, q3.y), sec_child = make_uint2(q3.z, q3.w);
+      const bool h1 = !is_inf(bb_hit1), h2 = !is_inf(bb_hit2);
+      if (h2) {
+        if (h1) {
+          // closest hit: push the more distant box first (tie: first child pushed first);
+          // any hit: unordered, left pushed then right (bvh.h:195-212)
+          if (!ANY_HIT && bb_hit2 > bb_hit1) {
+            uint2 t = first_child;
+            first_child = sec_child;
+            sec_child = t;
+          }
+          stack[sp++] = first_child;
+        }
+        cur = sec_child;  // would be pushed last and popped next
+      } else if (h1) {
+        cur = first_child;
+      } else {
+        have = sp > 0;
+        if (have) cur = stack[--sp];
+      }
+    }
+    if (have) {  // leaf
       if (COUNT) cnt->leaf++;
-      for (uint32_t i = 0; i < node.y; ++i) {
-        const uint32_t slot = node.x + i;
+      for (uint32_t i = 0; i < cur.y; ++i) {
+        const uint32_t slot = cur.x + i;
         const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + slot);
         const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
         const float a[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
@@ -245,34 +282,8 @@ VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt) 
           ph.leaf_slot = (int32_t)slot;
         }
       }
-    } else {  // inner: test both children of the pair record
-      if (COUNT) cnt->inner++;
-      const float4* rec = reinterpret_cast<const float4*>(sc.pairs + ((node.x - 1u) >> 1));
-      const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rec + 3));
-      const float lmin[3] = {q0.x, q0.y, q0.z}, rmin[3] = {q0.w, q1.x, q1.y};
-      const float lmax[3] = {q1.z, q1.w, q2.x}, rmax[3] = {q2.y, q2.z, q2.w};
-      const float bb_hit1 = slab(lmin, lmax, ray, pre);
-      const float bb_hit2 = slab(rmin, rmax, ray, pre);
-      uint2 first_child = make_uint2(q3.x, q3.y), sec_child = make_uint2(q3.z, q3.w);
-      if (ANY_HIT) {
-        if (!is_inf(bb_hit1)) stack[sp++] = first_child;
-        if (!is_inf(bb_hit2)) stack[sp++] = sec_child;
-      } else {
-        if (!is_inf(bb_hit2)) {
-          if (!is_inf(bb_hit1)) {
-            if (bb_hit2 > bb_hit1) {
-              uint2 t = first_child;
-              first_child = sec_child;
-              sec_child = t;
-            }
-            stack[sp++] = first_child;
-          }
-          stack[sp++] = sec_child;
-        } else if (!is_inf(bb_hit1)) {
-          stack[sp++] = first_child;
-        }
-      }
+      have = sp > 0;
+      if (have) cur = stack[--sp];
     }
   }
   return ph.leaf_slot >= 0;

@@ -319,10 +319,17 @@ VD HitInfo sphere_hit_info(const DScene& sc, const DLeafPrim& lp, const Ray& r) 
   float radius = lp.a[3];
   const V3 hit_p = r.o + r.dir * r.maxT;
   const V3 normal = normalize(hit_p - center);
-  float theta = m_acosf(-normal.y);
-  float phi = (float)((double)m_atan2f(-normal.z, normal.x) + VIMG_PI_D);
-  float u = (float)((double)phi / (2.f * VIMG_PI_D));
-  float v = (float)((double)theta / VIMG_PI_D);
+  // uv is only read by non-constant textures (col_at_ray_hit) and by the metallic-roughness
+  // texture; for every other material the acos/atan2 pair is dead code in the reference too
+  const vimg_material& m = sc.materials[sc.spheres[pr.a].material];
+  const bool needs_uv = (m.texture >= 0 && sc.textures[m.texture].type != VIMG_TEX_CONST) || m.texture_rg >= 0;
+  float u = 0.f, v = 0.f;
+  if (needs_uv) {
+    float theta = m_acosf(-normal.y);
+    float phi = (float)((double)m_atan2f(-normal.z, normal.x) + VIMG_PI_D);
+    u = (float)((double)phi / (2.f * VIMG_PI_D));
+    v = (float)((double)theta / VIMG_PI_D);
+  }
   V3 dpdu = mk3(-radius * normal.y, radius * normal.x, 0.f);
   V3 tangent = normalize(dpdu - normal * dot(normal, dpdu));
   HitInfo h;

@@ -6,8 +6,9 @@
 // keeps the reference's per-pixel sequential RNG stream (one path in flight per pixel,
 // include/integrators.h:116-131) but regroups paths between stages:
 //
-//   * a block owns WF_SLOTS path slots whose state lives in SHARED MEMORY (SoA);
-//   * slot stage (thread i works on slot i): pending shadow ray -> finish sample / pull the
+//   * a block owns WF_SLOTS path slots (more than it has threads) whose whole state lives in
+//     SHARED MEMORY (SoA);
+//   * slot stage (thread i works on slots i, i + WF_THREADS, ...): pending shadow ray -> finish sample / pull the
 //     next pixel / camera ray -> closest-hit traversal -> resolve (miss, emitter, Russian
 //     roulette, depth) -> classify the hit material;
 //   * block barrier; the live slots were bucketed by material class with warp ballots and
@@ -25,9 +26,12 @@
 
 namespace vimg {
 
-#ifndef WF_SLOTS
-#define WF_SLOTS 256
+#ifndef WF_THREADS
+#define WF_THREADS 512
 #endif
+#ifndef WF_SLOTS
+#define WF_SLOTS 1024  // path slots per block (a multiple of WF_THREADS): more slots than threads
+#endif                // so that the shade stage has enough items of every class to fill all warps
 
 enum : uint32_t {
   WF_ALIVE = 1u,       // slot owns a pixel with samples left
@@ -50,6 +54,8 @@ struct WfShared {
   int32_t hit_slot[WF_SLOTS];
   float hit_t[WF_SLOTS], e0[WF_SLOTS], e1[WF_SLOTS], e2[WF_SLOTS], inv_det[WF_SLOTS];
   float nee_wi[3][WF_SLOTS], nee_dist[WF_SLOTS], nee_c[3][WF_SLOTS];
+  float acc[3][WF_SLOTS], L[3][WF_SLOTS];  // pixel accumulator, bounce_result of the path in flight
+  uint32_t s[WF_SLOTS], pixel[WF_SLOTS];   // sample counter, local pixel number
   uint16_t list[WF_NUM_CLASSES][WF_SLOTS];
   uint32_t class_count[2][WF_NUM_CLASSES];
 };
@@ -105,243 +111,260 @@ VD uint32_t wf_material_class(uint32_t mat_type) {
 }
 
 template <int INTEGRATOR, bool COUNT>
-__global__ void __launch_bounds__(WF_SLOTS, 2)
+__global__ void __launch_bounds__(WF_THREADS, (WF_THREADS <= 256 ? 2 : 1))
 wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfArgs args,
                  float* __restrict__ out, DCounters* __restrict__ counters,
                  unsigned int* __restrict__ next_pixel) {
   constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
-  __shared__ WfShared sh;
-  const int i = threadIdx.x;
-  const uint32_t lane = i & 31;
+  extern __shared__ __align__(16) unsigned char wf_smem[];
+  WfShared& sh = *reinterpret_cast<WfShared*>(wf_smem);
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
 
-  // slot-private state: only the slot's home thread (thread i) ever touches it
-  V3 acc = mk3(0.f), L = mk3(0.f);
-  uint32_t s = 0, px = 0, py = 0;
-  size_t image_index = 0;
   bool exhausted = false;  // the frame has no more pixels to hand out
   PathCounters pc = {};
   uint32_t nan_samples = 0, n_samples = 0;
-  sh.flags[i] = 0;
-  if (i < (int)WF_NUM_CLASSES) sh.class_count[0][i] = sh.class_count[1][i] = 0;
+  for (int i = tid; i < WF_SLOTS; i += WF_THREADS) sh.flags[i] = 0;
+  if (tid < (int)WF_NUM_CLASSES) sh.class_count[0][tid] = sh.class_count[1][tid] = 0;
   __syncthreads();
 
   for (uint32_t iter = 0;; ++iter) {
-    uint32_t f = sh.flags[i];
-    uint32_t cls = WF_CLASS_NONE;
-
-    // finish the current sample of this slot's pixel (include/integrators.h:128-137)
-    auto finish = [&](V3 result) {
-      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
-      acc = acc + result;
-      n_samples++;
-      f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
-      if (++s == args.samples) {
-        acc = acc / (float)args.samples;
-        float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
-        o[0] = acc.x;
-        o[1] = acc.y;
-        o[2] = acc.z;
-        f &= ~WF_ALIVE;
-      }
-    };
-
-    // ================= slot stage (thread i <-> slot i) =================
-    // A. shadow ray requested by the last shade stage (mis_integrator.cpp:59-78)
-    if (MIS && (f & WF_NEE)) {
-      Ray sr;
-      sr.o = ld3(sh.ray_o, i);  // the shade stage left hit_p here
-      sr.dir = ld3(sh.nee_wi, i);
-      sr.minT = 0.0001f;
-      sr.maxT = sh.nee_dist[i] - 0.0001f;
-      PreHit ph;
-      pc.rays_shadow++;
-      const bool occluded = bvh_traverse<true, COUNT>(sc, sr, ph, &pc.trav);
-      if (!occluded && (f & WF_NEE_VALID)) L = L + ld3(sh.nee_c, i);
-      f &= ~(WF_NEE | WF_NEE_VALID);
-    }
-    if (f & WF_END) finish(MIS ? L : ld3(sh.nee_c, i));
-
-    // B. pull the next pixel of the frame, start the next sample
-    {
-      const bool want = !(f & WF_ALIVE) && !exhausted;
-      const uint32_t m = __ballot_sync(0xffffffffu, want);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(next_pixel, (unsigned int)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (want) {
-          const uint32_t p = base + __popc(m & lane_lt);
-          if (p >= args.n_local_pixels) {
-            exhausted = true;
-          } else if (wf_pixel_xy(args, sc.cam, p, px, py) && args.samples > 0) {
-            image_index = px + ((size_t)(H - 1 - py) * W);
-            Pcg32 r;
-            pcg32_seed(r, image_index, 0);
-            sh.rng[i] = r.state;
-            acc = mk3(0.f);
-            s = 0;
-            f = WF_ALIVE;
-          }
-        }
-      }
-    }
-    if ((f & WF_ALIVE) && !(f & WF_IN_PATH)) {
-      // camera ray (include/integrators.h:119-123); rand2 gets the first draw
-      Pcg32 r;
-      r.state = sh.rng[i];
-      r.inc = 1;
-      V2 off = random_x_y_r2(px + py + s);
-      float rand2 = rand_float(r);
-      float rand1 = rand_float(r);
-      Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
-      sh.rng[i] = r.state;
-      st3(sh.ray_o, i, cam.o);
-      st3(sh.ray_d, i, cam.dir);
-      sh.cone_w[i] = cam.cone.cone_width;
-      sh.cone_s[i] = cam.cone.spread_angle;
-      st3(sh.thr, i, mk3(1.0f));
-      sh.eta_scale[i] = 1;
-      sh.last_pdf[i] = 0.f;
-      sh.d[i] = 0;
-      L = mk3(0.0f);
-      f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
-    }
-
-    // C. closest-hit traversal + D. resolve
-    if (f & WF_IN_PATH) {
-      const uint32_t d = sh.d[i];
-      if (!MIS && d >= args.depth) {
-        finish(mk3(0.0f));  // material: for (d = 0; d < depth; ...) ran out -> vec3(0)
-      } else {
-        Ray ray;
-        ray.o = ld3(sh.ray_o, i);
-        ray.dir = ld3(sh.ray_d, i);
-        ray.minT = 0.0001f;
-        ray.maxT = CUDART_INF_F;
-        ray.cone.cone_width = sh.cone_w[i];
-        ray.cone.spread_angle = sh.cone_s[i];
-        PreHit ph;
-        pc.rays_closest++;
-        const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav);
-        const V3 thr = ld3(sh.thr, i);
-        if (!found) {
-          V3 bg = background_emit(sc, ray.dir, ray.cone);
-          if (!MIS) {
-            finish(thr * bg);
-          } else if (f & WF_FIRST) {
-            finish(bg);
-          } else {
-            const float last_pdf = sh.last_pdf[i];
-            if (last_pdf != 0 && sc.bg.emissive) {
-              float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
-              float mis_weight = balance_heuristic(last_pdf, light_pdf);
-              L = L + thr * mis_weight * bg;
-            }
-            finish(L);
-          }
-        } else {
-          const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
-          cls = wf_material_class(nmat.type);
-          if (MIS) {
-            if (mat_is_emissive(nmat)) {
-              cls = WF_CLASS_NONE;
-              const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
-              V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
-              if (f & WF_FIRST) {
-                finish(emit);
-              } else {
-                const float last_pdf = sh.last_pdf[i];
-                if (last_pdf != 0) {
-                  // ray.o is the previous hit point, ray.dir the sampled direction
-                  float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
-                  float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
-                  float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
-                  L = L + thr * mis_weight * emit;
-                } else {
-                  L = L + thr * emit;
-                }
-                finish(L);
-              }
-            } else {
-              bool go_on = true;
-              uint32_t dn = d;
-              if (!(f & WF_FIRST)) {
-                if (d > 5) {
-                  Pcg32 r;
-                  r.state = sh.rng[i];
-                  r.inc = 1;
-                  V3 t = thr;
-                  go_on = russian_roulette(r, sh.eta_scale[i], t);
-                  sh.rng[i] = r.state;
-                  if (go_on) st3(sh.thr, i, t);
-                }
-                dn = d + 1;
-              }
-              if (!go_on || dn >= args.depth || cls == WF_CLASS_NONE) {
-                // RR break / loop condition d < depth / base Material (delta, sample_mat -> nullopt)
-                cls = WF_CLASS_NONE;
-                finish(L);
-              } else {
-                sh.d[i] = dn;
-              }
-            }
-          } else if (cls == WF_CLASS_NONE) {
-            // material integrator on DiffuseLight / base Material: sample_mat -> nullopt,
-            // return throughput * emitted (mat_integrator.cpp:21-81)
-            V3 emitted_col = mk3(0.f);
-            if (mat_is_emissive(nmat)) {
-              const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
-              emitted_col = mat_emitted(nmat, ray.dir, next.hit_n_s);
-            }
-            finish(thr * emitted_col);
-          }
-          if (cls != WF_CLASS_NONE) {
-            sh.hit_slot[i] = ph.leaf_slot;
-            sh.hit_t[i] = ray.maxT;
-            sh.e0[i] = ph.e0;
-            sh.e1[i] = ph.e1;
-            sh.e2[i] = ph.e2;
-            sh.inv_det[i] = ph.inv_det;
-            f &= ~WF_FIRST;
-          }
-        }
-      }
-    }
-    sh.flags[i] = f;
-
-    // bucket the slots that need shading by material class (one list per class)
     uint32_t* counts = sh.class_count[iter & 1];
+    bool any_alive = false;
+
+    // ================= slot stage (thread tid <-> slots tid, tid + WF_THREADS, ...) =================
+#pragma unroll 1
+    for (int i = tid; i < WF_SLOTS; i += WF_THREADS) {
+      uint32_t f = sh.flags[i];
+      uint32_t cls = WF_CLASS_NONE;
+
+      // finish the current sample of this slot's pixel (include/integrators.h:128-137)
+      auto finish = [&](V3 result) {
+        if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
+        V3 acc = ld3(sh.acc, i) + result;
+        n_samples++;
+        f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
+        const uint32_t s = ++sh.s[i];
+        if (s == args.samples) {
+          acc = acc / (float)args.samples;
+          uint32_t px, py;
+          wf_pixel_xy(args, sc.cam, sh.pixel[i], px, py);
+          const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+          float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+          o[0] = acc.x;
+          o[1] = acc.y;
+          o[2] = acc.z;
+          f &= ~WF_ALIVE;
+        } else {
+          st3(sh.acc, i, acc);
+        }
+      };
+
+      // A. shadow ray requested by the last shade stage (mis_integrator.cpp:59-78)
+      if (MIS && (f & WF_NEE)) {
+        Ray sr;
+        sr.o = ld3(sh.ray_o, i);  // the shade stage left hit_p here
+        sr.dir = ld3(sh.nee_wi, i);
+        sr.minT = 0.0001f;
+        sr.maxT = sh.nee_dist[i] - 0.0001f;
+        PreHit ph;
+        pc.rays_shadow++;
+        const bool occluded = bvh_traverse<true, COUNT>(sc, sr, ph, &pc.trav);
+        if (!occluded && (f & WF_NEE_VALID)) st3(sh.L, i, ld3(sh.L, i) + ld3(sh.nee_c, i));
+        f &= ~(WF_NEE | WF_NEE_VALID);
+      }
+      if (f & WF_END) finish(MIS ? ld3(sh.L, i) : ld3(sh.nee_c, i));
+
+      // B. pull the next pixel of the frame, start the next sample
+      {
+        const bool want = !(f & WF_ALIVE) && !exhausted;
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(next_pixel, (unsigned int)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+          if (want) {
+            const uint32_t p = base + __popc(m & lane_lt);
+            uint32_t px, py;
+            if (p >= args.n_local_pixels) {
+              exhausted = true;
+            } else if (wf_pixel_xy(args, sc.cam, p, px, py) && args.samples > 0) {
+              Pcg32 r;
+              pcg32_seed(r, px + ((size_t)(H - 1 - py) * W), 0);
+              sh.rng[i] = r.state;
+              st3(sh.acc, i, mk3(0.f));
+              sh.s[i] = 0;
+              sh.pixel[i] = p;
+              f = WF_ALIVE;
+            }
+          }
+        }
+      }
+      if ((f & WF_ALIVE) && !(f & WF_IN_PATH)) {
+        // camera ray (include/integrators.h:119-123); rand2 gets the first draw
+        uint32_t px, py;
+        wf_pixel_xy(args, sc.cam, sh.pixel[i], px, py);
+        Pcg32 r;
+        r.state = sh.rng[i];
+        r.inc = 1;
+        V2 off = random_x_y_r2(px + py + sh.s[i]);
+        float rand2 = rand_float(r);
+        float rand1 = rand_float(r);
+        Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
+        sh.rng[i] = r.state;
+        st3(sh.ray_o, i, cam.o);
+        st3(sh.ray_d, i, cam.dir);
+        sh.cone_w[i] = cam.cone.cone_width;
+        sh.cone_s[i] = cam.cone.spread_angle;
+        st3(sh.thr, i, mk3(1.0f));
+        sh.eta_scale[i] = 1;
+        sh.last_pdf[i] = 0.f;
+        sh.d[i] = 0;
+        st3(sh.L, i, mk3(0.0f));
+        f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
+      }
+
+      // C. closest-hit traversal + D. resolve
+      if (f & WF_IN_PATH) {
+        const uint32_t d = sh.d[i];
+        if (!MIS && d >= args.depth) {
+          finish(mk3(0.0f));  // material: for (d = 0; d < depth; ...) ran out -> vec3(0)
+        } else {
+          Ray ray;
+          ray.o = ld3(sh.ray_o, i);
+          ray.dir = ld3(sh.ray_d, i);
+          ray.minT = 0.0001f;
+          ray.maxT = CUDART_INF_F;
+          ray.cone.cone_width = sh.cone_w[i];
+          ray.cone.spread_angle = sh.cone_s[i];
+          PreHit ph;
+          pc.rays_closest++;
+          const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav);
+          const V3 thr = ld3(sh.thr, i);
+          if (!found) {
+            V3 bg = background_emit(sc, ray.dir, ray.cone);
+            if (!MIS) {
+              finish(thr * bg);
+            } else if (f & WF_FIRST) {
+              finish(bg);
+            } else {
+              V3 L = ld3(sh.L, i);
+              const float last_pdf = sh.last_pdf[i];
+              if (last_pdf != 0 && sc.bg.emissive) {
+                float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
+                float mis_weight = balance_heuristic(last_pdf, light_pdf);
+                L = L + thr * mis_weight * bg;
+              }
+              finish(L);
+            }
+          } else {
+            const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
+            cls = wf_material_class(nmat.type);
+            if (MIS) {
+              if (mat_is_emissive(nmat)) {
+                cls = WF_CLASS_NONE;
+                const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+                V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
+                if (f & WF_FIRST) {
+                  finish(emit);
+                } else {
+                  V3 L = ld3(sh.L, i);
+                  const float last_pdf = sh.last_pdf[i];
+                  if (last_pdf != 0) {
+                    // ray.o is the previous hit point, ray.dir the sampled direction
+                    float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
+                    float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
+                    float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
+                    L = L + thr * mis_weight * emit;
+                  } else {
+                    L = L + thr * emit;
+                  }
+                  finish(L);
+                }
+              } else {
+                bool go_on = true;
+                uint32_t dn = d;
+                if (!(f & WF_FIRST)) {
+                  if (d > 5) {
+                    Pcg32 r;
+                    r.state = sh.rng[i];
+                    r.inc = 1;
+                    V3 t = thr;
+                    go_on = russian_roulette(r, sh.eta_scale[i], t);
+                    sh.rng[i] = r.state;
+                    if (go_on) st3(sh.thr, i, t);
+                  }
+                  dn = d + 1;
+                }
+                if (!go_on || dn >= args.depth || cls == WF_CLASS_NONE) {
+                  // RR break / loop condition d < depth / base Material (delta, sample_mat -> nullopt)
+                  cls = WF_CLASS_NONE;
+                  finish(ld3(sh.L, i));
+                } else {
+                  sh.d[i] = dn;
+                }
+              }
+            } else if (cls == WF_CLASS_NONE) {
+              // material integrator on DiffuseLight / base Material: sample_mat -> nullopt,
+              // return throughput * emitted (mat_integrator.cpp:21-81)
+              V3 emitted_col = mk3(0.f);
+              if (mat_is_emissive(nmat)) {
+                const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+                emitted_col = mat_emitted(nmat, ray.dir, next.hit_n_s);
+              }
+              finish(thr * emitted_col);
+            }
+            if (cls != WF_CLASS_NONE) {
+              sh.hit_slot[i] = ph.leaf_slot;
+              sh.hit_t[i] = ray.maxT;
+              sh.e0[i] = ph.e0;
+              sh.e1[i] = ph.e1;
+              sh.e2[i] = ph.e2;
+              sh.inv_det[i] = ph.inv_det;
+              f &= ~WF_FIRST;
+            }
+          }
+        }
+      }
+      sh.flags[i] = f;
+      any_alive |= (f & WF_ALIVE) != 0;
+
+      // bucket the slots that need shading by material class (one list per class)
 #pragma unroll
-    for (uint32_t c = 0; c < WF_NUM_CLASSES; ++c) {
-      const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&counts[c], (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (cls == c) sh.list[c][base + __popc(m & lane_lt)] = (uint16_t)i;
+      for (uint32_t c = 0; c < WF_NUM_CLASSES; ++c) {
+        const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&counts[c], (uint32_t)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+          if (cls == c) sh.list[c][base + __popc(m & lane_lt)] = (uint16_t)i;
+        }
       }
     }
     // barrier 1: lists complete; also the block-wide "anything left to do" vote
-    const int live = __syncthreads_or((f & WF_ALIVE) != 0 || !exhausted);
+    const int live = __syncthreads_or(any_alive || !exhausted);
     if (!live) break;
-    if (i < (int)WF_NUM_CLASSES) sh.class_count[(iter + 1) & 1][i] = 0;  // next iteration's counters
+    if (tid < (int)WF_NUM_CLASSES) sh.class_count[(iter + 1) & 1][tid] = 0;  // next iteration's counters
 
     // ================= shade stage (thread k <-> k-th bucketed slot) =================
     {
       const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
-      int j = -1;
-      // Principled first (longest), then Lambertian, then Dielectric: whole warps share a class
-      uint32_t k = (uint32_t)i;
+      // Principled first (longest), then Lambertian, then Dielectric; consecutive items share a
+      // class, so whole warps do
+#pragma unroll 1
+      for (uint32_t item = (uint32_t)tid; item < n0 + n1 + n2; item += WF_THREADS) {
+      int j;
+      uint32_t k = item;
       if (k < n1) {
         j = sh.list[WF_CLASS_PRINCIPLED][k];
       } else if ((k -= n1) < n0) {
         j = sh.list[WF_CLASS_LAMBERT][k];
-      } else if ((k -= n0) < n2) {
-        j = sh.list[WF_CLASS_DIELECTRIC][k];
+      } else {
+        j = sh.list[WF_CLASS_DIELECTRIC][k - n0];
       }
-      if (j >= 0) {
+      {
         uint32_t fj = sh.flags[j];
         Ray ray;
         ray.o = ld3(sh.ray_o, j);
@@ -473,6 +496,7 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         }
         sh.rng[j] = rng.state;
         sh.flags[j] = fj;
+      }
       }
     }
     __syncthreads();  // barrier 2: shade results visible to the slots' home threads

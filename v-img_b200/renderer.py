@@ -49,7 +49,8 @@ EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vi
 
 
 def lib_path():
-    return os.path.join(_HERE, "libvimg_cuda.so")
+    # VIMG_CUDA_LIB selects an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("VIMG_CUDA_LIB") or os.path.join(_HERE, "libvimg_cuda.so")
 
 
 _lib = None
