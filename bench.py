@@ -298,7 +298,7 @@ def cuda_line(w, args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": f"render_kernel<{integ}>", "launch_ms": 1e3 * launch_s,
+                     "kernel": f"wavefront_kernel<{integ}>", "launch_ms": 1e3 * launch_s,
                      "algorithmic_bytes_per_ray": bytes_per_ray,
                      "algorithmic_flops_per_ray": flops_per_ray,
                      "rays_per_launch": rays_per_launch_rank,

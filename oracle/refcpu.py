@@ -166,3 +166,28 @@ def digest(arr):
     import hashlib
     return hashlib.blake2b(np.ascontiguousarray(arr).view(np.uint8).ravel().tobytes(),
                            digest_size=8).hexdigest()
+
+
+# ---- plain-C restatement of the bit-exact core (oracle/vimg_oracle.c) -------------------------
+def restatement_path():
+    return os.path.join(_HERE, "_ref", "libvimg_oracle.so")
+
+
+_restatement = None
+
+
+def restatement_primary(desc_ptr, width, height, spp, normals=True):
+    """Run the C restatement on a flattened scene.  -> (ids, t, s_normal, g_normal, unsupported)"""
+    global _restatement
+    if _restatement is None:
+        _restatement = C.CDLL(restatement_path())
+        _restatement.vimg_oracle_primary.restype = C.c_int
+        _restatement.vimg_oracle_primary.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
+    ids = np.empty((height * width, spp), np.int32)
+    t = np.empty((height * width, spp), np.float32)
+    sn = np.empty((height, width, 3), np.float32) if normals else None
+    gn = np.empty((height, width, 3), np.float32) if normals else None
+    rc = _restatement.vimg_oracle_primary(desc_ptr, spp, ids.ctypes.data, t.ctypes.data,
+                                          sn.ctypes.data if normals else None,
+                                          gn.ctypes.data if normals else None)
+    return ids, t, sn, gn, bool(rc)

@@ -1,0 +1,331 @@
+/*
+ * vimg_oracle.c -- ORACLE / TEST INFRASTRUCTURE.  Never linked into the product.
+ *
+ * Plain-C restatement of the BIT-EXACT part of v-img's render hot path, working directly on a
+ * flattened scene (include/vimg_cuda.h):
+ *
+ *   per-pixel PCG32 stream + R2 jitter      include/integrators.h:109-123
+ *                                           include/rng/pcg_rand.h:15-33, sampling.h:85-105,228-239
+ *   thin-lens camera ray                    src/tl_camera.cpp:25-53, include/ray.h:36-48
+ *   closest-hit BVH traversal (scalar path) include/bvh.h:83-225, include/hit_utils.h:134-151
+ *   watertight ray/triangle                 include/geometry/triangle.h:78-180
+ *   ray/sphere                              include/geometry/sphere.h:13-100
+ *   geometric / shading normal images       src/integrators/normals.cpp:4-46,
+ *                                           src/geometry/triangle.cpp:13-43, sphere.cpp:12-14
+ *
+ * It is independent of the CUDA code (different language, different data layout: it walks the
+ * reference's own BVH arrays, not the GPU pair records) and of the glm shim (no vector
+ * library: every expression is written out).  PINNING: tests/test_oracle.py checks it against
+ * the compiled reference (oracle/_ref, parity flavour) through tests/golden -- primary-hit ids,
+ * hit distances and both normal images must match bit for bit.  The shading-normal image is
+ * restated for meshes WITHOUT normal maps (all JSON scenes); material / mis are not restated
+ * here -- for those the compiled reference itself is the oracle.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle/vimg_oracle.c -o oracle/_ref/libvimg_oracle.so -lm
+ * (no -march: the reference's parity build has no FMA contraction either.)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../include/vimg_cuda.h"
+
+typedef struct { float x, y, z; } v3;
+
+static v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 muls(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+/* glm::dot: tmp = a*b; (tmp.x + tmp.y) + tmp.z */
+static float dot(v3 a, v3 b) { float tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z; return tx + ty + tz; }
+/* glm::normalize: v * (1 / sqrt(dot(v, v))) */
+static v3 normalize(v3 v) { return muls(v, 1.0f / sqrtf(dot(v, v))); }
+static v3 cross(v3 a, v3 b) { return V(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+static float comp(v3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+/* ---- include/rng/pcg_rand.h:15-33 ---- */
+typedef struct { uint64_t state, inc; } pcg32;
+static uint32_t pcg32_random(pcg32* r) {
+  uint64_t old = r->state;
+  r->state = old * 6364136223846793005ULL + r->inc;
+  uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+  uint32_t rot = (uint32_t)(old >> 59u);
+  return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31));
+}
+static void pcg32_seed(pcg32* r, uint64_t initstate, uint64_t initseq) {
+  r->state = 0U;
+  r->inc = (initseq << 1u) | 1u;
+  pcg32_random(r);
+  r->state += initstate;
+  pcg32_random(r);
+}
+/* ---- include/rng/sampling.h:85-105 ---- */
+static float rand_float(pcg32* r) {
+  uint64_t r1 = pcg32_random(r), r2 = pcg32_random(r);
+  uint64_t u = (r1 << 32) | r2;
+  uint32_t z = u ? (uint32_t)__builtin_clzll(u) : 64u;
+  if (z <= 40) {
+    uint32_t bits = ((126 - z) << 23) | (((uint32_t)u) & 0x7fffff);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+  }
+  return 0x1.0p-64f * (float)((uint32_t)u);
+}
+/* ---- include/rng/sampling.h:228-239: g is a float, a1/a2 are folded in double then narrowed ---- */
+static void r2_offset(uint32_t n, float* ox, float* oy) {
+  const float g = 1.32471795724474602596;
+  const float a1 = 1.0 - (1.0 / g);
+  const float a2 = 1.0 - (1.0 / (g * g));
+  float x = a1 * n, y = a2 * n;
+  *ox = x - floorf(x);
+  *oy = y - floorf(y);
+}
+
+typedef struct { v3 o, dir; float minT, maxT; } ray_t;
+
+/* glm mat4 * vec4: (m0*v0 + m1*v1) + (m2*v2 + m3*v3), column-major */
+static void mat4_mul(const float* m, const float v[4], float out[4]) {
+  for (int r = 0; r < 4; ++r) out[r] = (m[r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]);
+}
+
+/* ---- src/tl_camera.cpp:25-53 (sample_disk: sampling.h:15-22) ---- */
+static ray_t generate_ray(const vimg_camera* c, float x, float y, float rand1, float rand2) {
+  float x_dir = (c->p_size[0] * (x / c->resolution[0])) - (c->p_size[0] / 2.0f);
+  float y_dir = (c->p_size[1] * (y / c->resolution[1])) - (c->p_size[1] / 2.0f);
+  v3 ray_dir = normalize(V(x_dir, y_dir, -1.0f));
+  ray_t r;
+  r.o = V(0.f, 0.f, 0.f);
+  r.dir = ray_dir;
+  r.minT = 0.0001f;
+  r.maxT = INFINITY;
+  if (c->aperture_radius > 0.f) {
+    float rr = sqrtf(rand1);
+    float phi = (float)(2.f * 3.141592653589793238462643383279502884 * rand2);
+    v3 ray_origin = V(c->aperture_radius * (rr * cosf(phi)), c->aperture_radius * (rr * sinf(phi)), 0.f);
+    float ft = c->focal_dist / fabsf(ray_dir.z);
+    v3 focal_plane_p = muls(ray_dir, ft);
+    r.o = ray_origin;
+    r.dir = normalize(sub(focal_plane_p, ray_origin));
+  }
+  float d4[4] = {r.dir.x, r.dir.y, r.dir.z, 0.0f}, o4[4] = {r.o.x, r.o.y, r.o.z, 1.0f}, d[4], o[4];
+  mat4_mul(c->cam_to_world, d4, d);
+  mat4_mul(c->cam_to_world, o4, o);
+  r.dir = normalize(V(d[0], d[1], d[2]));
+  r.o = V(o[0] / o[3], o[1] / o[3], o[2] / o[3]);
+  return r;
+}
+
+/* ---- include/hit_utils.h:134-151: glm::min/max and std::max/min written out (NaN order) ---- */
+static float gmin(float a, float b) { return (b < a) ? b : a; }
+static float gmax(float a, float b) { return (a < b) ? b : a; }
+static float slab(const ray_t* r, v3 inv, const float* bmin, const float* bmax) {
+  float lx = (bmin[0] - r->o.x) * inv.x, ly = (bmin[1] - r->o.y) * inv.y, lz = (bmin[2] - r->o.z) * inv.z;
+  float ux = (bmax[0] - r->o.x) * inv.x, uy = (bmax[1] - r->o.y) * inv.y, uz = (bmax[2] - r->o.z) * inv.z;
+  float tBoxMin = gmax(gmin(lx, ux), gmax(gmin(ly, uy), gmax(gmin(lz, uz), r->minT)));
+  float tBoxMax = gmin(gmax(lx, ux), gmin(gmax(ly, uy), gmin(gmax(lz, uz), r->maxT)));
+  return (tBoxMin <= tBoxMax) ? tBoxMin : INFINITY;
+}
+
+typedef struct { float e0, e1, e2, inv_det; int64_t prim; } prehit_t;
+
+static void tri_vertices(const vimg_scene_desc* d, const vimg_prim* p, v3* p0, v3* p1, v3* p2) {
+  const vimg_mesh* m = &d->meshes[p->a];
+  const uint32_t* idx = m->indices + 3 * (size_t)p->b;
+  const float* v = m->vertices;
+  *p0 = V(v[3 * idx[0]], v[3 * idx[0] + 1], v[3 * idx[0] + 2]);
+  *p1 = V(v[3 * idx[1]], v[3 * idx[1] + 1], v[3 * idx[1] + 2]);
+  *p2 = V(v[3 * idx[2]], v[3 * idx[2] + 1], v[3 * idx[2] + 2]);
+}
+
+/* ---- include/geometry/triangle.h:78-180 ---- */
+static int tri_hit(const vimg_scene_desc* d, const vimg_prim* p, ray_t* ray, prehit_t* ph) {
+  v3 p0, p1, p2;
+  tri_vertices(d, p, &p0, &p1, &p2);
+  v3 c = cross(sub(p2, p0), sub(p1, p0));
+  if (dot(c, c) == 0.f) return 0;
+  v3 p0t = sub(p0, ray->o), p1t = sub(p1, ray->o), p2t = sub(p2, ray->o);
+  float ax = fabsf(ray->dir.x), ay = fabsf(ray->dir.y), az = fabsf(ray->dir.z);
+  int kz = 0;
+  float mx = ax;
+  if (ay > mx) { kz = 1; mx = ay; }
+  if (az > mx) { kz = 2; mx = az; }
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  float dx = comp(ray->dir, kx), dy = comp(ray->dir, ky), dz = comp(ray->dir, kz);
+  float p0x = comp(p0t, kx), p0y = comp(p0t, ky), p0z = comp(p0t, kz);
+  float p1x = comp(p1t, kx), p1y = comp(p1t, ky), p1z = comp(p1t, kz);
+  float p2x = comp(p2t, kx), p2y = comp(p2t, ky), p2z = comp(p2t, kz);
+  float Sx = -dx / dz, Sy = -dy / dz, Sz = 1.f / dz;
+  p0x += Sx * p0z; p0y += Sy * p0z;
+  p1x += Sx * p1z; p1y += Sy * p1z;
+  p2x += Sx * p2z; p2y += Sy * p2z;
+  float cd;
+  cd = p1y * p2x; float e0 = fmaf(p1x, p2y, -cd);
+  cd = p2y * p0x; float e1 = fmaf(p2x, p0y, -cd);
+  cd = p0y * p1x; float e2 = fmaf(p0x, p1y, -cd);
+  if (e0 == 0.f || e1 == 0.f || e2 == 0.f) {
+    /* difference_of_products_double: double cd = (float product); fmal; narrowed to double, float */
+    double c0 = p1y * p2x, c1 = p2y * p0x, c2 = p0y * p1x;
+    e0 = (float)(double)fmal(p1x, p2y, -c0);
+    e1 = (float)(double)fmal(p2x, p0y, -c1);
+    e2 = (float)(double)fmal(p0x, p1y, -c2);
+  }
+  if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return 0;
+  float det = e0 + e1 + e2;
+  if (det == 0) return 0;
+  p0z *= Sz; p1z *= Sz; p2z *= Sz;
+  float tScaled = e0 * p0z + e1 * p1z + e2 * p2z;
+  if (det < 0 && (tScaled >= 0 || tScaled < ray->maxT * det || tScaled > ray->minT * det)) return 0;
+  else if (det > 0 && (tScaled <= 0 || tScaled > ray->maxT * det || tScaled < ray->minT * det)) return 0;
+  float invDet = 1.f / det;
+  ray->maxT = tScaled * invDet;
+  ph->e0 = e0; ph->e1 = e1; ph->e2 = e2; ph->inv_det = invDet;
+  return 1;
+}
+
+/* ---- include/geometry/sphere.h:13-100: q, x0, x1 in double (unqualified sqrt) ---- */
+static int sphere_hit(const vimg_sphere* s, ray_t* r) {
+  v3 center = V(s->center[0], s->center[1], s->center[2]);
+  float radius_squared = s->radius * s->radius;
+  v3 f = sub(r->o, center);
+  float a = dot(r->dir, r->dir);
+  float b_prime = dot(muls(f, -1.0f), r->dir);
+  float c = dot(f, f) - radius_squared;
+  v3 temp = add(f, muls(r->dir, b_prime / a));
+  float discriminant = radius_squared - dot(temp, temp);
+  if (discriminant < 0) return 0;
+  float sign = (b_prime > 0) ? 1.0f : -1.0f;
+  double q = b_prime + sign * sqrt((double)(a * discriminant));
+  float t0, t1;
+  if (discriminant == 0) t0 = t1 = (float)(c / q);
+  else { t0 = (float)(c / q); t1 = (float)(q / a); }
+  if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+  if (t0 < r->minT || t0 > r->maxT) {
+    t0 = t1;
+    if (t0 < r->minT || t0 > r->maxT) return 0;
+  }
+  r->maxT = t0;
+  return 1;
+}
+
+/* ---- include/bvh.h:83-225, closest hit, scalar branch ---- */
+static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
+  const vimg_bvh* b = &d->bvh;
+  ph->prim = -1;
+  if (b->n_nodes == 0) return -1;
+  v3 inv = V(1.0f / ray->dir.x, 1.0f / ray->dir.y, 1.0f / ray->dir.z);
+  const float* bb = b->bb_mins_maxes;
+  if (isinf(slab(ray, inv, bb + 0, bb + 6))) return -1;
+  uint64_t stack[128];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    uint64_t n = stack[--sp];
+    uint32_t first = b->nodes[2 * n], count = b->nodes[2 * n + 1];
+    if (count != 0) {
+      for (uint32_t i = 0; i < count; ++i) {
+        uint64_t prim = b->obj_indices[first + i];
+        const vimg_prim* p = &d->prims[prim];
+        int hit;
+        if (p->type == VIMG_PRIM_SPHERE) {
+          hit = sphere_hit(&d->spheres[p->a], ray);
+          if (hit) ph->e0 = ph->e1 = ph->e2 = ph->inv_det = 0.f;
+        } else {
+          hit = tri_hit(d, p, ray, ph);
+        }
+        if (hit) ph->prim = (int64_t)prim;  /* last successful primitive wins (bvh.h:155-158) */
+      }
+    } else {
+      uint64_t first_child = first, sec_child = first_child + 1;
+      uint64_t lmin = first_child * 2 + 2, lmax = lmin + 2, rmin = lmin + 1, rmax = lmax + 1;
+      float h1 = slab(ray, inv, bb + 3 * lmin, bb + 3 * lmax);
+      float h2 = slab(ray, inv, bb + 3 * rmin, bb + 3 * rmax);
+      if (!isinf(h2)) {
+        if (!isinf(h1)) {
+          if (h2 > h1) { uint64_t t = first_child; first_child = sec_child; sec_child = t; }
+          stack[sp++] = first_child;
+        }
+        stack[sp++] = sec_child;
+      } else if (!isinf(h1)) {
+        stack[sp++] = first_child;
+      }
+    }
+  }
+  return ph->prim;
+}
+
+/* hit_n_s / hit_n_g of Triangle::hit_info (triangle.cpp:13-43) and Sphere::hit_info (sphere.cpp:12-14);
+ * returns 0 if the mesh's material has a normal map (not restated) */
+static int hit_normals(const vimg_scene_desc* d, const ray_t* ray, const prehit_t* ph, v3* n_s, v3* n_g) {
+  const vimg_prim* p = &d->prims[ph->prim];
+  if (p->type == VIMG_PRIM_SPHERE) {
+    const vimg_sphere* s = &d->spheres[p->a];
+    v3 hit_p = add(ray->o, muls(ray->dir, ray->maxT));
+    *n_s = *n_g = normalize(sub(hit_p, V(s->center[0], s->center[1], s->center[2])));
+    return 1;
+  }
+  const vimg_mesh* m = &d->meshes[p->a];
+  if (d->materials[m->material].normal_map >= 0) return 0;
+  v3 p0, p1, p2;
+  tri_vertices(d, p, &p0, &p1, &p2);
+  float u = ph->e0 * ph->inv_det, v = ph->e1 * ph->inv_det, w = ph->e2 * ph->inv_det;
+  v3 tri_normal = normalize(cross(sub(p1, p0), sub(p2, p0)));
+  *n_g = tri_normal;
+  if (m->normals) {
+    const uint32_t* idx = m->indices + 3 * (size_t)p->b;
+    const float* nn = m->normals;
+    v3 n0 = V(nn[3 * idx[0]], nn[3 * idx[0] + 1], nn[3 * idx[0] + 2]);
+    v3 n1 = V(nn[3 * idx[1]], nn[3 * idx[1] + 1], nn[3 * idx[1] + 2]);
+    v3 n2 = V(nn[3 * idx[2]], nn[3 * idx[2] + 1], nn[3 * idx[2] + 2]);
+    *n_s = normalize(add(add(muls(n0, u), muls(n1, v)), muls(n2, w)));
+  } else {
+    *n_s = tri_normal;
+  }
+  return 1;
+}
+
+/* Primary-hit ids / distances for all samples and (optionally) the two normal images.
+ * out_ids, out_t: W*H*spp (index = image_index*spp + s); s_normal, g_normal: W*H*3 or NULL.
+ * Returns 0, or 1 if a normal-mapped mesh was hit while normal images were requested. */
+int vimg_oracle_primary(const vimg_scene_desc* d, uint32_t spp, int32_t* out_ids, float* out_t,
+                        float* s_normal, float* g_normal) {
+  const uint32_t W = (uint32_t)d->camera.resolution[0], H = (uint32_t)d->camera.resolution[1];
+  int unsupported = 0;
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t x = 0; x < W; ++x) {
+      size_t image_index = x + ((size_t)(H - 1 - y) * W);
+      pcg32 st;
+      pcg32_seed(&st, image_index, 0);
+      v3 acc_s = V(0, 0, 0), acc_g = V(0, 0, 0);
+      for (uint32_t s = 0; s < spp; ++s) {
+        float ox, oy;
+        r2_offset(x + y + s, &ox, &oy);
+        float rand2 = rand_float(&st); /* g++ evaluates the call's arguments right to left */
+        float rand1 = rand_float(&st);
+        ray_t ray = generate_ray(&d->camera, (float)x + ox, (float)y + oy, rand1, rand2);
+        prehit_t ph;
+        int64_t prim = bvh_closest(d, &ray, &ph);
+        if (out_ids) out_ids[image_index * spp + s] = (int32_t)prim;
+        if (out_t) out_t[image_index * spp + s] = ray.maxT;
+        if (s_normal || g_normal) {
+          v3 cs, cg;
+          if (prim >= 0) {
+            v3 ns, ng;
+            if (!hit_normals(d, &ray, &ph, &ns, &ng)) { unsupported = 1; ns = ng = V(0, 0, 0); }
+            cs = V((ns.x + 1.0f) / 2.0f, (ns.y + 1.0f) / 2.0f, (ns.z + 1.0f) / 2.0f);
+            cg = V((ng.x + 1.0f) / 2.0f, (ng.y + 1.0f) / 2.0f, (ng.z + 1.0f) / 2.0f);
+          } else { /* normals.cpp:17-22: a is computed in double */
+            v3 ud = normalize(ray.dir);
+            float a = (float)(0.5 * (ud.y + 1.0));
+            cs = cg = add(muls(V(1.0f, 1.0f, 1.0f), 1.0f - a), muls(V(0.5f, 0.7f, 1.0f), a));
+          }
+          acc_s = add(acc_s, cs);
+          acc_g = add(acc_g, cg);
+        }
+      }
+      if (s_normal) { s_normal[3 * image_index] = acc_s.x / (float)spp; s_normal[3 * image_index + 1] = acc_s.y / (float)spp; s_normal[3 * image_index + 2] = acc_s.z / (float)spp; }
+      if (g_normal) { g_normal[3 * image_index] = acc_g.x / (float)spp; g_normal[3 * image_index + 1] = acc_g.y / (float)spp; g_normal[3 * image_index + 2] = acc_g.z / (float)spp; }
+    }
+  return unsupported;
+}

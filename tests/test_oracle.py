@@ -86,3 +86,34 @@ def test_libm_restatement_is_bit_exact_on_this_host():
         pytest.skip("oracle/_ref/libm_check not built")
     out = subprocess.run([exe, "quick"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
+
+
+@pytest.mark.parametrize("name", ["cornell_small", "glass_small", "disney_small", "sphere_light_medium",
+                                  "cornell_dof", "synthetic_rg"])
+def test_c_restatement_matches_the_compiled_reference(vimg, man, name):
+    """oracle/vimg_oracle.c (plain C, no glm shim, reference BVH layout) against the golden
+    outputs of the compiled reference: ids, hit distances and both normal images, bit for bit."""
+    from oracle import refcpu
+    if not os.path.exists(refcpu.restatement_path()):
+        pytest.skip("oracle/_ref/libvimg_oracle.so not built")
+    e = man[name]
+    r = e["ref"]
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    ids, t, sn, gn, unsupported = refcpu.restatement_primary(d.ptr, e["width"], e["height"], r["ids_spp"])
+    assert refcpu.digest(ids) == r["ids_hash"]
+    assert refcpu.digest(t) == r["t_hash"]
+    if r["ids_spp"] == 4:  # the normal integrators always run 4 spp (src/main.cpp:223,232)
+        assert refcpu.digest(gn) == r["g_normal_hash"]
+        if not unsupported:
+            assert refcpu.digest(sn) == r["s_normal_hash"]
+
+
+def test_c_restatement_full_size_c2(vimg, man):
+    from oracle import refcpu
+    if not os.path.exists(refcpu.restatement_path()):
+        pytest.skip("oracle/_ref/libvimg_oracle.so not built")
+    e = man["cornell_box_spheres"]
+    d = vimg.LoadedDesc(golden_scene_path("cornell_box_spheres"))
+    ids, t, sn, gn, _ = refcpu.restatement_primary(d.ptr, e["width"], e["height"], 4)
+    assert refcpu.digest(ids) == e["ref"]["ids_hash"] and refcpu.digest(t) == e["ref"]["t_hash"]
+    assert refcpu.digest(sn) == e["ref"]["s_normal_hash"] and refcpu.digest(gn) == e["ref"]["g_normal_hash"]
