@@ -9,4 +9,4 @@ There is NO CPU fallback: importing works anywhere, but every compute call
 raises VimgError when the CUDA extension or a CUDA device is missing.
 """
 from .renderer import (INTEGRATORS, LoadedDesc, Scene, VimgError, device_count, lib_path,  # noqa: F401
-                       load_library)
+                       load_library, tile_owner)

@@ -460,6 +460,11 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
     stats->kernel_ms = ms;
     stats->total_ms = ms;
     stats->kernel_launches = 1;
+#ifdef WF_STAGE_CLOCKS
+    fprintf(stderr, "[wf stage cycles, summed over warps] shadow %llu regen %llu closest %llu resolve+bucket %llu "
+            "barrier1 %llu shade %llu barrier2 %llu\n", c.stage_clk[0], c.stage_clk[1], c.stage_clk[2],
+            c.stage_clk[3], c.stage_clk[4], c.stage_clk[5], c.stage_clk[6]);
+#endif
   }
   return VIMG_OK;
 }

@@ -110,6 +110,17 @@ VD uint32_t wf_material_class(uint32_t mat_type) {
   }
 }
 
+#ifdef WF_STAGE_CLOCKS
+#define WF_CLK(k)                                  \
+  do {                                             \
+    long long now__ = clock64();                   \
+    clk[k] += (unsigned long long)(now__ - t_prev); \
+    t_prev = now__;                                \
+  } while (0)
+#else
+#define WF_CLK(k) do {} while (0)
+#endif
+
 template <int INTEGRATOR, bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS, (WF_THREADS <= 256 ? 2 : 1))
 wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfArgs args,
@@ -123,6 +134,10 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
 
+#ifdef WF_STAGE_CLOCKS
+  unsigned long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_prev = clock64();
+#endif
   bool exhausted = false;  // the frame has no more pixels to hand out
   PathCounters pc = {};
   uint32_t nan_samples = 0, n_samples = 0;
@@ -176,6 +191,7 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         f &= ~(WF_NEE | WF_NEE_VALID);
       }
       if (f & WF_END) finish(MIS ? ld3(sh.L, i) : ld3(sh.nee_c, i));
+      WF_CLK(0);
 
       // B. pull the next pixel of the frame, start the next sample
       {
@@ -226,6 +242,7 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
       }
 
+      WF_CLK(1);
       // C. closest-hit traversal + D. resolve
       if (f & WF_IN_PATH) {
         const uint32_t d = sh.d[i];
@@ -242,6 +259,7 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
           PreHit ph;
           pc.rays_closest++;
           const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav);
+          WF_CLK(2);
           const V3 thr = ld3(sh.thr, i);
           if (!found) {
             V3 bg = background_emit(sc, ray.dir, ray.cone);
@@ -343,8 +361,10 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         }
       }
     }
+    WF_CLK(3);
     // barrier 1: lists complete; also the block-wide "anything left to do" vote
     const int live = __syncthreads_or(any_alive || !exhausted);
+    WF_CLK(4);
     if (!live) break;
     if (tid < (int)WF_NUM_CLASSES) sh.class_count[(iter + 1) & 1][tid] = 0;  // next iteration's counters
 
@@ -499,9 +519,15 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
       }
       }
     }
+    WF_CLK(5);
     __syncthreads();  // barrier 2: shade results visible to the slots' home threads
+    WF_CLK(6);
   }
 
+#ifdef WF_STAGE_CLOCKS
+  if (lane == 0)
+    for (int k = 0; k < 8; ++k) atomicAdd(&counters->stage_clk[k], clk[k]);
+#endif
   warp_add_counter(&counters->rays_closest, pc.rays_closest);
   warp_add_counter(&counters->rays_shadow, pc.rays_shadow);
   warp_add_counter(&counters->nan_samples, nan_samples);

@@ -102,6 +102,20 @@ def save_desc(desc_ptr, path):
         raise VimgError(f"vimg_scene_desc_save({path}) failed ({rc})")
 
 
+def tile_owner(width, height, n_ranks):
+    """Rank that renders each pixel: int32 [H, W], row 0 = top of the image.
+
+    Host-side mirror of the device mapping (vimg_wavefront.cuh::wf_pixel_xy): the reference's
+    8x8 tiles, numbered x-major like its work_list (include/integrators.h:57-65), are dealt
+    round-robin: tile t -> rank t % n_ranks.
+    """
+    tiles_y = (height + 7) // 8
+    y, x = np.mgrid[0:height, 0:width]          # y counts from the bottom row, like the reference
+    tile = (x // 8) * tiles_y + (y // 8)
+    owner = (tile % max(n_ranks, 1)).astype(np.int32)
+    return owner[::-1].copy()                   # image row 0 is y = H - 1
+
+
 class LoadedDesc:
     """A vimg_scene_desc read from a .vscene file; `.ptr` is its address (host memory)."""
 
