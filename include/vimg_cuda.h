@@ -229,6 +229,11 @@ typedef struct vimg_render_params {
 } vimg_render_params;
 
 #define VIMG_FLAG_COUNTERS 1u /* also gather traversal counters (slower)     */
+/* material / mis pipeline choice (default: queue wavefront; the env var
+ * VIMG_PIPELINE=block|queue overrides the default when neither flag is set).
+ * Both produce the same image bit for bit. */
+#define VIMG_FLAG_PIPELINE_BLOCK 2u /* persistent block-local wavefront kernel  */
+#define VIMG_FLAG_PIPELINE_QUEUE 4u /* multi-kernel queue wavefront             */
 
 typedef struct vimg_render_stats {
   uint64_t rays_closest;   /* BVH::hit<optional<HitInfo>> calls               */

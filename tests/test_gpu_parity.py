@@ -226,7 +226,7 @@ def test_device_frame_equals_host_frame(vimg):
     dev = sc.frame_tensor(ptr)
     assert dev.is_cuda and tuple(dev.shape) == host.shape
     assert np.array_equal(dev.cpu().numpy(), host)
-    assert st["kernel_launches"] == 1 and st["kernel_ms"] > 0
+    assert st["kernel_launches"] >= 1 and st["kernel_ms"] > 0
 
 
 def test_invalid_render_arguments(vimg):

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numbers>
 #include <string>
@@ -54,6 +56,15 @@ struct vimg_scene {
   unsigned int* d_next_pixel = nullptr;
   int wf_blocks[2][2] = {{0, 0}, {0, 0}};  // resident-grid size of wavefront_kernel<integrator, COUNT>
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // queue wavefront (vimg_queues.cuh): path-state pool, class mask of the scene's materials
+  QwState qw{};
+  void* qw_pool = nullptr;
+  uint32_t qw_capacity = 0;
+  uint32_t class_mask = 0;
+  QwCounters* h_alive = nullptr;  // pinned: queue-counter snapshots (termination test)
+  cudaEvent_t qw_ev[2] = {nullptr, nullptr};
+  int sm_count = 0;
+  uint32_t last_launches = 0;
 
   template <typename T> int upload(const T* host, size_t n, const T** out) {
     *out = nullptr;
@@ -192,6 +203,23 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     }
   }
 
+  // material class of every leaf record (queue wavefront: routing without pointer chasing)
+  std::vector<uint8_t> leaf_class(b.n_obj_indices);
+  for (uint64_t i = 0; i < b.n_obj_indices; ++i) {
+    const vimg_prim& pr = desc->prims[b.obj_indices[i]];
+    const uint32_t mat = pr.type == VIMG_PRIM_SPHERE ? desc->spheres[pr.a].material : desc->meshes[pr.a].material;
+    if (mat >= desc->n_materials) return fail(VIMG_ERR_INVALID_ARGUMENT, "primitive material index out of range");
+    uint8_t cl = WF_CLASS_NONE;
+    switch (desc->materials[mat].type) {
+      case VIMG_MAT_LAMBERTIAN: cl = WF_CLASS_LAMBERT; break;
+      case VIMG_MAT_PRINCIPLED: cl = WF_CLASS_PRINCIPLED; break;
+      case VIMG_MAT_DIELECTRIC: cl = WF_CLASS_DIELECTRIC; break;
+      case VIMG_MAT_DIFFUSE_LIGHT: cl = WF_CLASS_NONE | VIMG_LEAF_CLASS_EMISSIVE; break;
+      default: break;
+    }
+    leaf_class[i] = cl;
+  }
+
   // ---- textures --------------------------------------------------------------
   std::vector<DTexture> textures(desc->n_textures);
   std::vector<float> texels;
@@ -241,6 +269,14 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     if ((hm.type == VIMG_MAT_LAMBERTIAN || hm.type == VIMG_MAT_PRINCIPLED) && hm.texture < 0)
       return fail(VIMG_ERR_INVALID_ARGUMENT, "lambertian/principled material without a texture");
   }
+  for (uint32_t m = 0; m < desc->n_materials; ++m) {
+    switch (desc->materials[m].type) {
+      case VIMG_MAT_LAMBERTIAN: s->class_mask |= 1u << WF_CLASS_LAMBERT; break;
+      case VIMG_MAT_PRINCIPLED: s->class_mask |= 1u << WF_CLASS_PRINCIPLED; break;
+      case VIMG_MAT_DIELECTRIC: s->class_mask |= 1u << WF_CLASS_DIELECTRIC; break;
+      default: break;
+    }
+  }
   for (uint32_t i = 0; i < desc->n_spheres; ++i)
     if (desc->spheres[i].material >= desc->n_materials) return fail(VIMG_ERR_INVALID_ARGUMENT, "sphere material index out of range");
   for (uint32_t i = 0; i < desc->n_lights; ++i)
@@ -271,6 +307,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
 #define UP(call) if ((rc = (call)) != VIMG_OK) return rc
   UP(s->upload(pairs, &d.pairs));
   UP(s->upload(leaf, &d.leaf_prims));
+  UP(s->upload(leaf_class, &d.leaf_class));
   UP(s->upload(desc->prims, desc->n_prims, &d.prims));
   UP(s->upload(desc->spheres, desc->n_spheres, &d.spheres));
   UP(s->upload(meshes, &d.meshes));
@@ -324,8 +361,219 @@ static int wavefront_grid(vimg_scene* s, uint32_t n_pixels) {
   return (int)(needed < (uint32_t)cached ? needed : (uint32_t)cached);
 }
 
+
+// ---- queue wavefront driver (vimg_queues.cuh) --------------------------------------------
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  return (uint32_t)std::strtoul(v, nullptr, 10);
+}
+
+// path-state pool for `n` slots, carved from one allocation (256-byte aligned arrays)
+static int qw_reserve(vimg_scene* s, uint32_t n) {
+  if (s->qw_pool && s->qw_capacity >= n) {
+    s->qw.n_slots = n;
+    return VIMG_OK;
+  }
+  if (s->qw_pool) {
+    cudaFree(s->qw_pool);
+    s->qw_pool = nullptr;
+    s->qw_capacity = 0;
+  }
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t N = n;
+  const size_t o_ray_o = carve(N * 16), o_ray_d = carve(N * 16), o_thr = carve(N * 16), o_hit0 = carve(N * 16),
+               o_hit1 = carve(N * 8), o_nee_wi = carve(N * 16), o_nee_c = carve(N * 16);
+  size_t o_L[3], o_acc[3];
+  for (int k = 0; k < 3; ++k) o_L[k] = carve(N * 4);
+  for (int k = 0; k < 3; ++k) o_acc[k] = carve(N * 4);
+  const size_t o_last_pdf = carve(N * 4), o_rng = carve(N * 8), o_flags = carve(N * 4), o_d = carve(N * 4),
+               o_s = carve(N * 4), o_pixel = carve(N * 4), o_occl = carve(N);
+  size_t o_qc[2], o_qs[2], o_qe[2], o_qsh[WF_NUM_CLASSES];
+  for (int k = 0; k < 2; ++k) o_qc[k] = carve(N * 4);
+  for (int k = 0; k < 2; ++k) o_qs[k] = carve(N * 4);
+  for (int k = 0; k < 2; ++k) o_qe[k] = carve(N * 4);
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) o_qsh[k] = carve(N * 4);
+  const size_t o_cnt = carve(sizeof(QwCounters));
+  void* pool = nullptr;
+  CU_TRY(cudaMalloc(&pool, off));
+  s->qw_pool = pool;
+  s->qw_capacity = n;
+  char* b = static_cast<char*>(pool);
+  QwState& q = s->qw;
+  q.n_slots = n;
+  q.ray_o = reinterpret_cast<float4*>(b + o_ray_o);
+  q.ray_d = reinterpret_cast<float4*>(b + o_ray_d);
+  q.thr = reinterpret_cast<float4*>(b + o_thr);
+  q.hit0 = reinterpret_cast<float4*>(b + o_hit0);
+  q.hit1 = reinterpret_cast<float2*>(b + o_hit1);
+  q.nee_wi = reinterpret_cast<float4*>(b + o_nee_wi);
+  q.nee_c = reinterpret_cast<float4*>(b + o_nee_c);
+  for (int k = 0; k < 3; ++k) q.L[k] = reinterpret_cast<float*>(b + o_L[k]);
+  for (int k = 0; k < 3; ++k) q.acc[k] = reinterpret_cast<float*>(b + o_acc[k]);
+  q.last_pdf = reinterpret_cast<float*>(b + o_last_pdf);
+  q.rng = reinterpret_cast<unsigned long long*>(b + o_rng);
+  q.flags = reinterpret_cast<uint32_t*>(b + o_flags);
+  q.d = reinterpret_cast<uint32_t*>(b + o_d);
+  q.s = reinterpret_cast<uint32_t*>(b + o_s);
+  q.pixel = reinterpret_cast<uint32_t*>(b + o_pixel);
+  q.occl = reinterpret_cast<uint8_t*>(b + o_occl);
+  for (int k = 0; k < 2; ++k) q.q_closest[k] = reinterpret_cast<uint32_t*>(b + o_qc[k]);
+  for (int k = 0; k < 2; ++k) q.q_shadow[k] = reinterpret_cast<uint32_t*>(b + o_qs[k]);
+  for (int k = 0; k < 2; ++k) q.q_end[k] = reinterpret_cast<uint32_t*>(b + o_qe[k]);
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) q.q_shade[k] = reinterpret_cast<uint32_t*>(b + o_qsh[k]);
+  q.cnt = reinterpret_cast<QwCounters*>(b + o_cnt);
+  if (!s->h_alive) CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_alive), 2 * sizeof(QwCounters)));
+  for (int k = 0; k < 2; ++k)
+    if (!s->qw_ev[k]) CU_TRY(cudaEventCreateWithFlags(&s->qw_ev[k], cudaEventDisableTiming));
+  return VIMG_OK;
+}
+
+// VIMG_QW_PROFILE=1: one event after every launch, per-kernel totals printed to stderr
+struct QwProfile {
+  bool on = false, verbose = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  void mark(int k) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    kind.push_back(k);
+  }
+  void report() {
+    if (!on || ev.empty()) return;
+    static const char* names[] = {"start", "trace", "classify", "shade_principled", "shade_lambert",
+                                  "shade_dielectric", "end"};
+    double tot[7] = {0}, total = 0;
+    unsigned cnt[7] = {0};
+    cudaEventSynchronize(ev.back());
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      tot[kind[i]] += ms;
+      cnt[kind[i]]++;
+      total += ms;
+    }
+    fprintf(stderr, "[qw profile] %.2f ms:", total);
+    for (int k = 1; k < 7; ++k)
+      if (cnt[k]) fprintf(stderr, " %s %.2f ms (%.0f%%, %u launches, %.1f us avg)", names[k], tot[k], 100 * tot[k] / total, cnt[k], 1e3 * tot[k] / cnt[k]);
+    fprintf(stderr, "\n");
+    if (verbose) {
+      // per-launch times of the first iterations (fully loaded) and of a few later ones
+      for (size_t i = 1; i < ev.size(); ++i) {
+        const size_t iter = i / 5;
+        if (!(iter < 6 || (iter % 100) == 0)) continue;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        fprintf(stderr, "%s%s %.1f us", kind[i] == 1 ? "\n  it: " : ", ", names[kind[i]], 1e3 * ms);
+      }
+      fprintf(stderr, "\n");
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+
+template <int INTEGRATOR>
+static void qw_launch_shade(vimg_scene* s, const WfArgs& w, uint32_t parity, int grid, cudaStream_t st, QwProfile& prof) {
+  if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
+    qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
+    prof.mark(3);
+  }
+  if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
+    qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
+    prof.mark(4);
+  }
+  if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
+    qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
+    prof.mark(5);
+  }
+}
+
+// iota kernel: the initial END queue holds every slot (all without a pixel)
+__global__ void qw_iota_kernel(uint32_t* q, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) q[i] = i;
+}
+
+// One frame: end(0) | trace(1) classify(1) shade(1) end(1) | ...  until every queue is empty.
+// The host looks at the queue counters once per batch of iterations and keeps one batch queued
+// ahead of the check, so the device never waits for the host.
 template <bool COUNT>
-static void launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st) {
+static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, float* out, cudaStream_t st) {
+  const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
+  const uint32_t n_slots = std::max(1u, std::min(w.n_local_pixels, cap));
+  int rc = qw_reserve(s, n_slots);
+  if (rc != VIMG_OK) return rc;
+  if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+  const QwState& q = s->qw;
+  CU_TRY(cudaMemsetAsync(q.flags, 0, (size_t)n_slots * 4, st));
+  QwCounters init{};
+  init.n_end[0] = n_slots;
+  CU_TRY(cudaMemcpyAsync(q.cnt, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int slot_blocks = (int)((n_slots + QW_THREADS - 1) / QW_THREADS);
+  qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, st>>>(q.q_end[0], n_slots);
+  const int trace_full = s->sm_count * QW_TRACE_BLOCKS_PER_SM;
+  const int trace_need = (int)((2ull * n_slots + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS);
+  const int trace_grid = std::max(1, std::min(trace_full, trace_need));
+  const int item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8));
+  const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
+  const bool mis = integrator == VIMG_INTEGRATOR_MIS;
+  uint32_t launches = 1, it = 0;
+  const uint32_t n_shade = (uint32_t)__builtin_popcount(s->class_mask);
+  QwProfile prof;
+  prof.on = env_u32("VIMG_QW_PROFILE", 0) != 0;
+  prof.verbose = env_u32("VIMG_QW_PROFILE", 0) > 1;
+  prof.st = st;
+  prof.mark(0);
+  for (uint32_t b = 0;; ++b) {
+    for (uint32_t k = 0; k < batch; ++k, ++it) {
+      const uint32_t parity = it & 1u;
+      if (it > 0) {
+        qw_trace_kernel<COUNT><<<trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
+        prof.mark(1);
+        qw_classify_kernel<<<item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
+        prof.mark(2);
+        if (mis)
+          qw_launch_shade<VIMG_INTEGRATOR_MIS>(s, w, parity, item_grid, st, prof);
+        else
+          qw_launch_shade<VIMG_INTEGRATOR_MATERIAL>(s, w, parity, item_grid, st, prof);
+        launches += 2 + n_shade;
+      }
+      if (mis)
+        qw_end_kernel<VIMG_INTEGRATOR_MIS><<<item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
+      else
+        qw_end_kernel<VIMG_INTEGRATOR_MATERIAL><<<item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
+      prof.mark(6);
+      ++launches;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(&s->h_alive[b & 1], q.cnt, sizeof(QwCounters), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(s->qw_ev[b & 1], st));
+    if (b > 0) {
+      CU_TRY(cudaEventSynchronize(s->qw_ev[(b - 1) & 1]));
+      // queues the iteration after batch b-1 would consume: parity of its first iteration
+      const QwCounters& hc = s->h_alive[(b - 1) & 1];
+      const uint32_t p = (b * batch) & 1u;
+      if (hc.n_closest[p] == 0 && hc.n_shadow[p] == 0 && hc.n_end[p] == 0) break;  // batch b ran empty
+    }
+  }
+  prof.report();
+  s->last_launches = launches;
+  return VIMG_OK;
+}
+
+template <bool COUNT>
+static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st,
+                         uint32_t flags = 0) {
+  s->last_launches = 1;
   if (integrator == VIMG_INTEGRATOR_MATERIAL || integrator == VIMG_INTEGRATOR_MIS) {
     WfArgs w{};
     w.samples = a.samples;
@@ -337,7 +585,15 @@ static void launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrato
     w.single_x = a.single_x;
     w.single_y = a.single_y;
     w.n_local_pixels = a.single_x >= 0 ? 1u : a.n_local_tiles * 64u;
-    if (w.n_local_pixels == 0) return;
+    if (w.n_local_pixels == 0) return VIMG_OK;
+    // pipeline: the queue wavefront unless the caller (or VIMG_PIPELINE=block) asks for the
+    // block-local kernel
+    bool use_block = (flags & VIMG_FLAG_PIPELINE_BLOCK) != 0;
+    if (!(flags & (VIMG_FLAG_PIPELINE_BLOCK | VIMG_FLAG_PIPELINE_QUEUE))) {
+      const char* e = std::getenv("VIMG_PIPELINE");
+      use_block = e && std::strcmp(e, "block") == 0;
+    }
+    if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st);
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
     if (integrator == VIMG_INTEGRATOR_MIS) {
       const int g = wavefront_grid<VIMG_INTEGRATOR_MIS, COUNT>(s, w.n_local_pixels);
@@ -346,14 +602,15 @@ static void launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrato
       const int g = wavefront_grid<VIMG_INTEGRATOR_MATERIAL, COUNT>(s, w.n_local_pixels);
       wavefront_kernel<VIMG_INTEGRATOR_MATERIAL, COUNT><<<g, WF_THREADS, sizeof(WfShared), st>>>(s->d, w, out, s->d_counters, s->d_next_pixel);
     }
-    return;
+    return VIMG_OK;
   }
   const uint32_t blocks = a.single_x >= 0 ? 1 : (a.n_local_tiles + 1) / 2;
-  if (blocks == 0) return;
+  if (blocks == 0) return VIMG_OK;
   if (integrator == VIMG_INTEGRATOR_S_NORMAL)
     render_kernel<VIMG_INTEGRATOR_S_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters);
   else
     render_kernel<VIMG_INTEGRATOR_G_NORMAL, COUNT><<<blocks, 128, 0, st>>>(s->d, a, out, s->d_counters);
+  return VIMG_OK;
 }
 
 static int check_params(const vimg_scene* s, const vimg_render_params* p) {
@@ -388,6 +645,10 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_frame) cudaFree(s->d_frame);
   if (s->d_counters) cudaFree(s->d_counters);
   if (s->d_next_pixel) cudaFree(s->d_next_pixel);
+  if (s->qw_pool) cudaFree(s->qw_pool);
+  if (s->h_alive) cudaFreeHost(s->h_alive);
+  for (int k = 0; k < 2; ++k)
+    if (s->qw_ev[k]) cudaEventDestroy(s->qw_ev[k]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -436,9 +697,10 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
   if (a.n_ranks > 1) CU_TRY(cudaMemsetAsync(s->d_frame, 0, (size_t)s->W * s->H * 3 * sizeof(float), st));
   CU_TRY(cudaEventRecord(s->ev0, st));
   if (p->flags & VIMG_FLAG_COUNTERS)
-    launch_render<true>(s, a, p->integrator, s->d_frame, st);
+    rc = launch_render<true>(s, a, p->integrator, s->d_frame, st, p->flags);
   else
-    launch_render<false>(s, a, p->integrator, s->d_frame, st);
+    rc = launch_render<false>(s, a, p->integrator, s->d_frame, st, p->flags);
+  if (rc != VIMG_OK) return rc;
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(s->ev1, st));
   CU_TRY(cudaStreamSynchronize(st));
@@ -459,7 +721,7 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
     CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     stats->kernel_ms = ms;
     stats->total_ms = ms;
-    stats->kernel_launches = 1;
+    stats->kernel_launches = s->last_launches;
 #ifdef WF_STAGE_CLOCKS
     fprintf(stderr, "[wf stage cycles, summed over warps] shadow %llu regen %llu closest %llu resolve+bucket %llu "
             "barrier1 %llu shade %llu barrier2 %llu\n", c.stage_clk[0], c.stage_clk[1], c.stage_clk[2],
@@ -507,7 +769,11 @@ int vimg_trace_pixel(vimg_scene* s, const vimg_render_params* p, int x, int y, f
   float* d_px = nullptr;
   CU_TRY(cudaMalloc(&d_px, 3 * sizeof(float)));
   CU_TRY(cudaMemset(s->d_counters, 0, sizeof(DCounters)));
-  launch_render<false>(s, a, p->integrator, d_px, 0);
+  rc = launch_render<false>(s, a, p->integrator, d_px, 0, p->flags);
+  if (rc != VIMG_OK) {
+    cudaFree(d_px);
+    return rc;
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_px, 3 * sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(d_px);

@@ -26,6 +26,7 @@ VD void warp_add_counter(unsigned long long* dst, uint32_t v) {
 
 }  // namespace vimg
 #include "vimg_wavefront.cuh"
+#include "vimg_queues.cuh"
 namespace vimg {
 
 // maps the calling thread to its pixel; returns false if it has none

@@ -1,0 +1,821 @@
+// vimg_queues.cuh -- multi-kernel "queue wavefront" path tracer (material / mis).
+//
+// The block-local wavefront (vimg_wavefront.cuh) keeps all path state in shared memory, which
+// pins it to ONE 512-thread block per SM at 128 registers: 4 warps per scheduler, issue slots
+// 37 % busy, ~11 of 32 lanes active inside the traversal (profiles/r1f).  This pipeline trades
+// shared-memory state for occupancy and coherence:
+//
+//   * path state of N slots lives in HBM/L2 as SoA (16-byte records per field group);
+//   * TRACE kernel: small (<= 64 registers, 32+ warps per SM), persistent, pulls closest-hit and
+//     shadow rays from two queues; a lane whose ray ends is refilled from the warp's chunk, so
+//     the traversal loop runs with most lanes busy;
+//   * CLASSIFY kernel (thread <-> traced closest ray): routes the slot by what the ray hit into
+//     one SHADE queue per material class or into the END queue (miss, emitter, base Material);
+//   * SHADE kernels, one per material class (Lambertian, Principled, Dielectric), each compiled
+//     with only its own BSDF: pending shadow-ray result, Russian roulette and depth test, light
+//     sampling, BSDF sampling, both eval_pdf_pair calls, next ray and shadow-ray request;
+//   * END kernel (thread <-> ended path): miss / emitter contribution, sample accumulation,
+//     next pixel, next camera ray.
+//   Every kernel is driven by a queue of slot numbers, none walks the whole slot pool, so the
+//   long tail of a frame (a few pixels with very long paths) costs launch latency only.
+//
+// Per path the sequence of float operations and RNG draws is the reference's
+// (src/integrators/mis_integrator.cpp:18-189, mat_integrator.cpp:4-85) and identical to the
+// block-local kernel's, so the images agree bit for bit (tests/test_gpu_parity.py runs both).
+// The reference seeds one PCG stream per pixel and carries it over the pixel's samples
+// (include/integrators.h:116-131), so one path per pixel is in flight; a slot whose pixel is
+// complete pulls the next pixel of this rank's tile list.
+#pragma once
+#include "vimg_wavefront.cuh"
+
+namespace vimg {
+
+#ifndef QW_TRACE_THREADS
+#define QW_TRACE_THREADS 256
+#endif
+#ifndef QW_TRACE_BLOCKS_PER_SM
+#define QW_TRACE_BLOCKS_PER_SM 4  // 64 registers per thread, 32 warps per SM
+#endif
+#ifndef QW_REFILL_MIN
+#define QW_REFILL_MIN 12  // refill a warp's idle lanes once at least this many are idle
+#endif
+#ifndef QW_CHUNK
+#define QW_CHUNK 128  // rays a warp takes from the global cursor with one atomic
+#endif
+#define QW_THREADS 256  // classify / shade / end block size
+
+struct QwCounters {
+  uint32_t n_closest[2], n_shadow[2];  // queue lengths, double buffered by iteration parity
+  uint32_t n_end[2];
+  uint32_t n_shade[WF_NUM_CLASSES];
+  uint32_t cursor;      // trace kernel's work cursor
+  uint32_t next_pixel;  // next local pixel number to hand out
+  uint32_t pad_[1];
+};
+
+struct QwState {
+  uint32_t n_slots;
+  float4* ray_o;    // origin xyz (hit point after shading), cone_width
+  float4* ray_d;    // direction xyz, cone spread_angle
+  float4* thr;      // throughput rgb, eta_scale
+  float4* hit0;     // leaf slot (int bits), t, e0, e1      written by TRACE
+  float2* hit1;     // e2, inv_det                          written by TRACE
+  float4* nee_wi;   // shadow ray direction xyz, light distance
+  float4* nee_c;    // pending NEE contribution rgb (material: result of an ended path)
+  float* L[3];      // bounce_result of the path in flight
+  float* acc[3];    // pixel accumulator
+  float* last_pdf;
+  unsigned long long* rng;
+  uint32_t* flags;
+  uint32_t* d;
+  uint32_t* s;
+  uint32_t* pixel;
+  uint8_t* occl;  // shadow ray result, written by TRACE
+  uint32_t* q_closest[2];
+  uint32_t* q_shadow[2];
+  uint32_t* q_end[2];
+  uint32_t* q_shade[WF_NUM_CLASSES];
+  QwCounters* cnt;
+};
+
+VD V3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+VD float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+// Block-wide queue append.  Every thread of the block calls this (want may be false);
+// one global atomic per queue per block.  `s_cnt`/`s_base` are NQ shared words each.
+template <int NQ>
+struct QwAppend {
+  uint32_t off[NQ];
+  VD void count(uint32_t* s_cnt, const bool (&want)[NQ], uint32_t lane, uint32_t lane_lt) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const uint32_t m = __ballot_sync(0xffffffffu, want[q]);
+      uint32_t base = 0;
+      if (m) {
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_cnt[q], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      }
+      off[q] = base + __popc(m & lane_lt);
+    }
+  }
+};
+
+// ================================================================== TRACE ====
+// BVH::hit<closest> and BVH::occlude (include/bvh.h:83-225) for every queued ray; same
+// visiting order, box arithmetic and tie rules as bvh_traverse (vimg_bvh.cuh), restructured
+// as a persistent loop whose idle lanes are refilled.
+template <bool COUNT>
+__global__ void __launch_bounds__(QW_TRACE_THREADS, QW_TRACE_BLOCKS_PER_SM)
+qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
+                const uint32_t parity, DCounters* __restrict__ counters) {
+  QwCounters* c = st.cnt;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // queues of the NEXT iteration (their last consumer, the previous trace launch, is done)
+    c->n_closest[parity ^ 1u] = 0;
+    c->n_shadow[parity ^ 1u] = 0;
+    c->n_end[parity ^ 1u] = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) c->n_shade[k] = 0;
+  }
+  const uint32_t n_c = c->n_closest[parity], total = n_c + c->n_shadow[parity];
+  const uint32_t* __restrict__ qc = st.q_closest[parity];
+  const uint32_t* __restrict__ qs = st.q_shadow[parity];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+
+  // rays a warp takes from the global cursor with one atomic: large when there is plenty of
+  // work (few same-address atomics), one ray per lane when the queues are short (parallelism)
+  const uint32_t n_warps = gridDim.x * (QW_TRACE_THREADS / 32);
+  uint32_t chunk = (total / n_warps) & ~31u;
+  chunk = chunk < 32u ? 32u : (chunk > (uint32_t)QW_CHUNK ? (uint32_t)QW_CHUNK : chunk);
+  PathCounters pc = {};
+  uint32_t chunk_next = 0, chunk_end = 0;  // this warp's private range of work items
+  bool more = total > 0;
+
+  // per-lane ray in flight
+  bool have = false, any_hit = false;
+  uint32_t slot = 0;
+  Ray ray;
+  RayPre pre;
+  PreHit ph;
+  uint2 cur = make_uint2(0, 0);
+  int sp = 0;
+  uint2 stack[VIMG_STACK_MAX];
+  ray.minT = 0.0001f;
+  ray.maxT = 0.f;
+  ray.o = ray.dir = mk3(0.f);
+  pre.inv_dir = mk3(0.f);
+  pre.has_inf = false;
+  pre.kx = pre.ky = pre.kz = 0;
+  pre.Sx = pre.Sy = pre.Sz = 0.f;
+  ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
+  ph.leaf_slot = -1;
+
+  auto finish = [&](bool occluded) {
+    if (any_hit) {
+      st.occl[slot] = occluded ? 1 : 0;
+    } else {
+      st.hit0[slot] = make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1);
+      st.hit1[slot] = make_float2(ph.e2, ph.inv_det);
+    }
+    have = false;
+  };
+
+  for (;;) {
+    const uint32_t idle = __ballot_sync(0xffffffffu, !have);
+    if (idle == 0xffffffffu || (more && __popc(idle) >= QW_REFILL_MIN)) {
+      if (more) {
+        if (chunk_next == chunk_end) {
+          uint32_t b = 0;
+          if (lane == 0) b = atomicAdd(&c->cursor, chunk);
+          b = __shfl_sync(0xffffffffu, b, 0);
+          chunk_next = b < total ? b : total;
+          chunk_end = b + chunk < total ? b + chunk : total;
+          if (chunk_next == chunk_end) more = false;
+        }
+        if (!have) {
+          const uint32_t idx = chunk_next + __popc(idle & lane_lt);
+          if (idx < chunk_end) {
+            ray.minT = 0.0001f;
+            ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
+            ph.leaf_slot = -1;
+            if (idx < n_c) {
+              any_hit = false;
+              slot = qc[idx];
+              const float4 o4 = st.ray_o[slot], d4 = st.ray_d[slot];
+              ray.o = xyz(o4);
+              ray.dir = xyz(d4);
+              ray.maxT = CUDART_INF_F;
+              pc.rays_closest++;
+            } else {
+              // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
+              any_hit = true;
+              slot = qs[idx - n_c];
+              const float4 o4 = st.ray_o[slot], w4 = st.nee_wi[slot];
+              ray.o = xyz(o4);
+              ray.dir = xyz(w4);
+              ray.maxT = w4.w - 0.0001f;
+              pc.rays_shadow++;
+            }
+            have = true;
+            if (sc.n_nodes == 0) {
+              finish(false);
+            } else {
+              pre = ray_precompute(ray);
+              const float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
+              if (is_inf(root_hit)) {
+                finish(false);
+              } else {
+                cur = make_uint2(sc.root_first, sc.root_count);
+                sp = 0;
+              }
+            }
+          }
+        }
+        const uint32_t taken = chunk_next + __popc(idle);
+        chunk_next = taken < chunk_end ? taken : chunk_end;
+      }
+      if (!__any_sync(0xffffffffu, have)) {
+        if (!more) break;
+        continue;
+      }
+    }
+
+    // inner nodes: descend until this lane holds a leaf or its ray is done
+    while (have && cur.y == 0) {
+      if (COUNT) pc.trav.inner++;
+      const float4* rec = reinterpret_cast<const float4*>(sc.pairs + ((cur.x - 1u) >> 1));
+      const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rec + 3));
+      const float lmin[3] = {q0.x, q0.y, q0.z}, rmin[3] = {q0.w, q1.x, q1.y};
+      const float lmax[3] = {q1.z, q1.w, q2.x}, rmax[3] = {q2.y, q2.z, q2.w};
+      const float bb_hit1 = slab(lmin, lmax, ray, pre);
+      const float bb_hit2 = slab(rmin, rmax, ray, pre);
+      uint2 first_child = make_uint2(q3.x, q3.y), sec_child = make_uint2(q3.z, q3.w);
+      const bool h1 = !is_inf(bb_hit1), h2 = !is_inf(bb_hit2);
+      if (h2) {
+        if (h1) {
+          // closest hit: the more distant box is pushed first (tie: first child pushed first);
+          // any hit: unordered, left pushed then right (bvh.h:195-212)
+          if (!any_hit && bb_hit2 > bb_hit1) {
+            const uint2 t = first_child;
+            first_child = sec_child;
+            sec_child = t;
+          }
+          stack[sp++] = first_child;
+        }
+        cur = sec_child;
+      } else if (h1) {
+        cur = first_child;
+      } else if (sp > 0) {
+        cur = stack[--sp];
+      } else {
+        finish(false);
+      }
+    }
+    if (have) {  // leaf: primitives in obj_indices order, the last success wins
+      if (COUNT) pc.trav.leaf++;
+      bool occluded = false;
+      for (uint32_t i = 0; i < cur.y; ++i) {
+        const uint32_t ls = cur.x + i;
+        const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + ls);
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        const float a[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+        const uint32_t flags = __float_as_uint(r2.z);
+        bool hit;
+        if (flags & VIMG_LEAF_SPHERE) {
+          if (COUNT) pc.trav.sph++;
+          hit = sphere_hit(a, ray);
+          if (hit) ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
+        } else {
+          if (COUNT) pc.trav.tri++;
+          hit = tri_hit(a, flags, ray, pre, ph);
+        }
+        if (hit) {
+          ph.leaf_slot = (int32_t)ls;
+          if (any_hit) {
+            occluded = true;
+            break;
+          }
+        }
+      }
+      if (occluded) {
+        finish(true);
+      } else if (sp > 0) {
+        cur = stack[--sp];
+      } else {
+        finish(false);
+      }
+    }
+  }
+
+  warp_add_counter(&counters->rays_closest, pc.rays_closest);
+  warp_add_counter(&counters->rays_shadow, pc.rays_shadow);
+  if (COUNT) {
+    warp_add_counter(&counters->inner_nodes, pc.trav.inner);
+    warp_add_counter(&counters->leaf_nodes, pc.trav.leaf);
+    warp_add_counter(&counters->tri_tests, pc.trav.tri);
+    warp_add_counter(&counters->sphere_tests, pc.trav.sph);
+  }
+}
+
+// =============================================================== CLASSIFY ====
+// thread <-> closest ray of this iteration: route the slot by what the ray hit.  Shadeable
+// materials go to their class's shade queue; misses, emitter hits and base-Material hits end
+// the path and go to the END queue of this iteration.
+__global__ void __launch_bounds__(QW_THREADS)
+qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st, const uint32_t parity) {
+  __shared__ uint32_t s_cnt[WF_NUM_CLASSES + 1], s_base[WF_NUM_CLASSES + 1];
+  QwCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  if (blockIdx.x == 0 && tid == 0) c->cursor = 0;  // the next trace launch starts at item 0
+  const uint32_t n = c->n_closest[parity];
+  const uint32_t* __restrict__ q = st.q_closest[parity];
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t item = base + tid;
+    uint32_t cls = WF_CLASS_NONE + 1, j = 0;  // NONE + 1: no item
+    if (item < n) {
+      j = q[item];
+      const int32_t leaf_slot = __float_as_int(st.hit0[j].x);
+      cls = WF_CLASS_NONE;
+      if (leaf_slot >= 0) {
+        const uint32_t lc = sc.leaf_class[leaf_slot];
+        cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
+      }
+    }
+    bool want[WF_NUM_CLASSES + 1];
+#pragma unroll
+    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
+    QwAppend<WF_NUM_CLASSES + 1> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid < (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[tid], s_cnt[tid]);
+    } else if (tid == (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
+    }
+    __syncthreads();
+    if (cls < WF_NUM_CLASSES) st.q_shade[cls][s_base[cls] + ap.off[cls]] = j;
+    else if (cls == WF_CLASS_NONE) st.q_end[parity][s_base[WF_NUM_CLASSES] + ap.off[WF_NUM_CLASSES]] = j;
+    __syncthreads();
+  }
+}
+
+// ==================================================================== END ====
+// thread <-> slot whose path ended (miss, emitter hit, Russian roulette, depth, no scattering)
+// or that has no pixel yet.  Finishes the sample (include/integrators.h:128-137), hands out
+// the next pixel of this rank's tile list and generates the next camera ray (:116-123).
+template <int INTEGRATOR>
+__global__ void __launch_bounds__(QW_THREADS)
+qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
+              const __grid_constant__ WfArgs args, const uint32_t parity,
+              float* __restrict__ out, DCounters* __restrict__ counters) {
+  constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
+  __shared__ uint32_t s_cnt[1], s_base[1];
+  QwCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
+  const uint32_t n = c->n_end[parity];
+  const uint32_t* __restrict__ q = st.q_end[parity];
+  uint32_t nan_samples = 0, n_samples = 0;
+
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
+    const uint32_t item = base + tid;
+    const bool valid = item < n;
+    const uint32_t i = valid ? q[item] : 0u;
+    uint32_t f = valid ? st.flags[i] : 0u;
+    bool new_ray = false;
+
+    auto ldL = [&]() { return mk3(st.L[0][i], st.L[1][i], st.L[2][i]); };
+    auto finish = [&](V3 result) {
+      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
+      V3 acc = mk3(st.acc[0][i], st.acc[1][i], st.acc[2][i]) + result;
+      n_samples++;
+      f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
+      const uint32_t s = st.s[i] + 1;
+      st.s[i] = s;
+      if (s == args.samples) {
+        acc = acc / (float)args.samples;
+        uint32_t px, py;
+        wf_pixel_xy(args, sc.cam, st.pixel[i], px, py);
+        const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+        float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+        o[0] = acc.x;
+        o[1] = acc.y;
+        o[2] = acc.z;
+        f &= ~WF_ALIVE;
+      } else {
+        st.acc[0][i] = acc.x;
+        st.acc[1][i] = acc.y;
+        st.acc[2][i] = acc.z;
+      }
+    };
+
+    if (valid && (f & WF_IN_PATH)) {
+      // pending shadow ray of the last bounce (mis_integrator.cpp:64-78)
+      V3 L = mk3(0.f);
+      if (MIS) {
+        L = ldL();
+        if ((f & WF_NEE) && (f & WF_NEE_VALID) && !st.occl[i]) L = L + xyz(st.nee_c[i]);
+      }
+      if (f & WF_END) {
+        finish(MIS ? L : xyz(st.nee_c[i]));
+      } else {
+        const float4 o4 = st.ray_o[i], d4 = st.ray_d[i], h0 = st.hit0[i];
+        Ray ray;
+        ray.o = xyz(o4);
+        ray.dir = xyz(d4);
+        ray.minT = 0.0001f;
+        ray.maxT = h0.y;
+        ray.cone.cone_width = o4.w;
+        ray.cone.spread_angle = d4.w;
+        PreHit ph;
+        ph.leaf_slot = __float_as_int(h0.x);
+        if (ph.leaf_slot < 0) {
+          // miss (mis_integrator.cpp:36-38,173-185; mat_integrator.cpp:24-27)
+          V3 bg = background_emit(sc, ray.dir, ray.cone);
+          if (!MIS) {
+            finish(xyz(st.thr[i]) * bg);
+          } else if (f & WF_FIRST) {
+            finish(bg);
+          } else {
+            const float last_pdf = st.last_pdf[i];
+            if (last_pdf != 0 && sc.bg.emissive) {
+              float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
+              float mis_weight = balance_heuristic(last_pdf, light_pdf);
+              L = L + xyz(st.thr[i]) * mis_weight * bg;
+            }
+            finish(L);
+          }
+        } else {
+          const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
+          if (mat_is_emissive(nmat)) {
+            const float2 h1 = st.hit1[i];
+            ph.e0 = h0.z;
+            ph.e1 = h0.w;
+            ph.e2 = h1.x;
+            ph.inv_det = h1.y;
+            const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+            V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
+            if (!MIS) {
+              finish(xyz(st.thr[i]) * emit);  // sample_mat -> nullopt: throughput * emitted
+            } else if (f & WF_FIRST) {
+              finish(emit);
+            } else {
+              const V3 thr = xyz(st.thr[i]);
+              const float last_pdf = st.last_pdf[i];
+              if (last_pdf != 0) {
+                // ray.o is the previous hit point, ray.dir the sampled direction
+                float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
+                float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
+                float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
+                L = L + thr * mis_weight * emit;
+              } else {
+                L = L + thr * emit;
+              }
+              finish(L);
+            }
+          } else if (!MIS) {
+            finish(mk3(0.f));  // base Material: sample_mat -> nullopt, emitted = 0
+          } else {
+            // base Material under mis: the Russian-roulette draw still happens before
+            // sample_mat -> nullopt ends the path (mis_integrator.cpp:154-167, 83-88)
+            if (!(f & WF_FIRST) && st.d[i] > 5) {
+              Pcg32 r;
+              r.state = st.rng[i];
+              r.inc = 1;
+              float4 t4 = st.thr[i];
+              V3 t = xyz(t4);
+              russian_roulette(r, t4.w, t);
+              st.rng[i] = r.state;
+            }
+            finish(L);
+          }
+        }
+      }
+    }
+
+    // the next pixel of the frame for a slot without one
+    {
+      const bool want = valid && !(f & WF_ALIVE);
+      const uint32_t m = __ballot_sync(0xffffffffu, want);
+      if (m) {
+        uint32_t pbase = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) {
+          // no atomic once the frame is handed out
+          if (*reinterpret_cast<volatile uint32_t*>(&c->next_pixel) < args.n_local_pixels)
+            pbase = atomicAdd(&c->next_pixel, (uint32_t)__popc(m));
+          else
+            pbase = args.n_local_pixels;
+        }
+        pbase = __shfl_sync(0xffffffffu, pbase, __ffs(m) - 1);
+        if (want) {
+          // tiles overhanging the frame contain pixel numbers without a pixel: take the next
+          uint32_t p = pbase + __popc(m & lane_lt);
+          uint32_t px = 0, py = 0;
+          bool got = false;
+          while (p < args.n_local_pixels && !(got = wf_pixel_xy(args, sc.cam, p, px, py)))
+            p = atomicAdd(&c->next_pixel, 1u);
+          if (got) {
+            if (!MIS && args.depth == 0) {
+              // material_integrator with depth 0 never traces: every sample is vec3(0)
+              const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+              float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+              o[0] = o[1] = o[2] = 0.f;
+              n_samples += args.samples;
+            } else {
+              Pcg32 r;
+              pcg32_seed(r, px + ((size_t)(H - 1 - py) * W), 0);
+              st.rng[i] = r.state;
+              st.acc[0][i] = st.acc[1][i] = st.acc[2][i] = 0.f;
+              st.s[i] = 0;
+              st.pixel[i] = p;
+              f = WF_ALIVE;
+            }
+          }
+        }
+      }
+    }
+    // camera ray of the next sample (include/integrators.h:119-123); rand2 gets the first draw
+    if (f & WF_ALIVE) {
+      uint32_t px, py;
+      wf_pixel_xy(args, sc.cam, st.pixel[i], px, py);
+      Pcg32 r;
+      r.state = st.rng[i];
+      r.inc = 1;
+      V2 off = random_x_y_r2(px + py + st.s[i]);
+      float rand2 = rand_float(r);
+      float rand1 = rand_float(r);
+      Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
+      st.rng[i] = r.state;
+      st.ray_o[i] = f4(cam.o, cam.cone.cone_width);
+      st.ray_d[i] = f4(cam.dir, cam.cone.spread_angle);
+      st.thr[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      st.last_pdf[i] = 0.f;
+      st.d[i] = 0;
+      st.L[0][i] = st.L[1][i] = st.L[2][i] = 0.f;
+      f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
+      new_ray = true;
+    }
+    if (valid) st.flags[i] = f;
+
+    const bool want[1] = {new_ray};
+    QwAppend<1> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_closest[parity ^ 1u], s_cnt[0]);
+    __syncthreads();
+    if (new_ray) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = i;
+  }
+  warp_add_counter(&counters->nan_samples, nan_samples);
+  warp_add_counter(&counters->samples, n_samples);
+}
+
+// ================================================================== SHADE ====
+template <uint32_t CLASS>
+VD bool cls_sample(const DScene& sc, const vimg_material& m, V3 wi, const HitInfo& hit, Pcg32& rng,
+                   bool regularize, ScatterInfo& out) {
+  if constexpr (CLASS == WF_CLASS_LAMBERT) return lambertian_sample(wi, hit, rng, out);
+  else if constexpr (CLASS == WF_CLASS_DIELECTRIC) return dielectric_sample(m, wi, hit, rng, out);
+  else return principled_sample(sc, m, wi, hit, rng, regularize, out);
+}
+template <uint32_t CLASS>
+VD void cls_eval_pdf_pair(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, const HitInfo& hit,
+                          RayCone cone, bool regularize, V3& eval, float& pdf) {
+  if constexpr (CLASS == WF_CLASS_LAMBERT) {
+    lambertian_eval_pdf(sc, m, wi, wo, hit, cone, eval, pdf);
+  } else if constexpr (CLASS == WF_CLASS_PRINCIPLED) {
+    principled_eval_pdf(sc, m, wi, wo, hit, cone, regularize, eval, pdf);
+  } else {  // Dielectric inherits the base (0, 1) (material.h:56-60)
+    eval = mk3(0.f);
+    pdf = 1.0f;
+  }
+}
+template <uint32_t CLASS>
+VD V3 cls_eval_div_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, const HitInfo& hit,
+                       RayCone cone, bool regularize) {
+  if constexpr (CLASS == WF_CLASS_LAMBERT) {
+    return col_at_ray_hit(sc, m.texture, wi, cone, hit);
+  } else if constexpr (CLASS == WF_CLASS_DIELECTRIC) {
+    return mk3(1.f);
+  } else {
+    V3 e;
+    float p;
+    principled_eval_pdf(sc, m, wi, wo, hit, cone, regularize, e, p);
+    return e / p;
+  }
+}
+
+#ifndef QW_SHADE_MIN_BLOCKS_P
+#define QW_SHADE_MIN_BLOCKS_P 2  // Principled
+#endif
+#ifndef QW_SHADE_MIN_BLOCKS_L
+#define QW_SHADE_MIN_BLOCKS_L 2  // Lambertian, Dielectric
+#endif
+
+// thread <-> item of the class's shade queue: the body of the bounce loop at one hit
+// (mis_integrator.cpp:45-122, mat_integrator.cpp:21-83)
+template <int INTEGRATOR, uint32_t CLASS>
+__global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_SHADE_MIN_BLOCKS_P : QW_SHADE_MIN_BLOCKS_L)
+qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
+                const __grid_constant__ WfArgs args, const uint32_t parity) {
+  constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
+  __shared__ uint32_t s_cnt[4], s_base[4];
+  QwCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint32_t n = c->n_shade[CLASS];
+  const uint32_t* __restrict__ q = st.q_shade[CLASS];
+
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t item = base + tid;
+    bool want_closest = false, want_shadow = false, want_end_now = false, want_end_next = false;
+    uint32_t j = 0;
+    bool go = item < n;
+    uint32_t fj = 0;
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    Pcg32 rng;
+    rng.state = 0;
+    rng.inc = 1;
+    if (go) {
+      j = q[item];
+      fj = st.flags[j];
+      t4 = st.thr[j];
+      rng.state = st.rng[j];
+      if (MIS) {
+        // what mis_integrator does between the BVH::hit that found this surface and the next
+        // loop body: the shadow ray of the previous bounce (mis_integrator.cpp:64-78), Russian
+        // roulette (:154-167) and the loop condition d < depth
+        if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && !st.occl[j]) {
+          const float4 nc = st.nee_c[j];
+          st.L[0][j] += nc.x;
+          st.L[1][j] += nc.y;
+          st.L[2][j] += nc.z;
+        }
+        fj &= ~(WF_NEE | WF_NEE_VALID);
+        bool go_on = true;
+        const uint32_t d = st.d[j];
+        uint32_t dn = d;
+        if (!(fj & WF_FIRST)) {
+          if (d > 5) {
+            V3 t = xyz(t4);
+            go_on = russian_roulette(rng, t4.w, t);
+            if (go_on) t4 = f4(t, t4.w);
+          }
+          dn = d + 1;
+        }
+        fj &= ~WF_FIRST;
+        if (!go_on || dn >= args.depth) {
+          // the path returns bounce_result: the END kernel of this iteration finishes the sample
+          st.rng[j] = rng.state;
+          st.flags[j] = fj | WF_END;
+          want_end_now = true;
+          go = false;
+        } else if (dn != d) {
+          st.d[j] = dn;
+        }
+      } else {
+        fj &= ~WF_FIRST;
+      }
+    }
+    if (go) {
+      const float4 o4 = st.ray_o[j], d4 = st.ray_d[j], h0 = st.hit0[j];
+      const float2 h1 = st.hit1[j];
+      Ray ray;
+      ray.o = xyz(o4);
+      ray.dir = xyz(d4);
+      ray.minT = 0.0001f;
+      ray.maxT = h0.y;
+      ray.cone.cone_width = o4.w;
+      ray.cone.spread_angle = d4.w;
+      PreHit ph;
+      ph.leaf_slot = __float_as_int(h0.x);
+      ph.e0 = h0.z;
+      ph.e1 = h0.w;
+      ph.e2 = h1.x;
+      ph.inv_det = h1.y;
+      const HitInfo hit = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+      const vimg_material& mat = sc.materials[hit.mat];
+      V3 thr = xyz(t4);
+      bool nsb = (fj & WF_NSB) != 0;
+      float hit_dist = length(ray.o - hit.hit_p);
+      float surface_spread_angle
+          = spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s);
+
+      if (MIS) {
+        // ---- mis_integrator.cpp:45-117 at `hit` ----
+        bool nee = false, nee_valid = false;
+        EmitterInfo li;
+        V3 light_col = mk3(0.f);
+        if (CLASS != WF_CLASS_DIELECTRIC) {  // !mat->is_delta()
+          light_col = lights_sample(sc, hit.hit_p, rng, li);
+          nee = li.pdf != 0.f;
+        }
+        const RayCone nee_cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+        const bool nee_regularize = nsb;
+        ScatterInfo sm;
+        const bool scattered = cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sm);
+        RayCone cone = ray.cone;
+        float eta_scale = t4.w;
+        if (scattered) {
+          if (!sm.is_specular) nsb = true;
+          if (sm.eta != 0.f) {
+            eta_scale /= (sm.eta * sm.eta);
+            cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
+          } else {
+            cone = nee_cone;
+          }
+        }
+        // ONE inlined eval_pdf_pair site serves both calls of the loop body:
+        //   q = 0 light direction (mis_integrator.cpp:68-71), q = 1 sampled direction (:104-106)
+        V3 contrib = mk3(0.f), mat_sample_eval = mk3(0.f);
+        float mat_sample_pdf = 0.f;
+#pragma unroll 1
+        for (int qq = 0; qq < 2; ++qq) {
+          if (!(qq == 0 ? nee : scattered)) continue;
+          V3 e;
+          float p;
+          cls_eval_pdf_pair<CLASS>(sc, mat, ray.dir, qq == 0 ? li.wi : sm.wo, hit, qq == 0 ? nee_cone : cone,
+                                   qq == 0 ? nee_regularize : nsb, e, p);
+          if (qq == 0) {
+            if (p != 0 && !is_nan(p)) {
+              float G = li.G;
+              float mis_weight = balance_heuristic(li.pdf, p * G);
+              contrib = thr * e * mis_weight * G * light_col / li.pdf;
+              nee_valid = true;
+            }
+          } else {
+            mat_sample_eval = e;
+            mat_sample_pdf = p;
+          }
+        }
+        fj &= ~(WF_NSB | WF_NEE | WF_NEE_VALID | WF_END);
+        if (nsb) fj |= WF_NSB;
+        if (nee) {
+          fj |= WF_NEE | (nee_valid ? WF_NEE_VALID : 0u);
+          st.nee_wi[j] = f4(li.wi, li.dist);
+          st.nee_c[j] = f4(contrib, 0.f);
+          want_shadow = true;
+        }
+        if (!scattered || is_nan(mat_sample_pdf)) {
+          fj |= WF_END;  // return bounce_result (after the pending shadow ray)
+          st.ray_o[j] = f4(hit.hit_p, o4.w);  // origin of the shadow ray
+          want_end_next = true;
+        } else {
+          thr = thr * (mat_sample_eval / mat_sample_pdf);
+          st.thr[j] = f4(thr, eta_scale);
+          st.last_pdf[j] = mat_sample_pdf;
+          st.ray_o[j] = f4(hit.hit_p, cone.cone_width);  // origin of the shadow ray and of the next ray
+          st.ray_d[j] = f4(sm.wo, cone.spread_angle);
+          want_closest = true;
+        }
+      } else {
+        // ---- material_integrator, mat_integrator.cpp:21-83 at `hit` ----
+        V3 emitted_col = mat_emitted(mat, ray.dir, hit.hit_n_s);
+        ScatterInfo sr;
+        fj &= ~(WF_NSB | WF_END);
+        if (!cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sr)) {
+          st.nee_c[j] = f4(thr * emitted_col, 0.f);
+          fj |= WF_END;
+          want_end_now = true;
+        } else {
+          if (!sr.is_specular) nsb = true;
+          RayCone cone;
+          float eta_scale = t4.w;
+          if (sr.eta != 0.f) {
+            eta_scale /= (sr.eta * sr.eta);
+            cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo);
+          } else {
+            cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+          }
+          thr = thr * (emitted_col + cls_eval_div_pdf<CLASS>(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
+          const uint32_t d = st.d[j];
+          bool go_on = true;
+          if (d > 5) go_on = russian_roulette(rng, eta_scale, thr);
+          if (!go_on || d + 1 >= args.depth) {
+            // `break`, or the for loop runs out before the next BVH::hit: return vec3(0)
+            st.nee_c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fj |= WF_END;
+            want_end_now = true;
+          } else {
+            st.thr[j] = f4(thr, eta_scale);
+            st.ray_o[j] = f4(hit.hit_p, cone.cone_width);
+            st.ray_d[j] = f4(sr.wo, cone.spread_angle);
+            st.d[j] = d + 1;
+            want_closest = true;
+          }
+        }
+        if (nsb) fj |= WF_NSB;
+      }
+      st.rng[j] = rng.state;
+      st.flags[j] = fj;
+    }
+
+    const bool want[4] = {want_closest, want_shadow, want_end_now, want_end_next};
+    QwAppend<4> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_closest[parity ^ 1u], s_cnt[0]);
+    if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_shadow[parity ^ 1u], s_cnt[1]);
+    if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity], s_cnt[2]);
+    if (tid == 3 && s_cnt[3]) s_base[3] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[3]);
+    __syncthreads();
+    if (want_closest) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = j;
+    if (want_shadow) st.q_shadow[parity ^ 1u][s_base[1] + ap.off[1]] = j;
+    if (want_end_now) st.q_end[parity][s_base[2] + ap.off[2]] = j;
+    if (want_end_next) st.q_end[parity ^ 1u][s_base[3] + ap.off[3]] = j;
+  }
+}
+
+}  // namespace vimg

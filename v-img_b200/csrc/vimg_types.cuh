@@ -28,6 +28,7 @@ static_assert(sizeof(DPairNode) == 64, "pair record must be 64 bytes");
 
 #define VIMG_LEAF_SPHERE 1u
 #define VIMG_LEAF_DEGENERATE 2u /* length2(cross(e2,e1)) == 0 (triangle.h:92) */
+#define VIMG_LEAF_CLASS_EMISSIVE 4u /* leaf_class: the primitive's material is a DiffuseLight */
 
 struct __align__(16) DLeafPrim {
   float a[9];        // triangle: p0,p1,p2 | sphere: center.xyz, radius
@@ -90,6 +91,7 @@ struct DScene {
   // BVH
   const DPairNode* pairs;  // (n_nodes - 1) / 2 records, record of children (c, c+1) at (c-1)/2
   const DLeafPrim* leaf_prims;
+  const uint8_t* leaf_class;  // per leaf record: material class (bits 0-1) | VIMG_LEAF_CLASS_EMISSIVE
   float root_min[3], root_max[3];
   uint32_t root_first, root_count;  // nodes[0]
   uint32_t n_nodes;
