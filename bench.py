@@ -43,6 +43,9 @@ INTEG_NAMES = ["s_normal", "g_normal", "material", "mis"]
 # algorithmic cost model of SURVEY.md section 8(d), in the REFERENCE's data layout
 BYTES = {"inner_nodes": 56, "leaf_nodes": 8, "tri_tests": 56, "sphere_tests": 24}
 FLOPS = {"inner_nodes": 50, "tri_tests": 67, "sphere_tests": 40}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an `ncu --set full` capture
+# (profiles/r1s_queue_kernels_disney_8spp.txt, fully loaded iteration of disney_spheres)
+NCU_TRAFFIC = {"qw_trace_kernel": 194.644992e6 + 63.307008e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -199,7 +202,7 @@ def cuda_line(w, args):
 
     def step():
         """kernel(s) on this rank's tiles (+ NCCL reduce to rank 0); frame stays in HBM"""
-        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world)
+        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world, pipeline=args.pipeline)
         if world > 1:
             dist.reduce(scene.frame_tensor(ptr), dst=0, op=dist.ReduceOp.SUM)
         return ptr, st
@@ -249,7 +252,8 @@ def cuda_line(w, args):
     e2e_rays = 0
     for _ in range(e2e_steps):
         sc2 = vimg.Scene(desc.ptr, device=local_rank)
-        _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np)
+        _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np,
+                                      pipeline=args.pipeline)
         h2d = sc2.device_bytes
         sc2.close()
         e2e_rays += st2["rays_closest"] + st2["rays_shadow"]
@@ -267,19 +271,43 @@ def cuda_line(w, args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the render kernel: counted pass (untimed) gives per-ray algorithmic cost ----
+    # ---- roofline of the dominant kernel -----------------------------------------------------
+    # counted pass (untimed): per-ray algorithmic cost, in the reference's layout
     c_spp = min(spp, 16)
-    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True)
+    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True, pipeline=args.pipeline)
     c_rays = cst["rays_closest"] + cst["rays_shadow"]
     bytes_per_ray = sum(BYTES[k] * cst[k] for k in BYTES) / c_rays
     flops_per_ray = sum(FLOPS[k] * cst[k] for k in FLOPS) / c_rays
-    rays_per_launch = rays / max(launches, 1)
-    launch_s = kernel_ms_max / 1e3 / max(args.steps, 1)  # one launch per step per rank
-    rays_per_launch_rank = rays_per_launch  # rays of one rank's launch
     hbm_peak, peak_src = measured_peaks()
-    achieved = bytes_per_ray * rays_per_launch_rank / launch_s / 1e9
     samples_per_step = w["width"] * w["height"] * spp
     secs = elapsed_ms / 1e3
+    stages = None
+    if args.pipeline != "block" and integ in ("material", "mis"):
+        # queue wavefront: the TRACE kernel (BVH::hit / BVH::occlude of every queued ray) is the
+        # dominant kernel.  Its launches are timed with one CUDA event after every launch of a
+        # serial pass over the same frame (VIMG_FLAG_STAGE_TIMES): in the timed region above the
+        # shade / end launches of a pool overlap on side streams, so per-kernel events there would
+        # measure the overlap, not the kernel.
+        t_spp = min(spp, 64)
+        flush.zero_()
+        _, tst = scene.render_device(integ, t_spp, depth, rank=0, n_ranks=1, pipeline="queue", stage_times=True)
+        t_rays = tst["rays_closest"] + tst["rays_shadow"]
+        n_launch = max(tst["stage_launches"]["trace"], 1)
+        launch_s = tst["stage_ms"]["trace"] / 1e3 / n_launch
+        rays_per_launch_rank = t_rays / n_launch
+        kernel_name = "qw_trace_kernel"
+        stage_total = sum(tst["stage_ms"].values())
+        stages = {"spp": t_spp, "ms": tst["stage_ms"], "launches": tst["stage_launches"],
+                  "trace_share_of_step": tst["stage_ms"]["trace"] / stage_total,
+                  "note": "serial pass, one CUDA event per launch (VIMG_FLAG_STAGE_TIMES)"}
+        timing_note = (f"trace launches timed in a serial stage-timed pass at {t_spp} spp "
+                       f"({n_launch} launches, average duration)")
+    else:
+        rays_per_launch_rank = rays / max(launches, 1)
+        launch_s = kernel_ms_max / 1e3 / max(args.steps, 1)  # one launch per step per rank
+        kernel_name = f"wavefront_kernel<{integ}>"
+        timing_note = "one launch per step, CUDA events around it in the timed region"
+    achieved = bytes_per_ray * rays_per_launch_rank / launch_s / 1e9
 
     line = {
         "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world,
@@ -288,7 +316,7 @@ def cuda_line(w, args):
         "data": "synthetic", "impl": "cuda",
         "spp_mpix_per_s": samples_per_step * args.steps / secs / 1e6,
         "rays_per_sample": rays / (samples_per_step * args.steps),
-        "config": config_of(w, world),
+        "config": config_of(w, world, {"pipeline": args.pipeline or "queue (library default)"}),
         "clocks": clocks,
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": w["width"] * w["height"] * 12,
@@ -297,16 +325,21 @@ def cuda_line(w, args):
                 "path": "vimg_scene_create (H2D) + vimg_render into pinned host memory (kernel + D2H)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": f"wavefront_kernel<{integ}>", "launch_ms": 1e3 * launch_s,
+                     "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(kernel_name),
+                     "peak_source": peak_src,
+                     "kernel": kernel_name, "launch_ms": 1e3 * launch_s,
                      "algorithmic_bytes_per_ray": bytes_per_ray,
                      "algorithmic_flops_per_ray": flops_per_ray,
                      "rays_per_launch": rays_per_launch_rank,
                      "fp32_tflops_achieved": flops_per_ray * rays_per_launch_rank / launch_s / 1e12,
                      "note": "bytes in the reference's layout (56/inner, 8/leaf, 56/tri test, 24/sphere "
                              "test, SURVEY.md section 8(d)); per-ray averages from a counted pass at "
-                             f"{c_spp} spp, rays from the timed launches"},
+                             f"{c_spp} spp; {timing_note}; traffic = dram bytes of one fully loaded "
+                             "launch under ncu --set full (profiles/), mostly path state and queues: "
+                             "this scene's BVH (< 8 KiB) is L1 resident"},
     }
+    if stages:
+        line["stages"] = stages
     if not args.no_cpu and world == 1:
         r = time_reference(w, 1, 1, budget_s=16.0)
         if r is not None:
@@ -327,6 +360,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="disney_spheres")
+    ap.add_argument("--pipeline", default=None, choices=["queue", "block"],
+                    help="material / mis pipeline (default: the library's, the queue wavefront)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's spp (invalidates the number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

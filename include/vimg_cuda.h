@@ -234,6 +234,21 @@ typedef struct vimg_render_params {
  * Both produce the same image bit for bit. */
 #define VIMG_FLAG_PIPELINE_BLOCK 2u /* persistent block-local wavefront kernel  */
 #define VIMG_FLAG_PIPELINE_QUEUE 4u /* multi-kernel queue wavefront             */
+/* queue wavefront only: run the launches one after the other on one stream with a CUDA event
+ * after each, and report per-stage device time in vimg_render_stats.stage_ms (measurement
+ * mode: slower than the normal, concurrent schedule) */
+#define VIMG_FLAG_STAGE_TIMES 8u
+
+/* stages of the queue wavefront (vimg_render_stats.stage_ms / stage_launches) */
+typedef enum vimg_stage {
+  VIMG_STAGE_TRACE = 0,            /* BVH::hit / BVH::occlude for every queued ray          */
+  VIMG_STAGE_CLASSIFY = 1,         /* route each traced path by the material it hit        */
+  VIMG_STAGE_SHADE_PRINCIPLED = 2, /* light sampling + BSDF per material class             */
+  VIMG_STAGE_SHADE_LAMBERTIAN = 3,
+  VIMG_STAGE_SHADE_DIELECTRIC = 4,
+  VIMG_STAGE_END = 5,              /* sample accumulation, next pixel, next camera ray     */
+  VIMG_STAGE_COUNT = 6
+} vimg_stage;
 
 typedef struct vimg_render_stats {
   uint64_t rays_closest;   /* BVH::hit<optional<HitInfo>> calls               */
@@ -247,6 +262,8 @@ typedef struct vimg_render_stats {
   double kernel_ms;        /* device time of the render kernel(s), CUDA events */
   double total_ms;         /* kernel + D2H of the frame                       */
   uint32_t kernel_launches;
+  uint32_t stage_launches[VIMG_STAGE_COUNT]; /* VIMG_FLAG_STAGE_TIMES only                */
+  double stage_ms[VIMG_STAGE_COUNT];         /* VIMG_FLAG_STAGE_TIMES only                */
 } vimg_render_stats;
 
 typedef struct vimg_scene vimg_scene; /* opaque device-resident scene */

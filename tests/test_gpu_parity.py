@@ -292,3 +292,58 @@ def test_c4_synthetic_2m_triangles(vimg, refcpu):
 def test_c5_synthetic_10m_triangles(vimg, refcpu):
     """configs[4] geometry: 9 999 392 triangles (12.3 M nodes, depth 29) at 3840x2160."""
     _synthetic_case(vimg, refcpu, 2236, 3840, 2160, ids_spp=1, mis_spp=0)
+
+
+# ---- the two material / mis pipelines (vimg_queues.cuh, vimg_wavefront.cuh) ----
+@pytest.mark.parametrize("name", ["cornell_small", "glass_small", "disney_small", "sphere_light_small",
+                                  "cornell_skylight", "synthetic_small"])
+@pytest.mark.parametrize("integ", ["material", "mis"])
+def test_queue_and_block_pipelines_render_the_same_bits(vimg, man, name, integ):
+    """The queue wavefront (default) and the block-local wavefront kernel run every path through
+    the same float operations and RNG draws: images and ray / traversal counters are identical."""
+    sc = scene(vimg, name)
+    depth = man[name]["depth"]
+    q, qs = sc.scene_integrator(integ, 6, depth, counters=True, pipeline="queue")
+    b, bs = sc.scene_integrator(integ, 6, depth, counters=True, pipeline="block")
+    assert np.array_equal(q, b), f"{int((q != b).any(-1).sum())} pixels differ"
+    for k in ("rays_closest", "rays_shadow", "inner_nodes", "leaf_nodes", "tri_tests", "sphere_tests",
+              "samples", "nan_samples"):
+        assert qs[k] == bs[k], (k, qs[k], bs[k])
+    assert qs["kernel_launches"] > bs["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("integ,depth", [("material", 0), ("material", 1), ("mis", 0), ("mis", 1), ("mis", 3)])
+def test_pipelines_agree_at_small_depths(vimg, integ, depth):
+    sc = scene(vimg, "glass_small")
+    q, qs = sc.scene_integrator(integ, 3, depth, pipeline="queue")
+    b, bs = sc.scene_integrator(integ, 3, depth, pipeline="block")
+    assert np.array_equal(q, b)
+    assert qs["samples"] == bs["samples"] == sc.width * sc.height * 3
+
+
+def test_queue_pipeline_schedules_do_not_change_the_image(vimg, monkeypatch):
+    """Slot-pool size, number of pools, serial stage-timing mode: scheduling only."""
+    sc = scene(vimg, "disney_small")
+    base, st0 = sc.scene_integrator("mis", 8, 0xFFFFFFFF, pipeline="queue")
+    timed, st1 = sc.scene_integrator("mis", 8, 0xFFFFFFFF, pipeline="queue", stage_times=True)
+    assert np.array_equal(base, timed)
+    assert st1["stage_ms"]["trace"] > 0 and st1["stage_launches"]["trace"] > 0
+    assert abs(sum(st1["stage_ms"].values()) - st1["kernel_ms"]) < 0.5 * st1["kernel_ms"]
+    assert sum(st0["stage_ms"].values()) == 0
+    for env in ({"VIMG_QW_SLOTS": "4096"}, {"VIMG_QW_SLOTS": "70000", "VIMG_QW_POOLS": "1"},
+                {"VIMG_QW_POOLS": "4", "VIMG_QW_SLOTS": "300000"}, {"VIMG_QW_BATCH": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        img, _ = sc.scene_integrator("mis", 8, 0xFFFFFFFF, pipeline="queue")
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(img, base), env
+
+
+def test_trace_pixel_is_the_same_through_both_pipelines(vimg, man):
+    sc = scene(vimg, "disney_small")
+    e = man["disney_small"]
+    for (x, y) in [(3, 5), (e["width"] // 2, e["height"] // 3), (e["width"] - 1, e["height"] - 1)]:
+        a = sc.trace_pixel("mis", x, y, 16, 0xFFFFFFFF, pipeline="queue")
+        b = sc.trace_pixel("mis", x, y, 16, 0xFFFFFFFF, pipeline="block")
+        assert np.array_equal(a, b)

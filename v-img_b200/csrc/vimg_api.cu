@@ -45,6 +45,34 @@ float h_dot(H3 a, H3 b) {
 
 }  // namespace
 
+// One slot pool of the queue wavefront: its state in HBM, its streams and its host-side
+// bookkeeping.  Pools are independent pipelines over disjoint slots that pull pixels from one
+// shared counter; running two of them lets one pool's TRACE launch (issue bound) overlap the
+// other's SHADE / END launches (latency bound).
+constexpr int QW_MAX_POOLS = 4;
+struct QwPool {
+  QwState st{};
+  void* mem = nullptr;
+  uint32_t capacity = 0;
+  QwCounters* h_cnt = nullptr;  // pinned: queue-counter snapshots (termination test)
+  cudaStream_t main = nullptr, side[2] = {nullptr, nullptr};  // shade launches run beside END
+  cudaEvent_t snap[2] = {nullptr, nullptr}, fork = nullptr, join[2] = {nullptr, nullptr}, done = nullptr;
+  bool finished = false;
+  void destroy() {
+    if (mem) cudaFree(mem);
+    if (h_cnt) cudaFreeHost(h_cnt);
+    if (main) cudaStreamDestroy(main);
+    for (int k = 0; k < 2; ++k) {
+      if (side[k]) cudaStreamDestroy(side[k]);
+      if (snap[k]) cudaEventDestroy(snap[k]);
+      if (join[k]) cudaEventDestroy(join[k]);
+    }
+    if (fork) cudaEventDestroy(fork);
+    if (done) cudaEventDestroy(done);
+    *this = QwPool{};
+  }
+};
+
 struct vimg_scene {
   int device = 0;
   DScene d{};
@@ -56,15 +84,14 @@ struct vimg_scene {
   unsigned int* d_next_pixel = nullptr;
   int wf_blocks[2][2] = {{0, 0}, {0, 0}};  // resident-grid size of wavefront_kernel<integrator, COUNT>
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // queue wavefront (vimg_queues.cuh): path-state pool, class mask of the scene's materials
-  QwState qw{};
-  void* qw_pool = nullptr;
-  uint32_t qw_capacity = 0;
+  // queue wavefront (vimg_queues.cuh): slot pools, class mask of the scene's materials
+  QwPool qw[QW_MAX_POOLS];
   uint32_t class_mask = 0;
-  QwCounters* h_alive = nullptr;  // pinned: queue-counter snapshots (termination test)
-  cudaEvent_t qw_ev[2] = {nullptr, nullptr};
+  uint32_t* d_qw_next_pixel = nullptr;
   int sm_count = 0;
   uint32_t last_launches = 0;
+  double stage_ms[VIMG_STAGE_COUNT] = {0};
+  uint32_t stage_launches[VIMG_STAGE_COUNT] = {0};
 
   template <typename T> int upload(const T* host, size_t n, const T** out) {
     *out = nullptr;
@@ -370,15 +397,28 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 }
 
 // path-state pool for `n` slots, carved from one allocation (256-byte aligned arrays)
-static int qw_reserve(vimg_scene* s, uint32_t n) {
-  if (s->qw_pool && s->qw_capacity >= n) {
-    s->qw.n_slots = n;
+static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
+  if (!pool.h_cnt) {
+    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&pool.h_cnt), 2 * sizeof(QwCounters)));
+    CU_TRY(cudaStreamCreateWithFlags(&pool.main, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CU_TRY(cudaStreamCreateWithFlags(&pool.side[k], cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreateWithFlags(&pool.snap[k], cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&pool.join[k], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&pool.fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&pool.done, cudaEventDisableTiming));
+  }
+  if (!s->d_qw_next_pixel) CU_TRY(cudaMalloc(&s->d_qw_next_pixel, sizeof(uint32_t)));
+  pool.st.next_pixel = s->d_qw_next_pixel;
+  if (pool.mem && pool.capacity >= n) {
+    pool.st.n_slots = n;
     return VIMG_OK;
   }
-  if (s->qw_pool) {
-    cudaFree(s->qw_pool);
-    s->qw_pool = nullptr;
-    s->qw_capacity = 0;
+  if (pool.mem) {
+    cudaFree(pool.mem);
+    pool.mem = nullptr;
+    pool.capacity = 0;
   }
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -387,50 +427,29 @@ static int qw_reserve(vimg_scene* s, uint32_t n) {
     return at;
   };
   const size_t N = n;
-  const size_t o_ray_o = carve(N * 16), o_ray_d = carve(N * 16), o_thr = carve(N * 16), o_hit0 = carve(N * 16),
-               o_hit1 = carve(N * 8), o_nee_wi = carve(N * 16), o_nee_c = carve(N * 16);
-  size_t o_L[3], o_acc[3];
-  for (int k = 0; k < 3; ++k) o_L[k] = carve(N * 4);
-  for (int k = 0; k < 3; ++k) o_acc[k] = carve(N * 4);
-  const size_t o_last_pdf = carve(N * 4), o_rng = carve(N * 8), o_flags = carve(N * 4), o_d = carve(N * 4),
-               o_s = carve(N * 4), o_pixel = carve(N * 4), o_occl = carve(N);
+  const size_t o_ray = carve(N * sizeof(QwRay)), o_hit = carve(N * sizeof(QwHit)), o_path = carve(N * sizeof(QwPath)),
+               o_nee = carve(N * sizeof(QwNee)), o_pix = carve(N * sizeof(QwPix));
   size_t o_qc[2], o_qs[2], o_qe[2], o_qsh[WF_NUM_CLASSES];
   for (int k = 0; k < 2; ++k) o_qc[k] = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qs[k] = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qe[k] = carve(N * 4);
   for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) o_qsh[k] = carve(N * 4);
   const size_t o_cnt = carve(sizeof(QwCounters));
-  void* pool = nullptr;
-  CU_TRY(cudaMalloc(&pool, off));
-  s->qw_pool = pool;
-  s->qw_capacity = n;
-  char* b = static_cast<char*>(pool);
-  QwState& q = s->qw;
+  CU_TRY(cudaMalloc(&pool.mem, off));
+  pool.capacity = n;
+  char* b = static_cast<char*>(pool.mem);
+  QwState& q = pool.st;
   q.n_slots = n;
-  q.ray_o = reinterpret_cast<float4*>(b + o_ray_o);
-  q.ray_d = reinterpret_cast<float4*>(b + o_ray_d);
-  q.thr = reinterpret_cast<float4*>(b + o_thr);
-  q.hit0 = reinterpret_cast<float4*>(b + o_hit0);
-  q.hit1 = reinterpret_cast<float2*>(b + o_hit1);
-  q.nee_wi = reinterpret_cast<float4*>(b + o_nee_wi);
-  q.nee_c = reinterpret_cast<float4*>(b + o_nee_c);
-  for (int k = 0; k < 3; ++k) q.L[k] = reinterpret_cast<float*>(b + o_L[k]);
-  for (int k = 0; k < 3; ++k) q.acc[k] = reinterpret_cast<float*>(b + o_acc[k]);
-  q.last_pdf = reinterpret_cast<float*>(b + o_last_pdf);
-  q.rng = reinterpret_cast<unsigned long long*>(b + o_rng);
-  q.flags = reinterpret_cast<uint32_t*>(b + o_flags);
-  q.d = reinterpret_cast<uint32_t*>(b + o_d);
-  q.s = reinterpret_cast<uint32_t*>(b + o_s);
-  q.pixel = reinterpret_cast<uint32_t*>(b + o_pixel);
-  q.occl = reinterpret_cast<uint8_t*>(b + o_occl);
+  q.ray = reinterpret_cast<QwRay*>(b + o_ray);
+  q.hit = reinterpret_cast<QwHit*>(b + o_hit);
+  q.path = reinterpret_cast<QwPath*>(b + o_path);
+  q.nee = reinterpret_cast<QwNee*>(b + o_nee);
+  q.pix = reinterpret_cast<QwPix*>(b + o_pix);
   for (int k = 0; k < 2; ++k) q.q_closest[k] = reinterpret_cast<uint32_t*>(b + o_qc[k]);
   for (int k = 0; k < 2; ++k) q.q_shadow[k] = reinterpret_cast<uint32_t*>(b + o_qs[k]);
   for (int k = 0; k < 2; ++k) q.q_end[k] = reinterpret_cast<uint32_t*>(b + o_qe[k]);
   for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) q.q_shade[k] = reinterpret_cast<uint32_t*>(b + o_qsh[k]);
   q.cnt = reinterpret_cast<QwCounters*>(b + o_cnt);
-  if (!s->h_alive) CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_alive), 2 * sizeof(QwCounters)));
-  for (int k = 0; k < 2; ++k)
-    if (!s->qw_ev[k]) CU_TRY(cudaEventCreateWithFlags(&s->qw_ev[k], cudaEventDisableTiming));
   return VIMG_OK;
 }
 
@@ -448,7 +467,7 @@ struct QwProfile {
     ev.push_back(e);
     kind.push_back(k);
   }
-  void report() {
+  void report(bool print, double* stage_ms, uint32_t* stage_launches) {
     if (!on || ev.empty()) return;
     static const char* names[] = {"start", "trace", "classify", "shade_principled", "shade_lambert",
                                   "shade_dielectric", "end"};
@@ -462,11 +481,17 @@ struct QwProfile {
       cnt[kind[i]]++;
       total += ms;
     }
-    fprintf(stderr, "[qw profile] %.2f ms:", total);
-    for (int k = 1; k < 7; ++k)
-      if (cnt[k]) fprintf(stderr, " %s %.2f ms (%.0f%%, %u launches, %.1f us avg)", names[k], tot[k], 100 * tot[k] / total, cnt[k], 1e3 * tot[k] / cnt[k]);
-    fprintf(stderr, "\n");
-    if (verbose) {
+    for (int k = 1; k < 7; ++k) {  // profile kinds 1..6 = vimg_stage 0..5
+      stage_ms[k - 1] = tot[k];
+      stage_launches[k - 1] = cnt[k];
+    }
+    if (print) {
+      fprintf(stderr, "[qw profile] %.2f ms:", total);
+      for (int k = 1; k < 7; ++k)
+        if (cnt[k]) fprintf(stderr, " %s %.2f ms (%.0f%%, %u launches, %.1f us avg)", names[k], tot[k], 100 * tot[k] / total, cnt[k], 1e3 * tot[k] / cnt[k]);
+      fprintf(stderr, "\n");
+    }
+    if (print && verbose) {
       // per-launch times of the first iterations (fully loaded) and of a few later ones
       for (size_t i = 1; i < ev.size(); ++i) {
         const size_t iter = i / 5;
@@ -481,99 +506,197 @@ struct QwProfile {
   }
 };
 
-template <int INTEGRATOR>
-static void qw_launch_shade(vimg_scene* s, const WfArgs& w, uint32_t parity, int grid, cudaStream_t st, QwProfile& prof) {
-  if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-    qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
-    prof.mark(3);
-  }
-  if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
-    qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
-    prof.mark(4);
-  }
-  if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-    qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<grid, QW_THREADS, 0, st>>>(s->d, s->qw, w, parity);
-    prof.mark(5);
-  }
-}
-
 // iota kernel: the initial END queue holds every slot (all without a pixel)
 __global__ void qw_iota_kernel(uint32_t* q, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) q[i] = i;
 }
 
-// One frame: end(0) | trace(1) classify(1) shade(1) end(1) | ...  until every queue is empty.
-// The host looks at the queue counters once per batch of iterations and keeps one batch queued
-// ahead of the check, so the device never waits for the host.
-template <bool COUNT>
-static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, float* out, cudaStream_t st) {
-  const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
-  const uint32_t n_slots = std::max(1u, std::min(w.n_local_pixels, cap));
-  int rc = qw_reserve(s, n_slots);
-  if (rc != VIMG_OK) return rc;
-  if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
-  const QwState& q = s->qw;
-  CU_TRY(cudaMemsetAsync(q.flags, 0, (size_t)n_slots * 4, st));
-  QwCounters init{};
-  init.n_end[0] = n_slots;
-  CU_TRY(cudaMemcpyAsync(q.cnt, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-  const int slot_blocks = (int)((n_slots + QW_THREADS - 1) / QW_THREADS);
-  qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, st>>>(q.q_end[0], n_slots);
-  const int trace_full = s->sm_count * QW_TRACE_BLOCKS_PER_SM;
-  const int trace_need = (int)((2ull * n_slots + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS);
-  const int trace_grid = std::max(1, std::min(trace_full, trace_need));
-  const int item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8));
-  const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
-  const bool mis = integrator == VIMG_INTEGRATOR_MIS;
-  uint32_t launches = 1, it = 0;
-  const uint32_t n_shade = (uint32_t)__builtin_popcount(s->class_mask);
-  QwProfile prof;
-  prof.on = env_u32("VIMG_QW_PROFILE", 0) != 0;
-  prof.verbose = env_u32("VIMG_QW_PROFILE", 0) > 1;
-  prof.st = st;
-  prof.mark(0);
-  for (uint32_t b = 0;; ++b) {
-    for (uint32_t k = 0; k < batch; ++k, ++it) {
-      const uint32_t parity = it & 1u;
-      if (it > 0) {
-        qw_trace_kernel<COUNT><<<trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
-        prof.mark(1);
-        qw_classify_kernel<<<item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
-        prof.mark(2);
-        if (mis)
-          qw_launch_shade<VIMG_INTEGRATOR_MIS>(s, w, parity, item_grid, st, prof);
-        else
-          qw_launch_shade<VIMG_INTEGRATOR_MATERIAL>(s, w, parity, item_grid, st, prof);
-        launches += 2 + n_shade;
-      }
-      if (mis)
-        qw_end_kernel<VIMG_INTEGRATOR_MIS><<<item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
-      else
-        qw_end_kernel<VIMG_INTEGRATOR_MATERIAL><<<item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
-      prof.mark(6);
+struct QwLaunchCfg {
+  int trace_grid, item_grid;
+  bool concurrent;
+  uint32_t class_mask;
+};
+
+// one iteration of one pool: trace(it) classify(it) {shade(it) | end(it)}; iteration 0 is end only
+template <int INTEGRATOR, bool COUNT>
+static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& w, uint32_t it, const QwLaunchCfg& cfg,
+                                     float* out, QwProfile& prof) {
+  const QwState& q = pool.st;
+  const uint32_t parity = it & 1u;
+  cudaStream_t st = pool.main;
+  uint32_t launches = 0;
+  if (it > 0) {
+    qw_trace_kernel<COUNT><<<cfg.trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
+    prof.mark(1);
+    qw_classify_kernel<<<cfg.item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
+    prof.mark(2);
+    // shade launches only feed the next iteration, END only consumes what classify and the
+    // previous shade launches queued: fork them onto side streams, join before the next trace
+    cudaStream_t sp = st, sl = st;
+    if (cfg.concurrent) {
+      sp = pool.side[0];
+      sl = pool.side[1];
+      cudaEventRecord(pool.fork, st);
+      cudaStreamWaitEvent(sp, pool.fork, 0);
+      cudaStreamWaitEvent(sl, pool.fork, 0);
+    }
+    if (cfg.class_mask & (1u << WF_CLASS_PRINCIPLED)) {
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<cfg.item_grid, QW_THREADS, 0, sp>>>(s->d, q, w, parity);
+      prof.mark(3);
       ++launches;
     }
+    if (cfg.class_mask & (1u << WF_CLASS_LAMBERT)) {
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<cfg.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      prof.mark(4);
+      ++launches;
+    }
+    if (cfg.class_mask & (1u << WF_CLASS_DIELECTRIC)) {
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<cfg.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      prof.mark(5);
+      ++launches;
+    }
+    if (cfg.concurrent) {
+      cudaEventRecord(pool.join[0], sp);
+      cudaEventRecord(pool.join[1], sl);
+    }
+    launches += 2;
+  }
+  qw_end_kernel<INTEGRATOR><<<cfg.item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
+  prof.mark(6);
+  ++launches;
+  if (cfg.concurrent && it > 0) {
+    cudaStreamWaitEvent(st, pool.join[0], 0);
+    cudaStreamWaitEvent(st, pool.join[1], 0);
+  }
+  return launches;
+}
+
+// One frame.  Per pool: end(0) | trace(1) classify(1) shade(1) end(1) | ...  until every queue is
+// empty.  The host looks at the queue counters once per batch of iterations and keeps one batch
+// queued ahead of the check, so the device never waits for the host.
+template <int INTEGRATOR, bool COUNT>
+static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t caller, bool stage_times) {
+  QwProfile prof;
+  const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
+  prof.on = print_profile || stage_times;
+  prof.verbose = env_u32("VIMG_QW_PROFILE", 0) > 1;
+  const bool timeline = env_u32("VIMG_QW_TIMELINE", 0) != 0;  // ms and live paths per batch, to stderr
+  // the per-kernel profile needs serial launches on one stream
+  const bool concurrent = !prof.on && env_u32("VIMG_QW_SERIAL", 0) == 0;
+  const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
+  const uint32_t total_slots = std::max(1u, std::min(w.n_local_pixels, cap));
+  uint32_t n_pools = std::min<uint32_t>(QW_MAX_POOLS, std::max(1u, env_u32("VIMG_QW_POOLS", 2)));
+  if (!concurrent || total_slots < 65536u) n_pools = 1;  // small frames: one pool, lowest latency
+  const uint32_t per_pool = (total_slots + n_pools - 1) / n_pools;
+  if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+
+  int rc;
+  for (uint32_t p = 0; p < n_pools; ++p)
+    if ((rc = qw_reserve(s, s->qw[p], per_pool)) != VIMG_OK) return rc;
+  CU_TRY(cudaMemsetAsync(s->d_qw_next_pixel, 0, sizeof(uint32_t), caller));
+  cudaEvent_t start = s->qw[0].done;  // reused as the fork event of the caller's stream
+  const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
+  for (uint32_t p = 0; p < n_pools; ++p) {
+    QwPool& pool = s->qw[p];
+    pool.finished = false;
+    if (p == 0) CU_TRY(cudaEventRecord(start, caller));
+    CU_TRY(cudaStreamWaitEvent(pool.main, start, 0));
+    CU_TRY(cudaMemsetAsync(pool.st.path, 0, (size_t)per_pool * sizeof(QwPath), pool.main));  // flags = 0: no pixel yet
+    QwCounters init{};
+    init.n_end[0] = per_pool;
+    *pool.h_cnt = init;
+    CU_TRY(cudaMemcpyAsync(pool.st.cnt, pool.h_cnt, sizeof(init), cudaMemcpyHostToDevice, pool.main));
+    qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, pool.main>>>(pool.st.q_end[0], per_pool);
+  }
+  QwLaunchCfg cfg;
+  // with several pools in flight the persistent trace grid leaves room for the other pool's
+  // shade / end blocks on every SM
+  const int trace_per_sm = (int)env_u32("VIMG_QW_TRACE_BLOCKS", n_pools > 1 ? 3 : QW_TRACE_BLOCKS_PER_SM);
+  const int trace_full = s->sm_count * std::max(1, std::min(trace_per_sm, QW_TRACE_BLOCKS_PER_SM));
+  const int trace_need = (int)((2ull * per_pool + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS);
+  cfg.trace_grid = std::max(1, std::min(trace_full, trace_need));
+  cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8));
+  cfg.concurrent = concurrent;
+  cfg.class_mask = s->class_mask;
+  const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
+  uint32_t launches = n_pools, it = 0;
+  prof.st = s->qw[0].main;
+  prof.mark(0);
+  std::vector<cudaEvent_t> tl_ev;
+  std::vector<uint32_t> tl_live;
+  for (uint32_t b = 0;; ++b) {
+    for (uint32_t k = 0; k < batch; ++k, ++it)
+      for (uint32_t p = 0; p < n_pools; ++p)
+        if (!s->qw[p].finished) launches += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, s->qw[p], w, it, cfg, out, prof);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(&s->h_alive[b & 1], q.cnt, sizeof(QwCounters), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventRecord(s->qw_ev[b & 1], st));
+    for (uint32_t p = 0; p < n_pools; ++p) {
+      QwPool& pool = s->qw[p];
+      if (pool.finished) continue;
+      CU_TRY(cudaMemcpyAsync(&pool.h_cnt[b & 1], pool.st.cnt, sizeof(QwCounters), cudaMemcpyDeviceToHost, pool.main));
+      CU_TRY(cudaEventRecord(pool.snap[b & 1], pool.main));
+    }
+    if (timeline) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s->qw[0].main);
+      tl_ev.push_back(e);
+    }
     if (b > 0) {
-      CU_TRY(cudaEventSynchronize(s->qw_ev[(b - 1) & 1]));
-      // queues the iteration after batch b-1 would consume: parity of its first iteration
-      const QwCounters& hc = s->h_alive[(b - 1) & 1];
-      const uint32_t p = (b * batch) & 1u;
-      if (hc.n_closest[p] == 0 && hc.n_shadow[p] == 0 && hc.n_end[p] == 0) break;  // batch b ran empty
+      bool all_done = true;
+      uint32_t live = 0;
+      for (uint32_t p = 0; p < n_pools; ++p) {
+        QwPool& pool = s->qw[p];
+        if (pool.finished) continue;
+        CU_TRY(cudaEventSynchronize(pool.snap[(b - 1) & 1]));
+        // queues the iteration after batch b-1 consumes: parity of its first iteration
+        const QwCounters& hc = pool.h_cnt[(b - 1) & 1];
+        const uint32_t par = (b * batch) & 1u;
+        live += hc.n_closest[par];
+        if (hc.n_closest[par] == 0 && hc.n_shadow[par] == 0 && hc.n_end[par] == 0)
+          pool.finished = true;  // batch b only ran empty iterations for this pool
+        else
+          all_done = false;
+      }
+      if (timeline) tl_live.push_back(live);
+      if (all_done) break;
     }
   }
-  prof.report();
+  // the caller's stream continues when every pool is drained
+  for (uint32_t p = 0; p < n_pools; ++p) {
+    CU_TRY(cudaEventRecord(s->qw[p].done, s->qw[p].main));
+    CU_TRY(cudaStreamWaitEvent(caller, s->qw[p].done, 0));
+  }
+  prof.report(print_profile, s->stage_ms, s->stage_launches);
+  if (timeline && !tl_ev.empty()) {
+    cudaEventSynchronize(tl_ev.back());
+    fprintf(stderr, "[qw timeline] %u pool(s), batch of %u iterations: ms | closest rays queued after it\n", n_pools, batch);
+    const size_t step = std::max<size_t>(1, tl_ev.size() / 48);
+    for (size_t i = step; i < tl_ev.size(); i += step) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tl_ev[i - step], tl_ev[i]);
+      fprintf(stderr, "  batches %zu-%zu: %.3f ms/batch, live %u\n", i - step, i, ms / step,
+              i - 1 < tl_live.size() ? tl_live[i - 1] : 0u);
+    }
+    for (cudaEvent_t e : tl_ev) cudaEventDestroy(e);
+  }
   s->last_launches = launches;
   return VIMG_OK;
+}
+
+template <bool COUNT>
+static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, float* out, cudaStream_t st,
+                     bool stage_times) {
+  if (integrator == VIMG_INTEGRATOR_MIS) return qw_render_t<VIMG_INTEGRATOR_MIS, COUNT>(s, w, out, st, stage_times);
+  return qw_render_t<VIMG_INTEGRATOR_MATERIAL, COUNT>(s, w, out, st, stage_times);
 }
 
 template <bool COUNT>
 static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st,
                          uint32_t flags = 0) {
   s->last_launches = 1;
+  std::memset(s->stage_ms, 0, sizeof(s->stage_ms));
+  std::memset(s->stage_launches, 0, sizeof(s->stage_launches));
   if (integrator == VIMG_INTEGRATOR_MATERIAL || integrator == VIMG_INTEGRATOR_MIS) {
     WfArgs w{};
     w.samples = a.samples;
@@ -593,7 +716,7 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       const char* e = std::getenv("VIMG_PIPELINE");
       use_block = e && std::strcmp(e, "block") == 0;
     }
-    if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st);
+    if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st, (flags & VIMG_FLAG_STAGE_TIMES) != 0);
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
     if (integrator == VIMG_INTEGRATOR_MIS) {
       const int g = wavefront_grid<VIMG_INTEGRATOR_MIS, COUNT>(s, w.n_local_pixels);
@@ -645,10 +768,8 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_frame) cudaFree(s->d_frame);
   if (s->d_counters) cudaFree(s->d_counters);
   if (s->d_next_pixel) cudaFree(s->d_next_pixel);
-  if (s->qw_pool) cudaFree(s->qw_pool);
-  if (s->h_alive) cudaFreeHost(s->h_alive);
-  for (int k = 0; k < 2; ++k)
-    if (s->qw_ev[k]) cudaEventDestroy(s->qw_ev[k]);
+  for (QwPool& p : s->qw) p.destroy();
+  if (s->d_qw_next_pixel) cudaFree(s->d_qw_next_pixel);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -722,6 +843,8 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
     stats->kernel_ms = ms;
     stats->total_ms = ms;
     stats->kernel_launches = s->last_launches;
+    std::memcpy(stats->stage_ms, s->stage_ms, sizeof(s->stage_ms));
+    std::memcpy(stats->stage_launches, s->stage_launches, sizeof(s->stage_launches));
 #ifdef WF_STAGE_CLOCKS
     fprintf(stderr, "[wf stage cycles, summed over warps] shadow %llu regen %llu closest %llu resolve+bucket %llu "
             "barrier1 %llu shade %llu barrier2 %llu\n", c.stage_clk[0], c.stage_clk[1], c.stage_clk[2],

@@ -49,37 +49,55 @@ struct QwCounters {
   uint32_t n_end[2];
   uint32_t n_shade[WF_NUM_CLASSES];
   uint32_t cursor;      // trace kernel's work cursor
-  uint32_t next_pixel;  // next local pixel number to hand out
-  uint32_t pad_[1];
+  uint32_t pad_[2];
+};
+
+// Path state of one slot: five 32-byte records (one DRAM sector each), grouped by who reads and
+// writes them together, so that every kernel moves whole sectors with 16-byte loads and stores.
+struct __align__(32) QwRay {   // END / SHADE write; TRACE, SHADE, END read
+  float4 o_w;  // origin xyz (hit point after shading), cone_width
+  float4 d_s;  // direction xyz, cone spread_angle
+};
+struct __align__(32) QwHit {   // TRACE writes (closest ray: h0, h1; shadow ray: occl)
+  float4 h0;   // leaf slot (int bits), t, e0, e1
+  float2 h1;   // e2, inv_det
+  uint32_t occl, pad_;
+};
+struct __align__(32) QwPath {  // SHADE and END read and write
+  float4 thr_eta;  // throughput rgb, eta_scale
+  unsigned long long rng;
+  uint32_t flags, d;
+};
+struct __align__(32) QwNee {   // SHADE writes; TRACE reads wi_dist; SHADE / END read c_pdf
+  float4 wi_dist;  // shadow ray direction xyz, light distance
+  float4 c_pdf;    // pending NEE contribution rgb (material: result of an ended path), last_pdf
+};
+struct __align__(32) QwPix {   // END reads and writes; SHADE adds the NEE contribution to L
+  float4 L_s;        // bounce_result of the path in flight rgb, sample counter (uint bits)
+  float4 acc_pixel;  // pixel accumulator rgb, local pixel number (uint bits)
 };
 
 struct QwState {
   uint32_t n_slots;
-  float4* ray_o;    // origin xyz (hit point after shading), cone_width
-  float4* ray_d;    // direction xyz, cone spread_angle
-  float4* thr;      // throughput rgb, eta_scale
-  float4* hit0;     // leaf slot (int bits), t, e0, e1      written by TRACE
-  float2* hit1;     // e2, inv_det                          written by TRACE
-  float4* nee_wi;   // shadow ray direction xyz, light distance
-  float4* nee_c;    // pending NEE contribution rgb (material: result of an ended path)
-  float* L[3];      // bounce_result of the path in flight
-  float* acc[3];    // pixel accumulator
-  float* last_pdf;
-  unsigned long long* rng;
-  uint32_t* flags;
-  uint32_t* d;
-  uint32_t* s;
-  uint32_t* pixel;
-  uint8_t* occl;  // shadow ray result, written by TRACE
+  QwRay* ray;
+  QwHit* hit;
+  QwPath* path;
+  QwNee* nee;
+  QwPix* pix;
   uint32_t* q_closest[2];
   uint32_t* q_shadow[2];
   uint32_t* q_end[2];
   uint32_t* q_shade[WF_NUM_CLASSES];
   QwCounters* cnt;
+  uint32_t* next_pixel;  // next local pixel number to hand out (shared by all pools of a frame)
 };
 
 VD V3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 VD float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+// slot state is touched once per kernel: keep it out of L1 (which holds the scene tables)
+VD float4 ldg4(const float4* p) { return __ldcg(p); }
+VD void stg4(float4* p, float4 v) { __stcg(p, v); }
+VD uint4 ldg4u(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
 // Block-wide queue append.  Every thread of the block calls this (want may be false);
 // one global atomic per queue per block.  `s_cnt`/`s_base` are NQ shared words each.
@@ -132,8 +150,8 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   uint32_t chunk_next = 0, chunk_end = 0;  // this warp's private range of work items
   bool more = total > 0;
 
-  // per-lane ray in flight
-  bool have = false, any_hit = false;
+  // per-lane ray: `have` = in traversal, `done` = finished, result not stored yet
+  bool have = false, done = false, any_hit = false, occluded = false;
   uint32_t slot = 0;
   Ray ray;
   RayPre pre;
@@ -151,17 +169,17 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
   ph.leaf_slot = -1;
 
-  auto finish = [&](bool occluded) {
-    if (any_hit) {
-      st.occl[slot] = occluded ? 1 : 0;
-    } else {
-      st.hit0[slot] = make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1);
-      st.hit1[slot] = make_float2(ph.e2, ph.inv_det);
-    }
-    have = false;
-  };
-
   for (;;) {
+    if (done) {  // the one place results are stored
+      QwHit* h = st.hit + slot;
+      if (any_hit) {
+        h->occl = occluded ? 1u : 0u;
+      } else {
+        stg4(&h->h0, make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1));
+        h->h1 = make_float2(ph.e2, ph.inv_det);
+      }
+      done = false;
+    }
     const uint32_t idle = __ballot_sync(0xffffffffu, !have);
     if (idle == 0xffffffffu || (more && __popc(idle) >= QW_REFILL_MIN)) {
       if (more) {
@@ -179,35 +197,35 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             ray.minT = 0.0001f;
             ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
             ph.leaf_slot = -1;
+            occluded = false;
+            float4 o4, d4;
             if (idx < n_c) {
               any_hit = false;
               slot = qc[idx];
-              const float4 o4 = st.ray_o[slot], d4 = st.ray_d[slot];
-              ray.o = xyz(o4);
-              ray.dir = xyz(d4);
+              o4 = ldg4(&st.ray[slot].o_w);
+              d4 = ldg4(&st.ray[slot].d_s);
               ray.maxT = CUDART_INF_F;
               pc.rays_closest++;
             } else {
               // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
               any_hit = true;
               slot = qs[idx - n_c];
-              const float4 o4 = st.ray_o[slot], w4 = st.nee_wi[slot];
-              ray.o = xyz(o4);
-              ray.dir = xyz(w4);
-              ray.maxT = w4.w - 0.0001f;
+              o4 = ldg4(&st.ray[slot].o_w);
+              d4 = ldg4(&st.nee[slot].wi_dist);
+              ray.maxT = d4.w - 0.0001f;
               pc.rays_shadow++;
             }
-            have = true;
-            if (sc.n_nodes == 0) {
-              finish(false);
-            } else {
+            ray.o = xyz(o4);
+            ray.dir = xyz(d4);
+            done = true;
+            if (sc.n_nodes != 0) {
               pre = ray_precompute(ray);
               const float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
-              if (is_inf(root_hit)) {
-                finish(false);
-              } else {
+              if (!is_inf(root_hit)) {
                 cur = make_uint2(sc.root_first, sc.root_count);
                 sp = 0;
+                have = true;
+                done = false;
               }
             }
           }
@@ -215,7 +233,7 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         const uint32_t taken = chunk_next + __popc(idle);
         chunk_next = taken < chunk_end ? taken : chunk_end;
       }
-      if (!__any_sync(0xffffffffu, have)) {
+      if (!__any_sync(0xffffffffu, have || done)) {
         if (!more) break;
         continue;
       }
@@ -250,12 +268,12 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       } else if (sp > 0) {
         cur = stack[--sp];
       } else {
-        finish(false);
+        have = false;
+        done = true;
       }
     }
     if (have) {  // leaf: primitives in obj_indices order, the last success wins
       if (COUNT) pc.trav.leaf++;
-      bool occluded = false;
       for (uint32_t i = 0; i < cur.y; ++i) {
         const uint32_t ls = cur.x + i;
         const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + ls);
@@ -279,12 +297,11 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
           }
         }
       }
-      if (occluded) {
-        finish(true);
-      } else if (sp > 0) {
+      if (!occluded && sp > 0) {
         cur = stack[--sp];
       } else {
-        finish(false);
+        have = false;
+        done = true;
       }
     }
   }
@@ -320,7 +337,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
     uint32_t cls = WF_CLASS_NONE + 1, j = 0;  // NONE + 1: no item
     if (item < n) {
       j = q[item];
-      const int32_t leaf_slot = __float_as_int(st.hit0[j].x);
+      const int32_t leaf_slot = __float_as_int(__ldcg(&st.hit[j].h0.x));
       cls = WF_CLASS_NONE;
       if (leaf_slot >= 0) {
         const uint32_t lc = sc.leaf_class[leaf_slot];
@@ -371,45 +388,58 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
     const uint32_t item = base + tid;
     const bool valid = item < n;
     const uint32_t i = valid ? q[item] : 0u;
-    uint32_t f = valid ? st.flags[i] : 0u;
+    // the whole slot state in one round trip
+    uint4 pa1 = make_uint4(0, 0, 0, 0);
+    float4 thr4 = make_float4(0.f, 0.f, 0.f, 0.f), o4 = thr4, d4 = thr4, h0 = thr4, cp4 = thr4, L4 = thr4, ap4 = thr4;
+    uint4 hb = pa1;
+    if (valid) {
+      thr4 = ldg4(&st.path[i].thr_eta);
+      pa1 = ldg4u(&st.path[i].rng);
+      o4 = ldg4(&st.ray[i].o_w);
+      d4 = ldg4(&st.ray[i].d_s);
+      h0 = ldg4(&st.hit[i].h0);
+      hb = ldg4u(&st.hit[i].h1);
+      cp4 = ldg4(&st.nee[i].c_pdf);
+      L4 = ldg4(&st.pix[i].L_s);
+      ap4 = ldg4(&st.pix[i].acc_pixel);
+    }
+    uint32_t f = pa1.z;
+    const uint32_t d = pa1.w;
+    Pcg32 rng;
+    rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
+    rng.inc = 1;
+    V3 acc = xyz(ap4);
+    uint32_t s = __float_as_uint(L4.w), pixel = __float_as_uint(ap4.w);
+    const bool occl = hb.z != 0;
     bool new_ray = false;
 
-    auto ldL = [&]() { return mk3(st.L[0][i], st.L[1][i], st.L[2][i]); };
+    // finish the current sample of this slot's pixel (include/integrators.h:128-137)
     auto finish = [&](V3 result) {
       if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
-      V3 acc = mk3(st.acc[0][i], st.acc[1][i], st.acc[2][i]) + result;
+      acc = acc + result;
       n_samples++;
       f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
-      const uint32_t s = st.s[i] + 1;
-      st.s[i] = s;
+      s = s + 1;
       if (s == args.samples) {
-        acc = acc / (float)args.samples;
+        const V3 px_col = acc / (float)args.samples;
         uint32_t px, py;
-        wf_pixel_xy(args, sc.cam, st.pixel[i], px, py);
+        wf_pixel_xy(args, sc.cam, pixel, px, py);
         const size_t image_index = px + ((size_t)(H - 1 - py) * W);
         float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
-        o[0] = acc.x;
-        o[1] = acc.y;
-        o[2] = acc.z;
+        o[0] = px_col.x;
+        o[1] = px_col.y;
+        o[2] = px_col.z;
         f &= ~WF_ALIVE;
-      } else {
-        st.acc[0][i] = acc.x;
-        st.acc[1][i] = acc.y;
-        st.acc[2][i] = acc.z;
       }
     };
 
     if (valid && (f & WF_IN_PATH)) {
       // pending shadow ray of the last bounce (mis_integrator.cpp:64-78)
-      V3 L = mk3(0.f);
-      if (MIS) {
-        L = ldL();
-        if ((f & WF_NEE) && (f & WF_NEE_VALID) && !st.occl[i]) L = L + xyz(st.nee_c[i]);
-      }
+      V3 L = xyz(L4);
+      if (MIS && (f & WF_NEE) && (f & WF_NEE_VALID) && !occl) L = L + xyz(cp4);
       if (f & WF_END) {
-        finish(MIS ? L : xyz(st.nee_c[i]));
+        finish(MIS ? L : xyz(cp4));
       } else {
-        const float4 o4 = st.ray_o[i], d4 = st.ray_d[i], h0 = st.hit0[i];
         Ray ray;
         ray.o = xyz(o4);
         ray.dir = xyz(d4);
@@ -419,39 +449,37 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
         ray.cone.spread_angle = d4.w;
         PreHit ph;
         ph.leaf_slot = __float_as_int(h0.x);
+        const V3 thr = xyz(thr4);
+        const float last_pdf = cp4.w;
         if (ph.leaf_slot < 0) {
           // miss (mis_integrator.cpp:36-38,173-185; mat_integrator.cpp:24-27)
           V3 bg = background_emit(sc, ray.dir, ray.cone);
           if (!MIS) {
-            finish(xyz(st.thr[i]) * bg);
+            finish(thr * bg);
           } else if (f & WF_FIRST) {
             finish(bg);
           } else {
-            const float last_pdf = st.last_pdf[i];
             if (last_pdf != 0 && sc.bg.emissive) {
               float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
               float mis_weight = balance_heuristic(last_pdf, light_pdf);
-              L = L + xyz(st.thr[i]) * mis_weight * bg;
+              L = L + thr * mis_weight * bg;
             }
             finish(L);
           }
         } else {
           const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
           if (mat_is_emissive(nmat)) {
-            const float2 h1 = st.hit1[i];
             ph.e0 = h0.z;
             ph.e1 = h0.w;
-            ph.e2 = h1.x;
-            ph.inv_det = h1.y;
+            ph.e2 = __uint_as_float(hb.x);
+            ph.inv_det = __uint_as_float(hb.y);
             const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
             V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
             if (!MIS) {
-              finish(xyz(st.thr[i]) * emit);  // sample_mat -> nullopt: throughput * emitted
+              finish(thr * emit);  // sample_mat -> nullopt: throughput * emitted
             } else if (f & WF_FIRST) {
               finish(emit);
             } else {
-              const V3 thr = xyz(st.thr[i]);
-              const float last_pdf = st.last_pdf[i];
               if (last_pdf != 0) {
                 // ray.o is the previous hit point, ray.dir the sampled direction
                 float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
@@ -468,14 +496,9 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
           } else {
             // base Material under mis: the Russian-roulette draw still happens before
             // sample_mat -> nullopt ends the path (mis_integrator.cpp:154-167, 83-88)
-            if (!(f & WF_FIRST) && st.d[i] > 5) {
-              Pcg32 r;
-              r.state = st.rng[i];
-              r.inc = 1;
-              float4 t4 = st.thr[i];
-              V3 t = xyz(t4);
-              russian_roulette(r, t4.w, t);
-              st.rng[i] = r.state;
+            if (!(f & WF_FIRST) && d > 5) {
+              V3 t = thr;
+              russian_roulette(rng, thr4.w, t);
             }
             finish(L);
           }
@@ -491,8 +514,8 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
         uint32_t pbase = 0;
         if (lane == (uint32_t)(__ffs(m) - 1)) {
           // no atomic once the frame is handed out
-          if (*reinterpret_cast<volatile uint32_t*>(&c->next_pixel) < args.n_local_pixels)
-            pbase = atomicAdd(&c->next_pixel, (uint32_t)__popc(m));
+          if (*reinterpret_cast<volatile uint32_t*>(st.next_pixel) < args.n_local_pixels)
+            pbase = atomicAdd(st.next_pixel, (uint32_t)__popc(m));
           else
             pbase = args.n_local_pixels;
         }
@@ -503,7 +526,7 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
           uint32_t px = 0, py = 0;
           bool got = false;
           while (p < args.n_local_pixels && !(got = wf_pixel_xy(args, sc.cam, p, px, py)))
-            p = atomicAdd(&c->next_pixel, 1u);
+            p = atomicAdd(st.next_pixel, 1u);
           if (got) {
             if (!MIS && args.depth == 0) {
               // material_integrator with depth 0 never traces: every sample is vec3(0)
@@ -512,12 +535,10 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
               o[0] = o[1] = o[2] = 0.f;
               n_samples += args.samples;
             } else {
-              Pcg32 r;
-              pcg32_seed(r, px + ((size_t)(H - 1 - py) * W), 0);
-              st.rng[i] = r.state;
-              st.acc[0][i] = st.acc[1][i] = st.acc[2][i] = 0.f;
-              st.s[i] = 0;
-              st.pixel[i] = p;
+              pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), 0);
+              acc = mk3(0.f);
+              s = 0;
+              pixel = p;
               f = WF_ALIVE;
             }
           }
@@ -527,25 +548,25 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
     // camera ray of the next sample (include/integrators.h:119-123); rand2 gets the first draw
     if (f & WF_ALIVE) {
       uint32_t px, py;
-      wf_pixel_xy(args, sc.cam, st.pixel[i], px, py);
-      Pcg32 r;
-      r.state = st.rng[i];
-      r.inc = 1;
-      V2 off = random_x_y_r2(px + py + st.s[i]);
-      float rand2 = rand_float(r);
-      float rand1 = rand_float(r);
+      wf_pixel_xy(args, sc.cam, pixel, px, py);
+      V2 off = random_x_y_r2(px + py + s);
+      float rand2 = rand_float(rng);
+      float rand1 = rand_float(rng);
       Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
-      st.rng[i] = r.state;
-      st.ray_o[i] = f4(cam.o, cam.cone.cone_width);
-      st.ray_d[i] = f4(cam.dir, cam.cone.spread_angle);
-      st.thr[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-      st.last_pdf[i] = 0.f;
-      st.d[i] = 0;
-      st.L[0][i] = st.L[1][i] = st.L[2][i] = 0.f;
+      stg4(&st.ray[i].o_w, f4(cam.o, cam.cone.cone_width));
+      stg4(&st.ray[i].d_s, f4(cam.dir, cam.cone.spread_angle));
       f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
       new_ray = true;
     }
-    if (valid) st.flags[i] = f;
+    if (valid) {
+      // path: throughput 1, eta_scale 1, d 0; nee: last_pdf 0; pix: L 0, s, acc, pixel
+      stg4(&st.path[i].thr_eta, make_float4(1.f, 1.f, 1.f, 1.f));
+      __stcg(reinterpret_cast<uint4*>(&st.path[i].rng),
+             make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), f, 0u));
+      stg4(&st.nee[i].c_pdf, make_float4(0.f, 0.f, 0.f, 0.f));
+      stg4(&st.pix[i].L_s, make_float4(0.f, 0.f, 0.f, __uint_as_float(s)));
+      stg4(&st.pix[i].acc_pixel, f4(acc, __uint_as_float(pixel)));
+    }
 
     const bool want[1] = {new_ray};
     QwAppend<1> ap;
@@ -608,7 +629,7 @@ __global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_
 qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
                 const __grid_constant__ WfArgs args, const uint32_t parity) {
   constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
-  __shared__ uint32_t s_cnt[4], s_base[4];
+  __shared__ uint32_t s_cnt[3], s_base[3];
   QwCounters* c = st.cnt;
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
@@ -617,61 +638,66 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   const uint32_t* __restrict__ q = st.q_shade[CLASS];
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
-    if (tid < 4) s_cnt[tid] = 0;
+    if (tid < 3) s_cnt[tid] = 0;
     __syncthreads();
     const uint32_t item = base + tid;
-    bool want_closest = false, want_shadow = false, want_end_now = false, want_end_next = false;
-    uint32_t j = 0;
+    bool want_closest = false, want_shadow = false, want_end = false;
     bool go = item < n;
-    uint32_t fj = 0;
-    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t j = go ? q[item] : 0u;
+    // the whole slot state in one round trip
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), o4 = t4, d4 = t4, h0 = t4, cp4 = t4, L4 = t4;
+    uint4 pa1 = make_uint4(0, 0, 0, 0), hb = pa1;
+    if (go) {
+      t4 = ldg4(&st.path[j].thr_eta);
+      pa1 = ldg4u(&st.path[j].rng);
+      o4 = ldg4(&st.ray[j].o_w);
+      d4 = ldg4(&st.ray[j].d_s);
+      h0 = ldg4(&st.hit[j].h0);
+      hb = ldg4u(&st.hit[j].h1);
+      if (MIS) {
+        cp4 = ldg4(&st.nee[j].c_pdf);
+        L4 = ldg4(&st.pix[j].L_s);
+      }
+    }
+    uint32_t fj = pa1.z, d = pa1.w;
     Pcg32 rng;
-    rng.state = 0;
+    rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
     rng.inc = 1;
     if (go) {
-      j = q[item];
-      fj = st.flags[j];
-      t4 = st.thr[j];
-      rng.state = st.rng[j];
       if (MIS) {
         // what mis_integrator does between the BVH::hit that found this surface and the next
         // loop body: the shadow ray of the previous bounce (mis_integrator.cpp:64-78), Russian
         // roulette (:154-167) and the loop condition d < depth
-        if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && !st.occl[j]) {
-          const float4 nc = st.nee_c[j];
-          st.L[0][j] += nc.x;
-          st.L[1][j] += nc.y;
-          st.L[2][j] += nc.z;
+        if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && hb.z == 0) {
+          L4.x += cp4.x;
+          L4.y += cp4.y;
+          L4.z += cp4.z;
+          stg4(&st.pix[j].L_s, L4);
         }
         fj &= ~(WF_NEE | WF_NEE_VALID);
         bool go_on = true;
-        const uint32_t d = st.d[j];
-        uint32_t dn = d;
         if (!(fj & WF_FIRST)) {
           if (d > 5) {
             V3 t = xyz(t4);
             go_on = russian_roulette(rng, t4.w, t);
             if (go_on) t4 = f4(t, t4.w);
           }
-          dn = d + 1;
+          d = d + 1;
         }
         fj &= ~WF_FIRST;
-        if (!go_on || dn >= args.depth) {
-          // the path returns bounce_result: the END kernel of this iteration finishes the sample
-          st.rng[j] = rng.state;
-          st.flags[j] = fj | WF_END;
-          want_end_now = true;
+        if (!go_on || d >= args.depth) {
+          // the path returns bounce_result: the next END launch finishes the sample
+          fj |= WF_END;
+          __stcg(reinterpret_cast<uint4*>(&st.path[j].rng),
+                 make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
+          want_end = true;
           go = false;
-        } else if (dn != d) {
-          st.d[j] = dn;
         }
       } else {
         fj &= ~WF_FIRST;
       }
     }
     if (go) {
-      const float4 o4 = st.ray_o[j], d4 = st.ray_d[j], h0 = st.hit0[j];
-      const float2 h1 = st.hit1[j];
       Ray ray;
       ray.o = xyz(o4);
       ray.dir = xyz(d4);
@@ -683,15 +709,19 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       ph.leaf_slot = __float_as_int(h0.x);
       ph.e0 = h0.z;
       ph.e1 = h0.w;
-      ph.e2 = h1.x;
-      ph.inv_det = h1.y;
+      ph.e2 = __uint_as_float(hb.x);
+      ph.inv_det = __uint_as_float(hb.y);
       const HitInfo hit = wf_hit_info(sc, ph.leaf_slot, ph, ray);
       const vimg_material& mat = sc.materials[hit.mat];
       V3 thr = xyz(t4);
+      float eta_scale = t4.w;
       bool nsb = (fj & WF_NSB) != 0;
       float hit_dist = length(ray.o - hit.hit_p);
       float surface_spread_angle
           = spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s);
+      // records written back at the end (whole sectors)
+      float4 nee_wi = make_float4(0.f, 0.f, 0.f, 0.f), nee_c = nee_wi;
+      float4 new_o = f4(hit.hit_p, o4.w), new_d = d4;  // origin of the shadow ray and of the next ray
 
       if (MIS) {
         // ---- mis_integrator.cpp:45-117 at `hit` ----
@@ -707,7 +737,6 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         ScatterInfo sm;
         const bool scattered = cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sm);
         RayCone cone = ray.cone;
-        float eta_scale = t4.w;
         if (scattered) {
           if (!sm.is_specular) nsb = true;
           if (sm.eta != 0.f) {
@@ -744,20 +773,18 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         if (nsb) fj |= WF_NSB;
         if (nee) {
           fj |= WF_NEE | (nee_valid ? WF_NEE_VALID : 0u);
-          st.nee_wi[j] = f4(li.wi, li.dist);
-          st.nee_c[j] = f4(contrib, 0.f);
+          nee_wi = f4(li.wi, li.dist);
+          nee_c = f4(contrib, 0.f);
           want_shadow = true;
         }
         if (!scattered || is_nan(mat_sample_pdf)) {
           fj |= WF_END;  // return bounce_result (after the pending shadow ray)
-          st.ray_o[j] = f4(hit.hit_p, o4.w);  // origin of the shadow ray
-          want_end_next = true;
+          want_end = true;
         } else {
           thr = thr * (mat_sample_eval / mat_sample_pdf);
-          st.thr[j] = f4(thr, eta_scale);
-          st.last_pdf[j] = mat_sample_pdf;
-          st.ray_o[j] = f4(hit.hit_p, cone.cone_width);  // origin of the shadow ray and of the next ray
-          st.ray_d[j] = f4(sm.wo, cone.spread_angle);
+          nee_c.w = mat_sample_pdf;  // last_pdf
+          new_o.w = cone.cone_width;
+          new_d = f4(sm.wo, cone.spread_angle);
           want_closest = true;
         }
       } else {
@@ -766,13 +793,12 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         ScatterInfo sr;
         fj &= ~(WF_NSB | WF_END);
         if (!cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sr)) {
-          st.nee_c[j] = f4(thr * emitted_col, 0.f);
+          nee_c = f4(thr * emitted_col, 0.f);
           fj |= WF_END;
-          want_end_now = true;
+          want_end = true;
         } else {
           if (!sr.is_specular) nsb = true;
           RayCone cone;
-          float eta_scale = t4.w;
           if (sr.eta != 0.f) {
             eta_scale /= (sr.eta * sr.eta);
             cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo);
@@ -780,41 +806,44 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
           }
           thr = thr * (emitted_col + cls_eval_div_pdf<CLASS>(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
-          const uint32_t d = st.d[j];
           bool go_on = true;
           if (d > 5) go_on = russian_roulette(rng, eta_scale, thr);
           if (!go_on || d + 1 >= args.depth) {
             // `break`, or the for loop runs out before the next BVH::hit: return vec3(0)
-            st.nee_c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            nee_c = make_float4(0.f, 0.f, 0.f, 0.f);
             fj |= WF_END;
-            want_end_now = true;
+            want_end = true;
           } else {
-            st.thr[j] = f4(thr, eta_scale);
-            st.ray_o[j] = f4(hit.hit_p, cone.cone_width);
-            st.ray_d[j] = f4(sr.wo, cone.spread_angle);
-            st.d[j] = d + 1;
+            new_o.w = cone.cone_width;
+            new_d = f4(sr.wo, cone.spread_angle);
+            d = d + 1;
             want_closest = true;
           }
         }
         if (nsb) fj |= WF_NSB;
       }
-      st.rng[j] = rng.state;
-      st.flags[j] = fj;
+      stg4(&st.path[j].thr_eta, f4(thr, eta_scale));
+      __stcg(reinterpret_cast<uint4*>(&st.path[j].rng),
+             make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
+      stg4(&st.ray[j].o_w, new_o);
+      stg4(&st.ray[j].d_s, new_d);
+      stg4(&st.nee[j].wi_dist, nee_wi);
+      stg4(&st.nee[j].c_pdf, nee_c);
     }
 
-    const bool want[4] = {want_closest, want_shadow, want_end_now, want_end_next};
-    QwAppend<4> ap;
+    // every queue written here belongs to the NEXT iteration, so this launch is independent of
+    // the END launch of the same iteration and the two run concurrently
+    const bool want[3] = {want_closest, want_shadow, want_end};
+    QwAppend<3> ap;
     ap.count(s_cnt, want, lane, lane_lt);
     __syncthreads();
     if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_closest[parity ^ 1u], s_cnt[0]);
     if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_shadow[parity ^ 1u], s_cnt[1]);
-    if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity], s_cnt[2]);
-    if (tid == 3 && s_cnt[3]) s_base[3] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[3]);
+    if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[2]);
     __syncthreads();
     if (want_closest) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = j;
     if (want_shadow) st.q_shadow[parity ^ 1u][s_base[1] + ap.off[1]] = j;
-    if (want_end_now) st.q_end[parity][s_base[2] + ap.off[2]] = j;
-    if (want_end_next) st.q_end[parity ^ 1u][s_base[3] + ap.off[3]] = j;
+    if (want_end) st.q_end[parity ^ 1u][s_base[2] + ap.off[2]] = j;
   }
 }
 

@@ -10,6 +10,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 INTEGRATORS = {"s_normal": 0, "g_normal": 1, "material": 2, "mis": 3}
 UINT32_MAX = 0xFFFFFFFF  # "depth": -1 in a scene file (json_scene.cpp:186,193)
 FLAG_COUNTERS = 1
+FLAG_PIPELINE_BLOCK = 2   # persistent block-local wavefront kernel
+FLAG_PIPELINE_QUEUE = 4   # multi-kernel queue wavefront (default)
+FLAG_STAGE_TIMES = 8      # queue wavefront: serial launches, per-stage device times in the stats
+STAGES = ("trace", "classify", "shade_principled", "shade_lambertian", "shade_dielectric", "end")
+PIPELINES = {None: 0, "block": FLAG_PIPELINE_BLOCK, "queue": FLAG_PIPELINE_QUEUE}
 
 
 class VimgError(RuntimeError):
@@ -37,10 +42,14 @@ class RenderStats(C.Structure):
                 ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("nan_samples", C.c_uint64), ("samples", C.c_uint64),
                 ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("stage_launches", C.c_uint32 * 6),
+                ("stage_ms", C.c_double * 6)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["stage_ms"] = dict(zip(STAGES, self.stage_ms))
+        d["stage_launches"] = dict(zip(STAGES, self.stage_launches))
+        return d
 
 
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
@@ -189,11 +198,12 @@ class Scene:
     def device_bytes(self):
         return int(self._lib.vimg_scene_device_bytes(self._h))
 
-    def _params(self, func, samples, depth, rank, n_ranks, counters):
-        return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks,
-                            FLAG_COUNTERS if counters else 0)
+    def _params(self, func, samples, depth, rank, n_ranks, counters, pipeline=None, stage_times=False):
+        flags = (FLAG_COUNTERS if counters else 0) | PIPELINES[pipeline] | (FLAG_STAGE_TIMES if stage_times else 0)
+        return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks, flags)
 
-    def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None):
+    def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None,
+                         pipeline=None, stage_times=False):
         """Mirror of scene_integrator<F>() (include/integrators.h:36-153).
 
         Returns (image float32 [H, W, 3] in HOST memory, row 0 = top; stats dict).
@@ -203,15 +213,16 @@ class Scene:
             out = np.empty((self.height, self.width, 3), np.float32)
         assert out.dtype == np.float32 and out.size == self.height * self.width * 3
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times)
         _check(self._lib, self._lib.vimg_render(self._h, C.byref(p), out.ctypes.data, C.byref(st)),
                "vimg_render")
         return out, st.as_dict()
 
-    def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None):
+    def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None,
+                      pipeline=None, stage_times=False):
         """Render and leave the frame in HBM.  Returns (device pointer, stats dict)."""
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times)
         dev = C.c_void_p()
         _check(self._lib, self._lib.vimg_render_device(self._h, C.byref(p), C.byref(dev), stream,
                                                        C.byref(st)), "vimg_render_device")
@@ -229,10 +240,10 @@ class Scene:
                                       "data": (dev_ptr, False), "version": 3}
         return torch.as_tensor(h, device=f"cuda:{self.device}")
 
-    def trace_pixel(self, func, x, y, samples, depth):
+    def trace_pixel(self, func, x, y, samples, depth, pipeline=None):
         """Mirror of trace_pixel<F>() (include/integrators.h:181-220); y = 0 is the bottom row."""
         out = np.empty(3, np.float32)
-        p = self._params(func, samples, depth, 0, 1, False)
+        p = self._params(func, samples, depth, 0, 1, False, pipeline)
         _check(self._lib, self._lib.vimg_trace_pixel(self._h, C.byref(p), x, y, out.ctypes.data),
                "vimg_trace_pixel")
         return out
