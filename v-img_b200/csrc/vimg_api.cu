@@ -55,12 +55,15 @@ struct QwPool {
   void* mem = nullptr;
   uint32_t capacity = 0;
   QwCounters* h_cnt = nullptr;  // pinned: queue-counter snapshots (termination test)
+  uint32_t* h_next_pixel = nullptr;  // pinned: shared pixel counter at the same moments
   cudaStream_t main = nullptr, side[2] = {nullptr, nullptr};  // shade launches run beside END
   cudaEvent_t snap[2] = {nullptr, nullptr}, fork = nullptr, join[2] = {nullptr, nullptr}, done = nullptr;
   bool finished = false;
+  int trace_grid = 1, item_grid = 1;  // current launch sizes (shrink as the pool drains)
   void destroy() {
     if (mem) cudaFree(mem);
     if (h_cnt) cudaFreeHost(h_cnt);
+    if (h_next_pixel) cudaFreeHost(h_next_pixel);
     if (main) cudaStreamDestroy(main);
     for (int k = 0; k < 2; ++k) {
       if (side[k]) cudaStreamDestroy(side[k]);
@@ -400,6 +403,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
   if (!pool.h_cnt) {
     CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&pool.h_cnt), 2 * sizeof(QwCounters)));
+    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&pool.h_next_pixel), 2 * sizeof(uint32_t)));
     CU_TRY(cudaStreamCreateWithFlags(&pool.main, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
       CU_TRY(cudaStreamCreateWithFlags(&pool.side[k], cudaStreamNonBlocking));
@@ -433,7 +437,7 @@ static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
   for (int k = 0; k < 2; ++k) o_qc[k] = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qs[k] = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qe[k] = carve(N * 4);
-  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) o_qsh[k] = carve(N * 4);
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) o_qsh[k] = carve(N * 8);
   const size_t o_cnt = carve(sizeof(QwCounters));
   CU_TRY(cudaMalloc(&pool.mem, off));
   pool.capacity = n;
@@ -448,7 +452,7 @@ static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
   for (int k = 0; k < 2; ++k) q.q_closest[k] = reinterpret_cast<uint32_t*>(b + o_qc[k]);
   for (int k = 0; k < 2; ++k) q.q_shadow[k] = reinterpret_cast<uint32_t*>(b + o_qs[k]);
   for (int k = 0; k < 2; ++k) q.q_end[k] = reinterpret_cast<uint32_t*>(b + o_qe[k]);
-  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) q.q_shade[k] = reinterpret_cast<uint32_t*>(b + o_qsh[k]);
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) q.q_shade[k] = reinterpret_cast<uint2*>(b + o_qsh[k]);
   q.cnt = reinterpret_cast<QwCounters*>(b + o_cnt);
   return VIMG_OK;
 }
@@ -513,7 +517,7 @@ __global__ void qw_iota_kernel(uint32_t* q, uint32_t n) {
 }
 
 struct QwLaunchCfg {
-  int trace_grid, item_grid;
+  int trace_grid, item_grid;  // full-size grids
   bool concurrent;
   uint32_t class_mask;
 };
@@ -527,9 +531,9 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
   cudaStream_t st = pool.main;
   uint32_t launches = 0;
   if (it > 0) {
-    qw_trace_kernel<COUNT><<<cfg.trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
+    qw_trace_kernel<COUNT><<<pool.trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
     prof.mark(1);
-    qw_classify_kernel<<<cfg.item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
+    qw_classify_kernel<<<pool.item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
     prof.mark(2);
     // shade launches only feed the next iteration, END only consumes what classify and the
     // previous shade launches queued: fork them onto side streams, join before the next trace
@@ -542,17 +546,17 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
       cudaStreamWaitEvent(sl, pool.fork, 0);
     }
     if (cfg.class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<cfg.item_grid, QW_THREADS, 0, sp>>>(s->d, q, w, parity);
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<pool.item_grid, QW_THREADS, 0, sp>>>(s->d, q, w, parity);
       prof.mark(3);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_LAMBERT)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<cfg.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<pool.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
       prof.mark(4);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<cfg.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<pool.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
       prof.mark(5);
       ++launches;
     }
@@ -562,7 +566,7 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
     }
     launches += 2;
   }
-  qw_end_kernel<INTEGRATOR><<<cfg.item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
+  qw_end_kernel<INTEGRATOR><<<pool.item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
   prof.mark(6);
   ++launches;
   if (cfg.concurrent && it > 0) {
@@ -600,6 +604,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   for (uint32_t p = 0; p < n_pools; ++p) {
     QwPool& pool = s->qw[p];
     pool.finished = false;
+    pool.trace_grid = 0;  // set below
     if (p == 0) CU_TRY(cudaEventRecord(start, caller));
     CU_TRY(cudaStreamWaitEvent(pool.main, start, 0));
     CU_TRY(cudaMemsetAsync(pool.st.path, 0, (size_t)per_pool * sizeof(QwPath), pool.main));  // flags = 0: no pixel yet
@@ -619,6 +624,11 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8));
   cfg.concurrent = concurrent;
   cfg.class_mask = s->class_mask;
+  for (uint32_t p = 0; p < n_pools; ++p) {
+    s->qw[p].trace_grid = cfg.trace_grid;
+    s->qw[p].item_grid = cfg.item_grid;
+  }
+  const bool shrink = env_u32("VIMG_QW_SHRINK", 1) != 0;
   const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
   uint32_t launches = n_pools, it = 0;
   prof.st = s->qw[0].main;
@@ -634,6 +644,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
       QwPool& pool = s->qw[p];
       if (pool.finished) continue;
       CU_TRY(cudaMemcpyAsync(&pool.h_cnt[b & 1], pool.st.cnt, sizeof(QwCounters), cudaMemcpyDeviceToHost, pool.main));
+      CU_TRY(cudaMemcpyAsync(&pool.h_next_pixel[b & 1], s->d_qw_next_pixel, sizeof(uint32_t), cudaMemcpyDeviceToHost, pool.main));
       CU_TRY(cudaEventRecord(pool.snap[b & 1], pool.main));
     }
     if (timeline) {
@@ -657,6 +668,13 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
           pool.finished = true;  // batch b only ran empty iterations for this pool
         else
           all_done = false;
+        if (shrink && pool.h_next_pixel[(b - 1) & 1] >= w.n_local_pixels) {
+          // every pixel is handed out: the slots alive now bound every later queue of this pool,
+          // so the launches shrink with them (kernels stride over their queues, any grid is valid)
+          const uint64_t bound = (uint64_t)hc.n_closest[par] + hc.n_end[par];
+          pool.item_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.item_grid, (bound + QW_THREADS - 1) / QW_THREADS));
+          pool.trace_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.trace_grid, (2 * bound + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS));
+        }
       }
       if (timeline) tl_live.push_back(live);
       if (all_done) break;

@@ -87,7 +87,7 @@ struct QwState {
   uint32_t* q_closest[2];
   uint32_t* q_shadow[2];
   uint32_t* q_end[2];
-  uint32_t* q_shade[WF_NUM_CLASSES];
+  uint2* q_shade[WF_NUM_CLASSES];  // {slot, leaf record of the hit}: the shade launch fetches both at once
   QwCounters* cnt;
   uint32_t* next_pixel;  // next local pixel number to hand out (shared by all pools of a frame)
 };
@@ -335,9 +335,10 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
     __syncthreads();
     const uint32_t item = base + tid;
     uint32_t cls = WF_CLASS_NONE + 1, j = 0;  // NONE + 1: no item
+    int32_t leaf_slot = -1;
     if (item < n) {
       j = q[item];
-      const int32_t leaf_slot = __float_as_int(__ldcg(&st.hit[j].h0.x));
+      leaf_slot = __float_as_int(__ldcg(&st.hit[j].h0.x));
       cls = WF_CLASS_NONE;
       if (leaf_slot >= 0) {
         const uint32_t lc = sc.leaf_class[leaf_slot];
@@ -356,7 +357,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
       if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
     }
     __syncthreads();
-    if (cls < WF_NUM_CLASSES) st.q_shade[cls][s_base[cls] + ap.off[cls]] = j;
+    if (cls < WF_NUM_CLASSES) st.q_shade[cls][s_base[cls] + ap.off[cls]] = make_uint2(j, (uint32_t)leaf_slot);
     else if (cls == WF_CLASS_NONE) st.q_end[parity][s_base[WF_NUM_CLASSES] + ap.off[WF_NUM_CLASSES]] = j;
     __syncthreads();
   }
@@ -635,7 +636,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t n = c->n_shade[CLASS];
-  const uint32_t* __restrict__ q = st.q_shade[CLASS];
+  const uint2* __restrict__ q = st.q_shade[CLASS];
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
     if (tid < 3) s_cnt[tid] = 0;
@@ -643,11 +644,20 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     const uint32_t item = base + tid;
     bool want_closest = false, want_shadow = false, want_end = false;
     bool go = item < n;
-    const uint32_t j = go ? q[item] : 0u;
-    // the whole slot state in one round trip
+    const uint2 qi = go ? q[item] : make_uint2(0u, 0u);
+    const uint32_t j = qi.x;
+    // the whole slot state and the leaf record of the hit in one round trip
     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), o4 = t4, d4 = t4, h0 = t4, cp4 = t4, L4 = t4;
     uint4 pa1 = make_uint4(0, 0, 0, 0), hb = pa1;
+    DLeafPrim lp;
     if (go) {
+      {
+        const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + qi.y);
+        float4* dst = reinterpret_cast<float4*>(&lp);
+        dst[0] = __ldg(rec);
+        dst[1] = __ldg(rec + 1);
+        dst[2] = __ldg(rec + 2);
+      }
       t4 = ldg4(&st.path[j].thr_eta);
       pa1 = ldg4u(&st.path[j].rng);
       o4 = ldg4(&st.ray[j].o_w);
@@ -711,7 +721,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       ph.e1 = h0.w;
       ph.e2 = __uint_as_float(hb.x);
       ph.inv_det = __uint_as_float(hb.y);
-      const HitInfo hit = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+      const HitInfo hit = wf_hit_info(sc, lp, ph, ray);
       const vimg_material& mat = sc.materials[hit.mat];
       V3 thr = xyz(t4);
       float eta_scale = t4.w;

@@ -95,10 +95,13 @@ VD uint32_t wf_leaf_material(const DScene& sc, int32_t leaf_slot) {
   return (lp->flags & VIMG_LEAF_SPHERE) ? sc.spheres[pr.a].material : sc.meshes[pr.a].material;
 }
 
-VD HitInfo wf_hit_info(const DScene& sc, int32_t leaf_slot, const PreHit& ph, const Ray& ray) {
-  const DLeafPrim lp = sc.leaf_prims[leaf_slot];
+VD HitInfo wf_hit_info(const DScene& sc, const DLeafPrim& lp, const PreHit& ph, const Ray& ray) {
   if (lp.flags & VIMG_LEAF_SPHERE) return sphere_hit_info(sc, lp, ray);
   return triangle_hit_info(sc, lp, ph);
+}
+VD HitInfo wf_hit_info(const DScene& sc, int32_t leaf_slot, const PreHit& ph, const Ray& ray) {
+  const DLeafPrim lp = sc.leaf_prims[leaf_slot];
+  return wf_hit_info(sc, lp, ph, ray);
 }
 
 VD uint32_t wf_material_class(uint32_t mat_type) {
