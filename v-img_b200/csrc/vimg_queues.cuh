@@ -39,8 +39,11 @@ namespace vimg {
 #ifndef QW_REFILL_MIN
 #define QW_REFILL_MIN 12  // refill a warp's idle lanes once at least this many are idle
 #endif
+#ifndef QW_INNER_MIN_LANES
+#define QW_INNER_MIN_LANES 8  // leave the inner-node loop once fewer lanes than this are still in it
+#endif
 #ifndef QW_CHUNK
-#define QW_CHUNK 128  // rays a warp takes from the global cursor with one atomic
+#define QW_CHUNK 64  // rays a warp takes from the global cursor with one atomic
 #endif
 #define QW_THREADS 256  // classify / shade / end block size
 
@@ -261,6 +264,13 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             sec_child = t;
           }
           stack[sp++] = first_child;
+#ifdef QW_PREFETCH_PUSH
+          // the pushed node is visited later: start moving its record towards the SM now
+          if (first_child.y == 0)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.pairs + ((first_child.x - 1u) >> 1)));
+          else
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.leaf_prims + first_child.x));
+#endif
         }
         cur = sec_child;
       } else if (h1) {
@@ -271,8 +281,10 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         have = false;
         done = true;
       }
+      // most lanes of the warp wait with a leaf (or for a new ray): stop descending, serve them
+      if (QW_INNER_MIN_LANES > 0 && __popc(__activemask()) < QW_INNER_MIN_LANES) break;
     }
-    if (have) {  // leaf: primitives in obj_indices order, the last success wins
+    if (have && cur.y != 0) {  // leaf: primitives in obj_indices order, the last success wins
       if (COUNT) pc.trav.leaf++;
       for (uint32_t i = 0; i < cur.y; ++i) {
         const uint32_t ls = cur.x + i;
