@@ -200,9 +200,12 @@ def cuda_line(w, args):
     integ, spp, depth = w["integrator"], w["spp"], w["depth"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    streams = 1 if args.pipeline == "block" else max(1, args.spp_streams)
+
     def step():
         """kernel(s) on this rank's tiles (+ NCCL reduce to rank 0); frame stays in HBM"""
-        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world, pipeline=args.pipeline)
+        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world, pipeline=args.pipeline,
+                                      spp_streams=streams)
         if world > 1:
             dist.reduce(scene.frame_tensor(ptr), dst=0, op=dist.ReduceOp.SUM)
         return ptr, st
@@ -253,7 +256,7 @@ def cuda_line(w, args):
     for _ in range(e2e_steps):
         sc2 = vimg.Scene(desc.ptr, device=local_rank)
         _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np,
-                                      pipeline=args.pipeline)
+                                      pipeline=args.pipeline, spp_streams=streams)
         h2d = sc2.device_bytes
         sc2.close()
         e2e_rays += st2["rays_closest"] + st2["rays_shadow"]
@@ -274,7 +277,8 @@ def cuda_line(w, args):
     # ---- roofline of the dominant kernel -----------------------------------------------------
     # counted pass (untimed): per-ray algorithmic cost, in the reference's layout
     c_spp = min(spp, 16)
-    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True, pipeline=args.pipeline)
+    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True, pipeline=args.pipeline,
+                                 spp_streams=min(streams, c_spp))
     c_rays = cst["rays_closest"] + cst["rays_shadow"]
     bytes_per_ray = sum(BYTES[k] * cst[k] for k in BYTES) / c_rays
     flops_per_ray = sum(FLOPS[k] * cst[k] for k in FLOPS) / c_rays
@@ -290,7 +294,8 @@ def cuda_line(w, args):
         # measure the overlap, not the kernel.
         t_spp = min(spp, 64)
         flush.zero_()
-        _, tst = scene.render_device(integ, t_spp, depth, rank=0, n_ranks=1, pipeline="queue", stage_times=True)
+        _, tst = scene.render_device(integ, t_spp, depth, rank=0, n_ranks=1, pipeline="queue", stage_times=True,
+                                     spp_streams=min(streams, t_spp))
         t_rays = tst["rays_closest"] + tst["rays_shadow"]
         n_launch = max(tst["stage_launches"]["trace"], 1)
         launch_s = tst["stage_ms"]["trace"] / 1e3 / n_launch
@@ -316,7 +321,14 @@ def cuda_line(w, args):
         "data": "synthetic", "impl": "cuda",
         "spp_mpix_per_s": samples_per_step * args.steps / secs / 1e6,
         "rays_per_sample": rays / (samples_per_step * args.steps),
-        "config": config_of(w, world, {"pipeline": args.pipeline or "queue (library default)"}),
+        "config": config_of(w, world, {
+            "pipeline": args.pipeline or "queue (library default)",
+            "spp_streams": streams,
+            "rng": ("the reference's one PCG stream per pixel: image bit-identical to the CPU renderer"
+                    if streams == 1 else
+                    f"{streams} sample ranges per pixel, each with its own PCG stream (initseq = range), "
+                    "reference R2 jitter index: image within the stated relMSE tolerance of the CPU "
+                    "renderer (tests/test_gpu_streams.py); --spp-streams 1 gives the bit-identical image")}),
         "clocks": clocks,
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": w["width"] * w["height"] * 12,
@@ -363,6 +375,9 @@ def main():
     ap.add_argument("--pipeline", default=None, choices=["queue", "block"],
                     help="material / mis pipeline (default: the library's, the queue wavefront)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's spp (invalidates the number)")
+    ap.add_argument("--spp-streams", type=int, default=16,
+                    help="sample ranges per pixel with their own RNG streams (vimg_render_params.spp_streams); "
+                         "1 = the reference's single stream per pixel, bit-identical image")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     w = workload_info(args.workload, args.spp)

@@ -226,6 +226,16 @@ typedef struct vimg_render_params {
   uint32_t rank;         /* this process renders tiles rank, rank+n_ranks, ... */
   uint32_t n_ranks;      /* 0 or 1 => whole frame                            */
   uint32_t flags;        /* VIMG_FLAG_*                                      */
+  uint32_t spp_streams;  /* material / mis, queue wavefront only.  0 or 1: the reference's ONE PCG
+                            stream per pixel carried over all its samples (integrators.h:116-131),
+                            images bit-identical to the CPU renderer.  K > 1: the pixel's samples are
+                            split into K contiguous ranges [k*spp/K, (k+1)*spp/K), range k drawing
+                            from its own PCG stream (initstate = image_index, initseq = k; range 0
+                            starts exactly like the reference) with the reference's R2 jitter index
+                            x+y+s, so K paths per pixel are in flight instead of one.  Same estimator,
+                            different random numbers: the image agrees with the reference within the
+                            stated relMSE tolerance, not bit for bit.  Partial sums are combined in
+                            range order (deterministic, independent of n_ranks).               */
 } vimg_render_params;
 
 #define VIMG_FLAG_COUNTERS 1u /* also gather traversal counters (slower)     */

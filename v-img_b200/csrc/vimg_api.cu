@@ -91,6 +91,8 @@ struct vimg_scene {
   QwPool qw[QW_MAX_POOLS];
   uint32_t class_mask = 0;
   uint32_t* d_qw_next_pixel = nullptr;
+  float* d_partial = nullptr;  // spp_streams > 1: per-range partial sums, W*H*streams*3 floats
+  size_t partial_floats = 0;
   int sm_count = 0;
   uint32_t last_launches = 0;
   double stage_ms[VIMG_STAGE_COUNT] = {0};
@@ -313,6 +315,70 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     if (desc->lights[i] != VIMG_LIGHT_BACKGROUND && (desc->lights[i] < 0 || (uint64_t)desc->lights[i] >= desc->n_prims))
       return fail(VIMG_ERR_INVALID_ARGUMENT, "light index out of range");
 
+  // ---- shade records (per leaf entry) and light records (per light) ---------------
+  // the values hit-info and light sampling would gather through prim -> mesh -> indices ->
+  // normals / uvs, laid side by side (vimg_types.cuh)
+  std::vector<DShadeRec> shade_recs(b.n_obj_indices);
+  for (uint64_t i = 0; i < b.n_obj_indices; ++i) {
+    const vimg_prim& pr = desc->prims[b.obj_indices[i]];
+    DShadeRec& sr = shade_recs[i];
+    std::memset(&sr, 0, sizeof(sr));
+    if (pr.type == VIMG_PRIM_SPHERE) {
+      sr.material = desc->spheres[pr.a].material;
+      const vimg_material& m = desc->materials[sr.material];
+      if ((m.texture >= 0 && desc->textures[m.texture].type != VIMG_TEX_CONST) || m.texture_rg >= 0)
+        sr.flags |= VIMG_SHADE_SPHERE_NEEDS_UV;
+      continue;
+    }
+    const vimg_mesh& hm = desc->meshes[pr.a];
+    const DMesh& dm = meshes[pr.a];
+    const uint32_t* idx = hm.indices + 3 * (uint64_t)pr.b;
+    sr.material = hm.material;
+    if (hm.normals) {
+      sr.flags |= VIMG_SHADE_HAS_NORMALS;
+      for (int k = 0; k < 3; ++k) std::memcpy(sr.n + 3 * k, hm.normals + 3 * (uint64_t)idx[k], 12);
+    }
+    if (dm.uv_color >= 0) {
+      sr.flags |= VIMG_SHADE_HAS_UV;
+      const float* tc = hm.texcoords[hm.color_tex_uv];
+      for (int k = 0; k < 3; ++k) std::memcpy(sr.uv + 2 * k, tc + 2 * (uint64_t)idx[k], 8);
+    }
+    // the other two uv selectors: absent, or the colour set itself (interpolating the same
+    // arrays gives the same bits); anything else takes the general walk
+    if (dm.uv_mr >= 0 && dm.uv_mr != dm.uv_color) sr.flags |= VIMG_SHADE_GENERAL;
+    if (dm.uv_normal >= 0) sr.flags |= dm.uv_normal == dm.uv_color ? VIMG_SHADE_NORMAL_UV_SAME : VIMG_SHADE_GENERAL;
+  }
+  std::vector<DLightRec> light_recs(desc->n_lights);
+  for (uint32_t i = 0; i < desc->n_lights; ++i) {
+    DLightRec& lr = light_recs[i];
+    std::memset(&lr, 0, sizeof(lr));
+    if (desc->lights[i] == VIMG_LIGHT_BACKGROUND) {
+      lr.type = VIMG_LIGHTREC_BACKGROUND;
+      continue;
+    }
+    const vimg_prim& pr = desc->prims[desc->lights[i]];
+    if (pr.type == VIMG_PRIM_SPHERE) {
+      if (pr.a >= desc->n_spheres) return fail(VIMG_ERR_INVALID_ARGUMENT, "sphere index out of range");
+      const vimg_sphere& sp = desc->spheres[pr.a];
+      lr.type = VIMG_LIGHTREC_SPHERE;
+      std::memcpy(lr.p, sp.center, 12);
+      lr.p[3] = sp.radius;
+      lr.material = sp.material;
+    } else {
+      if (pr.a >= desc->n_meshes || pr.b >= desc->meshes[pr.a].n_tris)
+        return fail(VIMG_ERR_INVALID_ARGUMENT, "triangle primitive out of range");
+      const vimg_mesh& hm = desc->meshes[pr.a];
+      const uint32_t* idx = hm.indices + 3 * (uint64_t)pr.b;
+      lr.type = VIMG_LIGHTREC_TRIANGLE;
+      lr.material = hm.material;
+      lr.has_normals = hm.normals != nullptr;
+      for (int k = 0; k < 3; ++k) {
+        std::memcpy(lr.p + 3 * k, hm.vertices + 3 * (uint64_t)idx[k], 12);
+        if (hm.normals) std::memcpy(lr.n + 3 * k, hm.normals + 3 * (uint64_t)idx[k], 12);
+      }
+    }
+  }
+
   // ---- background ------------------------------------------------------------
   const vimg_background& hb = desc->background;
   d.bg.type = hb.type;
@@ -338,6 +404,8 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   UP(s->upload(pairs, &d.pairs));
   UP(s->upload(leaf, &d.leaf_prims));
   UP(s->upload(leaf_class, &d.leaf_class));
+  UP(s->upload(shade_recs, &d.shade_recs));
+  UP(s->upload(light_recs, &d.light_recs));
   UP(s->upload(desc->prims, desc->n_prims, &d.prims));
   UP(s->upload(desc->spheres, desc->n_spheres, &d.spheres));
   UP(s->upload(meshes, &d.meshes));
@@ -516,6 +584,23 @@ __global__ void qw_iota_kernel(uint32_t* q, uint32_t n) {
   if (i < n) q[i] = i;
 }
 
+// spp_streams > 1: thread <-> local pixel; the pixel's range sums are added in range order and
+// divided by spp (include/integrators.h:133-137 for one range)
+__global__ void qw_combine_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfArgs args,
+                                  float* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t px, py;
+  if (p >= args.n_local_pixels || !wf_pixel_xy(args, sc.cam, p, px, py)) return;
+  const size_t image_index = px + ((size_t)(sc.cam.res[1] - 1 - py) * sc.cam.res[0]);
+  const float* part = args.partial + 3 * image_index * args.streams;
+  V3 acc = mk3(part[0], part[1], part[2]);
+  for (uint32_t k = 1; k < args.streams; ++k) acc = acc + mk3(part[3 * k], part[3 * k + 1], part[3 * k + 2]);
+  acc = acc / (float)args.samples;
+  out[3 * image_index] = acc.x;
+  out[3 * image_index + 1] = acc.y;
+  out[3 * image_index + 2] = acc.z;
+}
+
 struct QwLaunchCfg {
   int trace_grid, item_grid;  // full-size grids
   bool concurrent;
@@ -589,7 +674,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   // the per-kernel profile needs serial launches on one stream
   const bool concurrent = !prof.on && env_u32("VIMG_QW_SERIAL", 0) == 0;
   const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
-  const uint32_t total_slots = std::max(1u, std::min(w.n_local_pixels, cap));
+  const uint32_t total_slots = std::max(1u, std::min(w.n_local_units, cap));
   uint32_t n_pools = std::min<uint32_t>(QW_MAX_POOLS, std::max(1u, env_u32("VIMG_QW_POOLS", 2)));
   if (!concurrent || total_slots < 65536u) n_pools = 1;  // small frames: one pool, lowest latency
   const uint32_t per_pool = (total_slots + n_pools - 1) / n_pools;
@@ -668,7 +753,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
           pool.finished = true;  // batch b only ran empty iterations for this pool
         else
           all_done = false;
-        if (shrink && pool.h_next_pixel[(b - 1) & 1] >= w.n_local_pixels) {
+        if (shrink && pool.h_next_pixel[(b - 1) & 1] >= w.n_local_units) {
           // every pixel is handed out: the slots alive now bound every later queue of this pool,
           // so the launches shrink with them (kernels stride over their queues, any grid is valid)
           const uint64_t bound = (uint64_t)hc.n_closest[par] + hc.n_end[par];
@@ -684,6 +769,10 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   for (uint32_t p = 0; p < n_pools; ++p) {
     CU_TRY(cudaEventRecord(s->qw[p].done, s->qw[p].main));
     CU_TRY(cudaStreamWaitEvent(caller, s->qw[p].done, 0));
+  }
+  if (w.streams > 1) {
+    qw_combine_kernel<<<(w.n_local_pixels + QW_THREADS - 1) / QW_THREADS, QW_THREADS, 0, caller>>>(s->d, w, out);
+    ++launches;
   }
   prof.report(print_profile, s->stage_ms, s->stage_launches);
   if (timeline && !tl_ev.empty()) {
@@ -711,7 +800,7 @@ static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, float*
 
 template <bool COUNT>
 static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st,
-                         uint32_t flags = 0) {
+                         uint32_t flags = 0, uint32_t spp_streams = 1) {
   s->last_launches = 1;
   std::memset(s->stage_ms, 0, sizeof(s->stage_ms));
   std::memset(s->stage_launches, 0, sizeof(s->stage_launches));
@@ -727,12 +816,36 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
     w.single_y = a.single_y;
     w.n_local_pixels = a.single_x >= 0 ? 1u : a.n_local_tiles * 64u;
     if (w.n_local_pixels == 0) return VIMG_OK;
+    // sample ranges: at least one sample each; trace_pixel and the no-trace corner (material,
+    // depth 0) keep the single stream
+    w.streams = std::max(1u, std::min(spp_streams, a.samples));
+    if (a.single_x >= 0 || (integrator == VIMG_INTEGRATOR_MATERIAL && a.depth == 0)) w.streams = 1;
+    if ((uint64_t)w.n_local_pixels * w.streams > 0xffffffffull || w.streams > 0xffffu)
+      return fail(VIMG_ERR_INVALID_ARGUMENT, "spp_streams too large for this frame");
+    w.n_local_units = w.n_local_pixels * w.streams;
+    w.partial = nullptr;
     // pipeline: the queue wavefront unless the caller (or VIMG_PIPELINE=block) asks for the
     // block-local kernel
     bool use_block = (flags & VIMG_FLAG_PIPELINE_BLOCK) != 0;
     if (!(flags & (VIMG_FLAG_PIPELINE_BLOCK | VIMG_FLAG_PIPELINE_QUEUE))) {
       const char* e = std::getenv("VIMG_PIPELINE");
       use_block = e && std::strcmp(e, "block") == 0;
+    }
+    if (use_block && w.streams > 1)
+      return fail(VIMG_ERR_UNSUPPORTED, "spp_streams > 1 needs the queue wavefront pipeline");
+    if (w.streams > 1) {
+      const size_t need = (size_t)s->W * s->H * w.streams * 3;
+      if (s->partial_floats < need) {
+        if (s->d_partial) cudaFree(s->d_partial);
+        s->d_partial = nullptr;
+        s->partial_floats = 0;
+        if (cudaMalloc(&s->d_partial, need * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(VIMG_ERR_OUT_OF_MEMORY, "partial-sum buffer of the sample ranges");
+        }
+        s->partial_floats = need;
+      }
+      w.partial = s->d_partial;
     }
     if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st, (flags & VIMG_FLAG_STAGE_TIMES) != 0);
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
@@ -788,6 +901,7 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_next_pixel) cudaFree(s->d_next_pixel);
   for (QwPool& p : s->qw) p.destroy();
   if (s->d_qw_next_pixel) cudaFree(s->d_qw_next_pixel);
+  if (s->d_partial) cudaFree(s->d_partial);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -836,9 +950,9 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
   if (a.n_ranks > 1) CU_TRY(cudaMemsetAsync(s->d_frame, 0, (size_t)s->W * s->H * 3 * sizeof(float), st));
   CU_TRY(cudaEventRecord(s->ev0, st));
   if (p->flags & VIMG_FLAG_COUNTERS)
-    rc = launch_render<true>(s, a, p->integrator, s->d_frame, st, p->flags);
+    rc = launch_render<true>(s, a, p->integrator, s->d_frame, st, p->flags, p->spp_streams);
   else
-    rc = launch_render<false>(s, a, p->integrator, s->d_frame, st, p->flags);
+    rc = launch_render<false>(s, a, p->integrator, s->d_frame, st, p->flags, p->spp_streams);
   if (rc != VIMG_OK) return rc;
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(s->ev1, st));

@@ -212,7 +212,8 @@ VD V2 texrg_get_at_uv(const DScene& sc, const DTextureRG& t, V2 uv) {
 
 // ------------------------------------------------------------------ hit info ----
 // Triangle::hit_info (src/geometry/triangle.cpp:13-153)
-VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const PreHit& pre) {
+// general case: walks the SoA pools (any combination of uv sets); out of line, rarely taken
+__device__ __noinline__ HitInfo triangle_hit_info_general(const DScene& sc, const DLeafPrim& lp, const PreHit& pre) {
   const vimg_prim pr = sc.prims[lp.prim_id];
   const DMesh& mesh = sc.meshes[pr.a];
   const uint32_t* idx = sc.tri_indices + 3 * ((size_t)mesh.tri_base + pr.b);
@@ -311,18 +312,121 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const PreHit
   return h;
 }
 
+// one shading / light record with 16-byte loads
+VD DShadeRec load_shade_rec(const DScene& sc, int32_t leaf_slot) {
+  DShadeRec r;
+  const uint4* src = reinterpret_cast<const uint4*>(sc.shade_recs + leaf_slot);
+  uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) dst[k] = __ldg(src + k);
+  return r;
+}
+VD DLightRec load_light_rec(const DScene& sc, int index) {
+  DLightRec r;
+  const uint4* src = reinterpret_cast<const uint4*>(sc.light_recs + index);
+  uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dst[k] = __ldg(src + k);
+  return r;
+}
+
+// Triangle::hit_info (src/geometry/triangle.cpp:13-153) from the leaf record (vertices) and the
+// shade record (vertex normals, colour uv set, material): the same values and the same
+// operations as the general walk, without its dependent loads
+VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShadeRec& sr, const PreHit& pre) {
+  if (sr.flags & VIMG_SHADE_GENERAL) return triangle_hit_info_general(sc, lp, pre);
+  V3 p0 = mk3(lp.a[0], lp.a[1], lp.a[2]), p1 = mk3(lp.a[3], lp.a[4], lp.a[5]),
+     p2 = mk3(lp.a[6], lp.a[7], lp.a[8]);
+  V3 edge1 = p1 - p0, edge2 = p2 - p0;
+  float u = pre.e0 * pre.inv_det, v = pre.e1 * pre.inv_det, w = pre.e2 * pre.inv_det;
+  const V3 tri_normal = normalize(cross(edge1, edge2));
+  V3 n0, n1, n2, shading_normal;
+  if (sr.flags & VIMG_SHADE_HAS_NORMALS) {
+    n0 = mk3(sr.n[0], sr.n[1], sr.n[2]);
+    n1 = mk3(sr.n[3], sr.n[4], sr.n[5]);
+    n2 = mk3(sr.n[6], sr.n[7], sr.n[8]);
+    shading_normal = normalize(u * n0 + v * n1 + w * n2);
+  } else {
+    n0 = n1 = n2 = tri_normal;
+    shading_normal = tri_normal;
+  }
+  const V3 hit_p = u * p0 + v * p1 + w * p2;
+
+  V2 uv = mk2(u, v);
+  V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(1, 1);
+  if (sr.flags & VIMG_SHADE_HAS_UV) {
+    uv0 = mk2(sr.uv[0], sr.uv[1]);
+    uv1 = mk2(sr.uv[2], sr.uv[3]);
+    uv2 = mk2(sr.uv[4], sr.uv[5]);
+    uv = u * uv0 + v * uv1 + w * uv2;
+  }
+  V2 duvds = uv2 - uv0;
+  V2 duvdt = uv2 - uv1;
+  float det = duvds.x * duvdt.y - duvdt.x * duvds.y;
+  float dsdu = 0.f, dtdu = 0.f, dsdv = 0.f, dtdv = 0.f;
+  V3 dpdu, dpdv;
+  if (fabsf(det) > 1e-8f && !is_nan(det)) {
+    dsdu = duvdt.y / det;
+    dtdu = -duvds.y / det;
+    dsdv = duvdt.x / det;
+    dtdv = -duvds.x / det;
+    V3 dpds = p2 - p0;
+    V3 dpdt = p2 - p1;
+    dpdu = dpds * dsdu + dpdt * dtdu;
+    dpdv = dpds * dsdv + dpdt * dtdv;
+  } else {
+    get_axis(shading_normal, dpdu, dpdv);
+  }
+
+  const int32_t normal_map = sc.materials[sr.material].normal_map;
+  if (normal_map >= 0) {
+    const V2 n_uv = (sr.flags & VIMG_SHADE_NORMAL_UV_SAME) ? uv : mk2(u, v);
+    V3 n_tangent_space = tex_get_normal(sc, sc.textures[normal_map], n_uv);
+    ONB onb_n_map = init_onb(shading_normal);
+    V3 local_space_normal = xform_with_onb(onb_n_map, n_tangent_space);
+    float ulen = length(dpdu), vlen = length(dpdv);
+    dpdu = normalize(gram_schmidt(dpdu, local_space_normal)) * ulen;
+    dpdv = normalize(cross(local_space_normal, dpdu)) * vlen;
+    shading_normal = local_space_normal;
+  }
+
+  V3 tangent = normalize(dpdu - shading_normal * dot(shading_normal, dpdu));
+  V3 dnds = n2 - n0;
+  V3 dndt = n2 - n1;
+  V3 dndu = dnds * dsdu + dndt * dtdu;
+  V3 dndv = dnds * dsdv + dndt * dtdv;
+  V3 bitangent = normalize(cross(shading_normal, tangent));
+  float mean_curvature = (dot(dndu, tangent) + dot(dndv, bitangent)) / 2.f;
+  float twice_tri_area = length(cross(p1 - p0, p2 - p0));
+  float uv_area = fabsf((uv1.x - uv0.x) * (uv2.y - uv0.y) - (uv2.x - uv0.x) * (uv1.y - uv0.y));
+
+  HitInfo h;
+  h.mat = sr.material;
+  h.prim = (int32_t)lp.prim_id;
+  h.hit_p = hit_p;
+  h.hit_n_s = shading_normal;
+  h.hit_n_g = tri_normal;
+  h.uv = uv;
+  h.mr_uv = uv;  // no metallic-roughness set, or the colour set itself (else VIMG_SHADE_GENERAL)
+  h.frame.u = tangent;
+  h.frame.v = bitangent;
+  h.frame.w = shading_normal;
+  h.primitive_area = twice_tri_area;
+  h.tex_coord_area = uv_area;
+  h.mean_curvature = mean_curvature;
+  return h;
+}
+
 // Sphere::hit_info (src/geometry/sphere.cpp:12-45).  dpdv is computed by the reference
 // but never used; uv needs acos/atan2 and double pi arithmetic.
-VD HitInfo sphere_hit_info(const DScene& sc, const DLeafPrim& lp, const Ray& r) {
-  const vimg_prim pr = sc.prims[lp.prim_id];
+VD HitInfo sphere_hit_info(const DLeafPrim& lp, const DShadeRec& sr, const Ray& r) {
   V3 center = mk3(lp.a[0], lp.a[1], lp.a[2]);
   float radius = lp.a[3];
   const V3 hit_p = r.o + r.dir * r.maxT;
   const V3 normal = normalize(hit_p - center);
   // uv is only read by non-constant textures (col_at_ray_hit) and by the metallic-roughness
   // texture; for every other material the acos/atan2 pair is dead code in the reference too
-  const vimg_material& m = sc.materials[sc.spheres[pr.a].material];
-  const bool needs_uv = (m.texture >= 0 && sc.textures[m.texture].type != VIMG_TEX_CONST) || m.texture_rg >= 0;
+  const bool needs_uv = (sr.flags & VIMG_SHADE_SPHERE_NEEDS_UV) != 0;
   float u = 0.f, v = 0.f;
   if (needs_uv) {
     float theta = m_acosf(-normal.y);
@@ -333,7 +437,7 @@ VD HitInfo sphere_hit_info(const DScene& sc, const DLeafPrim& lp, const Ray& r) 
   V3 dpdu = mk3(-radius * normal.y, radius * normal.x, 0.f);
   V3 tangent = normalize(dpdu - normal * dot(normal, dpdu));
   HitInfo h;
-  h.mat = sc.spheres[pr.a].material;
+  h.mat = sr.material;
   h.prim = (int32_t)lp.prim_id;
   h.hit_p = hit_p;
   h.hit_n_s = normal;
@@ -355,10 +459,11 @@ VD bool scene_hit(const DScene& sc, Ray& ray, HitInfo& hit, TravCounters* cnt) {
   PreHit ph;
   if (!bvh_traverse<false, COUNT>(sc, ray, ph, cnt)) return false;
   const DLeafPrim lp = sc.leaf_prims[ph.leaf_slot];
+  const DShadeRec sr = load_shade_rec(sc, ph.leaf_slot);
   if (lp.flags & VIMG_LEAF_SPHERE)
-    hit = sphere_hit_info(sc, lp, ray);
+    hit = sphere_hit_info(lp, sr, ray);
   else
-    hit = triangle_hit_info(sc, lp, ph);
+    hit = triangle_hit_info(sc, lp, sr, ph);
   return true;
 }
 

@@ -89,19 +89,15 @@ VD float background_pdf(const DScene& sc, V3 in_dir) {
 
 // ------------------------------------------------------------------ lights ----
 // Triangle::sample (triangle.cpp:178-233)
-VD V3 triangle_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32& rng, EmitterInfo& info) {
-  const vimg_prim pr = sc.prims[prim];
-  const DMesh& mesh = sc.meshes[pr.a];
-  const uint32_t* idx = sc.tri_indices + 3 * ((size_t)mesh.tri_base + pr.b);
-  const uint32_t i0 = idx[0] + mesh.vert_base, i1 = idx[1] + mesh.vert_base, i2 = idx[2] + mesh.vert_base;
-  V3 p0 = load3(sc.vertices, i0), p1 = load3(sc.vertices, i1), p2 = load3(sc.vertices, i2);
+VD V3 triangle_light_sample(const DScene& sc, const DLightRec& lr, V3 look_from, Pcg32& rng, EmitterInfo& info) {
+  V3 p0 = mk3(lr.p[0], lr.p[1], lr.p[2]), p1 = mk3(lr.p[3], lr.p[4], lr.p[5]), p2 = mk3(lr.p[6], lr.p[7], lr.p[8]);
   const V3 edge1 = p1 - p0, edge2 = p2 - p0;
   V3 tri_normal = normalize(cross(edge1, edge2));
   V3 n0, n1, n2;
-  if (mesh.has_normals) {
-    n0 = load3(sc.normals, i0);
-    n1 = load3(sc.normals, i1);
-    n2 = load3(sc.normals, i2);
+  if (lr.has_normals) {
+    n0 = mk3(lr.n[0], lr.n[1], lr.n[2]);
+    n1 = mk3(lr.n[3], lr.n[4], lr.n[5]);
+    n2 = mk3(lr.n[6], lr.n[7], lr.n[8]);
   } else {
     n0 = n1 = n2 = tri_normal;
   }
@@ -129,7 +125,7 @@ VD V3 triangle_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32
   info.pdf = pdf;
   info.dist = sqrtf(dist2);
   info.G = G;
-  return mat_emitted(sc.materials[mesh.material], info.wi, hit_n);
+  return mat_emitted(sc.materials[lr.material], info.wi, hit_n);
 }
 
 // Triangle::surf_pdf (triangle.cpp:235-248)
@@ -145,10 +141,9 @@ VD float triangle_surf_pdf(const DScene& sc, uint32_t prim) {
 }
 
 // Sphere::sample (sphere.cpp:58-118)
-VD V3 sphere_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32& rng, EmitterInfo& info) {
-  const vimg_sphere& s = sc.spheres[sc.prims[prim].a];
-  const V3 center = mk3(s.center[0], s.center[1], s.center[2]);
-  const float radius = s.radius;
+VD V3 sphere_light_sample(const DScene& sc, const DLightRec& lr, V3 look_from, Pcg32& rng, EmitterInfo& info) {
+  const V3 center = mk3(lr.p[0], lr.p[1], lr.p[2]);
+  const float radius = lr.p[3];
   float rand1 = rand_float(rng);
   float rand2 = rand_float(rng);
   V3 shading_normal;
@@ -185,7 +180,7 @@ VD V3 sphere_light_sample(const DScene& sc, uint32_t prim, V3 look_from, Pcg32& 
     info.dist = sqrtf(dist2);
     info.G = G;
   }
-  return mat_emitted(sc.materials[s.material], info.wi, shading_normal);
+  return mat_emitted(sc.materials[lr.material], info.wi, shading_normal);
 }
 
 // Sphere::surf_pdf (sphere.cpp:120-139)
@@ -252,16 +247,39 @@ VD V3 lights_sample(const DScene& sc, V3 look_from, Pcg32& rng, EmitterInfo& inf
   float sx = rnd * sc.n_lights;
   const int index_obj = std_clampi((int)sx, 0, (int)sc.n_lights - 1);
   const float prob_obj = 1.f / sc.n_lights;
-  const int32_t light = sc.lights[index_obj];
+  const DLightRec lr = load_light_rec(sc, index_obj);  // one record: no prim -> mesh -> vertex walk
   V3 col;
-  if (light == VIMG_LIGHT_BACKGROUND)
+  if (lr.type == VIMG_LIGHTREC_BACKGROUND)
     col = background_light_sample(sc, rng, info);
-  else if (sc.prims[light].type == VIMG_PRIM_SPHERE)
-    col = sphere_light_sample(sc, (uint32_t)light, look_from, rng, info);
+  else if (lr.type == VIMG_LIGHTREC_SPHERE)
+    col = sphere_light_sample(sc, lr, look_from, rng, info);
   else
-    col = triangle_light_sample(sc, (uint32_t)light, look_from, rng, info);
+    col = triangle_light_sample(sc, lr, look_from, rng, info);
   info.pdf *= prob_obj;
   return col;
+}
+
+// Triangle::surf_pdf / Sphere::surf_pdf of the emitter a ray hit, from its leaf record (the
+// same vertex / centre / radius values as the pools hold)
+VD float emitter_surf_pdf_leaf(const DLeafPrim& lp, V3 look_from, V3 point_on_light, V3 dir) {
+  if (lp.flags & VIMG_LEAF_SPHERE) {
+    const V3 center = mk3(lp.a[0], lp.a[1], lp.a[2]);
+    const float radius = lp.a[3];
+    if (length2(look_from - center) <= radius * radius) {
+      const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+      return 1.f / sphere_sa;
+    }
+    float cos_theta_max = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
+    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+    V3 shading_normal = normalize(point_on_light - center);
+    float cosine = fabsf(dot(shading_normal, -dir));
+    float dist2 = length2(point_on_light - look_from);
+    return pdf_solid_angle * cosine / dist2;
+  }
+  V3 p0 = mk3(lp.a[0], lp.a[1], lp.a[2]), p1 = mk3(lp.a[3], lp.a[4], lp.a[5]), p2 = mk3(lp.a[6], lp.a[7], lp.a[8]);
+  V3 edge1 = p1 - p0, edge2 = p2 - p0;
+  float area = length(cross(edge2, edge1)) / 2.0f;
+  return 1.f / area;
 }
 
 VD float emitter_surf_pdf(const DScene& sc, int32_t prim, V3 look_from, V3 look_at, V3 dir) {

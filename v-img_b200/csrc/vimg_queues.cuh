@@ -380,7 +380,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
 // or that has no pixel yet.  Finishes the sample (include/integrators.h:128-137), hands out
 // the next pixel of this rank's tile list and generates the next camera ray (:116-123).
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(QW_THREADS)
+__global__ void __launch_bounds__(QW_THREADS, 3)
 qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
               const __grid_constant__ WfArgs args, const uint32_t parity,
               float* __restrict__ out, DCounters* __restrict__ counters) {
@@ -420,7 +420,8 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
     const uint32_t d = pa1.w;
     Pcg32 rng;
     rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
-    rng.inc = 1;
+    uint32_t range = f >> WF_RANGE_SHIFT;  // sample range of the pixel this slot works on
+    rng.inc = ((uint64_t)range << 1) | 1u;
     V3 acc = xyz(ap4);
     uint32_t s = __float_as_uint(L4.w), pixel = __float_as_uint(ap4.w);
     const bool occl = hb.z != 0;
@@ -433,15 +434,27 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
       n_samples++;
       f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
       s = s + 1;
-      if (s == args.samples) {
-        const V3 px_col = acc / (float)args.samples;
+      if (args.streams == 1) {
+        if (s == args.samples) {
+          const V3 px_col = acc / (float)args.samples;
+          uint32_t px, py;
+          wf_pixel_xy(args, sc.cam, pixel, px, py);
+          const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+          float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+          o[0] = px_col.x;
+          o[1] = px_col.y;
+          o[2] = px_col.z;
+          f &= ~WF_ALIVE;
+        }
+      } else if (s == (uint32_t)(((uint64_t)(range + 1) * args.samples) / args.streams)) {
+        // end of this sample range: its partial sum; qw_combine_kernel adds the ranges in order
         uint32_t px, py;
         wf_pixel_xy(args, sc.cam, pixel, px, py);
         const size_t image_index = px + ((size_t)(H - 1 - py) * W);
-        float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
-        o[0] = px_col.x;
-        o[1] = px_col.y;
-        o[2] = px_col.z;
+        float* o = args.partial + 3 * (image_index * args.streams + range);
+        o[0] = acc.x;
+        o[1] = acc.y;
+        o[2] = acc.z;
         f &= ~WF_ALIVE;
       }
     };
@@ -486,7 +499,8 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
             ph.e1 = h0.w;
             ph.e2 = __uint_as_float(hb.x);
             ph.inv_det = __uint_as_float(hb.y);
-            const HitInfo next = wf_hit_info(sc, ph.leaf_slot, ph, ray);
+            const DLeafPrim nlp = sc.leaf_prims[ph.leaf_slot];
+            const HitInfo next = wf_hit_info(sc, nlp, load_shade_rec(sc, ph.leaf_slot), ph, ray);
             V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
             if (!MIS) {
               finish(thr * emit);  // sample_mat -> nullopt: throughput * emitted
@@ -495,7 +509,7 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
             } else {
               if (last_pdf != 0) {
                 // ray.o is the previous hit point, ray.dir the sampled direction
-                float light_pdf = emitter_surf_pdf(sc, next.prim, ray.o, next.hit_p, ray.dir) / sc.n_lights;
+                float light_pdf = emitter_surf_pdf_leaf(nlp, ray.o, next.hit_p, ray.dir) / sc.n_lights;
                 float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
                 float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
                 L = L + thr * mis_weight * emit;
@@ -527,20 +541,21 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
         uint32_t pbase = 0;
         if (lane == (uint32_t)(__ffs(m) - 1)) {
           // no atomic once the frame is handed out
-          if (*reinterpret_cast<volatile uint32_t*>(st.next_pixel) < args.n_local_pixels)
+          if (*reinterpret_cast<volatile uint32_t*>(st.next_pixel) < args.n_local_units)
             pbase = atomicAdd(st.next_pixel, (uint32_t)__popc(m));
           else
-            pbase = args.n_local_pixels;
+            pbase = args.n_local_units;
         }
         pbase = __shfl_sync(0xffffffffu, pbase, __ffs(m) - 1);
         if (want) {
           // tiles overhanging the frame contain pixel numbers without a pixel: take the next
-          uint32_t p = pbase + __popc(m & lane_lt);
+          uint32_t u = pbase + __popc(m & lane_lt), p = 0;
           uint32_t px = 0, py = 0;
           bool got = false;
-          while (p < args.n_local_pixels && !(got = wf_pixel_xy(args, sc.cam, p, px, py)))
-            p = atomicAdd(st.next_pixel, 1u);
+          while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.streams, px, py)))
+            u = atomicAdd(st.next_pixel, 1u);
           if (got) {
+            range = u - p * args.streams;
             if (!MIS && args.depth == 0) {
               // material_integrator with depth 0 never traces: every sample is vec3(0)
               const size_t image_index = px + ((size_t)(H - 1 - py) * W);
@@ -548,11 +563,11 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
               o[0] = o[1] = o[2] = 0.f;
               n_samples += args.samples;
             } else {
-              pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), 0);
+              pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), range);
               acc = mk3(0.f);
-              s = 0;
+              s = (uint32_t)(((uint64_t)range * args.samples) / args.streams);
               pixel = p;
-              f = WF_ALIVE;
+              f = WF_ALIVE | (range << WF_RANGE_SHIFT);
             }
           }
         }
@@ -568,7 +583,7 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
       Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
       stg4(&st.ray[i].o_w, f4(cam.o, cam.cone.cone_width));
       stg4(&st.ray[i].d_s, f4(cam.dir, cam.cone.spread_angle));
-      f = WF_ALIVE | WF_IN_PATH | WF_FIRST;
+      f = WF_ALIVE | WF_IN_PATH | WF_FIRST | (range << WF_RANGE_SHIFT);
       new_ray = true;
     }
     if (valid) {
@@ -662,6 +677,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), o4 = t4, d4 = t4, h0 = t4, cp4 = t4, L4 = t4;
     uint4 pa1 = make_uint4(0, 0, 0, 0), hb = pa1;
     DLeafPrim lp;
+    DShadeRec sr;
     if (go) {
       {
         const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + qi.y);
@@ -670,6 +686,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         dst[1] = __ldg(rec + 1);
         dst[2] = __ldg(rec + 2);
       }
+      sr = load_shade_rec(sc, (int32_t)qi.y);
       t4 = ldg4(&st.path[j].thr_eta);
       pa1 = ldg4u(&st.path[j].rng);
       o4 = ldg4(&st.ray[j].o_w);
@@ -684,7 +701,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     uint32_t fj = pa1.z, d = pa1.w;
     Pcg32 rng;
     rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
-    rng.inc = 1;
+    rng.inc = ((uint64_t)(fj >> WF_RANGE_SHIFT) << 1) | 1u;
     if (go) {
       if (MIS) {
         // what mis_integrator does between the BVH::hit that found this surface and the next
@@ -733,7 +750,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       ph.e1 = h0.w;
       ph.e2 = __uint_as_float(hb.x);
       ph.inv_det = __uint_as_float(hb.y);
-      const HitInfo hit = wf_hit_info(sc, lp, ph, ray);
+      const HitInfo hit = wf_hit_info(sc, lp, sr, ph, ray);
       const vimg_material& mat = sc.materials[hit.mat];
       V3 thr = xyz(t4);
       float eta_scale = t4.w;

@@ -10,8 +10,11 @@
 //    ids need that).
 //  * Leaf primitives: 48-byte records pre-gathered in obj_indices order (the
 //    reference chases obj_indices -> Surface* -> Mesh -> indices -> vertices).
-//  * Shading data (normals, uvs, materials, textures) stays in SoA pools that are
-//    read once per hit, not per traversal step.
+//  * Shading data: one 80-byte DShadeRec per leaf record (vertex normals, colour uv set,
+//    material) and one 96-byte DLightRec per light, pre-gathered so that hit-info and light
+//    sampling read ONE record with 16-byte loads instead of chasing
+//    prim -> mesh -> indices -> normals / uvs (four dependent loads).  The SoA pools stay for
+//    the general case (meshes whose textures use different uv sets).
 #pragma once
 #include <stdint.h>
 
@@ -37,6 +40,36 @@ struct __align__(16) DLeafPrim {
   uint32_t pad_;
 };
 static_assert(sizeof(DLeafPrim) == 48, "leaf record must be 48 bytes");
+
+// shading record of a leaf entry (same index as leaf_prims)
+#define VIMG_SHADE_HAS_NORMALS 1u      /* n[] valid (Mesh::normals not empty)                        */
+#define VIMG_SHADE_HAS_UV 2u           /* uv[] valid: the mesh has a colour uv set                   */
+#define VIMG_SHADE_NORMAL_UV_SAME 4u   /* the normal map reads the colour uv set (else: barycentrics) */
+#define VIMG_SHADE_GENERAL 8u          /* metallic-roughness / normal uv sets differ from the colour
+                                          set: hit-info walks the SoA pools                          */
+#define VIMG_SHADE_SPHERE_NEEDS_UV 16u /* sphere whose material reads uv (non-constant texture)      */
+struct __align__(16) DShadeRec {
+  float n[9];   // n0, n1, n2
+  float uv[6];  // uv0, uv1, uv2 of the colour set
+  uint32_t material;
+  uint32_t flags;
+  uint32_t pad_[3];
+};
+static_assert(sizeof(DShadeRec) == 80, "shade record must be 80 bytes");
+
+// light record, list_lights order (GroupOfEmitters::sample indexes it, emitters.h:39-56)
+#define VIMG_LIGHTREC_TRIANGLE 0u
+#define VIMG_LIGHTREC_SPHERE 1u
+#define VIMG_LIGHTREC_BACKGROUND 2u
+struct __align__(16) DLightRec {
+  float p[9];  // triangle: p0, p1, p2 | sphere: center.xyz, radius
+  float n[9];  // triangle vertex normals (has_normals)
+  uint32_t type;
+  uint32_t material;
+  uint32_t has_normals;
+  uint32_t pad_[3];
+};
+static_assert(sizeof(DLightRec) == 96, "light record must be 96 bytes");
 
 struct DMesh {
   uint32_t vert_base;    // into vertices / normals pools
@@ -92,6 +125,8 @@ struct DScene {
   const DPairNode* pairs;  // (n_nodes - 1) / 2 records, record of children (c, c+1) at (c-1)/2
   const DLeafPrim* leaf_prims;
   const uint8_t* leaf_class;  // per leaf record: material class (bits 0-1) | VIMG_LEAF_CLASS_EMISSIVE
+  const DShadeRec* shade_recs;  // per leaf record
+  const DLightRec* light_recs;  // per light
   float root_min[3], root_max[3];
   uint32_t root_first, root_count;  // nodes[0]
   uint32_t n_nodes;

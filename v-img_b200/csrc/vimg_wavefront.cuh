@@ -66,7 +66,15 @@ struct WfArgs {
   uint32_t tiles_x, tiles_y;
   uint32_t n_local_pixels;     // 64 * tiles owned by this rank
   int32_t single_x, single_y;  // >= 0: trace_pixel mode
+  // queue wavefront only: sample ranges per pixel (vimg_render_params.spp_streams, >= 1), the
+  // work units of this rank (n_local_pixels * streams; unit u = range u % streams of local pixel
+  // u / streams) and, for streams > 1, the partial sums [image_index][range] x rgb
+  uint32_t streams, n_local_units;
+  float* partial;
 };
+// a slot's sample range number lives in the upper half of its flag word
+#define WF_RANGE_SHIFT 16
+#define WF_FLAG_MASK 0xffffu
 
 VD V3 ld3(const float (*a)[WF_SLOTS], int i) { return mk3(a[0][i], a[1][i], a[2][i]); }
 VD void st3(float (*a)[WF_SLOTS], int i, V3 v) {
@@ -89,19 +97,16 @@ VD bool wf_pixel_xy(const WfArgs& a, const DCamera& cam, uint32_t p, uint32_t& x
   return x < (uint32_t)cam.res[0] && y < (uint32_t)cam.res[1];
 }
 
-VD uint32_t wf_leaf_material(const DScene& sc, int32_t leaf_slot) {
-  const DLeafPrim* lp = sc.leaf_prims + leaf_slot;
-  const vimg_prim pr = sc.prims[lp->prim_id];
-  return (lp->flags & VIMG_LEAF_SPHERE) ? sc.spheres[pr.a].material : sc.meshes[pr.a].material;
-}
+VD uint32_t wf_leaf_material(const DScene& sc, int32_t leaf_slot) { return sc.shade_recs[leaf_slot].material; }
 
-VD HitInfo wf_hit_info(const DScene& sc, const DLeafPrim& lp, const PreHit& ph, const Ray& ray) {
-  if (lp.flags & VIMG_LEAF_SPHERE) return sphere_hit_info(sc, lp, ray);
-  return triangle_hit_info(sc, lp, ph);
+VD HitInfo wf_hit_info(const DScene& sc, const DLeafPrim& lp, const DShadeRec& sr, const PreHit& ph, const Ray& ray) {
+  if (lp.flags & VIMG_LEAF_SPHERE) return sphere_hit_info(lp, sr, ray);
+  return triangle_hit_info(sc, lp, sr, ph);
 }
 VD HitInfo wf_hit_info(const DScene& sc, int32_t leaf_slot, const PreHit& ph, const Ray& ray) {
   const DLeafPrim lp = sc.leaf_prims[leaf_slot];
-  return wf_hit_info(sc, lp, ph, ray);
+  const DShadeRec sr = load_shade_rec(sc, leaf_slot);
+  return wf_hit_info(sc, lp, sr, ph, ray);
 }
 
 VD uint32_t wf_material_class(uint32_t mat_type) {

@@ -33,7 +33,8 @@ class _DescHead(C.Structure):  # leading members of vimg_scene_desc
 
 class RenderParams(C.Structure):
     _fields_ = [("integrator", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32),
-                ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("flags", C.c_uint32)]
+                ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("flags", C.c_uint32),
+                ("spp_streams", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
@@ -198,31 +199,36 @@ class Scene:
     def device_bytes(self):
         return int(self._lib.vimg_scene_device_bytes(self._h))
 
-    def _params(self, func, samples, depth, rank, n_ranks, counters, pipeline=None, stage_times=False):
+    def _params(self, func, samples, depth, rank, n_ranks, counters, pipeline=None, stage_times=False,
+                spp_streams=1):
         flags = (FLAG_COUNTERS if counters else 0) | PIPELINES[pipeline] | (FLAG_STAGE_TIMES if stage_times else 0)
-        return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks, flags)
+        return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks, flags,
+                            int(spp_streams))
 
     def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None,
-                         pipeline=None, stage_times=False):
+                         pipeline=None, stage_times=False, spp_streams=1):
         """Mirror of scene_integrator<F>() (include/integrators.h:36-153).
 
         Returns (image float32 [H, W, 3] in HOST memory, row 0 = top; stats dict).
         `out` may be a (pinned) float32 array to receive the frame.
+        `spp_streams` = 1 follows the reference's one RNG stream per pixel (bit-identical images);
+        K > 1 splits every pixel's samples into K ranges with their own streams
+        (vimg_render_params.spp_streams, include/vimg_cuda.h).
         """
         if out is None:
             out = np.empty((self.height, self.width, 3), np.float32)
         assert out.dtype == np.float32 and out.size == self.height * self.width * 3
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams)
         _check(self._lib, self._lib.vimg_render(self._h, C.byref(p), out.ctypes.data, C.byref(st)),
                "vimg_render")
         return out, st.as_dict()
 
     def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None,
-                      pipeline=None, stage_times=False):
+                      pipeline=None, stage_times=False, spp_streams=1):
         """Render and leave the frame in HBM.  Returns (device pointer, stats dict)."""
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams)
         dev = C.c_void_p()
         _check(self._lib, self._lib.vimg_render_device(self._h, C.byref(p), C.byref(dev), stream,
                                                        C.byref(st)), "vimg_render_device")
