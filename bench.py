@@ -121,9 +121,28 @@ def config_of(w, n_gpus, extra=None):
     return c
 
 
+class StdoutToStderr:
+    """The reference's scene_integrator prints its progress with std::cout (integrators.h:48,142);
+    bench.py's stdout carries exactly one JSON line, so fd 1 points at stderr while it runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # --------------------------------------------------------------------------- reference arm
 def time_reference(w, steps, warmup, budget_s=25.0):
     """Times the compiled reference (perf flavour) on the host cores.  Returns a dict."""
+    with StdoutToStderr():
+        return _time_reference(w, steps, warmup, budget_s)
+
+
+def _time_reference(w, steps, warmup, budget_s):
     from oracle import refcpu
     vimg = load_product()  # only for vimg_scene_desc_load (host-side file parsing, no GPU work)
     if not refcpu.available("perf"):
