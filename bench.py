@@ -272,15 +272,21 @@ def cuda_line(w, args):
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         sc2 = vimg.Scene(desc.ptr, device=local_rank)
         _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np,
                                       pipeline=args.pipeline, spp_streams=streams)
         h2d = sc2.device_bytes
         sc2.close()
         e2e_rays += st2["rays_closest"] + st2["rays_shadow"]
+        e2e_step_ms.append(1e3 * (time.perf_counter() - ts))
+    t_loop = time.perf_counter() - t0
     barrier()
     e2e_s = time.perf_counter() - t0
+    print(f"[bench e2e] rank {rank}: steps {['%.1f' % m for m in e2e_step_ms]} ms, loop {1e3 * t_loop:.1f} ms, "
+          f"with barrier {1e3 * e2e_s:.1f} ms", file=sys.stderr)
     te = torch.tensor([e2e_s, e2e_rays], dtype=torch.float64, device=dev)
     if world > 1:
         tem = te.clone()

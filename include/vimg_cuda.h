@@ -288,6 +288,12 @@ const char* vimg_last_error(void);
 int vimg_scene_create(const vimg_scene_desc* desc, int device_id, vimg_scene** out_scene);
 void vimg_scene_destroy(vimg_scene* scene);
 
+/* The material / mis pipeline keeps its render workspace (path-state pools, queues, partial
+ * sums: up to ~1 GB, sized by the frame, independent of the scene) in a process-wide cache, one
+ * idle workspace per device, so that creating a scene per frame does not allocate inside every
+ * render.  This frees the idle workspaces (scenes that are still alive keep theirs). */
+void vimg_release_workspaces(void);
+
 /* bytes of device memory the scene occupies (BVH + geometry + textures). */
 uint64_t vimg_scene_device_bytes(const vimg_scene* scene);
 

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <numbers>
 #include <string>
 #include <vector>
@@ -60,7 +62,17 @@ struct QwPool {
   cudaEvent_t snap[2] = {nullptr, nullptr}, fork = nullptr, join[2] = {nullptr, nullptr}, done = nullptr;
   bool finished = false;
   int trace_grid = 1, item_grid = 1;  // current launch sizes (shrink as the pool drains)
+  // one batch of iterations captured as a CUDA graph (launch sizes it was captured with)
+  cudaGraphExec_t batch_exec = nullptr;
+  int exec_trace_grid = 0, exec_item_grid = 0;
+  uint32_t graph_launches = 0;
+  void drop_graph() {
+    if (batch_exec) cudaGraphExecDestroy(batch_exec);
+    batch_exec = nullptr;
+    exec_trace_grid = exec_item_grid = 0;
+  }
   void destroy() {
+    drop_graph();
     if (mem) cudaFree(mem);
     if (h_cnt) cudaFreeHost(h_cnt);
     if (h_next_pixel) cudaFreeHost(h_next_pixel);
@@ -76,6 +88,52 @@ struct QwPool {
   }
 };
 
+// Render workspace of the queue wavefront: slot pools, shared unit counter, partial sums.
+// It is independent of the scene (sized by slots and frame), so a scene takes an idle one of
+// its device from a process-wide cache at its first render and gives it back when it is
+// destroyed: a caller that creates a scene per frame (bench.py's end-to-end step, the
+// reference's main.cpp) does not pay cudaMalloc / cudaFree of ~1 GB inside every render.
+struct QwWorkspace {
+  QwPool qw[QW_MAX_POOLS];
+  uint32_t* d_next_pixel = nullptr;
+  float* d_partial = nullptr;  // spp_streams > 1: per-range partial sums, W*H*streams*3 floats
+  size_t partial_floats = 0;
+  void destroy() {
+    for (QwPool& p : qw) p.destroy();
+    if (d_next_pixel) cudaFree(d_next_pixel);
+    if (d_partial) cudaFree(d_partial);
+    d_next_pixel = nullptr;
+    d_partial = nullptr;
+    partial_floats = 0;
+  }
+};
+static std::mutex g_ws_mu;
+static std::map<int, QwWorkspace*> g_ws_idle;  // device -> one idle workspace
+
+static QwWorkspace* ws_acquire(int device) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_ws_idle.find(device);
+  if (it != g_ws_idle.end() && it->second) {
+    QwWorkspace* w = it->second;
+    it->second = nullptr;
+    return w;
+  }
+  return new QwWorkspace();
+}
+static void ws_release(int device, QwWorkspace* w) {
+  if (!w) return;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    QwWorkspace*& slot = g_ws_idle[device];
+    if (!slot) {
+      slot = w;
+      return;
+    }
+  }
+  w->destroy();
+  delete w;
+}
+
 struct vimg_scene {
   int device = 0;
   DScene d{};
@@ -88,11 +146,8 @@ struct vimg_scene {
   int wf_blocks[2][2] = {{0, 0}, {0, 0}};  // resident-grid size of wavefront_kernel<integrator, COUNT>
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // queue wavefront (vimg_queues.cuh): slot pools, class mask of the scene's materials
-  QwPool qw[QW_MAX_POOLS];
+  QwWorkspace* ws = nullptr;  // taken at the first material / mis render
   uint32_t class_mask = 0;
-  uint32_t* d_qw_next_pixel = nullptr;
-  float* d_partial = nullptr;  // spp_streams > 1: per-range partial sums, W*H*streams*3 floats
-  size_t partial_floats = 0;
   int sm_count = 0;
   uint32_t last_launches = 0;
   double stage_ms[VIMG_STAGE_COUNT] = {0};
@@ -481,8 +536,8 @@ static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
     CU_TRY(cudaEventCreateWithFlags(&pool.fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&pool.done, cudaEventDisableTiming));
   }
-  if (!s->d_qw_next_pixel) CU_TRY(cudaMalloc(&s->d_qw_next_pixel, sizeof(uint32_t)));
-  pool.st.next_pixel = s->d_qw_next_pixel;
+  if (!s->ws->d_next_pixel) CU_TRY(cudaMalloc(&s->ws->d_next_pixel, sizeof(uint32_t)));
+  pool.st.next_pixel = s->ws->d_next_pixel;
   if (pool.mem && pool.capacity >= n) {
     pool.st.n_slots = n;
     return VIMG_OK;
@@ -499,10 +554,10 @@ static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
     return at;
   };
   const size_t N = n;
-  const size_t o_ray = carve(N * sizeof(QwRay)), o_hit = carve(N * sizeof(QwHit)), o_path = carve(N * sizeof(QwPath)),
-               o_nee = carve(N * sizeof(QwNee)), o_pix = carve(N * sizeof(QwPix));
+  const size_t o_slot = carve(N * sizeof(QwSlot));
   size_t o_qc[2], o_qs[2], o_qe[2], o_qsh[WF_NUM_CLASSES];
   for (int k = 0; k < 2; ++k) o_qc[k] = carve(N * 4);
+  const size_t o_ql = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qs[k] = carve(N * 4);
   for (int k = 0; k < 2; ++k) o_qe[k] = carve(N * 4);
   for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) o_qsh[k] = carve(N * 8);
@@ -512,12 +567,9 @@ static int qw_reserve(vimg_scene* s, QwPool& pool, uint32_t n) {
   char* b = static_cast<char*>(pool.mem);
   QwState& q = pool.st;
   q.n_slots = n;
-  q.ray = reinterpret_cast<QwRay*>(b + o_ray);
-  q.hit = reinterpret_cast<QwHit*>(b + o_hit);
-  q.path = reinterpret_cast<QwPath*>(b + o_path);
-  q.nee = reinterpret_cast<QwNee*>(b + o_nee);
-  q.pix = reinterpret_cast<QwPix*>(b + o_pix);
+  q.slot = reinterpret_cast<QwSlot*>(b + o_slot);
   for (int k = 0; k < 2; ++k) q.q_closest[k] = reinterpret_cast<uint32_t*>(b + o_qc[k]);
+  q.q_leaf = reinterpret_cast<int32_t*>(b + o_ql);
   for (int k = 0; k < 2; ++k) q.q_shadow[k] = reinterpret_cast<uint32_t*>(b + o_qs[k]);
   for (int k = 0; k < 2; ++k) q.q_end[k] = reinterpret_cast<uint32_t*>(b + o_qe[k]);
   for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) q.q_shade[k] = reinterpret_cast<uint2*>(b + o_qsh[k]);
@@ -682,17 +734,17 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
 
   int rc;
   for (uint32_t p = 0; p < n_pools; ++p)
-    if ((rc = qw_reserve(s, s->qw[p], per_pool)) != VIMG_OK) return rc;
-  CU_TRY(cudaMemsetAsync(s->d_qw_next_pixel, 0, sizeof(uint32_t), caller));
-  cudaEvent_t start = s->qw[0].done;  // reused as the fork event of the caller's stream
+    if ((rc = qw_reserve(s, s->ws->qw[p], per_pool)) != VIMG_OK) return rc;
+  CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
+  cudaEvent_t start = s->ws->qw[0].done;  // reused as the fork event of the caller's stream
   const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
   for (uint32_t p = 0; p < n_pools; ++p) {
-    QwPool& pool = s->qw[p];
+    QwPool& pool = s->ws->qw[p];
     pool.finished = false;
     pool.trace_grid = 0;  // set below
     if (p == 0) CU_TRY(cudaEventRecord(start, caller));
     CU_TRY(cudaStreamWaitEvent(pool.main, start, 0));
-    CU_TRY(cudaMemsetAsync(pool.st.path, 0, (size_t)per_pool * sizeof(QwPath), pool.main));  // flags = 0: no pixel yet
+    CU_TRY(cudaMemsetAsync(pool.st.slot, 0, (size_t)per_pool * sizeof(QwSlot), pool.main));  // flags = 0: no pixel yet
     QwCounters init{};
     init.n_end[0] = per_pool;
     *pool.h_cnt = init;
@@ -702,47 +754,89 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   QwLaunchCfg cfg;
   // with several pools in flight the persistent trace grid leaves room for the other pool's
   // shade / end blocks on every SM
-  const int trace_per_sm = (int)env_u32("VIMG_QW_TRACE_BLOCKS", n_pools > 1 ? 3 : QW_TRACE_BLOCKS_PER_SM);
+  const int trace_per_sm = (int)env_u32("VIMG_QW_TRACE_BLOCKS", QW_TRACE_BLOCKS_PER_SM);
   const int trace_full = s->sm_count * std::max(1, std::min(trace_per_sm, QW_TRACE_BLOCKS_PER_SM));
   const int trace_need = (int)((2ull * per_pool + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS);
   cfg.trace_grid = std::max(1, std::min(trace_full, trace_need));
-  cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8));
+  cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8 * (256 / QW_THREADS)));
   cfg.concurrent = concurrent;
   cfg.class_mask = s->class_mask;
   for (uint32_t p = 0; p < n_pools; ++p) {
-    s->qw[p].trace_grid = cfg.trace_grid;
-    s->qw[p].item_grid = cfg.item_grid;
+    s->ws->qw[p].trace_grid = cfg.trace_grid;
+    s->ws->qw[p].item_grid = cfg.item_grid;
   }
   const bool shrink = env_u32("VIMG_QW_SHRINK", 1) != 0;
-  const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
+  // VIMG_QW_GRAPH=1: batches after the first are replayed from a CUDA graph per pool (trace /
+  // classify / shade on side streams / end, `batch` iterations): one host call per batch
+  // instead of ~12 per iteration.  The graph holds the frame's arguments and the pool's launch
+  // sizes, so it is captured per frame and again when the launches shrink (sizes are rounded up
+  // to powers of two to keep that rare).  Off by default: measured on B200 the replay is 2 %
+  // SLOWER than stream launches (disney_spheres 128 spp: 252.6 vs 247.4 ms) -- the host is not
+  // the bottleneck, the kernels run back to back either way; it is kept for hosts whose launch
+  // thread is contended.
+  const bool use_graph = concurrent && env_u32("VIMG_QW_GRAPH", 0) != 0;
+  uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
+  if (use_graph) batch = (batch + 1) & ~1u;  // even: every replay sees the same queue parities
+  for (uint32_t p = 0; p < n_pools; ++p) s->ws->qw[p].drop_graph();
+  auto pow2_at_least = [](uint64_t v) {
+    uint64_t r = 1;
+    while (r < v) r <<= 1;
+    return r;
+  };
   uint32_t launches = n_pools, it = 0;
-  prof.st = s->qw[0].main;
+  prof.st = s->ws->qw[0].main;
   prof.mark(0);
   std::vector<cudaEvent_t> tl_ev;
   std::vector<uint32_t> tl_live;
   for (uint32_t b = 0;; ++b) {
-    for (uint32_t k = 0; k < batch; ++k, ++it)
-      for (uint32_t p = 0; p < n_pools; ++p)
-        if (!s->qw[p].finished) launches += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, s->qw[p], w, it, cfg, out, prof);
+    if (!use_graph || b == 0) {
+      for (uint32_t k = 0; k < batch; ++k)
+        for (uint32_t p = 0; p < n_pools; ++p)
+          if (!s->ws->qw[p].finished)
+            launches += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, s->ws->qw[p], w, it + k, cfg, out, prof);
+    } else {
+      for (uint32_t p = 0; p < n_pools; ++p) {
+        QwPool& pool = s->ws->qw[p];
+        if (pool.finished) continue;
+        if (!pool.batch_exec || pool.exec_trace_grid != pool.trace_grid || pool.exec_item_grid != pool.item_grid) {
+          pool.drop_graph();
+          cudaGraph_t g = nullptr;
+          uint32_t n = 0;
+          CU_TRY(cudaStreamBeginCapture(pool.main, cudaStreamCaptureModeRelaxed));
+          for (uint32_t k = 0; k < batch; ++k)
+            n += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, pool, w, batch + k, cfg, out, prof);
+          CU_TRY(cudaStreamEndCapture(pool.main, &g));
+          cudaError_t e = cudaGraphInstantiate(&pool.batch_exec, g, 0);
+          cudaGraphDestroy(g);
+          if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+          pool.exec_trace_grid = pool.trace_grid;
+          pool.exec_item_grid = pool.item_grid;
+          pool.graph_launches = n;
+        }
+        CU_TRY(cudaGraphLaunch(pool.batch_exec, pool.main));
+        launches += pool.graph_launches;
+      }
+    }
+    it += batch;
     CU_TRY(cudaGetLastError());
     for (uint32_t p = 0; p < n_pools; ++p) {
-      QwPool& pool = s->qw[p];
+      QwPool& pool = s->ws->qw[p];
       if (pool.finished) continue;
       CU_TRY(cudaMemcpyAsync(&pool.h_cnt[b & 1], pool.st.cnt, sizeof(QwCounters), cudaMemcpyDeviceToHost, pool.main));
-      CU_TRY(cudaMemcpyAsync(&pool.h_next_pixel[b & 1], s->d_qw_next_pixel, sizeof(uint32_t), cudaMemcpyDeviceToHost, pool.main));
+      CU_TRY(cudaMemcpyAsync(&pool.h_next_pixel[b & 1], s->ws->d_next_pixel, sizeof(uint32_t), cudaMemcpyDeviceToHost, pool.main));
       CU_TRY(cudaEventRecord(pool.snap[b & 1], pool.main));
     }
     if (timeline) {
       cudaEvent_t e;
       cudaEventCreate(&e);
-      cudaEventRecord(e, s->qw[0].main);
+      cudaEventRecord(e, s->ws->qw[0].main);
       tl_ev.push_back(e);
     }
     if (b > 0) {
       bool all_done = true;
       uint32_t live = 0;
       for (uint32_t p = 0; p < n_pools; ++p) {
-        QwPool& pool = s->qw[p];
+        QwPool& pool = s->ws->qw[p];
         if (pool.finished) continue;
         CU_TRY(cudaEventSynchronize(pool.snap[(b - 1) & 1]));
         // queues the iteration after batch b-1 consumes: parity of its first iteration
@@ -754,11 +848,16 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
         else
           all_done = false;
         if (shrink && pool.h_next_pixel[(b - 1) & 1] >= w.n_local_units) {
-          // every pixel is handed out: the slots alive now bound every later queue of this pool,
+          // every unit is handed out: the slots alive now bound every later queue of this pool,
           // so the launches shrink with them (kernels stride over their queues, any grid is valid)
           const uint64_t bound = (uint64_t)hc.n_closest[par] + hc.n_end[par];
-          pool.item_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.item_grid, (bound + QW_THREADS - 1) / QW_THREADS));
-          pool.trace_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.trace_grid, (2 * bound + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS));
+          uint64_t ig = (bound + QW_THREADS - 1) / QW_THREADS, tg = (2 * bound + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS;
+          if (use_graph) {
+            ig = pow2_at_least(ig);
+            tg = pow2_at_least(tg);
+          }
+          pool.item_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.item_grid, ig));
+          pool.trace_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.trace_grid, tg));
         }
       }
       if (timeline) tl_live.push_back(live);
@@ -767,8 +866,8 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   }
   // the caller's stream continues when every pool is drained
   for (uint32_t p = 0; p < n_pools; ++p) {
-    CU_TRY(cudaEventRecord(s->qw[p].done, s->qw[p].main));
-    CU_TRY(cudaStreamWaitEvent(caller, s->qw[p].done, 0));
+    CU_TRY(cudaEventRecord(s->ws->qw[p].done, s->ws->qw[p].main));
+    CU_TRY(cudaStreamWaitEvent(caller, s->ws->qw[p].done, 0));
   }
   if (w.streams > 1) {
     qw_combine_kernel<<<(w.n_local_pixels + QW_THREADS - 1) / QW_THREADS, QW_THREADS, 0, caller>>>(s->d, w, out);
@@ -833,19 +932,20 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
     }
     if (use_block && w.streams > 1)
       return fail(VIMG_ERR_UNSUPPORTED, "spp_streams > 1 needs the queue wavefront pipeline");
+    if (!use_block && !s->ws) s->ws = ws_acquire(s->device);
     if (w.streams > 1) {
       const size_t need = (size_t)s->W * s->H * w.streams * 3;
-      if (s->partial_floats < need) {
-        if (s->d_partial) cudaFree(s->d_partial);
-        s->d_partial = nullptr;
-        s->partial_floats = 0;
-        if (cudaMalloc(&s->d_partial, need * sizeof(float)) != cudaSuccess) {
+      if (s->ws->partial_floats < need) {
+        if (s->ws->d_partial) cudaFree(s->ws->d_partial);
+        s->ws->d_partial = nullptr;
+        s->ws->partial_floats = 0;
+        if (cudaMalloc(&s->ws->d_partial, need * sizeof(float)) != cudaSuccess) {
           cudaGetLastError();
           return fail(VIMG_ERR_OUT_OF_MEMORY, "partial-sum buffer of the sample ranges");
         }
-        s->partial_floats = need;
+        s->ws->partial_floats = need;
       }
-      w.partial = s->d_partial;
+      w.partial = s->ws->d_partial;
     }
     if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st, (flags & VIMG_FLAG_STAGE_TIMES) != 0);
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
@@ -892,6 +992,20 @@ int vimg_cuda_device_count(void) {
 
 const char* vimg_last_error(void) { return g_last_error.c_str(); }
 
+void vimg_release_workspaces(void) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_ws_idle) {
+    if (!kv.second) continue;
+    cudaSetDevice(kv.first);
+    kv.second->destroy();
+    delete kv.second;
+    kv.second = nullptr;
+  }
+  cudaSetDevice(cur);
+}
+
 void vimg_scene_destroy(vimg_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
@@ -899,9 +1013,8 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_frame) cudaFree(s->d_frame);
   if (s->d_counters) cudaFree(s->d_counters);
   if (s->d_next_pixel) cudaFree(s->d_next_pixel);
-  for (QwPool& p : s->qw) p.destroy();
-  if (s->d_qw_next_pixel) cudaFree(s->d_qw_next_pixel);
-  if (s->d_partial) cudaFree(s->d_partial);
+  ws_release(s->device, s->ws);
+  s->ws = nullptr;
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -917,6 +1030,17 @@ int vimg_scene_create(const vimg_scene_desc* desc, int device_id, vimg_scene** o
   if (n == 0) return fail(VIMG_ERR_NO_DEVICE, "no CUDA device visible: the cuda render device has no CPU fallback");
   if (device_id < 0 || device_id >= n) return fail(VIMG_ERR_INVALID_ARGUMENT, "device_id out of range");
   CU_TRY(cudaSetDevice(device_id));
+  {
+    // experiment knob: L2 fetch granularity hint (bytes) for the scattered 32-byte state records
+    const uint32_t g = env_u32("VIMG_L2_FETCH", 0);
+    if (g) {
+      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+      size_t got = 0;
+      cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+      fprintf(stderr, "[vimg] cudaLimitMaxL2FetchGranularity requested %u, now %zu\n", g, got);
+      cudaGetLastError();
+    }
+  }
   vimg_scene* s = new vimg_scene();
   s->device = device_id;
   int rc = build_scene(desc, s);

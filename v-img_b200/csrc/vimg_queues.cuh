@@ -45,7 +45,12 @@ namespace vimg {
 #ifndef QW_CHUNK
 #define QW_CHUNK 64  // rays a warp takes from the global cursor with one atomic
 #endif
+#ifndef QW_THREADS
 #define QW_THREADS 256  // classify / shade / end block size
+#endif
+#ifndef QW_END_MIN_BLOCKS
+#define QW_END_MIN_BLOCKS 3
+#endif
 
 struct QwCounters {
   uint32_t n_closest[2], n_shadow[2];  // queue lengths, double buffered by iteration parity
@@ -80,14 +85,24 @@ struct __align__(32) QwPix {   // END reads and writes; SHADE adds the NEE contr
   float4 acc_pixel;  // pixel accumulator rgb, local pixel number (uint bits)
 };
 
+// The five records of a slot lie side by side (160 bytes): a kernel that gathers a slot's state
+// touches one DRAM page and 2.5-3 64-byte bursts instead of five pages (measured: DRAM read
+// traffic of the END / SHADE kernels was 2.5x their sector bytes with five separate arrays).
+struct __align__(32) QwSlot {
+  QwRay ray;
+  QwHit hit;
+  QwPath path;
+  QwNee nee;
+  QwPix pix;
+};
+static_assert(sizeof(QwSlot) == 160, "slot state must be 160 bytes");
+
 struct QwState {
   uint32_t n_slots;
-  QwRay* ray;
-  QwHit* hit;
-  QwPath* path;
-  QwNee* nee;
-  QwPix* pix;
+  QwSlot* slot;
   uint32_t* q_closest[2];
+  int32_t* q_leaf;  // leaf record hit by closest ray i of the queue TRACE just consumed (-1: miss):
+                    // CLASSIFY reads it next to q_closest[i], coalesced, instead of gathering slot state
   uint32_t* q_shadow[2];
   uint32_t* q_end[2];
   uint2* q_shade[WF_NUM_CLASSES];  // {slot, leaf record of the hit}: the shade launch fetches both at once
@@ -155,7 +170,7 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
 
   // per-lane ray: `have` = in traversal, `done` = finished, result not stored yet
   bool have = false, done = false, any_hit = false, occluded = false;
-  uint32_t slot = 0;
+  uint32_t slot = 0, qpos = 0;
   Ray ray;
   RayPre pre;
   PreHit ph;
@@ -174,12 +189,13 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
 
   for (;;) {
     if (done) {  // the one place results are stored
-      QwHit* h = st.hit + slot;
+      QwHit* h = &st.slot[slot].hit;
       if (any_hit) {
         h->occl = occluded ? 1u : 0u;
       } else {
         stg4(&h->h0, make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1));
         h->h1 = make_float2(ph.e2, ph.inv_det);
+        st.q_leaf[qpos] = ph.leaf_slot;
       }
       done = false;
     }
@@ -205,16 +221,17 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             if (idx < n_c) {
               any_hit = false;
               slot = qc[idx];
-              o4 = ldg4(&st.ray[slot].o_w);
-              d4 = ldg4(&st.ray[slot].d_s);
+              qpos = idx;
+              o4 = ldg4(&st.slot[slot].ray.o_w);
+              d4 = ldg4(&st.slot[slot].ray.d_s);
               ray.maxT = CUDART_INF_F;
               pc.rays_closest++;
             } else {
               // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
               any_hit = true;
               slot = qs[idx - n_c];
-              o4 = ldg4(&st.ray[slot].o_w);
-              d4 = ldg4(&st.nee[slot].wi_dist);
+              o4 = ldg4(&st.slot[slot].ray.o_w);
+              d4 = ldg4(&st.slot[slot].nee.wi_dist);
               ray.maxT = d4.w - 0.0001f;
               pc.rays_shadow++;
             }
@@ -350,7 +367,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
     int32_t leaf_slot = -1;
     if (item < n) {
       j = q[item];
-      leaf_slot = __float_as_int(__ldcg(&st.hit[j].h0.x));
+      leaf_slot = __ldcg(&st.q_leaf[item]);
       cls = WF_CLASS_NONE;
       if (leaf_slot >= 0) {
         const uint32_t lc = sc.leaf_class[leaf_slot];
@@ -380,7 +397,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
 // or that has no pixel yet.  Finishes the sample (include/integrators.h:128-137), hands out
 // the next pixel of this rank's tile list and generates the next camera ray (:116-123).
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(QW_THREADS, 3)
+__global__ void __launch_bounds__(QW_THREADS, QW_END_MIN_BLOCKS)
 qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
               const __grid_constant__ WfArgs args, const uint32_t parity,
               float* __restrict__ out, DCounters* __restrict__ counters) {
@@ -406,15 +423,15 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
     float4 thr4 = make_float4(0.f, 0.f, 0.f, 0.f), o4 = thr4, d4 = thr4, h0 = thr4, cp4 = thr4, L4 = thr4, ap4 = thr4;
     uint4 hb = pa1;
     if (valid) {
-      thr4 = ldg4(&st.path[i].thr_eta);
-      pa1 = ldg4u(&st.path[i].rng);
-      o4 = ldg4(&st.ray[i].o_w);
-      d4 = ldg4(&st.ray[i].d_s);
-      h0 = ldg4(&st.hit[i].h0);
-      hb = ldg4u(&st.hit[i].h1);
-      cp4 = ldg4(&st.nee[i].c_pdf);
-      L4 = ldg4(&st.pix[i].L_s);
-      ap4 = ldg4(&st.pix[i].acc_pixel);
+      thr4 = ldg4(&st.slot[i].path.thr_eta);
+      pa1 = ldg4u(&st.slot[i].path.rng);
+      o4 = ldg4(&st.slot[i].ray.o_w);
+      d4 = ldg4(&st.slot[i].ray.d_s);
+      h0 = ldg4(&st.slot[i].hit.h0);
+      hb = ldg4u(&st.slot[i].hit.h1);
+      cp4 = ldg4(&st.slot[i].nee.c_pdf);
+      L4 = ldg4(&st.slot[i].pix.L_s);
+      ap4 = ldg4(&st.slot[i].pix.acc_pixel);
     }
     uint32_t f = pa1.z;
     const uint32_t d = pa1.w;
@@ -581,19 +598,19 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
       float rand2 = rand_float(rng);
       float rand1 = rand_float(rng);
       Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
-      stg4(&st.ray[i].o_w, f4(cam.o, cam.cone.cone_width));
-      stg4(&st.ray[i].d_s, f4(cam.dir, cam.cone.spread_angle));
+      stg4(&st.slot[i].ray.o_w, f4(cam.o, cam.cone.cone_width));
+      stg4(&st.slot[i].ray.d_s, f4(cam.dir, cam.cone.spread_angle));
       f = WF_ALIVE | WF_IN_PATH | WF_FIRST | (range << WF_RANGE_SHIFT);
       new_ray = true;
     }
     if (valid) {
       // path: throughput 1, eta_scale 1, d 0; nee: last_pdf 0; pix: L 0, s, acc, pixel
-      stg4(&st.path[i].thr_eta, make_float4(1.f, 1.f, 1.f, 1.f));
-      __stcg(reinterpret_cast<uint4*>(&st.path[i].rng),
+      stg4(&st.slot[i].path.thr_eta, make_float4(1.f, 1.f, 1.f, 1.f));
+      __stcg(reinterpret_cast<uint4*>(&st.slot[i].path.rng),
              make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), f, 0u));
-      stg4(&st.nee[i].c_pdf, make_float4(0.f, 0.f, 0.f, 0.f));
-      stg4(&st.pix[i].L_s, make_float4(0.f, 0.f, 0.f, __uint_as_float(s)));
-      stg4(&st.pix[i].acc_pixel, f4(acc, __uint_as_float(pixel)));
+      stg4(&st.slot[i].nee.c_pdf, make_float4(0.f, 0.f, 0.f, 0.f));
+      stg4(&st.slot[i].pix.L_s, make_float4(0.f, 0.f, 0.f, __uint_as_float(s)));
+      stg4(&st.slot[i].pix.acc_pixel, f4(acc, __uint_as_float(pixel)));
     }
 
     const bool want[1] = {new_ray};
@@ -687,15 +704,15 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         dst[2] = __ldg(rec + 2);
       }
       sr = load_shade_rec(sc, (int32_t)qi.y);
-      t4 = ldg4(&st.path[j].thr_eta);
-      pa1 = ldg4u(&st.path[j].rng);
-      o4 = ldg4(&st.ray[j].o_w);
-      d4 = ldg4(&st.ray[j].d_s);
-      h0 = ldg4(&st.hit[j].h0);
-      hb = ldg4u(&st.hit[j].h1);
+      t4 = ldg4(&st.slot[j].path.thr_eta);
+      pa1 = ldg4u(&st.slot[j].path.rng);
+      o4 = ldg4(&st.slot[j].ray.o_w);
+      d4 = ldg4(&st.slot[j].ray.d_s);
+      h0 = ldg4(&st.slot[j].hit.h0);
+      hb = ldg4u(&st.slot[j].hit.h1);
       if (MIS) {
-        cp4 = ldg4(&st.nee[j].c_pdf);
-        L4 = ldg4(&st.pix[j].L_s);
+        cp4 = ldg4(&st.slot[j].nee.c_pdf);
+        L4 = ldg4(&st.slot[j].pix.L_s);
       }
     }
     uint32_t fj = pa1.z, d = pa1.w;
@@ -711,7 +728,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
           L4.x += cp4.x;
           L4.y += cp4.y;
           L4.z += cp4.z;
-          stg4(&st.pix[j].L_s, L4);
+          stg4(&st.slot[j].pix.L_s, L4);
         }
         fj &= ~(WF_NEE | WF_NEE_VALID);
         bool go_on = true;
@@ -727,7 +744,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         if (!go_on || d >= args.depth) {
           // the path returns bounce_result: the next END launch finishes the sample
           fj |= WF_END;
-          __stcg(reinterpret_cast<uint4*>(&st.path[j].rng),
+          __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng),
                  make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
           want_end = true;
           go = false;
@@ -861,13 +878,13 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         }
         if (nsb) fj |= WF_NSB;
       }
-      stg4(&st.path[j].thr_eta, f4(thr, eta_scale));
-      __stcg(reinterpret_cast<uint4*>(&st.path[j].rng),
+      stg4(&st.slot[j].path.thr_eta, f4(thr, eta_scale));
+      __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng),
              make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
-      stg4(&st.ray[j].o_w, new_o);
-      stg4(&st.ray[j].d_s, new_d);
-      stg4(&st.nee[j].wi_dist, nee_wi);
-      stg4(&st.nee[j].c_pdf, nee_c);
+      stg4(&st.slot[j].ray.o_w, new_o);
+      stg4(&st.slot[j].ray.d_s, new_d);
+      stg4(&st.slot[j].nee.wi_dist, nee_wi);
+      stg4(&st.slot[j].nee.c_pdf, nee_c);
     }
 
     // every queue written here belongs to the NEXT iteration, so this launch is independent of

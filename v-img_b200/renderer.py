@@ -55,7 +55,7 @@ class RenderStats(C.Structure):
 
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
-           "vimg_trace_ids", "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
+           "vimg_trace_ids", "vimg_release_workspaces", "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
 
 
 def lib_path():
