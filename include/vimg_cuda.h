@@ -324,6 +324,30 @@ int vimg_trace_pixel(vimg_scene* scene, const vimg_render_params* params, int x,
  * out_t (nullable): same shape, the hit distance ray.maxT (inf on miss). */
 int vimg_trace_ids(vimg_scene* scene, uint32_t samples, int32_t* out_prim_id, float* out_t);
 
+/* ---- post-process chain (the step right after the path: src/main.cpp:304-356) ----------- */
+/* enum class tonemapper (include/color_utils.h:7) + "no tonemapper" (main.cpp:325-327). */
+typedef enum vimg_tonemapper {
+  VIMG_TONEMAP_CLAMP = 0,    /* simple_clamp   include/color_utils.h:21-25 */
+  VIMG_TONEMAP_AGX = 1,      /* agx            src/tonemap/agx.cpp          */
+  VIMG_TONEMAP_REINHARD = 2, /* reinhard_lum   src/tonemap/reinhard.cpp     */
+  VIMG_TONEMAP_ACES = 3,     /* aces           src/tonemap/aces.cpp         */
+  VIMG_TONEMAP_NONE = 4
+} vimg_tonemapper;
+
+/* Tonemapper, sRGB OETF (color_utils.h:50-68) and main.cpp's 8-bit quantisation (NaN pixel ->
+ * magenta, int(255.999 * v) clamped; main.cpp:339-356) of a linear image, on device `device_id`.
+ * rgb: HOST, n_pixels * 3 floats.  out_rgb8 (nullable): HOST, n_pixels * 3 bytes = the PNG
+ * payload.  out_srgb (nullable): HOST, n_pixels * 3 floats, the image after gamma (what
+ * main.cpp prints for -d).  kernel_ms (nullable): device time of the kernels. */
+int vimg_postprocess(const float* rgb, uint64_t n_pixels, uint32_t tonemapper, int device_id,
+                     uint8_t* out_rgb8, float* out_srgb, double* kernel_ms);
+
+/* scene_integrator + the post-process chain without leaving the device: renders like
+ * vimg_render() (single rank) and copies back W*H*3 BYTES instead of W*H*12.
+ * stats->kernel_ms covers render + post-process kernels, total_ms adds the copy. */
+int vimg_render_srgb8(vimg_scene* scene, const vimg_render_params* params, uint32_t tonemapper,
+                      uint8_t* out_rgb8, vimg_render_stats* stats /* nullable */);
+
 /* ---- scene blob I/O (flattened scene cache; used for test fixtures) ------ */
 /* serialise a descriptor to a single relocatable file and back.  A loaded
  * scene owns its arrays; free with vimg_scene_desc_free(). */

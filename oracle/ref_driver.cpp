@@ -18,6 +18,7 @@
 //            node / primitive-test counters) for the roofline cross-check.
 #include <background.h>
 #include <bvh.h>
+#include <color_utils.h>
 #include <geometry/mesh.h>
 #include <geometry/sphere.h>
 #include <geometry/triangle.h>
@@ -31,6 +32,8 @@
 #include <texture/texture_RGB.h>
 
 #include <chrono>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -430,6 +433,40 @@ double vref_render(void* h, int integrator, uint32_t spp, uint32_t depth, int th
   s.depth = keep_depth;
   if (out_rgb) std::memcpy(out_rgb, img.data(), img.size() * sizeof(glm::vec3));
   return sec;
+}
+
+// The post-process chain of src/main.cpp:304-356 on a W*H linear image: the reference's OWN
+// tonemapper (color_utils.h:21-25 simple_clamp, src/tonemap/{agx,reinhard,aces}.cpp), its sRGB
+// OETF (color_utils.h:50-68), then main.cpp's NaN -> magenta and int(255.999 * v) quantisation
+// loop (main.cpp:339-356; it lives inside main(), so it is restated here line by line).
+// tonemapper: 0 clamp, 1 agx, 2 reinhard, 3 aces (enum class tonemapper), anything else = none.
+// out_srgb (nullable): the float image after gamma; out_rgb8 (nullable): the PNG bytes.
+void vref_postprocess(const float* rgb, uint64_t n_pixels, int tonemapper, float* out_srgb,
+                      uint8_t* out_rgb8) {
+  std::vector<glm::vec3> acc_image(n_pixels);
+  std::memcpy(acc_image.data(), rgb, n_pixels * sizeof(glm::vec3));
+  switch (tonemapper) {
+    case 0: simple_clamp(acc_image); break;
+    case 1: agx(acc_image); break;
+    case 2: reinhard_lum(acc_image); break;
+    case 3: aces(acc_image); break;
+    default: break;
+  }
+  sRGB_gamma_correction(acc_image);
+  if (out_srgb) std::memcpy(out_srgb, acc_image.data(), n_pixels * sizeof(glm::vec3));
+  if (!out_rgb8) return;
+  uint64_t index = 0;
+  for (size_t i = 0; i < acc_image.size(); i++) {
+    if (std::isnan(acc_image[i][0]) || std::isnan(acc_image[i][1]) || std::isnan(acc_image[i][2])) {
+      out_rgb8[index++] = 255;
+      out_rgb8[index++] = 0;
+      out_rgb8[index++] = 255;
+    } else {
+      out_rgb8[index++] = std::clamp(static_cast<int>(255.999 * acc_image[i][0]), 0, 255);
+      out_rgb8[index++] = std::clamp(static_cast<int>(255.999 * acc_image[i][1]), 0, 255);
+      out_rgb8[index++] = std::clamp(static_cast<int>(255.999 * acc_image[i][2]), 0, 255);
+    }
+  }
 }
 
 // trace_pixel (include/integrators.h:181-220)

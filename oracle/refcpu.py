@@ -52,6 +52,8 @@ def _load(flavour):
                                      C.c_void_p]
     lib.vref_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.vref_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    lib.vref_postprocess.restype = None
+    lib.vref_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     lib.vref_flavour.restype = C.c_int
     lib.vref_hardware_threads.restype = C.c_int
     _libs[flavour] = lib
@@ -191,3 +193,31 @@ def restatement_primary(desc_ptr, width, height, spp, normals=True):
                                           sn.ctypes.data if normals else None,
                                           gn.ctypes.data if normals else None)
     return ids, t, sn, gn, bool(rc)
+
+
+# ---- post-process chain (src/main.cpp:304-356) ---------------------------------------------------
+TONEMAPPERS = {"clamp": 0, "agx": 1, "reinhard": 2, "aces": 3, "none": 4}
+
+
+def postprocess(img, tonemapper, flavour="parity"):
+    """The reference's own tonemapper + sRGB OETF + main.cpp's 8-bit quantisation.
+    -> (float32 image after gamma, uint8 image), both shaped like `img`."""
+    img = np.ascontiguousarray(img, np.float32)
+    srgb = np.empty_like(img)
+    rgb8 = np.empty(img.shape, np.uint8)
+    _load(flavour).vref_postprocess(img.ctypes.data, img.size // 3, TONEMAPPERS[tonemapper],
+                                    srgb.ctypes.data, rgb8.ctypes.data)
+    return srgb, rgb8
+
+
+def restatement_postprocess(img, tonemapper):
+    """Same chain through the plain-C restatement (oracle/vimg_oracle.c)."""
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_postprocess.restype = None
+    lib.vimg_oracle_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    img = np.ascontiguousarray(img, np.float32)
+    srgb = np.empty_like(img)
+    rgb8 = np.empty(img.shape, np.uint8)
+    lib.vimg_oracle_postprocess(img.ctypes.data, img.size // 3, TONEMAPPERS[tonemapper],
+                                srgb.ctypes.data, rgb8.ctypes.data)
+    return srgb, rgb8

@@ -240,24 +240,16 @@ inline vec3 sqrt(const vec3& v) { return vec3(std::sqrt(v.x), std::sqrt(v.y), st
 // ------------------------------------------------------------------ matrices
 struct mat3 {
   vec3 c[3];
-  mat3() : mat3(1.0f) {}
-  explicit mat3(float d) {
-    c[0] = vec3(d, 0, 0);
-    c[1] = vec3(0, d, 0);
-    c[2] = vec3(0, 0, d);
-  }
-  mat3(const vec3& a, const vec3& b, const vec3& cc) {
-    c[0] = a;
-    c[1] = b;
-    c[2] = cc;
-  }
-  mat3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
-    c[0] = vec3(a0, a1, a2);
-    c[1] = vec3(b0, b1, b2);
-    c[2] = vec3(c0, c1, c2);
-  }
-  vec3& operator[](int i) { return c[i]; }
-  const vec3& operator[](int i) const { return c[i]; }
+  constexpr mat3() : mat3(1.0f) {}
+  constexpr explicit mat3(float d) : c{vec3(d, 0, 0), vec3(0, d, 0), vec3(0, 0, d)} {}
+  constexpr mat3(const vec3& a, const vec3& b, const vec3& cc) : c{a, b, cc} {}
+  // nine scalars of any arithmetic type (agx.cpp passes double literals), column by column
+  template <typename A0, typename A1, typename A2, typename B0, typename B1, typename B2, typename C0,
+            typename C1, typename C2>
+  constexpr mat3(A0 a0, A1 a1, A2 a2, B0 b0, B1 b1, B2 b2, C0 c0, C1 c1, C2 c2)
+      : c{vec3(a0, a1, a2), vec3(b0, b1, b2), vec3(c0, c1, c2)} {}
+  constexpr vec3& operator[](int i) { return c[i]; }
+  constexpr const vec3& operator[](int i) const { return c[i]; }
 };
 // type_mat3x3.inl: m * v = m0*v0 + m1*v1 + m2*v2 written per component
 inline vec3 operator*(const mat3& m, const vec3& v) {

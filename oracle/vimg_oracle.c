@@ -329,3 +329,135 @@ int vimg_oracle_primary(const vimg_scene_desc* d, uint32_t spp, int32_t* out_ids
     }
   return unsupported;
 }
+
+/* ============================================================================================
+ * Post-process chain: src/main.cpp:304-356
+ *
+ *   tonemapper        include/color_utils.h:21-25 (clamp), src/tonemap/aces.cpp:5-31,
+ *                     src/tonemap/agx.cpp:6-99, src/tonemap/reinhard.cpp:3-37
+ *   sRGB OETF         include/color_utils.h:50-68
+ *   8-bit quantise    src/main.cpp:339-356 (NaN pixel -> magenta, int(255.999 * v) clamped)
+ *
+ * Every glm expression is written out per component in glm's evaluation order (mat3 * vec3 =
+ * m[0][r]*v.x + m[1][r]*v.y + m[2][r]*v.z; clamp = min(max(x, lo), hi) with glm's ternaries, which
+ * let NaN through).  powf / log2f are the host libm's, i.e. what the reference calls.
+ * PINNING: tests/test_oracle.py compares it byte for byte and float for float with the compiled
+ * reference's own functions (oracle/_ref, vref_postprocess) on the golden images and on a
+ * synthetic ramp with NaN / inf / negative / huge values.
+ * ============================================================================================ */
+static float glm_min(float a, float b) { return (b < a) ? b : a; }
+static float glm_max(float a, float b) { return (a < b) ? b : a; }
+static float glm_clamp(float x, float lo, float hi) { return glm_min(glm_max(x, lo), hi); }
+/* color_utils.h:9-11 */
+static float pp_luminance(v3 c) { return dot(c, V(0.212671f, 0.715160f, 0.072169f)); }
+static v3 mat3_mul(const float m[9], v3 v) { /* m column-major: m[3*col + row] */
+  return V(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z,
+           m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+
+/* aces.cpp:5-25 */
+static float aces_fit1(float v) {
+  float a = v * (v + 0.0245786f) - 0.000090537f;
+  float b = v * (0.983729f * v + 0.4329510f) + 0.238081f;
+  return a / b;
+}
+static v3 pp_aces(v3 v) {
+  static const float in_m[9] = {0.59719f, 0.07600f, 0.02840f, 0.35458f, 0.90834f, 0.13383f,
+                                0.04823f, 0.01566f, 0.83777f};
+  static const float out_m[9] = {1.60475f, -0.10208f, -0.00327f, -0.53108f, 1.10813f, -0.07276f,
+                                 -0.07367f, -0.00605f, 1.07602f};
+  v = mat3_mul(in_m, v);
+  v = V(aces_fit1(v.x), aces_fit1(v.y), aces_fit1(v.z));
+  return mat3_mul(out_m, v);
+}
+
+/* agx.cpp:6-14: (((((15.5*x4)*x2 - (40.14*x4)*x) + 31.96*x4) - (6.868*x2)*x) + 0.4298*x2) + 0.1191*x) - 0.00232 */
+static float agx_contrast1(float x) {
+  float x2 = x * x, x4 = x2 * x2;
+  return 15.5f * x4 * x2 - 40.14f * x4 * x + 31.96f * x4 - 6.868f * x2 * x + 0.4298f * x2 + 0.1191f * x
+         - 0.00232f;
+}
+static v3 pp_agx(v3 val) {
+  /* agx.cpp:17-19, 41-44: double literals narrowed to float by glm::mat3's constructor */
+  static const float agx_mat[9] = {(float)0.842479062253094, (float)0.0423282422610123, (float)0.0423756549057051,
+                                   (float)0.0784335999999992, (float)0.878468636469772, (float)0.0784336,
+                                   (float)0.0792237451477643, (float)0.0791661274605434, (float)0.879142973793104};
+  static const float agx_mat_inv[9] = {(float)1.19687900512017, (float)-0.0528968517574562, (float)-0.0529716355144438,
+                                       (float)-0.0980208811401368, (float)1.15190312990417, (float)-0.0980434501171241,
+                                       (float)-0.0990297440797205, (float)-0.0989611768448433, (float)1.15107367264116};
+  const float min_ev = -12.47393f, max_ev = 4.026069f;
+  /* agx(): inset, log2 encoding, sigmoid (agx.cpp:16-37) */
+  val = mat3_mul(agx_mat, val);
+  val = V(glm_clamp(log2f(val.x), min_ev, max_ev), glm_clamp(log2f(val.y), min_ev, max_ev),
+          glm_clamp(log2f(val.z), min_ev, max_ev));
+  val = V((val.x - min_ev) / (max_ev - min_ev), (val.y - min_ev) / (max_ev - min_ev),
+          (val.z - min_ev) / (max_ev - min_ev));
+  val = V(agx_contrast1(val.x), agx_contrast1(val.y), agx_contrast1(val.z));
+  /* agxLook(): slope 1, offset 0, power 1, sat 1 (agx.cpp:69-82) */
+  val = V(powf(val.x * 1.0f + 0.0f, 1.0f), powf(val.y * 1.0f + 0.0f, 1.0f), powf(val.z * 1.0f + 0.0f, 1.0f));
+  {
+    float luma = pp_luminance(val);
+    val = V(luma + 1.0f * (val.x - luma), luma + 1.0f * (val.y - luma), luma + 1.0f * (val.z - luma));
+  }
+  /* agxEotf(): outset, negative -> 0, pow 2.2 (agx.cpp:39-66) */
+  val = mat3_mul(agx_mat_inv, val);
+  if (val.x < 0.f) val.x = 0.f;
+  if (val.y < 0.f) val.y = 0.f;
+  if (val.z < 0.f) val.z = 0.f;
+  return V(powf(val.x, 2.2f), powf(val.y, 2.2f), powf(val.z, 2.2f));
+}
+
+/* color_utils.h:50-68, one channel */
+static float srgb_oetf1(float p) {
+  p = glm_clamp(p, 0.0f, 1.0f);
+  if (p < 0.0031308f) return p * 12.92f;
+  return 1.055f * powf(p, 1.0f / 2.4f) - 0.055f;
+}
+
+/* tonemapper: 0 clamp, 1 agx, 2 reinhard, 3 aces, else none.  out_srgb / out_rgb8 nullable. */
+void vimg_oracle_postprocess(const float* rgb, uint64_t n_pixels, int tonemapper, float* out_srgb,
+                             uint8_t* out_rgb8) {
+  float largest_L = 0.0f;
+  if (tonemapper == 2) { /* reinhard.cpp:3-13 */
+    for (uint64_t i = 0; i < n_pixels; ++i) {
+      float l = pp_luminance(V(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
+      if (l > largest_L) largest_L = l;
+    }
+  }
+  for (uint64_t i = 0; i < n_pixels; ++i) {
+    v3 c = V(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    switch (tonemapper) {
+      case 0: c = V(glm_clamp(c.x, 0.f, 1.f), glm_clamp(c.y, 0.f, 1.f), glm_clamp(c.z, 0.f, 1.f)); break;
+      case 1: c = pp_agx(c); break;
+      case 2: { /* reinhard.cpp:16-37 */
+        float in_L = pp_luminance(c);
+        float numerator = in_L * (1.0f + (in_L / (largest_L * largest_L)));
+        float new_L = numerator / (1.0f + in_L);
+        float l_in = pp_luminance(c);
+        if (l_in > 0.f) c = muls(c, new_L / l_in);
+        else c = V(0.f, 0.f, 0.f);
+        break;
+      }
+      case 3: c = pp_aces(c); break;
+      default: break;
+    }
+    c = V(srgb_oetf1(c.x), srgb_oetf1(c.y), srgb_oetf1(c.z));
+    if (out_srgb) {
+      out_srgb[3 * i] = c.x;
+      out_srgb[3 * i + 1] = c.y;
+      out_srgb[3 * i + 2] = c.z;
+    }
+    if (out_rgb8) {
+      if (isnan(c.x) || isnan(c.y) || isnan(c.z)) { /* main.cpp:342-346 */
+        out_rgb8[3 * i] = 255;
+        out_rgb8[3 * i + 1] = 0;
+        out_rgb8[3 * i + 2] = 255;
+      } else { /* main.cpp:348-351: double product, truncation, std::clamp(int, 0, 255) */
+        int r = (int)(255.999 * c.x), g = (int)(255.999 * c.y), b = (int)(255.999 * c.z);
+        out_rgb8[3 * i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        out_rgb8[3 * i + 1] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+        out_rgb8[3 * i + 2] = (uint8_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+      }
+    }
+  }
+}

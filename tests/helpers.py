@@ -43,3 +43,23 @@ def rel_mse(img, ref, eps=1e-2):
     img = np.asarray(img, np.float64)
     ref = np.asarray(ref, np.float64)
     return float(np.mean((img - ref) ** 2 / (ref ** 2 + eps)))
+
+
+def post_inputs():
+    """Linear images the post-process tests feed to the chain of src/main.cpp:304-356: three
+    reference renders from tests/golden/ref and a synthetic ramp with the awkward values
+    (NaN, +-inf, negative, zero, denormal, huge, the OETF's branch point, values around 1)."""
+    out = {}
+    for name, key in (("disney_small", "mis_256"), ("cornell_small", "mis_256"), ("synthetic_small", "mis_64")):
+        out[f"{name}/{key}"] = np.ascontiguousarray(golden_ref(name)[key], np.float32)
+    rng = np.random.default_rng(20261018)
+    ramp = (rng.random((64, 257, 3), dtype=np.float32) ** 4 * 20).astype(np.float32)
+    ramp[1] = np.linspace(0, 1.25, 257, dtype=np.float32)[:, None]
+    ramp[2] = np.linspace(0.0031, 0.0032, 257, dtype=np.float32)[:, None]
+    ramp[3] = np.geomspace(1e-12, 1e6, 257).astype(np.float32)[:, None]
+    specials = [[np.nan, 1, 2], [1, np.nan, 0.5], [np.inf, 0.5, 0.1], [-1, -2, 0.3], [0, 0, 0], [1e30, 1e-30, 5],
+                [-np.inf, 1, 1], [1e-42, 1e-40, 1e-39], [1, 1, 1], [0.0031308, 0.0031307, 0.0031309],
+                [-0.0, 0.0, -0.0], [3.4e38, 3.4e38, 3.4e38], [0.5, 0.25, 0.125]]
+    ramp[0, :len(specials)] = np.array(specials, np.float32)
+    out["ramp"] = ramp
+    return out

@@ -8,5 +8,5 @@ library with ctypes and mirrors the reference's render entry points
 There is NO CPU fallback: importing works anywhere, but every compute call
 raises VimgError when the CUDA extension or a CUDA device is missing.
 """
-from .renderer import (INTEGRATORS, LoadedDesc, Scene, VimgError, device_count, lib_path,  # noqa: F401
-                       load_library, tile_owner)
+from .renderer import (INTEGRATORS, TONEMAPPERS, LoadedDesc, Scene, VimgError, device_count,  # noqa: F401
+                       lib_path, load_library, postprocess, tile_owner)

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "vimg_kernels.cuh"
+#include "vimg_post.cuh"
 
 using namespace vimg;
 
@@ -146,6 +147,8 @@ struct vimg_scene {
   int wf_blocks[2][2] = {{0, 0}, {0, 0}};  // resident-grid size of wavefront_kernel<integrator, COUNT>
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // queue wavefront (vimg_queues.cuh): slot pools, class mask of the scene's materials
+  uint8_t* d_rgb8 = nullptr;      // vimg_render_srgb8: quantised frame
+  uint32_t* d_post_max = nullptr;  // ... and the reinhard tonemapper's largest luminance (float bits)
   QwWorkspace* ws = nullptr;  // taken at the first material / mis render
   uint32_t class_mask = 0;
   int sm_count = 0;
@@ -758,7 +761,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   const int trace_full = s->sm_count * std::max(1, std::min(trace_per_sm, QW_TRACE_BLOCKS_PER_SM));
   const int trace_need = (int)((2ull * per_pool + QW_TRACE_THREADS - 1) / QW_TRACE_THREADS);
   cfg.trace_grid = std::max(1, std::min(trace_full, trace_need));
-  cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * 8 * (256 / QW_THREADS)));
+  cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 8) * (256 / QW_THREADS)));
   cfg.concurrent = concurrent;
   cfg.class_mask = s->class_mask;
   for (uint32_t p = 0; p < n_pools; ++p) {
@@ -1015,6 +1018,8 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_next_pixel) cudaFree(s->d_next_pixel);
   ws_release(s->device, s->ws);
   s->ws = nullptr;
+  if (s->d_rgb8) cudaFree(s->d_rgb8);
+  if (s->d_post_max) cudaFree(s->d_post_max);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -1134,6 +1139,132 @@ int vimg_render(vimg_scene* s, const vimg_render_params* p, float* out_rgb, vimg
   }
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  return rc;
+}
+
+// tonemap + OETF + quantise of `n_pixels` pixels already in HBM, on `st`
+static int post_launch(const float* d_rgb, uint64_t n_pixels, uint32_t tonemapper, float* d_srgb, uint8_t* d_rgb8,
+                       uint32_t* d_max_bits, int sm_count, cudaStream_t st) {
+  if (n_pixels == 0) return VIMG_OK;
+  const int threads = 256;
+  const uint64_t quads = (n_pixels + 3) / 4;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((quads + threads - 1) / threads, (uint64_t)sm_count * 16));
+  if (tonemapper == VIMG_TONEMAP_REINHARD) {
+    CU_TRY(cudaMemsetAsync(d_max_bits, 0, sizeof(uint32_t), st));
+    post_max_luminance_kernel<<<sm_count * 8, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits);
+  }
+  switch (tonemapper) {
+    case VIMG_TONEMAP_CLAMP: post_kernel<VIMG_TONEMAP_CLAMP><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_AGX: post_kernel<VIMG_TONEMAP_AGX><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_REINHARD: post_kernel<VIMG_TONEMAP_REINHARD><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_ACES: post_kernel<VIMG_TONEMAP_ACES><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+    default: post_kernel<VIMG_TONEMAP_NONE><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+  }
+  CU_TRY(cudaGetLastError());
+  return VIMG_OK;
+}
+
+int vimg_postprocess(const float* rgb, uint64_t n_pixels, uint32_t tonemapper, int device_id, uint8_t* out_rgb8,
+                     float* out_srgb, double* kernel_ms) {
+  if (!rgb || (!out_rgb8 && !out_srgb)) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  if (tonemapper > VIMG_TONEMAP_NONE) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown tonemapper");
+  const int n = vimg_cuda_device_count();
+  if (n == 0) return fail(VIMG_ERR_NO_DEVICE, "no CUDA device visible: the cuda render device has no CPU fallback");
+  if (device_id < 0 || device_id >= n) return fail(VIMG_ERR_INVALID_ARGUMENT, "device_id out of range");
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (n_pixels == 0) return VIMG_OK;
+  CU_TRY(cudaSetDevice(device_id));
+  int sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id));
+  float *d_in = nullptr, *d_f = nullptr;
+  uint8_t* d_b = nullptr;
+  uint32_t* d_max = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = VIMG_OK;
+  auto cleanup = [&]() {
+    if (d_in) cudaFree(d_in);
+    if (d_f) cudaFree(d_f);
+    if (d_b) cudaFree(d_b);
+    if (d_max) cudaFree(d_max);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define PP_TRY(call)                                                                   \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      cleanup();                                                                       \
+      return fail(VIMG_ERR_CUDA, std::string("vimg_postprocess: ") + cudaGetErrorString(e_)); \
+    }                                                                                  \
+  } while (0)
+  const size_t fbytes = (size_t)n_pixels * 3 * sizeof(float);
+  PP_TRY(cudaMalloc(&d_in, fbytes));
+  if (out_srgb) PP_TRY(cudaMalloc(&d_f, fbytes));
+  if (out_rgb8) PP_TRY(cudaMalloc(&d_b, (size_t)n_pixels * 3 + 16));
+  PP_TRY(cudaMalloc(&d_max, sizeof(uint32_t)));
+  PP_TRY(cudaEventCreate(&e0));
+  PP_TRY(cudaEventCreate(&e1));
+  PP_TRY(cudaMemcpy(d_in, rgb, fbytes, cudaMemcpyHostToDevice));
+  PP_TRY(cudaEventRecord(e0, 0));
+  rc = post_launch(d_in, n_pixels, tonemapper, d_f, d_b, d_max, sms, 0);
+  if (rc != VIMG_OK) {
+    cleanup();
+    return rc;
+  }
+  PP_TRY(cudaEventRecord(e1, 0));
+  if (out_srgb) PP_TRY(cudaMemcpy(out_srgb, d_f, fbytes, cudaMemcpyDeviceToHost));
+  if (out_rgb8) PP_TRY(cudaMemcpy(out_rgb8, d_b, (size_t)n_pixels * 3, cudaMemcpyDeviceToHost));
+  PP_TRY(cudaEventSynchronize(e1));
+  if (kernel_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+#undef PP_TRY
+  cleanup();
+  return VIMG_OK;
+}
+
+int vimg_render_srgb8(vimg_scene* s, const vimg_render_params* p, uint32_t tonemapper, uint8_t* out_rgb8,
+                      vimg_render_stats* stats) {
+  if (!out_rgb8) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  if (tonemapper > VIMG_TONEMAP_NONE) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown tonemapper");
+  int rc = check_params(s, p);
+  if (rc != VIMG_OK) return rc;
+  if (p->n_ranks > 1) return fail(VIMG_ERR_UNSUPPORTED, "vimg_render_srgb8 renders the whole frame (n_ranks <= 1)");
+  CU_TRY(cudaSetDevice(s->device));
+  const size_t n_pixels = (size_t)s->W * s->H;
+  if (!s->d_rgb8) {
+    CU_TRY(cudaMalloc(&s->d_rgb8, n_pixels * 3 + 16));
+    CU_TRY(cudaMalloc(&s->d_post_max, sizeof(uint32_t)));
+  }
+  if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+  cudaEvent_t t0, t1, t2;
+  CU_TRY(cudaEventCreate(&t0));
+  CU_TRY(cudaEventCreate(&t1));
+  CU_TRY(cudaEventCreate(&t2));
+  cudaEventRecord(t0, 0);
+  float* dev = nullptr;
+  rc = vimg_render_device(s, p, &dev, nullptr, stats);
+  if (rc == VIMG_OK) rc = post_launch(dev, n_pixels, tonemapper, nullptr, s->d_rgb8, s->d_post_max, s->sm_count, 0);
+  cudaEventRecord(t1, 0);
+  if (rc == VIMG_OK) {
+    cudaError_t e = cudaMemcpy(out_rgb8, s->d_rgb8, n_pixels * 3, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(VIMG_ERR_CUDA, std::string("rgb8 D2H: ") + cudaGetErrorString(e));
+  }
+  cudaEventRecord(t2, 0);
+  cudaEventSynchronize(t2);
+  if (rc == VIMG_OK && stats) {
+    float k = 0, t = 0;
+    cudaEventElapsedTime(&k, t0, t1);
+    cudaEventElapsedTime(&t, t0, t2);
+    stats->kernel_ms = k;
+    stats->total_ms = t;
+    stats->kernel_launches += tonemapper == VIMG_TONEMAP_REINHARD ? 2 : 1;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaEventDestroy(t2);
   return rc;
 }
 

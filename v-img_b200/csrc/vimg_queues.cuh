@@ -411,6 +411,8 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
   const uint32_t n = c->n_end[parity];
   const uint32_t* __restrict__ q = st.q_end[parity];
   uint32_t nan_samples = 0, n_samples = 0;
+  // one look at the unit counter per warp and launch, in flight together with the first gathers
+  bool exhausted = *reinterpret_cast<volatile uint32_t*>(st.next_pixel) >= args.n_local_units;
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
     if (tid == 0) s_cnt[0] = 0;
@@ -557,13 +559,12 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
       if (m) {
         uint32_t pbase = 0;
         if (lane == (uint32_t)(__ffs(m) - 1)) {
-          // no atomic once the frame is handed out
-          if (*reinterpret_cast<volatile uint32_t*>(st.next_pixel) < args.n_local_units)
-            pbase = atomicAdd(st.next_pixel, (uint32_t)__popc(m));
-          else
-            pbase = args.n_local_units;
+          // no atomic once the frame is handed out (the counter was looked at when the launch
+          // started; a warp that sees it run out remembers)
+          pbase = exhausted ? args.n_local_units : atomicAdd(st.next_pixel, (uint32_t)__popc(m));
         }
         pbase = __shfl_sync(0xffffffffu, pbase, __ffs(m) - 1);
+        exhausted = exhausted || pbase >= args.n_local_units;
         if (want) {
           // tiles overhanging the frame contain pixel numbers without a pixel: take the next
           uint32_t u = pbase + __popc(m & lane_lt), p = 0;

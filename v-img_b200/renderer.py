@@ -31,6 +31,10 @@ class _DescHead(C.Structure):  # leading members of vimg_scene_desc
     _fields_ = [("abi_version", C.c_uint32), ("camera", _Camera)]
 
 
+# enum class tonemapper (include/color_utils.h:7) + none
+TONEMAPPERS = {"clamp": 0, "agx": 1, "reinhard": 2, "aces": 3, "none": 4}
+
+
 class RenderParams(C.Structure):
     _fields_ = [("integrator", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32),
                 ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("flags", C.c_uint32),
@@ -55,7 +59,8 @@ class RenderStats(C.Structure):
 
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
-           "vimg_trace_ids", "vimg_release_workspaces", "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
+           "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8",
+           "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
 
 
 def lib_path():
@@ -86,6 +91,10 @@ def load_library():
                                 C.POINTER(RenderStats)]
     lib.vimg_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(C.c_void_p),
                                        C.c_void_p, C.POINTER(RenderStats)]
+    lib.vimg_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_double)]
+    lib.vimg_render_srgb8.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.c_void_p,
+                                      C.POINTER(RenderStats)]
     lib.vimg_trace_pixel.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_int, C.c_int,
                                      C.c_void_p]
     lib.vimg_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -246,6 +255,16 @@ class Scene:
                                       "data": (dev_ptr, False), "version": 3}
         return torch.as_tensor(h, device=f"cuda:{self.device}")
 
+    def render_srgb8(self, func, samples, depth, tonemapper="clamp", spp_streams=1, pipeline=None):
+        """scene_integrator + tonemapper + sRGB OETF + 8-bit quantisation (src/main.cpp:219-356)
+        without leaving the device.  Returns (uint8 [H, W, 3] = the PNG payload, stats dict)."""
+        out = np.empty((self.height, self.width, 3), np.uint8)
+        st = RenderStats()
+        p = self._params(func, samples, depth, 0, 1, False, pipeline, False, spp_streams)
+        _check(self._lib, self._lib.vimg_render_srgb8(self._h, C.byref(p), TONEMAPPERS[tonemapper],
+                                                      out.ctypes.data, C.byref(st)), "vimg_render_srgb8")
+        return out, st.as_dict()
+
     def trace_pixel(self, func, x, y, samples, depth, pipeline=None):
         """Mirror of trace_pixel<F>() (include/integrators.h:181-220); y = 0 is the bottom row."""
         out = np.empty(3, np.float32)
@@ -262,3 +281,19 @@ class Scene:
                                                    t.ctypes.data if want_t else None),
                "vimg_trace_ids")
         return ids, t
+
+
+def postprocess(img, tonemapper="clamp", device=0, want_srgb=True):
+    """Mirror of src/main.cpp:304-356 on a linear float image [..., 3]: tonemapper, sRGB OETF,
+    8-bit quantisation, on the GPU.  Returns (uint8 image, float32 image after gamma or None,
+    kernel milliseconds)."""
+    lib = load_library()
+    img = np.ascontiguousarray(img, np.float32)
+    assert img.shape[-1] == 3
+    rgb8 = np.empty(img.shape, np.uint8)
+    srgb = np.empty_like(img) if want_srgb else None
+    ms = C.c_double()
+    _check(lib, lib.vimg_postprocess(img.ctypes.data, img.size // 3, TONEMAPPERS[tonemapper], device,
+                                     rgb8.ctypes.data, srgb.ctypes.data if want_srgb else None,
+                                     C.byref(ms)), "vimg_postprocess")
+    return rgb8, srgb, ms.value
