@@ -324,6 +324,14 @@ int vimg_trace_pixel(vimg_scene* scene, const vimg_render_params* params, int x,
  * out_t (nullable): same shape, the hit distance ray.maxT (inf on miss). */
 int vimg_trace_ids(vimg_scene* scene, uint32_t samples, int32_t* out_prim_id, float* out_t);
 
+/* Replaces heatmap_img() (src/integrators/heatmap.cpp:39-147; main.cpp:249-255 calls it with 4
+ * spp for the -m flag): per pixel the cost BVH::hit<float> accumulates over the integrators'
+ * camera rays (0.5 root box + 1 per inner node + 1 per primitive test on the reference's scalar
+ * path), truncated mean over `samples`, turbo colour map of mean / factor (factor <= 0 => 20).
+ * out_rgb: HOST, W*H*3 floats, row 0 = top.  out_cost (nullable): HOST, W*H floats, the
+ * truncated mean cost per pixel (what the colour map is applied to). */
+int vimg_heatmap(vimg_scene* scene, uint32_t samples, float factor, float* out_rgb, float* out_cost);
+
 /* ---- post-process chain (the step right after the path: src/main.cpp:304-356) ----------- */
 /* enum class tonemapper (include/color_utils.h:7) + "no tonemapper" (main.cpp:325-327). */
 typedef enum vimg_tonemapper {

@@ -469,6 +469,18 @@ void vref_postprocess(const float* rgb, uint64_t n_pixels, int tonemapper, float
   }
 }
 
+// The reference's own heat map (src/integrators/heatmap.cpp:39-147, called from main.cpp:249-255
+// with spp fixed to 4).  factor <= 0 takes the reference's default 20.
+void vref_heatmap(void* h, uint32_t spp, float factor, float* out_rgb) {
+  auto* sc = static_cast<RefScene*>(h);
+  integrator_data& s = sc->settings;
+  uint32_t keep_spp = s.samples;
+  if (spp) s.samples = spp;
+  std::vector<glm::vec3> img = heatmap_img(s, sc->bvh, sc->list_objects, factor);
+  s.samples = keep_spp;
+  std::memcpy(out_rgb, img.data(), img.size() * sizeof(glm::vec3));
+}
+
 // trace_pixel (include/integrators.h:181-220)
 void vref_trace_pixel(void* h, int integrator, uint32_t spp, uint32_t depth, int x, int y,
                       float out_rgb[3]) {

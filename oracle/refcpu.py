@@ -52,6 +52,8 @@ def _load(flavour):
                                      C.c_void_p]
     lib.vref_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.vref_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    lib.vref_heatmap.restype = None
+    lib.vref_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p]
     lib.vref_postprocess.restype = None
     lib.vref_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     lib.vref_flavour.restype = C.c_int
@@ -132,6 +134,12 @@ class RefScene:
         out = np.empty(3, np.float32)
         self._lib.vref_trace_pixel(self._h, INTEGRATORS[integrator], spp, depth, x, y,
                                    out.ctypes.data)
+        return out
+
+    def heatmap(self, spp=4, factor=20.0):
+        """heatmap_img (src/integrators/heatmap.cpp:39-147) -> float32 [H, W, 3]"""
+        out = np.empty((self.height, self.width, 3), np.float32)
+        self._lib.vref_heatmap(self._h, spp, factor, out.ctypes.data)
         return out
 
     def trace_ids(self, spp):
@@ -221,3 +229,14 @@ def restatement_postprocess(img, tonemapper):
     lib.vimg_oracle_postprocess(img.ctypes.data, img.size // 3, TONEMAPPERS[tonemapper],
                                 srgb.ctypes.data, rgb8.ctypes.data)
     return srgb, rgb8
+
+
+def restatement_heatmap(desc_ptr, width, height, spp=4, factor=20.0):
+    """BVH heat map through the plain-C restatement -> (rgb float32 [H, W, 3], cost float32 [H, W])"""
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_heatmap.restype = None
+    lib.vimg_oracle_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
+    rgb = np.empty((height, width, 3), np.float32)
+    cost = np.empty((height, width), np.float32)
+    lib.vimg_oracle_heatmap(desc_ptr, spp, factor, rgb.ctypes.data, cost.ctypes.data)
+    return rgb, cost

@@ -210,13 +210,19 @@ static int sphere_hit(const vimg_sphere* s, ray_t* r) {
 }
 
 /* ---- include/bvh.h:83-225, closest hit, scalar branch ---- */
-static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
+/* `cost` (nullable): what BVH::hit<float> returns for the heat map (bvh.h:128-131,159-163,189-192):
+ * traversal_cost 0.5 for the root box, 2 * 0.5 per inner node popped (scalar branch), intersection_cost
+ * 1 per primitive test */
+static int64_t bvh_closest_cost(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph, float* cost) {
   const vimg_bvh* b = &d->bvh;
   ph->prim = -1;
+  if (cost) *cost = 0.f;
   if (b->n_nodes == 0) return -1;
   v3 inv = V(1.0f / ray->dir.x, 1.0f / ray->dir.y, 1.0f / ray->dir.z);
   const float* bb = b->bb_mins_maxes;
-  if (isinf(slab(ray, inv, bb + 0, bb + 6))) return -1;
+  const float root_hit = slab(ray, inv, bb + 0, bb + 6);
+  if (cost) *cost += 0.5f;
+  if (isinf(root_hit)) return -1;
   uint64_t stack[128];
   int sp = 0;
   stack[sp++] = 0;
@@ -228,6 +234,7 @@ static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
         uint64_t prim = b->obj_indices[first + i];
         const vimg_prim* p = &d->prims[prim];
         int hit;
+        if (cost) *cost += 1.f;
         if (p->type == VIMG_PRIM_SPHERE) {
           hit = sphere_hit(&d->spheres[p->a], ray);
           if (hit) ph->e0 = ph->e1 = ph->e2 = ph->inv_det = 0.f;
@@ -241,6 +248,7 @@ static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
       uint64_t lmin = first_child * 2 + 2, lmax = lmin + 2, rmin = lmin + 1, rmax = lmax + 1;
       float h1 = slab(ray, inv, bb + 3 * lmin, bb + 3 * lmax);
       float h2 = slab(ray, inv, bb + 3 * rmin, bb + 3 * rmax);
+      if (cost) *cost += 0.5f * 2.f;
       if (!isinf(h2)) {
         if (!isinf(h1)) {
           if (h2 > h1) { uint64_t t = first_child; first_child = sec_child; sec_child = t; }
@@ -253,6 +261,9 @@ static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
     }
   }
   return ph->prim;
+}
+static int64_t bvh_closest(const vimg_scene_desc* d, ray_t* ray, prehit_t* ph) {
+  return bvh_closest_cost(d, ray, ph, 0);
 }
 
 /* hit_n_s / hit_n_g of Triangle::hit_info (triangle.cpp:13-43) and Sphere::hit_info (sphere.cpp:12-14);
@@ -460,4 +471,57 @@ void vimg_oracle_postprocess(const float* rgb, uint64_t n_pixels, int tonemapper
       }
     }
   }
+}
+
+/* ============================================================================================
+ * BVH heat map: src/integrators/heatmap.cpp:20-147
+ *   per pixel: the integrators' camera rays (same PCG stream, R2 jitter), BVH::hit<float> cost of
+ *   each, float sum, static_cast<uint32_t>(sum / spp) stored as float, turbo_colormap(v / factor).
+ * glm::dot(vec4) = (x*x' + y*y') + (z*z' + w*w'), dot(vec2) = x*x' + y*y'; the colour-map constants
+ * are double literals narrowed to float by the glm constructors.
+ * out_rgb: W*H*3; out_cost (nullable): W*H, the truncated mean cost.
+ * ============================================================================================ */
+static float dot4(const float a[4], const float b[4]) {
+  float tx = a[0] * b[0], ty = a[1] * b[1], tz = a[2] * b[2], tw = a[3] * b[3];
+  return (tx + ty) + (tz + tw);
+}
+static float dot2(const float a[2], const float b[2]) { return a[0] * b[0] + a[1] * b[1]; }
+static v3 turbo_colormap(float x) { /* heatmap.cpp:20-37 */
+  static const float r4[4] = {(float)0.13572138, (float)4.61539260, (float)-42.66032258, (float)132.13108234};
+  static const float g4[4] = {(float)0.09140261, (float)2.19418839, (float)4.84296658, (float)-14.18503333};
+  static const float b4[4] = {(float)0.10667330, (float)12.64194608, (float)-60.58204836, (float)110.36276771};
+  static const float r2[2] = {(float)-152.94239396, (float)59.28637943};
+  static const float g2[2] = {(float)4.27729857, (float)2.82956604};
+  static const float b2[2] = {(float)-89.90310912, (float)27.34824973};
+  x = (x < 0.f) ? 0.f : ((1.f < x) ? 1.f : x); /* std::clamp */
+  const float v4[4] = {1.0f, x, x * x, x * x * x};
+  const float v2[2] = {v4[2] * v4[2], v4[3] * v4[2]};
+  return V(dot4(v4, r4) + dot2(v2, r2), dot4(v4, g4) + dot2(v2, g2), dot4(v4, b4) + dot2(v2, b2));
+}
+void vimg_oracle_heatmap(const vimg_scene_desc* d, uint32_t spp, float factor, float* out_rgb, float* out_cost) {
+  const uint32_t W = (uint32_t)d->camera.resolution[0], H = (uint32_t)d->camera.resolution[1];
+  if (factor <= 0) factor = 20.f; /* heatmap.cpp:135-137 */
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t x = 0; x < W; ++x) {
+      size_t image_index = x + ((size_t)(H - 1 - y) * W);
+      pcg32 st;
+      pcg32_seed(&st, image_index, 0);
+      float acc = 0.f;
+      for (uint32_t s = 0; s < spp; ++s) {
+        float ox, oy, cost;
+        r2_offset(x + y + s, &ox, &oy);
+        float rand2 = rand_float(&st);
+        float rand1 = rand_float(&st);
+        ray_t ray = generate_ray(&d->camera, (float)x + ox, (float)y + oy, rand1, rand2);
+        prehit_t ph;
+        bvh_closest_cost(d, &ray, &ph, &cost);
+        acc += cost;
+      }
+      const float hits = (float)(uint32_t)(acc / spp);
+      if (out_cost) out_cost[image_index] = hits;
+      v3 c = turbo_colormap(hits / factor);
+      out_rgb[3 * image_index] = c.x;
+      out_rgb[3 * image_index + 1] = c.y;
+      out_rgb[3 * image_index + 2] = c.z;
+    }
 }

@@ -1142,6 +1142,23 @@ int vimg_render(vimg_scene* s, const vimg_render_params* p, float* out_rgb, vimg
   return rc;
 }
 
+int vimg_heatmap(vimg_scene* s, uint32_t samples, float factor, float* out_rgb, float* out_cost) {
+  if (!s || !out_rgb || samples == 0) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument / zero samples");
+  CU_TRY(cudaSetDevice(s->device));
+  if (factor <= 0) factor = 20.f;  // heatmap.cpp:135-137
+  const size_t n = (size_t)s->W * s->H;
+  float* d_cost = nullptr;
+  if (out_cost) CU_TRY(cudaMalloc(&d_cost, n * sizeof(float)));
+  const RenderArgs a = make_args(s, samples, 0, 0, 1);
+  heatmap_kernel<<<(a.n_local_tiles + 1) / 2, 128>>>(s->d, a, factor, s->d_frame, d_cost);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out_rgb, s->d_frame, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && out_cost) e = cudaMemcpy(out_cost, d_cost, n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (d_cost) cudaFree(d_cost);
+  if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("heatmap: ") + cudaGetErrorString(e));
+  return VIMG_OK;
+}
+
 // tonemap + OETF + quantise of `n_pixels` pixels already in HBM, on `st`
 static int post_launch(const float* d_rgb, uint64_t n_pixels, uint32_t tonemapper, float* d_srgb, uint8_t* d_rgb8,
                        uint32_t* d_max_bits, int sm_count, cudaStream_t st) {

@@ -100,6 +100,62 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderA
   }
 }
 
+// turbo_colormap (src/integrators/heatmap.cpp:20-37): double literals narrowed to float by the
+// glm constructors; glm::dot(vec4) = (x*x' + y*y') + (z*z' + w*w'), dot(vec2) = x*x' + y*y'
+VD V3 turbo_colormap(float x) {
+  const float r4[4] = {(float)0.13572138, (float)4.61539260, (float)-42.66032258, (float)132.13108234};
+  const float g4[4] = {(float)0.09140261, (float)2.19418839, (float)4.84296658, (float)-14.18503333};
+  const float b4[4] = {(float)0.10667330, (float)12.64194608, (float)-60.58204836, (float)110.36276771};
+  const float r2[2] = {(float)-152.94239396, (float)59.28637943};
+  const float g2[2] = {(float)4.27729857, (float)2.82956604};
+  const float b2[2] = {(float)-89.90310912, (float)27.34824973};
+  x = std_clamp(x, 0.f, 1.f);
+  const float v4[4] = {1.0f, x, x * x, x * x * x};
+  const float v2[2] = {v4[2] * v4[2], v4[3] * v4[2]};
+  auto dot4 = [&](const float (&c)[4]) {
+    float tx = v4[0] * c[0], ty = v4[1] * c[1], tz = v4[2] * c[2], tw = v4[3] * c[3];
+    return (tx + ty) + (tz + tw);
+  };
+  auto dot2 = [&](const float (&c)[2]) { return v2[0] * c[0] + v2[1] * c[1]; };
+  return mk3(dot4(r4) + dot2(r2), dot4(g4) + dot2(g2), dot4(b4) + dot2(b2));
+}
+
+// heatmap_img (src/integrators/heatmap.cpp:39-147): the integrators' camera rays, the cost
+// BVH::hit<float> accumulates along the closest-hit traversal (bvh.h:128-131,159-163,189-192:
+// 0.5 for the root box, 2 * 0.5 per inner node popped on the scalar path, 1 per primitive test --
+// all dyadic, so the float sums are exact in any order), truncated mean over the samples,
+// turbo colour map of mean / factor.  out_cost (nullable): the truncated mean, W*H floats.
+__global__ void __launch_bounds__(128)
+heatmap_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderArgs args, const float factor,
+               float* __restrict__ out, float* __restrict__ out_cost) {
+  uint32_t x, y;
+  if (!thread_pixel(args, sc.cam, x, y)) return;
+  const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
+  const size_t image_index = x + ((size_t)(H - 1 - y) * W);
+  const uint32_t image_seq_start = x + y;
+  Pcg32 rng;
+  pcg32_seed(rng, image_index, 0);
+  float acc = 0.f;
+  for (uint32_t s = 0; s < args.samples; s++) {
+    V2 off = random_x_y_r2(image_seq_start + s);
+    float rand2 = rand_float(rng);
+    float rand1 = rand_float(rng);
+    Ray ray = generate_ray(sc.cam, (float)x + off.x, (float)y + off.y, rand1, rand2);
+    PreHit ph;
+    TravCounters tc = {};
+    bvh_traverse<false, true>(sc, ray, ph, &tc);
+    // an empty BVH returns 0 before the root test (bvh.h:100-102)
+    const float cost = sc.n_nodes == 0 ? 0.f : 0.5f + (float)tc.inner + (float)(tc.tri + tc.sph);
+    acc += cost;
+  }
+  const float hits = (float)(uint32_t)(acc / (float)args.samples);
+  if (out_cost) out_cost[image_index] = hits;
+  const V3 c = turbo_colormap(hits / factor);
+  out[3 * image_index] = c.x;
+  out[3 * image_index + 1] = c.y;
+  out[3 * image_index + 2] = c.z;
+}
+
 // primary-hit primitive ids (parity hook): camera + closest-hit traversal only
 __global__ void __launch_bounds__(128)
 trace_ids_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderArgs args,

@@ -59,7 +59,7 @@ class RenderStats(C.Structure):
 
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
-           "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8",
+           "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8", "vimg_heatmap",
            "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
 
 
@@ -95,6 +95,7 @@ def load_library():
                                      C.POINTER(C.c_double)]
     lib.vimg_render_srgb8.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.c_void_p,
                                       C.POINTER(RenderStats)]
+    lib.vimg_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
     lib.vimg_trace_pixel.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_int, C.c_int,
                                      C.c_void_p]
     lib.vimg_trace_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -264,6 +265,15 @@ class Scene:
         _check(self._lib, self._lib.vimg_render_srgb8(self._h, C.byref(p), TONEMAPPERS[tonemapper],
                                                       out.ctypes.data, C.byref(st)), "vimg_render_srgb8")
         return out, st.as_dict()
+
+    def heatmap(self, samples=4, factor=20.0):
+        """Mirror of heatmap_img() (src/integrators/heatmap.cpp:39-147; the -m flag).
+        Returns (rgb float32 [H, W, 3], truncated mean BVH cost float32 [H, W])."""
+        rgb = np.empty((self.height, self.width, 3), np.float32)
+        cost = np.empty((self.height, self.width), np.float32)
+        _check(self._lib, self._lib.vimg_heatmap(self._h, samples, factor, rgb.ctypes.data, cost.ctypes.data),
+               "vimg_heatmap")
+        return rgb, cost
 
     def trace_pixel(self, func, x, y, samples, depth, pipeline=None):
         """Mirror of trace_pixel<F>() (include/integrators.h:181-220); y = 0 is the bottom row."""
