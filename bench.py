@@ -126,11 +126,15 @@ class StdoutToStderr:
     bench.py's stdout carries exactly one JSON line, so fd 1 points at stderr while it runs."""
 
     def __enter__(self):
+        import ctypes
+        self.libc = ctypes.CDLL(None)
         sys.stdout.flush()
+        self.libc.fflush(None)
         self.saved = os.dup(1)
         os.dup2(2, 1)
 
     def __exit__(self, *exc):
+        self.libc.fflush(None)  # the reference's text sits in C stdio's buffer when fd 1 is a file
         os.dup2(self.saved, 1)
         os.close(self.saved)
 
@@ -377,6 +381,18 @@ def cuda_line(w, args):
     }
     if stages:
         line["stages"] = stages
+    # ---- the step after the path: tonemapper + sRGB OETF + 8-bit quantisation
+    # on the device.  HBM bound: 12 B read + 3 B written per pixel; timed on a 4K frame (the 1800x800
+    # frame of this workload is 22 MB: one launch of ~10 us, launch-latency bound)
+    post = {}
+    rng = np.random.default_rng(0)
+    big = (rng.random((2160, 3840, 3), dtype=np.float32) * 4).astype(np.float32)
+    for tm in ("clamp", "aces", "reinhard", "agx"):
+        best = min(vimg.postprocess(big, tm, device=local_rank, want_srgb=False)[2] for _ in range(5))
+        nbytes = big.size // 3 * 15 + (big.size // 3 * 12 if tm == "reinhard" else 0)
+        post[tm] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
+    line["postprocess"] = {"frame": "3840x2160 synthetic, bytes = 15 per pixel (+12 for reinhard's luminance pass)",
+                           "per_tonemapper": post}
     if not args.no_cpu and world == 1:
         r = time_reference(w, 1, 1, budget_s=16.0)
         if r is not None:
