@@ -456,6 +456,14 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     d.bg.emissive = !(hb.color[0] == 0.f && hb.color[1] == 0.f && hb.color[2] == 0.f);
   }
 
+  // who reads a ray cone: image colour textures and the env map (vimg_types.cuh)
+  d.uses_cones = hb.type == VIMG_BG_ENVMAP ? 1u : 0u;
+  for (uint32_t m = 0; m < desc->n_materials; ++m) {
+    const int32_t t = desc->materials[m].texture;
+    if (t >= 0 && desc->textures[t].type == VIMG_TEX_IMAGE) d.uses_cones = 1u;
+  }
+  if (const char* e = std::getenv("VIMG_FORCE_CONES")) d.uses_cones = std::atoi(e) ? 1u : d.uses_cones;
+
   // ---- upload ------------------------------------------------------------------
   int rc;
 #define UP(call) if ((rc = (call)) != VIMG_OK) return rc

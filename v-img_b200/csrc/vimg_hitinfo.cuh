@@ -391,14 +391,18 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
   }
 
   V3 tangent = normalize(dpdu - shading_normal * dot(shading_normal, dpdu));
-  V3 dnds = n2 - n0;
-  V3 dndt = n2 - n1;
-  V3 dndu = dnds * dsdu + dndt * dtdu;
-  V3 dndv = dnds * dsdv + dndt * dtdv;
   V3 bitangent = normalize(cross(shading_normal, tangent));
-  float mean_curvature = (dot(dndu, tangent) + dot(dndv, bitangent)) / 2.f;
-  float twice_tri_area = length(cross(p1 - p0, p2 - p0));
-  float uv_area = fabsf((uv1.x - uv0.x) * (uv2.y - uv0.y) - (uv2.x - uv0.x) * (uv1.y - uv0.y));
+  // curvature and the two areas only feed ray cones / texture LOD (DScene::uses_cones)
+  float mean_curvature = 0.f, twice_tri_area = 1.f, uv_area = 1.f;
+  if (sc.uses_cones) {
+    V3 dnds = n2 - n0;
+    V3 dndt = n2 - n1;
+    V3 dndu = dnds * dsdu + dndt * dtdu;
+    V3 dndv = dnds * dsdv + dndt * dtdv;
+    mean_curvature = (dot(dndu, tangent) + dot(dndv, bitangent)) / 2.f;
+    twice_tri_area = length(cross(p1 - p0, p2 - p0));
+    uv_area = fabsf((uv1.x - uv0.x) * (uv2.y - uv0.y) - (uv2.x - uv0.x) * (uv1.y - uv0.y));
+  }
 
   HitInfo h;
   h.mat = sr.material;

@@ -773,9 +773,11 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       V3 thr = xyz(t4);
       float eta_scale = t4.w;
       bool nsb = (fj & WF_NSB) != 0;
-      float hit_dist = length(ray.o - hit.hit_p);
+      // ray cones: skipped when nothing in the scene reads them (DScene::uses_cones)
+      const bool cones = sc.uses_cones != 0;
+      float hit_dist = cones ? length(ray.o - hit.hit_p) : 0.f;
       float surface_spread_angle
-          = spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s);
+          = cones ? spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s) : 0.f;
       // records written back at the end (whole sectors)
       float4 nee_wi = make_float4(0.f, 0.f, 0.f, 0.f), nee_c = nee_wi;
       float4 new_o = f4(hit.hit_p, o4.w), new_d = d4;  // origin of the shadow ray and of the next ray
@@ -789,7 +791,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
           light_col = lights_sample(sc, hit.hit_p, rng, li);
           nee = li.pdf != 0.f;
         }
-        const RayCone nee_cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+        const RayCone nee_cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
         const bool nee_regularize = nsb;
         ScatterInfo sm;
         const bool scattered = cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sm);
@@ -798,7 +800,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
           if (!sm.is_specular) nsb = true;
           if (sm.eta != 0.f) {
             eta_scale /= (sm.eta * sm.eta);
-            cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
+            if (cones) cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
           } else {
             cone = nee_cone;
           }
@@ -858,9 +860,9 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
           RayCone cone;
           if (sr.eta != 0.f) {
             eta_scale /= (sr.eta * sr.eta);
-            cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo);
+            cone = cones ? propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo) : ray.cone;
           } else {
-            cone = propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist);
+            cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
           }
           thr = thr * (emitted_col + cls_eval_div_pdf<CLASS>(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
           bool go_on = true;

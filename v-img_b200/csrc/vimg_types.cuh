@@ -147,6 +147,10 @@ struct DScene {
   const float* rg_texels;
   const int32_t* lights;
   uint32_t n_lights;
+  // ray cones (ray.h:44-174) only feed the mip level of image textures (col_at_ray_hit) and of the
+  // env map (background_emit); a scene with neither never reads them, so their propagation (two
+  // double sin / cos pairs and an acos per refraction) is skipped.  Images are unchanged.
+  uint32_t uses_cones;
   DBackground bg;
 };
 
