@@ -47,25 +47,10 @@ VD bool lambertian_sample(V3 wi, const HitInfo& hit, Pcg32& rng, ScatterInfo& ou
   return true;
 }
 
-// (double)x / pi for a float x in [0, 2] with three double operations instead of the division
-// subroutine: q0 = x * RN(1/pi), r = x - q0 * pi (exact with fma), q = q0 + r * RN(1/pi) is the
-// correctly rounded quotient (Markstein); oracle/tools/divpi_check.c compares it with the IEEE
-// quotient for EVERY float in [0, 2]: zero mismatches.  Outside that range: the division itself.
-VD double div_pi(float x) {
-  const double xd = (double)x;
-#ifdef VIMG_NO_DIVPI
-  return xd / VIMG_PI_D;
-#endif
-  if (!(x >= 0.f && x <= 2.f)) return xd / VIMG_PI_D;
-  const double q0 = xd * VIMG_INV_PI_D;
-  const double r = fma(-q0, VIMG_PI_D, xd);
-  return fma(r, VIMG_INV_PI_D, q0);
-}
-
 // Lambertian::eval_pdf_pair (lambertian.cpp:46-54): max(0, wo.n_s) / pi in double, narrowed
 VD void lambertian_eval_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo,
                             const HitInfo& hit, RayCone cone, V3& eval, float& pdf) {
-  float dot_product = (float)div_pi(std_max(0.0f, dot(wo, hit.hit_n_s)));
+  float dot_product = (float)((double)std_max(0.0f, dot(wo, hit.hit_n_s)) / VIMG_PI_D);
   eval = col_at_ray_hit(sc, m.texture, wi, cone, hit) * dot_product;
   pdf = dot_product;
 }
