@@ -332,6 +332,26 @@ int vimg_trace_ids(vimg_scene* scene, uint32_t samples, int32_t* out_prim_id, fl
  * truncated mean cost per pixel (what the colour map is applied to). */
 int vimg_heatmap(vimg_scene* scene, uint32_t samples, float factor, float* out_rgb, float* out_cost);
 
+/* ---- scene preparation (the step before the path; the reference does it in its constructors) */
+/* Number of mip levels ImageTexture's constructor builds (src/image_texture.cpp:73-78):
+ * min(ceil(log2(float(min(w, h)))), 15), at least 1 (level 0).  *out_floats (nullable) receives
+ * the number of floats of levels 1 .. n-1 together (level l is max(w>>l,1) x max(h>>l,1) x 3). */
+uint32_t vimg_mip_chain_levels(uint32_t width, uint32_t height, uint64_t* out_floats);
+
+/* Replaces the mip-chain loop of ImageTexture::ImageTexture (image_texture.cpp:59-130):
+ * level0: HOST, width*height*3 floats (linear RGB, row 0 = top); out_levels: HOST, the floats of
+ * levels 1 .. n-1 one after the other (size from vimg_mip_chain_levels).  wrap_u / wrap_v:
+ * vimg_wrap.  kernel_ms (nullable): device time of the level kernels. */
+int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, uint32_t wrap_u,
+                         uint32_t wrap_v, int device_id, float* out_levels, double* kernel_ms);
+
+/* Replaces ArraySampling2D's constructor for an env map (include/rng/sampling.h:167-197, called
+ * from EnvMap's constructor, background.h:83): image: HOST, width*height*3 floats;
+ * out_row_cdf: HOST, height+1 floats; out_col_cdfs: HOST, height*(width+1) floats -- the
+ * vimg_background fields of the same names. */
+int vimg_build_envmap_cdf(const float* image, uint32_t width, uint32_t height, int device_id,
+                          float* out_row_cdf, float* out_col_cdfs, double* kernel_ms);
+
 /* ---- post-process chain (the step right after the path: src/main.cpp:304-356) ----------- */
 /* enum class tonemapper (include/color_utils.h:7) + "no tonemapper" (main.cpp:325-327). */
 typedef enum vimg_tonemapper {

@@ -9,4 +9,5 @@ There is NO CPU fallback: importing works anywhere, but every compute call
 raises VimgError when the CUDA extension or a CUDA device is missing.
 """
 from .renderer import (INTEGRATORS, TONEMAPPERS, LoadedDesc, Scene, VimgError, device_count,  # noqa: F401
-                       lib_path, load_library, postprocess, tile_owner)
+                       lib_path, load_library, postprocess, tile_owner, build_mip_chain, build_envmap_cdf,
+                       desc_envmap, desc_image_textures)

@@ -16,6 +16,7 @@
 
 #include "vimg_kernels.cuh"
 #include "vimg_post.cuh"
+#include "vimg_prep.cuh"
 
 using namespace vimg;
 
@@ -1148,6 +1149,128 @@ int vimg_render(vimg_scene* s, const vimg_render_params* p, float* out_rgb, vimg
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   return rc;
+}
+
+uint32_t vimg_mip_chain_levels(uint32_t width, uint32_t height, uint64_t* out_floats) {
+  if (out_floats) *out_floats = 0;
+  if (width == 0 || height == 0) return 0;
+  const uint32_t size = std::min(width, height);
+  // image_texture.cpp:73-78: the loop runs for l = 1 .. num_levels - 1; level 0 always exists
+  const int num_levels = std::min((int)std::ceil(std::log2(float(size))), 15);
+  const uint32_t n = (uint32_t)std::max(num_levels, 1);
+  uint64_t floats = 0;
+  uint32_t w = width, h = height;
+  for (uint32_t l = 1; l < n; ++l) {
+    w = std::max(w / 2u, 1u);
+    h = std::max(h / 2u, 1u);
+    floats += (uint64_t)w * h * 3;
+  }
+  if (out_floats) *out_floats = floats;
+  return n;
+}
+
+// device selection + argument checks shared by the scene-preparation entry points
+static int prep_device(int device_id, int* sms) {
+  const int n = vimg_cuda_device_count();
+  if (n == 0) return fail(VIMG_ERR_NO_DEVICE, "no CUDA device visible: the cuda render device has no CPU fallback");
+  if (device_id < 0 || device_id >= n) return fail(VIMG_ERR_INVALID_ARGUMENT, "device_id out of range");
+  CU_TRY(cudaSetDevice(device_id));
+  CU_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device_id));
+  return VIMG_OK;
+}
+
+int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, uint32_t wrap_u, uint32_t wrap_v,
+                         int device_id, float* out_levels, double* kernel_ms) {
+  if (!level0 || width == 0 || height == 0) return fail(VIMG_ERR_INVALID_ARGUMENT, "null / empty image");
+  if (wrap_u > VIMG_WRAP_REPEAT || wrap_v > VIMG_WRAP_REPEAT) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown wrap mode");
+  if (kernel_ms) *kernel_ms = 0.0;
+  uint64_t floats = 0;
+  const uint32_t n_levels = vimg_mip_chain_levels(width, height, &floats);
+  if (n_levels <= 1) return VIMG_OK;
+  if (!out_levels) return fail(VIMG_ERR_INVALID_ARGUMENT, "null output");
+  int sms = 0, rc = prep_device(device_id, &sms);
+  if (rc != VIMG_OK) return rc;
+  float* d_all = nullptr;  // level 0 followed by levels 1 .. n-1
+  const size_t l0 = (size_t)width * height * 3;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_all, (l0 + floats) * sizeof(float));
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMemcpy(d_all, level0, l0 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cudaEventRecord(e0, 0);
+    const float* prev = d_all;
+    float* next = d_all + l0;
+    uint32_t pw = width, ph = height;
+    for (uint32_t l = 1; l < n_levels; ++l) {
+      const uint32_t nw = std::max(pw / 2u, 1u), nh = std::max(ph / 2u, 1u);
+      prep_mip_level_kernel<<<dim3((nw + 255) / 256, nh), 256>>>(prev, pw, ph, next, nw, nh, wrap_u, wrap_v);
+      prev = next;
+      next += (size_t)nw * nh * 3;
+      pw = nw;
+      ph = nh;
+    }
+    cudaEventRecord(e1, 0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_levels, d_all + l0, floats * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  if (d_all) cudaFree(d_all);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("vimg_build_mip_chain: ") + cudaGetErrorString(e));
+  return VIMG_OK;
+}
+
+int vimg_build_envmap_cdf(const float* image, uint32_t width, uint32_t height, int device_id, float* out_row_cdf,
+                          float* out_col_cdfs, double* kernel_ms) {
+  if (!image || !out_row_cdf || !out_col_cdfs || width == 0 || height == 0)
+    return fail(VIMG_ERR_INVALID_ARGUMENT, "null / empty argument");
+  if (kernel_ms) *kernel_ms = 0.0;
+  int sms = 0, rc = prep_device(device_id, &sms);
+  if (rc != VIMG_OK) return rc;
+  // sampling.h:181-183: v = (y + 0.5f) / height; float sin_elevation = std::sin(std::numbers::pi * v)
+  std::vector<float> sin_elev(height);
+  for (uint32_t y = 0; y < height; ++y) {
+    const float v = (static_cast<float>(y) + 0.5f) / static_cast<float>(height);
+    sin_elev[y] = (float)std::sin(std::numbers::pi * v);
+  }
+  const size_t n_img = (size_t)width * height * 3, n_col = (size_t)height * (width + 1);
+  float *d_img = nullptr, *d_sin = nullptr, *d_col = nullptr, *d_int = nullptr, *d_row = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, n_img * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_sin, height * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_col, n_col * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_int, height * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_row, ((size_t)height + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMemcpy(d_img, image, n_img * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_sin, sin_elev.data(), height * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cudaEventRecord(e0, 0);
+    prep_row_cdf_kernel<<<(height + 127) / 128, 128>>>(d_img, width, height, d_sin, d_col, d_int);
+    prep_row_prob_kernel<<<1, 32>>>(d_int, height, d_row);
+    cudaEventRecord(e1, 0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_col_cdfs, d_col, n_col * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_row_cdf, d_row, ((size_t)height + 1) * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  for (float* p : {d_img, d_sin, d_col, d_int, d_row})
+    if (p) cudaFree(p);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("vimg_build_envmap_cdf: ") + cudaGetErrorString(e));
+  return VIMG_OK;
 }
 
 int vimg_heatmap(vimg_scene* s, uint32_t samples, float factor, float* out_rgb, float* out_cost) {

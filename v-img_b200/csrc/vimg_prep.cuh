@@ -1,0 +1,110 @@
+// vimg_prep.cuh -- scene-preparation kernels, the step BEFORE the render path (SURVEY.md 8(f)
+// rank 3): what the reference's constructors compute on the host in seconds per 2K texture.
+//
+//   mip chain        ImageTexture::ImageTexture (src/image_texture.cpp:59-130): every level is
+//                    the previous one through Wronski's 8-tap downsampling filter, each tap a
+//                    bilinear fetch with col_at_uv_mipmap (:132-161), negative results set to 0
+//   env-map CDFs     ArraySampling2D / ArraySampling1D (include/rng/sampling.h:114-135,167-197):
+//                    luminance * sin(elevation) per pixel, one running float sum per row, the
+//                    row integrals summed the same way
+//
+// Both must be bit-compatible with the host versions or the parity of everything that reads a
+// texture moves.  The filter is float +, *, and the bilinear fetch the render kernels already
+// use.  The CDFs are SEQUENTIAL float sums (cdf[x] = cdf[x-1] + |f|): float addition is not
+// associative, so each row is summed by one thread in the reference's order (H rows in parallel),
+// and the sin(elevation) factors -- H values of std::sin(double) -- are computed on the host with
+// the host libm, which is what the reference calls.
+#pragma once
+#include "vimg_hitinfo.cuh"
+
+namespace vimg {
+
+// ImageTexture::col_at_uv_mipmap on a bare level (same expressions as col_at_uv_mipmap above)
+VD V3 bilinear_level(const float* __restrict__ lvl, uint32_t mip_w, uint32_t mip_h, uint32_t wrap_u,
+                     uint32_t wrap_v, V2 uv) {
+  float pixel_u = handle_wrapping(uv.x, wrap_u) * mip_w;
+  float pixel_v = handle_wrapping(uv.y, wrap_v) * mip_h;
+  int curr_x = std_clampi((int)pixel_u, 0, (int)mip_w - 1);
+  int curr_y = std_clampi((int)pixel_v, 0, (int)mip_h - 1);
+  int next_x = std_clampi(curr_x + 1, 0, (int)mip_w - 1);
+  int next_y = std_clampi(curr_y + 1, 0, (int)mip_h - 1);
+  float x_fraction = pixel_u - curr_x;
+  float y_fraction = pixel_v - curr_y;
+  V3 x0 = load3(lvl, curr_x + curr_y * mip_w), x1 = load3(lvl, next_x + curr_y * mip_w);
+  V3 a = mix(x0, x1, x_fraction);
+  V3 y0 = load3(lvl, curr_x + next_y * mip_w), y1 = load3(lvl, next_x + next_y * mip_w);
+  V3 b = mix(y0, y1, x_fraction);
+  return mix(a, b, y_fraction);
+}
+
+// one mip level from the previous one (image_texture.cpp:84-122); thread <-> output pixel
+__global__ void __launch_bounds__(256)
+prep_mip_level_kernel(const float* __restrict__ prev, uint32_t prev_w, uint32_t prev_h, float* __restrict__ next,
+                      uint32_t next_w, uint32_t next_h, uint32_t wrap_u, uint32_t wrap_v) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= next_w || y >= next_h) return;
+  const V2 inv_res = mk2(1.f / prev_w, 1.f / prev_h);
+  const V2 curr_uv = mk2((float)(2 * x), (float)(2 * y)) * inv_res;
+  // glm::vec2(-0.75777, ...) / (2.907, 0.0): double literals narrowed to float
+  const float k = (float)0.75777, f = (float)2.907;
+  const float tap[8][2] = {{-k, -k}, {k, -k}, {k, k}, {-k, k}, {-f, 0.f}, {f, 0.f}, {0.f, -f}, {0.f, f}};
+  V3 sum = mk3(0.f);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float wgt = t < 4 ? 0.37487566f : -0.12487566f;
+    const V2 uv = curr_uv + mk2(tap[t][0], tap[t][1]) * inv_res;
+    sum = sum + wgt * bilinear_level(prev, prev_w, prev_h, wrap_u, wrap_v, uv);
+  }
+  if (sum.x < 0) sum.x = 0.f;
+  if (sum.y < 0) sum.y = 0.f;
+  if (sum.z < 0) sum.z = 0.f;
+  float* o = next + 3 * ((size_t)x + (size_t)y * next_w);
+  o[0] = sum.x;
+  o[1] = sum.y;
+  o[2] = sum.z;
+}
+
+// ArraySampling2D rows (sampling.h:176-193) + ArraySampling1D (:118-135): thread <-> image row;
+// writes the row's normalised CDF (W + 1 floats) and its integral
+__global__ void __launch_bounds__(128)
+prep_row_cdf_kernel(const float* __restrict__ image, uint32_t width, uint32_t height,
+                    const float* __restrict__ sin_elevation, float* __restrict__ col_cdfs,
+                    float* __restrict__ row_integrals) {
+  const uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= height) return;
+  const float se = sin_elevation[y];
+  float* cdf = col_cdfs + (size_t)y * (width + 1);
+  const float* row = image + 3 * (size_t)y * width;
+  float run = 0.f;
+  cdf[0] = 0.f;
+  for (uint32_t x = 0; x < width; ++x) {
+    const float lum = dot(mk3(row[3 * x], row[3 * x + 1], row[3 * x + 2]), mk3(0.212671f, 0.715160f, 0.072169f)) * se;
+    run = run + fabsf(lum);
+    cdf[x + 1] = run;
+  }
+  const float func_int = run;
+  row_integrals[y] = func_int;
+  if (func_int == 0.f) {
+    for (uint32_t i = 0; i <= width; ++i) cdf[i] = (float)i / (float)width;
+  } else {
+    for (uint32_t i = 0; i <= width; ++i) cdf[i] = cdf[i] / func_int;
+  }
+}
+
+// row_probabilities = ArraySampling1D(row integrals): H values, one thread, the reference's order
+__global__ void prep_row_prob_kernel(const float* __restrict__ row_integrals, uint32_t height, float* __restrict__ row_cdf) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float run = 0.f;
+  row_cdf[0] = 0.f;
+  for (uint32_t y = 0; y < height; ++y) {
+    run = run + fabsf(row_integrals[y]);
+    row_cdf[y + 1] = run;
+  }
+  if (run == 0.f) {
+    for (uint32_t i = 0; i <= height; ++i) row_cdf[i] = (float)i / (float)height;
+  } else {
+    for (uint32_t i = 0; i <= height; ++i) row_cdf[i] = row_cdf[i] / run;
+  }
+}
+
+}  // namespace vimg

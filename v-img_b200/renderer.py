@@ -27,6 +27,37 @@ class _Camera(C.Structure):
                 ("aperture_radius", C.c_float), ("focal_dist", C.c_float)]
 
 
+class _Bvh(C.Structure):  # vimg_bvh
+    _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_uint64), ("bb_mins_maxes", C.c_void_p),
+                ("n_bb_slots", C.c_uint64), ("obj_indices", C.c_void_p), ("n_obj_indices", C.c_uint64),
+                ("max_depth", C.c_uint32)]
+
+
+class _Texture(C.Structure):  # vimg_texture
+    _fields_ = [("type", C.c_uint32), ("col_a", C.c_float * 3), ("col_b", C.c_float * 3),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("n_levels", C.c_uint32),
+                ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32), ("levels", C.POINTER(C.POINTER(C.c_float)))]
+
+
+class _Background(C.Structure):  # vimg_background
+    _fields_ = [("type", C.c_uint32), ("color", C.c_float * 3), ("image", C.c_int32),
+                ("world_to_env", C.c_float * 16), ("env_to_world", C.c_float * 16),
+                ("radiance_scale", C.c_float), ("cdf_width", C.c_uint32), ("cdf_height", C.c_uint32),
+                ("row_cdf", C.POINTER(C.c_float)), ("col_cdfs", C.POINTER(C.c_float))]
+
+
+class _Desc(C.Structure):  # vimg_scene_desc (include/vimg_cuda.h), pointers kept opaque where unused
+    _fields_ = [("abi_version", C.c_uint32), ("camera", _Camera), ("bvh", _Bvh),
+                ("prims", C.c_void_p), ("n_prims", C.c_uint64),
+                ("spheres", C.c_void_p), ("n_spheres", C.c_uint32),
+                ("meshes", C.c_void_p), ("n_meshes", C.c_uint32),
+                ("materials", C.c_void_p), ("n_materials", C.c_uint32),
+                ("textures", C.POINTER(_Texture)), ("n_textures", C.c_uint32),
+                ("textures_rg", C.c_void_p), ("n_textures_rg", C.c_uint32),
+                ("lights", C.c_void_p), ("n_lights", C.c_uint32),
+                ("background", _Background)]
+
+
 class _DescHead(C.Structure):  # leading members of vimg_scene_desc
     _fields_ = [("abi_version", C.c_uint32), ("camera", _Camera)]
 
@@ -60,6 +91,7 @@ class RenderStats(C.Structure):
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
            "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8", "vimg_heatmap",
+           "vimg_mip_chain_levels", "vimg_build_mip_chain", "vimg_build_envmap_cdf",
            "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
 
 
@@ -95,6 +127,12 @@ def load_library():
                                      C.POINTER(C.c_double)]
     lib.vimg_render_srgb8.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.c_void_p,
                                       C.POINTER(RenderStats)]
+    lib.vimg_mip_chain_levels.restype = C.c_uint32
+    lib.vimg_mip_chain_levels.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.vimg_build_mip_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                         C.c_void_p, C.POINTER(C.c_double)]
+    lib.vimg_build_envmap_cdf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_double)]
     lib.vimg_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
     lib.vimg_trace_pixel.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_int, C.c_int,
                                      C.c_void_p]
@@ -147,6 +185,12 @@ class LoadedDesc:
             raise VimgError(f"vimg_scene_desc_load({path}) failed ({rc})")
         self.ptr = d.value
 
+    def image_textures(self):
+        return desc_image_textures(self.ptr)
+
+    def envmap(self):
+        return desc_envmap(self.ptr)
+
     def close(self):
         if self.ptr:
             self._lib.vimg_scene_desc_free(self.ptr)
@@ -157,6 +201,40 @@ class LoadedDesc:
             self.close()
         except Exception:
             pass
+
+
+class _DescViews:
+    """readers of a vimg_scene_desc in host memory (tests of the scene-preparation kernels)"""
+
+    @staticmethod
+    def image_textures(ptr):
+        """[(index, wrap_u, wrap_v, [level arrays float32 [h, w, 3]])] of the image textures"""
+        d = _Desc.from_address(ptr)
+        out = []
+        for i in range(d.n_textures):
+            t = d.textures[i]
+            if t.type != 2:  # VIMG_TEX_IMAGE
+                continue
+            levels = []
+            for lv in range(t.n_levels):
+                w, h = max(t.width >> lv, 1), max(t.height >> lv, 1)
+                levels.append(np.ctypeslib.as_array(t.levels[lv], shape=(h, w, 3)).copy())
+            out.append((i, int(t.wrap_u), int(t.wrap_v), levels))
+        return out
+
+    @staticmethod
+    def envmap(ptr):
+        """(image texture index, row_cdf [H+1], col_cdfs [H, W+1]) of an env-map background, or None"""
+        b = _Desc.from_address(ptr).background
+        if b.type != 1:  # VIMG_BG_ENVMAP
+            return None
+        h, w = int(b.cdf_height), int(b.cdf_width)
+        return (int(b.image), np.ctypeslib.as_array(b.row_cdf, shape=(h + 1,)).copy(),
+                np.ctypeslib.as_array(b.col_cdfs, shape=(h, w + 1)).copy())
+
+
+desc_image_textures = _DescViews.image_textures
+desc_envmap = _DescViews.envmap
 
 
 class Scene:
@@ -307,3 +385,37 @@ def postprocess(img, tonemapper="clamp", device=0, want_srgb=True):
                                      rgb8.ctypes.data, srgb.ctypes.data if want_srgb else None,
                                      C.byref(ms)), "vimg_postprocess")
     return rgb8, srgb, ms.value
+
+
+def build_mip_chain(level0, wrap_u=0, wrap_v=0, device=0):
+    """Mirror of the mip-chain loop of ImageTexture's constructor (src/image_texture.cpp:59-130).
+    level0: float32 [H, W, 3].  Returns ([level 1, level 2, ...] float32 arrays, kernel ms)."""
+    lib = load_library()
+    level0 = np.ascontiguousarray(level0, np.float32)
+    h, w = level0.shape[:2]
+    floats = C.c_uint64()
+    n = lib.vimg_mip_chain_levels(w, h, C.byref(floats))
+    buf = np.empty(floats.value, np.float32)
+    ms = C.c_double()
+    _check(lib, lib.vimg_build_mip_chain(level0.ctypes.data, w, h, wrap_u, wrap_v, device, buf.ctypes.data,
+                                         C.byref(ms)), "vimg_build_mip_chain")
+    levels, off = [], 0
+    for lv in range(1, n):
+        w, h = max(w // 2, 1), max(h // 2, 1)
+        levels.append(buf[off:off + w * h * 3].reshape(h, w, 3))
+        off += w * h * 3
+    return levels, ms.value
+
+
+def build_envmap_cdf(image, device=0):
+    """Mirror of ArraySampling2D's constructor (include/rng/sampling.h:167-197).
+    image: float32 [H, W, 3].  Returns (row_cdf [H+1], col_cdfs [H, W+1], kernel ms)."""
+    lib = load_library()
+    image = np.ascontiguousarray(image, np.float32)
+    h, w = image.shape[:2]
+    row = np.empty(h + 1, np.float32)
+    col = np.empty((h, w + 1), np.float32)
+    ms = C.c_double()
+    _check(lib, lib.vimg_build_envmap_cdf(image.ctypes.data, w, h, device, row.ctypes.data, col.ctypes.data,
+                                          C.byref(ms)), "vimg_build_envmap_cdf")
+    return row, col, ms.value
