@@ -291,7 +291,9 @@ void vimg_scene_destroy(vimg_scene* scene);
 /* The material / mis pipeline keeps its render workspace (path-state pools, queues, partial
  * sums: up to ~1 GB, sized by the frame, independent of the scene) in a process-wide cache, one
  * idle workspace per device, so that creating a scene per frame does not allocate inside every
- * render.  This frees the idle workspaces (scenes that are still alive keep theirs). */
+ * render; the device allocation that holds a destroyed scene's arrays and frame is kept the same
+ * way (one per device) for the next vimg_scene_create().  This frees what is idle (scenes that
+ * are still alive keep theirs). */
 void vimg_release_workspaces(void);
 
 /* bytes of device memory the scene occupies (BVH + geometry + textures). */
