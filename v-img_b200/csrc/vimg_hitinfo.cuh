@@ -333,6 +333,10 @@ VD DLightRec load_light_rec(const DScene& sc, int index) {
 // Triangle::hit_info (src/geometry/triangle.cpp:13-153) from the leaf record (vertices) and the
 // shade record (vertex normals, colour uv set, material): the same values and the same
 // operations as the general walk, without its dependent loads
+// NEED_FRAME = false: the caller reads neither the tangent frame nor anything derived from the
+// uv derivatives (Lambertian, Dielectric, emitters); they are then computed only if a normal map
+// or the ray cones need them.
+template <bool NEED_FRAME = true>
 VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShadeRec& sr, const PreHit& pre) {
   if (sr.flags & VIMG_SHADE_GENERAL) return triangle_hit_info_general(sc, lp, pre);
   V3 p0 = mk3(lp.a[0], lp.a[1], lp.a[2]), p1 = mk3(lp.a[3], lp.a[4], lp.a[5]),
@@ -360,12 +364,16 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
     uv2 = mk2(sr.uv[4], sr.uv[5]);
     uv = u * uv0 + v * uv1 + w * uv2;
   }
+  const int32_t normal_map = sc.materials[sr.material].normal_map;
+  const bool derivs = NEED_FRAME || sc.uses_cones != 0 || normal_map >= 0;
   V2 duvds = uv2 - uv0;
   V2 duvdt = uv2 - uv1;
   float det = duvds.x * duvdt.y - duvdt.x * duvds.y;
   float dsdu = 0.f, dtdu = 0.f, dsdv = 0.f, dtdv = 0.f;
-  V3 dpdu, dpdv;
-  if (fabsf(det) > 1e-8f && !is_nan(det)) {
+  V3 dpdu = mk3(0.f), dpdv = mk3(0.f);
+  if (!derivs) {
+    // nothing reads dpdu / dpdv
+  } else if (fabsf(det) > 1e-8f && !is_nan(det)) {
     dsdu = duvdt.y / det;
     dtdu = -duvds.y / det;
     dsdv = duvdt.x / det;
@@ -378,7 +386,6 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
     get_axis(shading_normal, dpdu, dpdv);
   }
 
-  const int32_t normal_map = sc.materials[sr.material].normal_map;
   if (normal_map >= 0) {
     const V2 n_uv = (sr.flags & VIMG_SHADE_NORMAL_UV_SAME) ? uv : mk2(u, v);
     V3 n_tangent_space = tex_get_normal(sc, sc.textures[normal_map], n_uv);
@@ -390,8 +397,11 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
     shading_normal = local_space_normal;
   }
 
-  V3 tangent = normalize(dpdu - shading_normal * dot(shading_normal, dpdu));
-  V3 bitangent = normalize(cross(shading_normal, tangent));
+  V3 tangent = mk3(0.f), bitangent = mk3(0.f);
+  if (NEED_FRAME || sc.uses_cones != 0) {
+    tangent = normalize(dpdu - shading_normal * dot(shading_normal, dpdu));
+    bitangent = normalize(cross(shading_normal, tangent));
+  }
   // curvature and the two areas only feed ray cones / texture LOD (DScene::uses_cones)
   float mean_curvature = 0.f, twice_tri_area = 1.f, uv_area = 1.f;
   if (sc.uses_cones) {
@@ -467,7 +477,7 @@ VD bool scene_hit(const DScene& sc, Ray& ray, HitInfo& hit, TravCounters* cnt) {
   if (lp.flags & VIMG_LEAF_SPHERE)
     hit = sphere_hit_info(lp, sr, ray);
   else
-    hit = triangle_hit_info(sc, lp, sr, ph);
+    hit = triangle_hit_info<true>(sc, lp, sr, ph);
   return true;
 }
 

@@ -519,7 +519,8 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
             ph.e2 = __uint_as_float(hb.x);
             ph.inv_det = __uint_as_float(hb.y);
             const DLeafPrim nlp = sc.leaf_prims[ph.leaf_slot];
-            const HitInfo next = wf_hit_info(sc, nlp, load_shade_rec(sc, ph.leaf_slot), ph, ray);
+            // an emitter's hit: position and normals only
+            const HitInfo next = wf_hit_info<false>(sc, nlp, load_shade_rec(sc, ph.leaf_slot), ph, ray);
             V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
             if (!MIS) {
               finish(thr * emit);  // sample_mat -> nullopt: throughput * emitted
@@ -768,7 +769,8 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       ph.e1 = h0.w;
       ph.e2 = __uint_as_float(hb.x);
       ph.inv_det = __uint_as_float(hb.y);
-      const HitInfo hit = wf_hit_info(sc, lp, sr, ph, ray);
+      // the tangent frame is read by the Principled BSDF only
+      const HitInfo hit = wf_hit_info<CLASS == WF_CLASS_PRINCIPLED>(sc, lp, sr, ph, ray);
       const vimg_material& mat = sc.materials[hit.mat];
       V3 thr = xyz(t4);
       float eta_scale = t4.w;

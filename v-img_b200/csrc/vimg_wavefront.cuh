@@ -99,14 +99,15 @@ VD bool wf_pixel_xy(const WfArgs& a, const DCamera& cam, uint32_t p, uint32_t& x
 
 VD uint32_t wf_leaf_material(const DScene& sc, int32_t leaf_slot) { return sc.shade_recs[leaf_slot].material; }
 
+template <bool NEED_FRAME = true>
 VD HitInfo wf_hit_info(const DScene& sc, const DLeafPrim& lp, const DShadeRec& sr, const PreHit& ph, const Ray& ray) {
   if (lp.flags & VIMG_LEAF_SPHERE) return sphere_hit_info(lp, sr, ray);
-  return triangle_hit_info(sc, lp, sr, ph);
+  return triangle_hit_info<NEED_FRAME>(sc, lp, sr, ph);
 }
 VD HitInfo wf_hit_info(const DScene& sc, int32_t leaf_slot, const PreHit& ph, const Ray& ray) {
   const DLeafPrim lp = sc.leaf_prims[leaf_slot];
   const DShadeRec sr = load_shade_rec(sc, leaf_slot);
-  return wf_hit_info(sc, lp, sr, ph, ray);
+  return wf_hit_info<true>(sc, lp, sr, ph, ray);
 }
 
 VD uint32_t wf_material_class(uint32_t mat_type) {
