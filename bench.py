@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--pipeline", default=None, choices=["queue", "block"],
                     help="material / mis pipeline (default: the library's, the queue wavefront)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's spp (invalidates the number)")
-    ap.add_argument("--spp-streams", type=int, default=16,
+    ap.add_argument("--spp-streams", type=int, default=64,
                     help="sample ranges per pixel with their own RNG streams (vimg_render_params.spp_streams); "
                          "1 = the reference's single stream per pixel, bit-identical image")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
