@@ -42,6 +42,9 @@ def test_bytes_identical_to_the_reference(vimg, golden_post, tm):
         ref8 = golden_post[f"{name}|{tm}|rgb8"]
         diff = int((rgb8 != ref8).sum())
         assert diff == 0, f"{name}/{tm}: {diff} bytes differ"
+        # bytes only: the OETF + quantisation go through the 256-threshold table instead of pow
+        only8, none, _ = vimg.postprocess(img, tm, want_srgb=False)
+        assert none is None and np.array_equal(only8, ref8), f"{name}/{tm}: threshold path differs"
         if name == "ramp":
             ref_bits = golden_post[f"{name}|{tm}|srgb_bits"]
             got_bits = srgb.view(np.uint32)
@@ -67,8 +70,10 @@ def test_oetf_pow_branch_every_float(vimg, refcpu):
         bits = np.concatenate([bits, np.full(pad, hi, np.uint32)])
         img = bits.view(np.float32).reshape(-1, 3)
         g8, gs, _ = vimg.postprocess(img, "none")
+        t8, _, _ = vimg.postprocess(img, "none", want_srgb=False)  # threshold-table path
         cs, c8 = refcpu.restatement_postprocess(img, "none")
         assert np.array_equal(g8, c8), f"bytes differ in [{start:#x}, {start + step:#x})"
+        assert np.array_equal(t8, c8), f"threshold-path bytes differ in [{start:#x}, {start + step:#x})"
         differing_floats += int((gs.view(np.uint32) != cs.view(np.uint32)).sum())
         total += len(bits)
     print(f"OETF pow branch: {total} floats, bytes identical, {differing_floats} floats differ in the last bit "
@@ -86,6 +91,18 @@ def test_render_srgb8_equals_render_then_postprocess(vimg, refcpu, man, tm):
     _, ref8 = refcpu.restatement_postprocess(img, tm)
     assert np.array_equal(rgb8, ref8)
     assert st["samples"] == 16 * sc.width * sc.height and st["total_ms"] >= st["kernel_ms"] > 0
+
+
+def test_threshold_path_below_the_pow_branch(vimg, refcpu):
+    """linear branch of the OETF, zeros, denormals, negative zero, values above 1: bytes-only path"""
+    vals = np.concatenate([np.linspace(0, 0.0031308, 4099, dtype=np.float32), np.array(
+        [0.0, -0.0, 1e-45, 1e-39, 0.0031307, 0.0031308, 0.0031309, 1.0, 1.0000001, 2.0, 1e30, np.inf, -np.inf, -1.0],
+        np.float32)])
+    vals = np.concatenate([vals, np.zeros((-len(vals)) % 3, np.float32)]).reshape(-1, 3)
+    for tm in ("none", "clamp"):
+        t8, _, _ = vimg.postprocess(vals, tm, want_srgb=False)
+        _, c8 = refcpu.restatement_postprocess(vals, tm)
+        assert np.array_equal(t8, c8), tm
 
 
 def test_postprocess_arguments(vimg):

@@ -1368,10 +1368,31 @@ int vimg_heatmap(vimg_scene* s, uint32_t samples, float factor, float* out_rgb, 
   return VIMG_OK;
 }
 
+// the 256 OETF + quantisation thresholds of a device (vimg_post.cuh), built at first use
+static std::map<int, uint32_t*> g_post_thresholds;
+static const uint32_t* post_thresholds(int device, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  uint32_t*& t = g_post_thresholds[device];
+  if (!t) {
+    if (cudaMalloc(&t, 256 * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      t = nullptr;
+      return nullptr;  // the pow path needs no table
+    }
+    post_build_thresholds_kernel<<<1, 256, 0, st>>>(t);
+    cudaStreamSynchronize(st);  // once per device: later calls may come on any stream
+  }
+  return t;
+}
+
 // tonemap + OETF + quantise of `n_pixels` pixels already in HBM, on `st`
 static int post_launch(const float* d_rgb, uint64_t n_pixels, uint32_t tonemapper, float* d_srgb, uint8_t* d_rgb8,
                        uint32_t* d_max_bits, int sm_count, cudaStream_t st) {
   if (n_pixels == 0) return VIMG_OK;
+  int device = 0;
+  cudaGetDevice(&device);
+  // bytes only: threshold search instead of pow (VIMG_POST_POW=1 forces the pow path)
+  const uint32_t* d_thr = (d_srgb == nullptr && env_u32("VIMG_POST_POW", 0) == 0) ? post_thresholds(device, st) : nullptr;
   const int threads = 256;
   const uint64_t quads = (n_pixels + 3) / 4;
   const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((quads + threads - 1) / threads, (uint64_t)sm_count * 16));
@@ -1380,11 +1401,11 @@ static int post_launch(const float* d_rgb, uint64_t n_pixels, uint32_t tonemappe
     post_max_luminance_kernel<<<sm_count * 8, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits);
   }
   switch (tonemapper) {
-    case VIMG_TONEMAP_CLAMP: post_kernel<VIMG_TONEMAP_CLAMP><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
-    case VIMG_TONEMAP_AGX: post_kernel<VIMG_TONEMAP_AGX><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
-    case VIMG_TONEMAP_REINHARD: post_kernel<VIMG_TONEMAP_REINHARD><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
-    case VIMG_TONEMAP_ACES: post_kernel<VIMG_TONEMAP_ACES><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
-    default: post_kernel<VIMG_TONEMAP_NONE><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_CLAMP: post_kernel<VIMG_TONEMAP_CLAMP><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_thr, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_AGX: post_kernel<VIMG_TONEMAP_AGX><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_thr, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_REINHARD: post_kernel<VIMG_TONEMAP_REINHARD><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_thr, d_srgb, d_rgb8); break;
+    case VIMG_TONEMAP_ACES: post_kernel<VIMG_TONEMAP_ACES><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_thr, d_srgb, d_rgb8); break;
+    default: post_kernel<VIMG_TONEMAP_NONE><<<grid, threads, 0, st>>>(d_rgb, n_pixels, d_max_bits, d_thr, d_srgb, d_rgb8); break;
   }
   CU_TRY(cudaGetLastError());
   return VIMG_OK;

@@ -91,6 +91,41 @@ VD uint32_t post_quantise(float v) {  // main.cpp:348-351
   return (uint32_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
 }
 
+// Byte path without pow: byte(p) = quantise(oetf(p)) is a non-decreasing step function of the
+// clamped input p in [0, 1], so it is fully described by 256 thresholds T[b] = the smallest float
+// whose byte is >= b.  They are found once per device by bisection over the float bit patterns
+// WITH the functions above, so the byte of every float is by construction the one the pow path
+// gives (which tests/test_gpu_post.py compares with the CPU's for every float of the pow branch);
+// a pixel then costs three 8-step searches in shared memory instead of three double-precision
+// pow evaluations, and the kernel is bound by its 15 bytes per pixel.
+__global__ void post_build_thresholds_kernel(uint32_t* __restrict__ thr) {
+  const uint32_t b = threadIdx.x;  // 256 threads
+  uint32_t lo = 0u, hi = 0x3f800000u;  // bit patterns of 0.0f .. 1.0f order like the values
+  if (b == 0) {
+    thr[0] = 0u;
+    return;
+  }
+  if (post_quantise(post_srgb_oetf(__uint_as_float(hi))) < b) {  // never reached (byte(1.0) = 255)
+    thr[b] = 0xffffffffu;
+    return;
+  }
+  while (lo < hi) {  // invariant: byte(hi) >= b
+    const uint32_t mid = lo + (hi - lo) / 2u;
+    if (post_quantise(post_srgb_oetf(__uint_as_float(mid))) >= b) hi = mid;
+    else lo = mid + 1u;
+  }
+  thr[b] = hi;
+}
+VD uint32_t post_byte_from_thresholds(const uint32_t* s_thr, float c) {
+  // glm::clamp(c, 0, 1) lets -0.0 through; + 0.0f turns it into +0.0 so that the bits order
+  const uint32_t bits = __float_as_uint(glm_clamp(c, 0.0f, 1.0f) + 0.0f);
+  uint32_t b = 0;
+#pragma unroll
+  for (uint32_t step = 128; step > 0; step >>= 1)
+    if (s_thr[b + step] <= bits) b += step;
+  return b;
+}
+
 // largest luminance of the frame (reinhard.cpp:3-13): `if (curr > largest)` from 0, so NaN and
 // negative luminances never win and the result is a non-negative float, whose bit pattern
 // orders like the value: atomicMax on the bits
@@ -109,7 +144,7 @@ __global__ void post_max_luminance_kernel(const float* __restrict__ rgb, uint64_
 }
 
 template <int TM>
-VD void post_pixel(V3 c, float largest_L, V3& srgb, uint32_t& r8, uint32_t& g8, uint32_t& b8) {
+VD V3 post_tonemap(V3 c, float largest_L) {
   if (TM == VIMG_TONEMAP_CLAMP) {
     c = mk3(glm_clamp(c.x, 0.f, 1.f), glm_clamp(c.y, 0.f, 1.f), glm_clamp(c.z, 0.f, 1.f));
   } else if (TM == VIMG_TONEMAP_AGX) {
@@ -122,6 +157,28 @@ VD void post_pixel(V3 c, float largest_L, V3& srgb, uint32_t& r8, uint32_t& g8, 
   } else if (TM == VIMG_TONEMAP_ACES) {
     c = post_aces(c);
   }
+  return c;
+}
+
+// bytes only: the OETF and the quantisation through the threshold table (NaN passes through
+// glm's clamp and the OETF, so a NaN channel after the tonemapper is a magenta pixel)
+template <int TM>
+VD void post_pixel_bytes(V3 c, float largest_L, const uint32_t* s_thr, uint32_t& r8, uint32_t& g8, uint32_t& b8) {
+  c = post_tonemap<TM>(c, largest_L);
+  if (is_nan(c.x) || is_nan(c.y) || is_nan(c.z)) {
+    r8 = 255;
+    g8 = 0;
+    b8 = 255;
+  } else {
+    r8 = post_byte_from_thresholds(s_thr, c.x);
+    g8 = post_byte_from_thresholds(s_thr, c.y);
+    b8 = post_byte_from_thresholds(s_thr, c.z);
+  }
+}
+
+template <int TM>
+VD void post_pixel(V3 c, float largest_L, V3& srgb, uint32_t& r8, uint32_t& g8, uint32_t& b8) {
+  c = post_tonemap<TM>(c, largest_L);
   srgb = mk3(post_srgb_oetf(c.x), post_srgb_oetf(c.y), post_srgb_oetf(c.z));
   if (is_nan(srgb.x) || is_nan(srgb.y) || is_nan(srgb.z)) {  // main.cpp:342-346
     r8 = 255;
@@ -139,7 +196,15 @@ VD void post_pixel(V3 c, float largest_L, V3& srgb, uint32_t& r8, uint32_t& g8, 
 template <int TM>
 __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ rgb, uint64_t n_pixels,
                                                    const uint32_t* __restrict__ max_bits,
+                                                   const uint32_t* __restrict__ thresholds,
                                                    float* __restrict__ out_srgb, uint8_t* __restrict__ out_rgb8) {
+  __shared__ uint32_t s_thr[257];
+  const bool bytes_only = out_srgb == nullptr && thresholds != nullptr;
+  if (bytes_only) {
+    s_thr[threadIdx.x] = thresholds[threadIdx.x];  // blockDim.x == 256
+    if (threadIdx.x == 0) s_thr[256] = 0xffffffffu;
+    __syncthreads();
+  }
   const float largest_L = TM == VIMG_TONEMAP_REINHARD ? __uint_as_float(*max_bits) : 0.f;
   const uint64_t n_quads = n_pixels / 4;
   for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_quads; q += (uint64_t)gridDim.x * blockDim.x) {
@@ -150,6 +215,11 @@ __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ rgb
     uint32_t by[12];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (bytes_only) {
+        post_pixel_bytes<TM>(mk3(in[3 * k], in[3 * k + 1], in[3 * k + 2]), largest_L, s_thr, by[3 * k], by[3 * k + 1],
+                             by[3 * k + 2]);
+        continue;
+      }
       V3 s;
       post_pixel<TM>(mk3(in[3 * k], in[3 * k + 1], in[3 * k + 2]), largest_L, s, by[3 * k], by[3 * k + 1], by[3 * k + 2]);
       of[3 * k] = s.x;
@@ -172,9 +242,12 @@ __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ rgb
   // the last n_pixels % 4 pixels
   const uint64_t tail = n_quads * 4 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (tail < n_pixels) {
-    V3 s;
+    V3 s = mk3(0.f);
     uint32_t r8, g8, b8;
-    post_pixel<TM>(mk3(rgb[3 * tail], rgb[3 * tail + 1], rgb[3 * tail + 2]), largest_L, s, r8, g8, b8);
+    if (bytes_only)
+      post_pixel_bytes<TM>(mk3(rgb[3 * tail], rgb[3 * tail + 1], rgb[3 * tail + 2]), largest_L, s_thr, r8, g8, b8);
+    else
+      post_pixel<TM>(mk3(rgb[3 * tail], rgb[3 * tail + 1], rgb[3 * tail + 2]), largest_L, s, r8, g8, b8);
     if (out_srgb) {
       out_srgb[3 * tail] = s.x;
       out_srgb[3 * tail + 1] = s.y;
