@@ -240,3 +240,41 @@ def restatement_heatmap(desc_ptr, width, height, spp=4, factor=20.0):
     cost = np.empty((height, width), np.float32)
     lib.vimg_oracle_heatmap(desc_ptr, spp, factor, rgb.ctypes.data, cost.ctypes.data)
     return rgb, cost
+
+
+def restatement_mip_chain(level0, wrap_u, wrap_v):
+    """mip levels 1.. of ImageTexture's constructor through the plain-C restatement"""
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_mip_levels.restype = C.c_uint32
+    lib.vimg_oracle_mip_levels.argtypes = [C.c_uint32, C.c_uint32]
+    lib.vimg_oracle_mip_chain.restype = None
+    lib.vimg_oracle_mip_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    level0 = np.ascontiguousarray(level0, np.float32)
+    h, w = level0.shape[:2]
+    n = lib.vimg_oracle_mip_levels(w, h)
+    shapes = []
+    for _ in range(1, n):
+        w, h = max(w // 2, 1), max(h // 2, 1)
+        shapes.append((h, w, 3))
+    buf = np.empty(sum(a * b * c for a, b, c in shapes), np.float32)
+    lib.vimg_oracle_mip_chain(level0.ctypes.data, level0.shape[1], level0.shape[0], wrap_u, wrap_v, buf.ctypes.data)
+    out, off = [], 0
+    for shp in shapes:
+        k = shp[0] * shp[1] * 3
+        out.append(buf[off:off + k].reshape(shp))
+        off += k
+    return out
+
+
+def restatement_envmap_cdf(image):
+    """(row_cdf, col_cdfs) of ArraySampling2D through the plain-C restatement"""
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_envmap_cdf.restype = None
+    lib.vimg_oracle_envmap_cdf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    image = np.ascontiguousarray(image, np.float32)
+    h, w = image.shape[:2]
+    row = np.empty(h + 1, np.float32)
+    col = np.empty((h, w + 1), np.float32)
+    scratch = np.empty(w + h, np.float32)
+    lib.vimg_oracle_envmap_cdf(image.ctypes.data, w, h, row.ctypes.data, col.ctypes.data, scratch.ctypes.data)
+    return row, col

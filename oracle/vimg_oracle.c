@@ -525,3 +525,116 @@ void vimg_oracle_heatmap(const vimg_scene_desc* d, uint32_t spp, float factor, f
       out_rgb[3 * image_index + 2] = c.z;
     }
 }
+
+/* ============================================================================================
+ * Scene preparation
+ *   mip chain        ImageTexture::ImageTexture, src/image_texture.cpp:59-130 (Wronski 8-tap filter
+ *                    over bilinear fetches, col_at_uv_mipmap :132-161, handle_wrapping
+ *                    include/texture/texture_common.h:22-53)
+ *   env-map CDFs     ArraySampling2D / ArraySampling1D, include/rng/sampling.h:114-135,167-197
+ * PINNING: tests/test_prep.py -- the golden .vscene files carry the levels and CDFs the
+ * reference's constructors built; level 0 in, everything else out, bit for bit.
+ * ============================================================================================ */
+static int clampi(int v, int lo, int hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+static float std_clampf(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+static float handle_wrapping(float coord, uint32_t mode) { /* texture_common.h:22-53 */
+  switch (mode) {
+    case VIMG_WRAP_REPEAT: {
+      float fraction = coord - (float)(int)coord;
+      return signbit(fraction) ? 1.f + fraction : fraction;
+    }
+    case VIMG_WRAP_MIRRORED_REPEAT: {
+      int int_part = (int)coord;
+      float fraction = coord - (float)int_part;
+      if (signbit(fraction)) {
+        if (int_part % 2) return fabsf(fraction);
+        return 1.f + fraction;
+      }
+      return fraction;
+    }
+    default: return std_clampf(coord, 0.f, 1.f);
+  }
+}
+static v3 mix3(v3 x, v3 y, float a) { /* glm::mix(x, y, a) = x * (1 - a) + y * a */
+  return add(muls(x, 1.0f - a), muls(y, a));
+}
+static v3 texel(const float* lvl, size_t i) { return V(lvl[3 * i], lvl[3 * i + 1], lvl[3 * i + 2]); }
+static v3 bilinear_level(const float* lvl, uint32_t mip_w, uint32_t mip_h, uint32_t wrap_u, uint32_t wrap_v,
+                         float u, float v) { /* image_texture.cpp:132-161 */
+  float pixel_u = handle_wrapping(u, wrap_u) * mip_w;
+  float pixel_v = handle_wrapping(v, wrap_v) * mip_h;
+  int curr_x = clampi((int)pixel_u, 0, (int)mip_w - 1), curr_y = clampi((int)pixel_v, 0, (int)mip_h - 1);
+  int next_x = clampi(curr_x + 1, 0, (int)mip_w - 1), next_y = clampi(curr_y + 1, 0, (int)mip_h - 1);
+  float x_fraction = pixel_u - curr_x, y_fraction = pixel_v - curr_y;
+  v3 a = mix3(texel(lvl, curr_x + (size_t)curr_y * mip_w), texel(lvl, next_x + (size_t)curr_y * mip_w), x_fraction);
+  v3 b = mix3(texel(lvl, curr_x + (size_t)next_y * mip_w), texel(lvl, next_x + (size_t)next_y * mip_w), x_fraction);
+  return mix3(a, b, y_fraction);
+}
+/* number of levels the constructor builds (image_texture.cpp:73-78), level 0 included */
+uint32_t vimg_oracle_mip_levels(uint32_t width, uint32_t height) {
+  uint32_t size = width < height ? width : height;
+  int n = (int)ceilf(log2f((float)size));
+  if (n > 15) n = 15;
+  return (uint32_t)(n < 1 ? 1 : n);
+}
+/* levels 1 .. n-1 one after the other into out_levels */
+void vimg_oracle_mip_chain(const float* level0, uint32_t width, uint32_t height, uint32_t wrap_u, uint32_t wrap_v,
+                           float* out_levels) {
+  const uint32_t n = vimg_oracle_mip_levels(width, height);
+  const float* prev = level0;
+  float* next = out_levels;
+  uint32_t pw = width, ph = height;
+  const float k = (float)0.75777, f = (float)2.907;
+  const float tap[8][2] = {{-k, -k}, {k, -k}, {k, k}, {-k, k}, {-f, 0.f}, {f, 0.f}, {0.f, -f}, {0.f, f}};
+  for (uint32_t l = 1; l < n; ++l) {
+    const uint32_t nw = pw / 2u > 1u ? pw / 2u : 1u, nh = ph / 2u > 1u ? ph / 2u : 1u;
+    for (uint32_t y = 0; y < nh; ++y)
+      for (uint32_t x = 0; x < nw; ++x) {
+        const float irx = 1.f / pw, iry = 1.f / ph;
+        const float cu = (float)(2 * x) * irx, cv = (float)(2 * y) * iry;
+        v3 sum = V(0.f, 0.f, 0.f);
+        for (int t = 0; t < 8; ++t) {
+          const float w = t < 4 ? 0.37487566f : -0.12487566f;
+          v3 c = bilinear_level(prev, pw, ph, wrap_u, wrap_v, cu + tap[t][0] * irx, cv + tap[t][1] * iry);
+          sum = add(sum, muls(c, w));
+        }
+        if (sum.x < 0) sum.x = 0.f;
+        if (sum.y < 0) sum.y = 0.f;
+        if (sum.z < 0) sum.z = 0.f;
+        float* o = next + 3 * ((size_t)x + (size_t)y * nw);
+        o[0] = sum.x;
+        o[1] = sum.y;
+        o[2] = sum.z;
+      }
+    prev = next;
+    next += (size_t)nw * nh * 3;
+    pw = nw;
+    ph = nh;
+  }
+}
+/* ArraySampling1D (sampling.h:114-135) on n values: cdf has n + 1 entries; returns func_int */
+static float cdf_1d(const float* f, size_t n, float* cdf) {
+  cdf[0] = 0.f;
+  for (size_t x = 1; x < n + 1; ++x) cdf[x] = cdf[x - 1] + fabsf(f[x - 1]);
+  const float func_int = cdf[n];
+  if (func_int == 0)
+    for (size_t i = 0; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+  else
+    for (size_t i = 0; i < n + 1; ++i) cdf[i] /= func_int;
+  return func_int;
+}
+/* ArraySampling2D (sampling.h:167-197): row_cdf height + 1, col_cdfs height * (width + 1); `scratch`:
+ * width + height floats */
+void vimg_oracle_envmap_cdf(const float* image, uint32_t width, uint32_t height, float* row_cdf, float* col_cdfs,
+                            float* scratch) {
+  float* lum = scratch;
+  float* row_int = scratch + width;
+  for (uint32_t y = 0; y < height; ++y) {
+    float v = ((float)y + 0.5f) / (float)height;
+    float sin_elevation = (float)sin(3.141592653589793238462643383279502884 * v);
+    for (uint32_t x = 0; x < width; ++x)
+      lum[x] = pp_luminance(texel(image, (size_t)y * width + x)) * sin_elevation;
+    row_int[y] = cdf_1d(lum, width, col_cdfs + (size_t)y * (width + 1));
+  }
+  cdf_1d(row_int, height, row_cdf);
+}

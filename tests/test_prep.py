@@ -33,6 +33,30 @@ def test_level_count_matches_the_reference_constructor():
                 assert floats.value == sum(lv.size for lv in levels[1:])
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_restatement_matches_the_reference_built_levels_and_cdfs(name):
+    """the plain-C restatement (oracle/vimg_oracle.c) against what the reference's constructors built"""
+    import os
+    from oracle import refcpu
+    if not os.path.exists(refcpu.restatement_path()):
+        pytest.skip("oracle/_ref/libvimg_oracle.so not built")
+    vimg = load_product()
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    textures = d.image_textures()
+    for idx, wrap_u, wrap_v, levels in textures:
+        if len(levels) < 2:
+            continue
+        built = refcpu.restatement_mip_chain(levels[0], wrap_u, wrap_v)
+        assert len(built) == len(levels) - 1
+        for got, ref in zip(built, levels[1:]):
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"{name} texture {idx}"
+    tex, row_ref, col_ref = d.envmap()
+    level0 = [lv for i, _, _, lv in textures if i == tex][0][0]
+    row, col = refcpu.restatement_envmap_cdf(level0)
+    assert np.array_equal(col.view(np.uint32), col_ref.view(np.uint32))
+    assert np.array_equal(row.view(np.uint32), row_ref.view(np.uint32))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SCENES)
 def test_mip_chain_bit_exact(vimg, name):
