@@ -354,6 +354,33 @@ int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, u
 int vimg_build_envmap_cdf(const float* image, uint32_t width, uint32_t height, int device_id,
                           float* out_row_cdf, float* out_col_cdfs, double* kernel_ms);
 
+/* Replaces make_texture's byte -> float loop (src/scene_loading/gltf_loading.cpp:139-143) followed by
+ * ImageTexture::convert_sRGB_to_linear (src/image_texture.cpp:257-263; pix_sRGB_to_linear,
+ * include/color_utils.h:28-47): rgb8: HOST, n_pixels * 3 bytes (the decoded image);
+ * out_rgb: HOST, n_pixels * 3 floats, linear.  3 bytes per pixel cross PCIe instead of 12. */
+int vimg_convert_srgb8_to_linear(const uint8_t* rgb8, uint64_t n_pixels, int device_id, float* out_rgb,
+                                 double* kernel_ms);
+
+/* Replaces the same loop followed by ImageTexture::convert_RGB_to_normal (src/image_texture.cpp:265-275):
+ * p / 127.5f - 1, x and y times `scale` (glTF normalTexture.scale), glm::normalize. */
+int vimg_convert_rgb8_to_normal(const uint8_t* rgb8, uint64_t n_pixels, float scale, int device_id,
+                                float* out_rgb, double* kernel_ms);
+
+/* make_texture's TextureType::Image case as a whole (gltf_loading.cpp:147-156): decoded sRGB bytes ->
+ * linear level 0 -> the constructor's mip chain, without leaving the device.  out_level0: HOST,
+ * width*height*3 floats; out_levels: HOST, levels 1 .. n-1 (size from vimg_mip_chain_levels). */
+int vimg_build_image_texture(const uint8_t* srgb8, uint32_t width, uint32_t height, uint32_t wrap_u,
+                             uint32_t wrap_v, int device_id, float* out_level0, float* out_levels,
+                             double* kernel_ms);
+
+/* Parity hook: the device's copies of the glibc float functions the path calls (std::sin, std::cos,
+ * std::log, std::log2, std::pow, std::acos, std::atan2 on floats: include/rng/sampling.h, background.h,
+ * tl_camera.cpp, color_utils.h, agx.cpp, principled BSDF), evaluated on caller-given inputs so that a
+ * test can compare them with the host libm bit for bit.
+ * fn: 0 sinf, 1 cosf, 2 logf, 3 log2f, 4 powf(x, y), 5 acosf, 6 atan2f(x = y-argument, y = x-argument),
+ * 7 atanf.  x, y (y only for fn 4 and 6), out: HOST, n floats. */
+int vimg_libm_eval(uint32_t fn, const float* x, const float* y, uint64_t n, int device_id, float* out);
+
 /* ---- post-process chain (the step right after the path: src/main.cpp:304-356) ----------- */
 /* enum class tonemapper (include/color_utils.h:7) + "no tonemapper" (main.cpp:325-327). */
 typedef enum vimg_tonemapper {

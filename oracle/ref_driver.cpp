@@ -469,6 +469,30 @@ void vref_postprocess(const float* rgb, uint64_t n_pixels, int tonemapper, float
   }
 }
 
+// The reference's glTF texture conversions: make_texture's byte -> float loop
+// (src/scene_loading/gltf_loading.cpp:139-143; the function is static there, so the three lines are
+// restated) followed by the reference's OWN ImageTexture::convert_sRGB_to_linear /
+// convert_RGB_to_normal (src/image_texture.cpp:257-275).  out: n_pixels * 3 floats.
+static std::vector<glm::vec3> bytes_to_image(const uint8_t* char_arr, uint64_t n_pixels) {
+  std::vector<glm::vec3> image(n_pixels);
+  for (size_t i = 0; i < image.size(); i++) {
+    image[i].x = char_arr[i * 3];
+    image[i].y = char_arr[i * 3 + 1];
+    image[i].z = char_arr[i * 3 + 2];
+  }
+  return image;
+}
+void vref_convert_srgb8_to_linear(const uint8_t* rgb8, uint64_t n_pixels, float* out) {
+  std::vector<glm::vec3> image = bytes_to_image(rgb8, n_pixels);
+  ImageTexture::convert_sRGB_to_linear(image);
+  std::memcpy(out, image.data(), n_pixels * sizeof(glm::vec3));
+}
+void vref_convert_rgb8_to_normal(const uint8_t* rgb8, uint64_t n_pixels, float scale, float* out) {
+  std::vector<glm::vec3> image = bytes_to_image(rgb8, n_pixels);
+  ImageTexture::convert_RGB_to_normal(image, scale);
+  std::memcpy(out, image.data(), n_pixels * sizeof(glm::vec3));
+}
+
 // The reference's own heat map (src/integrators/heatmap.cpp:39-147, called from main.cpp:249-255
 // with spp fixed to 4).  factor <= 0 takes the reference's default 20.
 void vref_heatmap(void* h, uint32_t spp, float factor, float* out_rgb) {

@@ -278,3 +278,58 @@ def restatement_envmap_cdf(image):
     scratch = np.empty(w + h, np.float32)
     lib.vimg_oracle_envmap_cdf(image.ctypes.data, w, h, row.ctypes.data, col.ctypes.data, scratch.ctypes.data)
     return row, col
+
+
+# ---- glTF texture conversions (gltf_loading.cpp:139-162, image_texture.cpp:257-275) --------------
+def convert_srgb8_to_linear(rgb8, flavour="parity"):
+    """make_texture's byte -> float loop + the reference's own ImageTexture::convert_sRGB_to_linear"""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    lib = _load(flavour)
+    lib.vref_convert_srgb8_to_linear.restype = None
+    lib.vref_convert_srgb8_to_linear.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.vref_convert_srgb8_to_linear(rgb8.ctypes.data, rgb8.size // 3, out.ctypes.data)
+    return out
+
+
+def convert_rgb8_to_normal(rgb8, scale, flavour="parity"):
+    """make_texture's byte -> float loop + the reference's own ImageTexture::convert_RGB_to_normal"""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    lib = _load(flavour)
+    lib.vref_convert_rgb8_to_normal.restype = None
+    lib.vref_convert_rgb8_to_normal.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+    lib.vref_convert_rgb8_to_normal(rgb8.ctypes.data, rgb8.size // 3, scale, out.ctypes.data)
+    return out
+
+
+def restatement_srgb8_to_linear(rgb8):
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_srgb8_to_linear.restype = None
+    lib.vimg_oracle_srgb8_to_linear.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    lib.vimg_oracle_srgb8_to_linear(rgb8.ctypes.data, rgb8.size // 3, out.ctypes.data)
+    return out
+
+
+def restatement_rgb8_to_normal(rgb8, scale):
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_rgb8_to_normal.restype = None
+    lib.vimg_oracle_rgb8_to_normal.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    lib.vimg_oracle_rgb8_to_normal(rgb8.ctypes.data, rgb8.size // 3, scale, out.ctypes.data)
+    return out
+
+
+def host_libm(fn, x, y=None):
+    """glibc's float function number `fn` (numbering of vimg_libm_eval) on float32 arrays"""
+    lib = C.CDLL(restatement_path())
+    lib.vimg_oracle_libm.restype = None
+    lib.vimg_oracle_libm.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    x = np.ascontiguousarray(x, np.float32)
+    y = None if y is None else np.ascontiguousarray(y, np.float32)
+    out = np.empty(x.shape, np.float32)
+    lib.vimg_oracle_libm(fn, x.ctypes.data, None if y is None else y.ctypes.data, x.size, out.ctypes.data)
+    return out

@@ -638,3 +638,51 @@ void vimg_oracle_envmap_cdf(const float* image, uint32_t width, uint32_t height,
   }
   cdf_1d(row_int, height, row_cdf);
 }
+
+/* ---- glTF texture conversions (src/scene_loading/gltf_loading.cpp:139-162) --------------------
+ * make_texture's byte -> float loop (:139-143) followed by
+ *   ImageTexture::convert_sRGB_to_linear  src/image_texture.cpp:257-263: image /= 255.f, then
+ *       pix_sRGB_to_linear (include/color_utils.h:28-47) per component, std::pow = the host's powf
+ *   ImageTexture::convert_RGB_to_normal   src/image_texture.cpp:265-275: image / 127.5f - 1,
+ *       x and y times scale, glm::normalize
+ * PINNING: tests/golden/prep/convert.npz holds what the compiled reference's own two functions
+ * return for every byte value and a random image (tests/golden/make_golden_convert.py). */
+void vimg_oracle_srgb8_to_linear(const uint8_t* rgb8, uint64_t n_pixels, float* out) {
+  for (uint64_t i = 0; i < 3 * n_pixels; ++i) {
+    float p = (float)rgb8[i];
+    p = p / 255.f;
+    out[i] = p <= 0.04045f ? p / 12.92f : powf((p + 0.055f) / 1.055f, 2.4f);
+  }
+}
+
+void vimg_oracle_rgb8_to_normal(const uint8_t* rgb8, uint64_t n_pixels, float scale, float* out) {
+  for (uint64_t i = 0; i < n_pixels; ++i) {
+    v3 n = V((float)rgb8[3 * i] / 127.5f - 1.f, (float)rgb8[3 * i + 1] / 127.5f - 1.f,
+             (float)rgb8[3 * i + 2] / 127.5f - 1.f);
+    n.x *= scale;
+    n.y *= scale;
+    n = normalize(n);
+    out[3 * i] = n.x;
+    out[3 * i + 1] = n.y;
+    out[3 * i + 2] = n.z;
+  }
+}
+
+/* ---- the host libm on arrays (what the reference's std::sin / std::pow / ... on floats call) ----
+ * fn numbering of vimg_libm_eval (include/vimg_cuda.h); lets tests/test_libm.py compare the device's
+ * restatements with THIS machine's glibc bit for bit. */
+void vimg_oracle_libm(uint32_t fn, const float* x, const float* y, uint64_t n, float* out) {
+  for (uint64_t i = 0; i < n; ++i) {
+    const float a = x[i], b = y ? y[i] : 0.f;
+    switch (fn) {
+      case 0: out[i] = sinf(a); break;
+      case 1: out[i] = cosf(a); break;
+      case 2: out[i] = logf(a); break;
+      case 3: out[i] = log2f(a); break;
+      case 4: out[i] = powf(a, b); break;
+      case 5: out[i] = acosf(a); break;
+      case 6: out[i] = atan2f(a, b); break;
+      default: out[i] = atanf(a); break;
+    }
+  }
+}

@@ -63,3 +63,19 @@ def post_inputs():
     ramp[0, :len(specials)] = np.array(specials, np.float32)
     out["ramp"] = ramp
     return out
+
+
+NORMAL_SCALES = (1.0, 0.5, 2.0)
+
+
+def convert_inputs():
+    """8-bit RGB images the texture-conversion tests feed to make_texture's Image / Normals cases
+    (src/scene_loading/gltf_loading.cpp:133-166): every byte value in every channel (with the
+    other channels varying), and a random 96x61 image (odd width: vector-path tails)."""
+    out = {}
+    b = np.arange(256, dtype=np.uint8)
+    out["all_bytes"] = np.stack([b, np.roll(b, 85), b[::-1]], axis=1).reshape(16, 16, 3)
+    out["grid"] = np.stack(list(np.meshgrid(b[::5], b[::5], indexing="ij")) + [np.full((52, 52), 255, np.uint8)], axis=2)
+    rng = np.random.default_rng(20261019)
+    out["random"] = rng.integers(0, 256, size=(61, 97, 3), dtype=np.uint8)
+    return out

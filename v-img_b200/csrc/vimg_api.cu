@@ -1257,6 +1257,124 @@ static int prep_device(int device_id, int* sms) {
   return VIMG_OK;
 }
 
+// levels 1 .. n-1 behind level 0 in d_all, one launch per level (image_texture.cpp:80-125)
+static void launch_mip_levels(float* d_all, uint32_t width, uint32_t height, uint32_t n_levels, uint32_t wrap_u,
+                              uint32_t wrap_v) {
+  const float* prev = d_all;
+  float* next = d_all + (size_t)width * height * 3;
+  uint32_t pw = width, ph = height;
+  for (uint32_t l = 1; l < n_levels; ++l) {
+    const uint32_t nw = std::max(pw / 2u, 1u), nh = std::max(ph / 2u, 1u);
+    prep_mip_level_kernel<<<dim3((nw + 255) / 256, nh), 256>>>(prev, pw, ph, next, nw, nh, wrap_u, wrap_v);
+    prev = next;
+    next += (size_t)nw * nh * 3;
+    pw = nw;
+    ph = nh;
+  }
+}
+
+// blocks of 256 threads for `items` grid-stride work items: a multiple of the SM count, at most 8 per SM
+static unsigned prep_grid(uint64_t items, int sms) {
+  const uint64_t want = (items + 255) / 256;
+  const uint64_t cap = (uint64_t)sms * 8;
+  if (want >= cap) return (unsigned)cap;
+  return (unsigned)std::max<uint64_t>(1, want);
+}
+
+// shared body of the byte conversions and vimg_build_image_texture: bytes in, floats out
+//   mode 0: sRGB -> linear; mode 1: RGB -> normal (scale); mode 2: sRGB -> linear + mip chain
+static int convert_bytes(const char* what, int mode, const uint8_t* rgb8, uint32_t width, uint64_t n_pixels,
+                         uint32_t height, float scale, uint32_t wrap_u, uint32_t wrap_v, int device_id,
+                         float* out_rgb, float* out_levels, double* kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (n_pixels == 0) return VIMG_OK;
+  if (!rgb8 || !out_rgb) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  int sms = 0, rc = prep_device(device_id, &sms);
+  if (rc != VIMG_OK) return rc;
+  uint64_t floats = 0;
+  uint32_t n_levels = 1;
+  if (mode == 2) {
+    n_levels = vimg_mip_chain_levels(width, height, &floats);
+    if (n_levels > 1 && !out_levels) return fail(VIMG_ERR_INVALID_ARGUMENT, "null output");
+  }
+  const size_t l0 = (size_t)n_pixels * 3;
+  uint8_t* d_in = nullptr;
+  float* d_all = nullptr;  // the converted image (level 0) followed by levels 1 .. n-1
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, l0);
+  if (e == cudaSuccess) e = cudaMalloc(&d_all, (l0 + floats) * sizeof(float));
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, rgb8, l0, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cudaEventRecord(e0, 0);
+    if (mode == 1)
+      prep_rgb8_to_normal_kernel<<<prep_grid((n_pixels + 3) / 4, sms), 256>>>(d_in, n_pixels, scale, d_all);
+    else
+      prep_srgb8_to_linear_kernel<<<prep_grid((l0 + 15) / 16, sms), 256>>>(d_in, l0, d_all);
+    if (n_levels > 1) launch_mip_levels(d_all, width, height, n_levels, wrap_u, wrap_v);
+    cudaEventRecord(e1, 0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_all, l0 * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && floats) e = cudaMemcpy(out_levels, d_all + l0, floats * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  if (d_in) cudaFree(d_in);
+  if (d_all) cudaFree(d_all);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return VIMG_OK;
+}
+
+int vimg_convert_srgb8_to_linear(const uint8_t* rgb8, uint64_t n_pixels, int device_id, float* out_rgb,
+                                 double* kernel_ms) {
+  return convert_bytes("vimg_convert_srgb8_to_linear", 0, rgb8, 0, n_pixels, 0, 0.f, 0, 0, device_id, out_rgb, nullptr,
+                       kernel_ms);
+}
+
+int vimg_convert_rgb8_to_normal(const uint8_t* rgb8, uint64_t n_pixels, float scale, int device_id, float* out_rgb,
+                                double* kernel_ms) {
+  return convert_bytes("vimg_convert_rgb8_to_normal", 1, rgb8, 0, n_pixels, 0, scale, 0, 0, device_id, out_rgb, nullptr,
+                       kernel_ms);
+}
+
+int vimg_build_image_texture(const uint8_t* srgb8, uint32_t width, uint32_t height, uint32_t wrap_u, uint32_t wrap_v,
+                             int device_id, float* out_level0, float* out_levels, double* kernel_ms) {
+  if (width == 0 || height == 0) return fail(VIMG_ERR_INVALID_ARGUMENT, "empty image");
+  if (wrap_u > VIMG_WRAP_REPEAT || wrap_v > VIMG_WRAP_REPEAT) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown wrap mode");
+  return convert_bytes("vimg_build_image_texture", 2, srgb8, width, (uint64_t)width * height, height, 0.f, wrap_u, wrap_v,
+                       device_id, out_level0, out_levels, kernel_ms);
+}
+
+int vimg_libm_eval(uint32_t fn, const float* x, const float* y, uint64_t n, int device_id, float* out) {
+  if (fn > 7) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown function");
+  if (n == 0) return VIMG_OK;
+  const bool two = fn == 4 || fn == 6;
+  if (!x || !out || (two && !y)) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  int sms = 0, rc = prep_device(device_id, &sms);
+  if (rc != VIMG_OK) return rc;
+  float *d_x = nullptr, *d_y = nullptr, *d_o = nullptr;
+  cudaError_t e = cudaMalloc(&d_x, n * sizeof(float));
+  if (e == cudaSuccess && two) e = cudaMalloc(&d_y, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_o, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_x, x, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && two) e = cudaMemcpy(d_y, y, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    libm_eval_kernel<<<prep_grid(n, sms), 256>>>(fn, d_x, d_y, n, d_o);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_o, n * sizeof(float), cudaMemcpyDeviceToHost);
+  for (float* p : {d_x, d_y, d_o})
+    if (p) cudaFree(p);
+  if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("vimg_libm_eval: ") + cudaGetErrorString(e));
+  return VIMG_OK;
+}
+
 int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, uint32_t wrap_u, uint32_t wrap_v,
                          int device_id, float* out_levels, double* kernel_ms) {
   if (!level0 || width == 0 || height == 0) return fail(VIMG_ERR_INVALID_ARGUMENT, "null / empty image");
@@ -1277,17 +1395,7 @@ int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, u
   if (e == cudaSuccess) e = cudaMemcpy(d_all, level0, l0 * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     cudaEventRecord(e0, 0);
-    const float* prev = d_all;
-    float* next = d_all + l0;
-    uint32_t pw = width, ph = height;
-    for (uint32_t l = 1; l < n_levels; ++l) {
-      const uint32_t nw = std::max(pw / 2u, 1u), nh = std::max(ph / 2u, 1u);
-      prep_mip_level_kernel<<<dim3((nw + 255) / 256, nh), 256>>>(prev, pw, ph, next, nw, nh, wrap_u, wrap_v);
-      prev = next;
-      next += (size_t)nw * nh * 3;
-      pw = nw;
-      ph = nh;
-    }
+    launch_mip_levels(d_all, width, height, n_levels, wrap_u, wrap_v);
     cudaEventRecord(e1, 0);
     e = cudaGetLastError();
   }

@@ -90,13 +90,12 @@ VD V4 mat4_mul(const float* m, V4 v) {
 }
 
 // ---- libm ------------------------------------------------------------------
-// The reference calls glibc.  sinf/cosf decide sampled directions (and, with a
-// thin-lens camera, the primary rays of the bit-exact targets), so they are
-// restated exactly (vimg_libm.cuh).  logf/log2f/acosf/atan2f only feed
-// tolerance-checked quantities (texture LOD, env-map uv); glibc's are
-// correctly rounded in all but rare cases while CUDA's float versions are 1-2
-// ulp, so they are evaluated in double and rounded once.  Double expressions of
-// the reference call the double functions directly.
+// The reference calls glibc.  Every FLOAT libm function on the path -- sinf / cosf (sampled
+// directions, thin-lens primary rays), logf (clearcoat), log2f (texture LOD), acosf / atan2f
+// (env-map uv, ray-cone spread), powf (post-process, sRGB) -- is restated operation by operation
+// in vimg_libm.cuh and checked against the host libm over all float inputs.  Double expressions
+// of the reference call the double functions directly (CUDA's, ~1 ulp in double,
+// rounded to float afterwards).
 // CUDA's double-precision library functions expand to hundreds of instructions each when
 // inlined; the render kernels call them from many places, so they live in ONE out-of-line
 // copy each (instruction-cache footprint, see DESIGN.md "Kernel structure").
@@ -110,12 +109,20 @@ VNI double d_acos(double x) { return acos(x); }
 VNI double d_atan2(double y, double x) { return atan2(y, x); }
 
 #ifndef VIMG_FAST_LIBM
+// glibc's float functions restated operation by operation (vimg_libm.cuh; every one checked against
+// the host libm over all float inputs by oracle/tools/libm_check.cpp), one out-of-line copy each
+VNI float g_logf(float x) { return vimg_libm::glibc_logf(x); }
+VNI float g_log2f(float x) { return vimg_libm::glibc_log2f(x); }
+VNI float g_acosf(float x) { return vimg_libm::glibc_acosf(x); }
+VNI float g_atan2f(float y, float x) { return vimg_libm::glibc_atan2f(y, x); }
+VNI float g_powf(float x, float y) { return vimg_libm::glibc_powf(x, y); }
 VD float m_sinf(float x) { return vimg_libm::glibc_sinf(x); }  // bit-exact glibc sinf, |x| < 120
 VD float m_cosf(float x) { return vimg_libm::glibc_cosf(x); }
-VD float m_logf(float x) { return (float)d_log((double)x); }
-VD float m_log2f(float x) { return (float)d_log2((double)x); }
-VD float m_acosf(float x) { return (float)d_acos((double)x); }
-VD float m_atan2f(float y, float x) { return (float)d_atan2((double)y, (double)x); }
+VD float m_logf(float x) { return g_logf(x); }
+VD float m_log2f(float x) { return g_log2f(x); }
+VD float m_acosf(float x) { return g_acosf(x); }
+VD float m_atan2f(float y, float x) { return g_atan2f(y, x); }
+VD float m_powf(float x, float y) { return g_powf(x, y); }
 #else
 VD float m_sinf(float x) { return sinf(x); }
 VD float m_cosf(float x) { return cosf(x); }
@@ -123,6 +130,7 @@ VD float m_logf(float x) { return logf(x); }
 VD float m_log2f(float x) { return log2f(x); }
 VD float m_acosf(float x) { return acosf(x); }
 VD float m_atan2f(float y, float x) { return atan2f(y, x); }
+VD float m_powf(float x, float y) { return powf(x, y); }
 #endif
 
 #define VIMG_PI_D 3.141592653589793238462643383279502884  /* std::numbers::pi   */

@@ -11,10 +11,9 @@
 //
 // Arithmetic: every glm expression written out per component in glm's order, no FMA contraction
 // (the library is built with -fmad=false), IEEE division: the +, -, *, / part is bit-identical
-// to the CPU.  std::pow / std::log2 on floats are glibc's powf / log2f there; here they are the
-// double-precision functions rounded once to float, which agrees with glibc except for rare
-// last-bit cases (glibc's powf is 0.5 ulp + 2^-30 relative).  tests/test_gpu_post.py checks
-// EVERY float input of the OETF's pow branch and finds the quantised byte identical.
+// to the CPU.  std::pow / std::log2 on floats are glibc's powf / log2f there and the exact
+// restatements of vimg_libm.cuh here, so the float image after gamma is bit-identical too.
+// tests/test_gpu_post.py checks EVERY float input of the OETF's pow branch.
 // HBM bound: 12 bytes read + 3 bytes written per pixel (+ 12 when the float image is kept).
 #pragma once
 #include "vimg_math.cuh"
@@ -22,7 +21,6 @@
 namespace vimg {
 
 VD float glm_clamp(float x, float lo, float hi) { return glm_min(glm_max(x, lo), hi); }
-VD float m_powf(float x, float y) { return (float)d_pow((double)x, (double)y); }
 
 // luminance (color_utils.h:9-11)
 VD float post_luminance(V3 c) { return dot(c, mk3(0.212671f, 0.715160f, 0.072169f)); }

@@ -7,6 +7,8 @@
 //   env-map CDFs     ArraySampling2D / ArraySampling1D (include/rng/sampling.h:114-135,167-197):
 //                    luminance * sin(elevation) per pixel, one running float sum per row, the
 //                    row integrals summed the same way
+//   byte conversions ImageTexture::convert_sRGB_to_linear / convert_RGB_to_normal
+//                    (src/image_texture.cpp:257-275) on the decoded 8-bit image
 //
 // Both must be bit-compatible with the host versions or the parity of everything that reads a
 // texture moves.  The filter is float +, *, and the bilinear fetch the render kernels already
@@ -104,6 +106,98 @@ __global__ void prep_row_prob_kernel(const float* __restrict__ row_integrals, ui
     for (uint32_t i = 0; i <= height; ++i) row_cdf[i] = (float)i / (float)height;
   } else {
     for (uint32_t i = 0; i <= height; ++i) row_cdf[i] = row_cdf[i] / run;
+  }
+}
+
+// ---- glTF texture conversions (src/scene_loading/gltf_loading.cpp:133-166) ----------------------
+// make_texture turns the decoded 8-bit image into floats (:139-143) and calls
+//   ImageTexture::convert_sRGB_to_linear (image_texture.cpp:257-263): p / 255.f, then
+//       pix_sRGB_to_linear (color_utils.h:28-47) = p / 12.92f or powf((p + 0.055f) / 1.055f, 2.4f)
+//   ImageTexture::convert_RGB_to_normal  (image_texture.cpp:265-275): p / 127.5f - 1, x and y
+//       times scale, glm::normalize
+// Here the BYTES go to the device (3 B per pixel over PCIe instead of 12) and the floats are
+// produced there.  HBM bound: 3 bytes read + 12 written per pixel.
+
+// the value of one colour byte; powf is glibc's, restated exactly (vimg_libm.cuh)
+VD float prep_srgb_byte_to_linear(uint32_t b) {
+  float p = (float)b;
+  p = p / 255.f;
+  if (p <= 0.04045f) return p / 12.92f;
+  return vimg_libm::glibc_powf((p + 0.055f) / 1.055f, 2.4f);
+}
+
+// A channel has 256 possible inputs: every block evaluates the function once per byte value into
+// shared memory (one powf per thread), then streams: thread <-> 16 consecutive channel bytes
+// (one 16-byte load, four 16-byte stores).  n = number of channel bytes (3 * pixels).
+__global__ void __launch_bounds__(256)
+prep_srgb8_to_linear_kernel(const uint8_t* __restrict__ in, uint64_t n, float* __restrict__ out) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = prep_srgb_byte_to_linear(threadIdx.x);
+  __syncthreads();
+  const uint64_t n16 = n / 16, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = make_float4(lut[w[k] & 255u], lut[(w[k] >> 8) & 255u], lut[(w[k] >> 16) & 255u], lut[w[k] >> 24]);
+  }
+  // tail: fewer than 16 bytes
+  const uint64_t t = n16 * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = lut[in[t]];
+}
+
+// thread <-> 4 pixels = 12 bytes in (three 4-byte loads), 48 bytes out (three 16-byte stores)
+VD V3 prep_normal_of_bytes(uint32_t r, uint32_t g, uint32_t b, float scale) {
+  V3 n = mk3((float)r / 127.5f - 1.f, (float)g / 127.5f - 1.f, (float)b / 127.5f - 1.f);
+  n.x *= scale;
+  n.y *= scale;
+  return normalize(n);
+}
+__global__ void __launch_bounds__(256)
+prep_rgb8_to_normal_kernel(const uint8_t* __restrict__ in, uint64_t n_pixels, float scale, float* __restrict__ out) {
+  const uint64_t n4 = n_pixels / 4, stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t i = tid; i < n4; i += stride) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(in) + 3 * i;
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    const V3 a = prep_normal_of_bytes(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, scale);
+    const V3 b = prep_normal_of_bytes(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, scale);
+    const V3 c = prep_normal_of_bytes((w1 >> 16) & 255u, w1 >> 24, w2 & 255u, scale);
+    const V3 d = prep_normal_of_bytes((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24, scale);
+    float4* o = reinterpret_cast<float4*>(out) + 3 * i;
+    o[0] = make_float4(a.x, a.y, a.z, b.x);
+    o[1] = make_float4(b.y, b.z, c.x, c.y);
+    o[2] = make_float4(c.z, d.x, d.y, d.z);
+  }
+  const uint64_t t = n4 * 4 + tid;  // tail: fewer than 4 pixels
+  if (t < n_pixels) {
+    const V3 a = prep_normal_of_bytes(in[3 * t], in[3 * t + 1], in[3 * t + 2], scale);
+    out[3 * t] = a.x;
+    out[3 * t + 1] = a.y;
+    out[3 * t + 2] = a.z;
+  }
+}
+
+// parity hook (vimg_libm_eval): the DEVICE copies of glibc's float functions on caller-given inputs
+__global__ void __launch_bounds__(256)
+libm_eval_kernel(uint32_t fn, const float* __restrict__ x, const float* __restrict__ y, uint64_t n, float* __restrict__ out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = x[i], b = y ? y[i] : 0.f;
+    float r;
+    switch (fn) {
+      case 0: r = m_sinf(a); break;
+      case 1: r = m_cosf(a); break;
+      case 2: r = m_logf(a); break;
+      case 3: r = m_log2f(a); break;
+      case 4: r = m_powf(a, b); break;
+      case 5: r = m_acosf(a); break;
+      case 6: r = m_atan2f(a, b); break;
+      default: r = vimg_libm::glibc_atanf(a); break;
+    }
+    out[i] = r;
   }
 }
 

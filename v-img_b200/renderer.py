@@ -92,6 +92,7 @@ EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vi
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
            "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8", "vimg_heatmap",
            "vimg_mip_chain_levels", "vimg_build_mip_chain", "vimg_build_envmap_cdf",
+           "vimg_convert_srgb8_to_linear", "vimg_convert_rgb8_to_normal", "vimg_build_image_texture", "vimg_libm_eval",
            "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
 
 
@@ -133,6 +134,12 @@ def load_library():
                                          C.c_void_p, C.POINTER(C.c_double)]
     lib.vimg_build_envmap_cdf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_double)]
+    lib.vimg_convert_srgb8_to_linear.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    lib.vimg_convert_rgb8_to_normal.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p,
+                                                C.POINTER(C.c_double)]
+    lib.vimg_build_image_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib.vimg_libm_eval.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.vimg_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
     lib.vimg_trace_pixel.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_int, C.c_int,
                                      C.c_void_p]
@@ -419,3 +426,64 @@ def build_envmap_cdf(image, device=0):
     _check(lib, lib.vimg_build_envmap_cdf(image.ctypes.data, w, h, device, row.ctypes.data, col.ctypes.data,
                                           C.byref(ms)), "vimg_build_envmap_cdf")
     return row, col, ms.value
+
+
+def convert_srgb8_to_linear(rgb8, device=0):
+    """Mirror of make_texture's byte -> float loop + ImageTexture::convert_sRGB_to_linear
+    (src/scene_loading/gltf_loading.cpp:139-150, src/image_texture.cpp:257-263).
+    rgb8: uint8 [..., 3].  Returns (float32 array of the same shape, kernel ms)."""
+    lib = load_library()
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    ms = C.c_double()
+    _check(lib, lib.vimg_convert_srgb8_to_linear(rgb8.ctypes.data, rgb8.size // 3, device, out.ctypes.data,
+                                                 C.byref(ms)), "vimg_convert_srgb8_to_linear")
+    return out, ms.value
+
+
+def convert_rgb8_to_normal(rgb8, scale=1.0, device=0):
+    """Mirror of make_texture's byte -> float loop + ImageTexture::convert_RGB_to_normal
+    (src/scene_loading/gltf_loading.cpp:139-162, src/image_texture.cpp:265-275)."""
+    lib = load_library()
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    out = np.empty(rgb8.shape, np.float32)
+    ms = C.c_double()
+    _check(lib, lib.vimg_convert_rgb8_to_normal(rgb8.ctypes.data, rgb8.size // 3, scale, device,
+                                                out.ctypes.data, C.byref(ms)), "vimg_convert_rgb8_to_normal")
+    return out, ms.value
+
+
+def build_image_texture(srgb8, wrap_u=0, wrap_v=0, device=0):
+    """make_texture's TextureType::Image case (gltf_loading.cpp:147-156): decoded sRGB bytes [H, W, 3]
+    -> ([level 0, level 1, ...] float32 arrays, kernel ms), converted and filtered on the device."""
+    lib = load_library()
+    srgb8 = np.ascontiguousarray(srgb8, np.uint8)
+    h, w = srgb8.shape[:2]
+    floats = C.c_uint64()
+    n = lib.vimg_mip_chain_levels(w, h, C.byref(floats))
+    level0 = np.empty((h, w, 3), np.float32)
+    buf = np.empty(floats.value, np.float32)
+    ms = C.c_double()
+    _check(lib, lib.vimg_build_image_texture(srgb8.ctypes.data, w, h, wrap_u, wrap_v, device, level0.ctypes.data,
+                                             buf.ctypes.data, C.byref(ms)), "vimg_build_image_texture")
+    levels, off = [level0], 0
+    for lv in range(1, n):
+        w, h = max(w // 2, 1), max(h // 2, 1)
+        levels.append(buf[off:off + w * h * 3].reshape(h, w, 3))
+        off += w * h * 3
+    return levels, ms.value
+
+
+LIBM_FUNCTIONS = {"sinf": 0, "cosf": 1, "logf": 2, "log2f": 3, "powf": 4, "acosf": 5, "atan2f": 6, "atanf": 7}
+
+
+def libm_eval(fn, x, y=None, device=0):
+    """Parity hook: the device's restatement of glibc's float function `fn` on the float32 array x
+    (and y for powf / atan2f; atan2f(x, y) takes x as the first argument like the C function)."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, np.float32)
+    y = None if y is None else np.ascontiguousarray(y, np.float32)
+    out = np.empty(x.shape, np.float32)
+    _check(lib, lib.vimg_libm_eval(LIBM_FUNCTIONS[fn], x.ctypes.data, None if y is None else y.ctypes.data, x.size,
+                                   device, out.ctypes.data), "vimg_libm_eval")
+    return out
