@@ -249,6 +249,17 @@ typedef struct vimg_render_params {
  * mode: slower than the normal, concurrent schedule) */
 #define VIMG_FLAG_STAGE_TIMES 8u
 
+/* material / mis: every BVH traversal starts from an empty stack.  The reference does not: its
+ * per-thread `thread_stack` is shared by BVH::occlude and BVH::hit, BVH::occlude returns on the first
+ * hit without emptying it (include/bvh.h:165-168) and BVH::hit pushes the root on top of what is there
+ * (bvh.h:143), so the closest-hit traversal of a path's next segment also visits the nodes its shadow
+ * ray left behind (mis_integrator.cpp:64 -> :119) -- without their box test.  By default (one RNG
+ * stream per pixel) the device reproduces that, which is what makes mis images bit-identical where the
+ * slab test is not conservative (self-intersections at t just above minT); it costs the extra node
+ * visits the reference also pays (measured: 8-13 % of the frame).  This flag drops it; spp_streams > 1
+ * (not bit-identical by construction) implies it. */
+#define VIMG_FLAG_FRESH_STACK 16u
+
 /* stages of the queue wavefront (vimg_render_stats.stage_ms / stage_launches) */
 typedef enum vimg_stage {
   VIMG_STAGE_TRACE = 0,            /* BVH::hit / BVH::occlude for every queued ray          */

@@ -99,17 +99,39 @@ def test_material_and_mis_images_within_tolerance(vimg, man, name, key, bound):
     ("glass_small", "mis_64", 1.0), ("glass_small", "material_64", 1.0),
     ("disney_small", "mis_256", 1.0), ("disney_small", "material_32", 1.0),
     ("sphere_light_small", "mis_64", 1.0), ("sphere_light_medium", "material_64", 1.0),
-    ("cornell_checker", "mis_64", 1.0), ("cornell_skylight", "mis_64", 0.99),
-    ("synthetic_small", "mis_64", 0.85), ("synthetic_rg", "mis_64", 0.85)])
+    ("cornell_checker", "mis_64", 1.0), ("cornell_skylight", "mis_64", 1.0), ("cornell_skylight", "material_64", 1.0),
+    ("synthetic_small", "mis_64", 1.0), ("synthetic_small", "material_32", 1.0), ("synthetic_rg", "mis_64", 0.99)])
 def test_paths_stay_on_the_reference_rng_trajectory(vimg, man, name, key, min_identical):
-    """With glibc's sinf/cosf restated exactly (vimg_libm.cuh) and the reference's float/double
-    promotions kept, whole images of the Lambertian / glass / Disney scenes come out BIT-IDENTICAL
-    to the CPU reference at equal spp; textured env-map scenes keep > 85 % identical pixels (their
-    log2f / acosf / atan2f calls are not restated bit-exactly)."""
+    """With glibc's float functions restated exactly (vimg_libm.cuh), the reference's float/double
+    promotions kept and its carried-over traversal stack reproduced (bvh_traverse), whole images come out
+    BIT-IDENTICAL to the CPU reference at equal spp: Lambertian / glass / Disney scenes, the sky-light
+    scene, and the textured env-map scene.  synthetic_rg (separate metallic-roughness uv set) keeps
+    99.7 % identical pixels, the rest differ in the last bit of one channel."""
     v = man[name]["ref"][key]
     img, _ = scene(vimg, name).scene_integrator(key.rsplit("_", 1)[0], v["spp"], v["depth"])
     same = float((img == golden_ref(name)[key]).all(-1).mean())
     assert same >= min_identical, same
+
+
+def test_fresh_stack_flag_stays_within_tolerance(vimg, man):
+    """VIMG_FLAG_FRESH_STACK drops the reference's carried-over traversal stack (include/bvh.h:143,165-168):
+    on the sky-light scene -- half of its shadow rays are occluded, so stale nodes are common -- a few
+    paths re-hit the wall they leave in the reference only: 27 of 16384 pixels differ (the same 27 the
+    reference itself changes when its stack is cleared before BVH::hit, measured on the CPU), relMSE
+    stays three orders of magnitude inside the bound.  Both pipelines implement the flag identically."""
+    name, key = "cornell_skylight", "mis_64"
+    v = man[name]["ref"][key]
+    sc = scene(vimg, name)
+    ref = golden_ref(name)[key]
+    exact, _ = sc.scene_integrator("mis", v["spp"], v["depth"])
+    fresh, st = sc.scene_integrator("mis", v["spp"], v["depth"], fresh_stack=True)
+    fresh_b, _ = sc.scene_integrator("mis", v["spp"], v["depth"], fresh_stack=True, pipeline="block")
+    assert np.array_equal(exact, ref)
+    assert np.array_equal(fresh, fresh_b)
+    differing = int((fresh != ref).any(-1).sum())
+    err = rel_mse(fresh, ref)
+    print(f"fresh stack: {differing} of {ref.shape[0] * ref.shape[1]} pixels differ, relMSE {err:.3e}")
+    assert 0 < differing <= 64 and err < 1e-4 and st["nan_samples"] == 0
 
 
 def test_full_size_c2_against_the_live_reference(vimg, refcpu, man):
@@ -277,7 +299,7 @@ def _synthetic_case(vimg, refcpu, G, width, height, ids_spp, mis_spp):
         err = rel_mse(g, r)
         print(f"   mis {mis_spp} spp: relMSE {err:.3e}, bit-identical pixels {same:.4f}, "
               f"{(st['rays_closest'] + st['rays_shadow']) / st['kernel_ms'] / 1e3:.0f} Mrays/s")
-        assert err < 1e-6 and same > 0.9 and st["nan_samples"] == 0
+        assert err < 1e-6 and same > 0.99 and st["nan_samples"] == 0
     sc.close()
     rs.close()
 

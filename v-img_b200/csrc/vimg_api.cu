@@ -1013,6 +1013,7 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       return fail(VIMG_ERR_INVALID_ARGUMENT, "spp_streams too large for this frame");
     w.n_local_units = w.n_local_pixels * w.streams;
     w.partial = nullptr;
+    w.fresh_stack = ((flags & VIMG_FLAG_FRESH_STACK) || w.streams > 1) ? 1u : 0u;
     // pipeline: the queue wavefront unless the caller (or VIMG_PIPELINE=block) asks for the
     // block-local kernel
     bool use_block = (flags & VIMG_FLAG_PIPELINE_BLOCK) != 0;

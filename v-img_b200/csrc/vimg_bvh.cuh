@@ -206,27 +206,37 @@ struct TravCounters {
 };
 
 #ifndef VIMG_STACK_MAX
-#define VIMG_STACK_MAX 64  // bvh.max_depth + 2 entries are enough (integrators.h:98-99)
+#define VIMG_STACK_MAX 64  // bvh.max_depth + 2 entries per traversal (integrators.h:98-99), twice with stale entries below
 #endif
 
 // BVH::hit<T> (include/bvh.h:83-225).  ANY_HIT=false: closest hit, ordered push (far child
 // first; on a tie the FIRST child is pushed first so the SECOND is visited first), last
 // successful primitive wins, popped nodes are not re-tested against the shrunken maxT.
 // ANY_HIT=true: BVH::occlude, unordered push (left then right), early exit.
+//
+// The stack belongs to the caller, like the reference's per-thread `thread_stack`, and that matters:
+// BVH::hit pushes the root ON TOP of whatever the vector holds (bvh.h:143, no clear()), and
+// BVH::occlude returns from the middle of its loop on the first hit (bvh.h:165-168), leaving the
+// nodes it had pushed but not visited.  The closest-hit call that follows on the same thread -- the
+// next segment of the same path, mis_integrator.cpp:64 -> :119 -- first runs its own traversal and
+// then pops those STALE nodes too, testing their primitives without the box test that would have
+// culled them.  That changes results where the float slab test is not conservative: a path leaving
+// a wall re-hits the same wall at t just above minT (measured on cornell_skylight: 27 of 16384
+// pixels at 64 spp differ without this).  So: `sp` entries of `stack` are kept below the root on
+// entry, and an any-hit traversal that ends early leaves its unvisited entries there on return.
 template <bool ANY_HIT, bool COUNT>
-VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt) {
+VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt, uint2* stack, int& sp) {
   ph.leaf_slot = -1;
   if (sc.n_nodes == 0) return false;
   const RayPre pre = ray_precompute(ray);
   float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
   if (is_inf(root_hit)) return false;
+  if (sp + (int)sc.stack_cap > VIMG_STACK_MAX) sp = 0;  // no room for stale entries below a full traversal
 
   // "while-while" traversal: every lane first descends through inner nodes until it holds a
   // leaf (or runs dry), then the warp tests leaf primitives together.  Per ray the sequence of
   // box tests, pushes and primitive tests is exactly the reference's push-then-pop order:
   // instead of pushing the child that would be popped next, it is kept in `cur`.
-  uint2 stack[VIMG_STACK_MAX];
-  int sp = 0;
   uint2 cur = make_uint2(sc.root_first, sc.root_count);
   bool have = true;
   while (have) {
@@ -287,6 +297,14 @@ VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt) 
     }
   }
   return ph.leaf_slot >= 0;
+}
+
+// a traversal that starts from an empty stack (camera rays of the normal integrators, ids, heat map)
+template <bool ANY_HIT, bool COUNT>
+VD bool bvh_traverse(const DScene& sc, Ray& ray, PreHit& ph, TravCounters* cnt) {
+  uint2 stack[VIMG_STACK_MAX];
+  int sp = 0;
+  return bvh_traverse<ANY_HIT, COUNT>(sc, ray, ph, cnt, stack, sp);
 }
 
 }  // namespace vimg

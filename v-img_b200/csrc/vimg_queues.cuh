@@ -42,6 +42,8 @@ namespace vimg {
 #ifndef QW_INNER_MIN_LANES
 #define QW_INNER_MIN_LANES 8  // leave the inner-node loop once fewer lanes than this are still in it
 #endif
+// a closest-ray queue entry with this bit carries the slot's shadow ray too (traced first, same lane)
+#define QW_PAIR_BIT 0x80000000u
 #ifndef QW_CHUNK
 #define QW_CHUNK 64  // rays a warp takes from the global cursor with one atomic
 #endif
@@ -169,7 +171,9 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   bool more = total > 0;
 
   // per-lane ray: `have` = in traversal, `done` = finished, result not stored yet
-  bool have = false, done = false, any_hit = false, occluded = false;
+  // `pair`: this lane traces a shadow ray whose path goes on -- the closest ray of the same slot follows
+  // on the same lane and inherits the stack the occlusion traversal leaves (see bvh_traverse)
+  bool have = false, done = false, any_hit = false, occluded = false, pair = false;
   uint32_t slot = 0, qpos = 0;
   Ray ray;
   RayPre pre;
@@ -190,9 +194,35 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   for (;;) {
     if (done) {  // the one place results are stored
       QwHit* h = &st.slot[slot].hit;
+      bool store_closest = !any_hit;
       if (any_hit) {
         h->occl = occluded ? 1u : 0u;
-      } else {
+        if (pair) {
+          // mis_integrator.cpp:64 -> :119 on one thread_stack: BVH::hit pushes the root on top of what
+          // BVH::occlude left when it returned early (sp entries; 0 after a completed traversal)
+          pair = false;
+          any_hit = false;
+          occluded = false;
+          const float4 d4 = ldg4(&st.slot[slot].ray.d_s);
+          ray.dir = xyz(d4);
+          ray.maxT = CUDART_INF_F;
+          ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;  // the occluder's record is not a hit of this ray
+          ph.leaf_slot = -1;
+          pc.rays_closest++;
+          store_closest = true;
+          if (sc.n_nodes != 0) {
+            pre = ray_precompute(ray);
+            const float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
+            if (!is_inf(root_hit)) {
+              if (sp + (int)sc.stack_cap > VIMG_STACK_MAX) sp = 0;
+              cur = make_uint2(sc.root_first, sc.root_count);
+              have = true;
+              store_closest = false;
+            }
+          }
+        }
+      }
+      if (store_closest) {
         stg4(&h->h0, make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1));
         h->h1 = make_float2(ph.e2, ph.inv_det);
         st.q_leaf[qpos] = ph.leaf_slot;
@@ -217,18 +247,28 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
             ph.leaf_slot = -1;
             occluded = false;
+            sp = 0;  // an earlier shadow ray of this lane may have ended with entries left
             float4 o4, d4;
             if (idx < n_c) {
-              any_hit = false;
-              slot = qc[idx];
+              const uint32_t entry = qc[idx];
+              slot = entry & ~QW_PAIR_BIT;
               qpos = idx;
               o4 = ldg4(&st.slot[slot].ray.o_w);
-              d4 = ldg4(&st.slot[slot].ray.d_s);
-              ray.maxT = CUDART_INF_F;
-              pc.rays_closest++;
+              pair = (entry & QW_PAIR_BIT) != 0;
+              any_hit = pair;
+              if (pair) {  // the shadow ray first, then the closest ray from the same origin
+                d4 = ldg4(&st.slot[slot].nee.wi_dist);
+                ray.maxT = d4.w - 0.0001f;
+                pc.rays_shadow++;
+              } else {
+                d4 = ldg4(&st.slot[slot].ray.d_s);
+                ray.maxT = CUDART_INF_F;
+                pc.rays_closest++;
+              }
             } else {
               // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
               any_hit = true;
+              pair = false;
               slot = qs[idx - n_c];
               o4 = ldg4(&st.slot[slot].ray.o_w);
               d4 = ldg4(&st.slot[slot].nee.wi_dist);
@@ -243,7 +283,6 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
               const float root_hit = slab(sc.root_min, sc.root_max, ray, pre);
               if (!is_inf(root_hit)) {
                 cur = make_uint2(sc.root_first, sc.root_count);
-                sp = 0;
                 have = true;
                 done = false;
               }
@@ -366,7 +405,7 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
     uint32_t cls = WF_CLASS_NONE + 1, j = 0;  // NONE + 1: no item
     int32_t leaf_slot = -1;
     if (item < n) {
-      j = q[item];
+      j = q[item] & ~QW_PAIR_BIT;
       leaf_slot = __ldcg(&st.q_leaf[item]);
       cls = WF_CLASS_NONE;
       if (leaf_slot >= 0) {
@@ -481,6 +520,10 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
     if (valid && (f & WF_IN_PATH)) {
       // pending shadow ray of the last bounce (mis_integrator.cpp:64-78)
       V3 L = xyz(L4);
+#ifdef VIMG_DEBUG_NEE
+      if (MIS) printf("D end: s=%u nee=%d valid=%d occl=%d c=%.9g %.9g %.9g L=%.9g %.9g %.9g END=%d leaf=%d lastpdf=%.9g\n", s, (f & WF_NEE) != 0, (f & WF_NEE_VALID) != 0, (int)occl,
+                      cp4.x, cp4.y, cp4.z, L4.x, L4.y, L4.z, (f & WF_END) != 0, __float_as_int(h0.x), cp4.w);
+#endif
       if (MIS && (f & WF_NEE) && (f & WF_NEE_VALID) && !occl) L = L + xyz(cp4);
       if (f & WF_END) {
         finish(MIS ? L : xyz(cp4));
@@ -507,6 +550,10 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
             if (last_pdf != 0 && sc.bg.emissive) {
               float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
               float mis_weight = balance_heuristic(last_pdf, light_pdf);
+#ifdef VIMG_DEBUG_NEE
+              printf("D miss: thr=%.9g %.9g %.9g bg=%.9g %.9g %.9g light_pdf=%.9g w=%.9g dir=%.9g %.9g %.9g cone=%.9g %.9g\n", thr.x, thr.y, thr.z, bg.x, bg.y, bg.z,
+                     light_pdf, mis_weight, ray.dir.x, ray.dir.y, ray.dir.z, ray.cone.cone_width, ray.cone.spread_angle);
+#endif
               L = L + thr * mis_weight * bg;
             }
             finish(L);
@@ -726,6 +773,9 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         // what mis_integrator does between the BVH::hit that found this surface and the next
         // loop body: the shadow ray of the previous bounce (mis_integrator.cpp:64-78), Russian
         // roulette (:154-167) and the loop condition d < depth
+#ifdef VIMG_DEBUG_NEE
+        if (fj & WF_NEE) printf("D shade: pending nee valid=%d occl=%u c=%.9g %.9g %.9g\n", (fj & WF_NEE_VALID) != 0, hb.z, cp4.x, cp4.y, cp4.z);
+#endif
         if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && hb.z == 0) {
           L4.x += cp4.x;
           L4.y += cp4.y;
@@ -830,6 +880,11 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
             mat_sample_pdf = p;
           }
         }
+#ifdef VIMG_DEBUG_NEE
+        printf("D bounce d=%u class=%u hp=%.9g %.9g %.9g n=%.9g %.9g %.9g nee=%d wi=%.9g %.9g %.9g lpdf=%.9g dist=%g valid=%d c=%.9g %.9g %.9g scat=%d wo=%.9g %.9g %.9g mpdf=%.9g thr=%.9g %.9g %.9g\n",
+               d, CLASS, hit.hit_p.x, hit.hit_p.y, hit.hit_p.z, hit.hit_n_s.x, hit.hit_n_s.y, hit.hit_n_s.z, (int)nee, li.wi.x, li.wi.y, li.wi.z, li.pdf, li.dist, (int)nee_valid,
+               contrib.x, contrib.y, contrib.z, (int)scattered, sm.wo.x, sm.wo.y, sm.wo.z, mat_sample_pdf, thr.x, thr.y, thr.z);
+#endif
         fj &= ~(WF_NSB | WF_NEE | WF_NEE_VALID | WF_END);
         if (nsb) fj |= WF_NSB;
         if (nee) {
@@ -894,6 +949,11 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
 
     // every queue written here belongs to the NEXT iteration, so this launch is independent of
     // the END launch of the same iteration and the two run concurrently
+    // a path that goes on after requesting a shadow ray: ONE trace item, the shadow ray first and the
+    // closest ray after it on the same lane (QW_PAIR_BIT), because the reference's closest-hit
+    // traversal inherits the stack its occlusion traversal left behind (see bvh_traverse)
+    const bool pair = want_closest && want_shadow && !args.fresh_stack;
+    if (pair) want_shadow = false;
     const bool want[3] = {want_closest, want_shadow, want_end};
     QwAppend<3> ap;
     ap.count(s_cnt, want, lane, lane_lt);
@@ -902,7 +962,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_shadow[parity ^ 1u], s_cnt[1]);
     if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[2]);
     __syncthreads();
-    if (want_closest) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = j;
+    if (want_closest) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = pair ? (j | QW_PAIR_BIT) : j;
     if (want_shadow) st.q_shadow[parity ^ 1u][s_base[1] + ap.off[1]] = j;
     if (want_end) st.q_end[parity ^ 1u][s_base[2] + ap.off[2]] = j;
   }

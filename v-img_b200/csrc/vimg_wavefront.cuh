@@ -71,6 +71,9 @@ struct WfArgs {
   // u / streams) and, for streams > 1, the partial sums [image_index][range] x rgb
   uint32_t streams, n_local_units;
   float* partial;
+  // 1: every traversal starts from an empty stack (VIMG_FLAG_FRESH_STACK, or streams > 1); 0: a path's
+  // closest-hit traversal inherits what its shadow ray's traversal left (the reference's thread_stack)
+  uint32_t fresh_stack;
 };
 // a slot's sample range number lives in the upper half of its flag word
 #define WF_RANGE_SHIFT 16
@@ -186,6 +189,10 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         }
       };
 
+      // nodes an occluded shadow ray left unvisited: inherited by the closest-hit traversal of the
+      // same path's next segment (the reference's shared thread_stack, see bvh_traverse)
+      uint2 stk[VIMG_STACK_MAX];
+      int stale = 0;
       // A. shadow ray requested by the last shade stage (mis_integrator.cpp:59-78)
       if (MIS && (f & WF_NEE)) {
         Ray sr;
@@ -195,11 +202,15 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
         sr.maxT = sh.nee_dist[i] - 0.0001f;
         PreHit ph;
         pc.rays_shadow++;
-        const bool occluded = bvh_traverse<true, COUNT>(sc, sr, ph, &pc.trav);
+        const bool occluded = bvh_traverse<true, COUNT>(sc, sr, ph, &pc.trav, stk, stale);
         if (!occluded && (f & WF_NEE_VALID)) st3(sh.L, i, ld3(sh.L, i) + ld3(sh.nee_c, i));
         f &= ~(WF_NEE | WF_NEE_VALID);
       }
-      if (f & WF_END) finish(MIS ? ld3(sh.L, i) : ld3(sh.nee_c, i));
+      if (f & WF_END) {
+        finish(MIS ? ld3(sh.L, i) : ld3(sh.nee_c, i));
+        stale = 0;  // only within a path (the queue pipeline cannot carry a stack across samples)
+      }
+      if (args.fresh_stack) stale = 0;
       WF_CLK(0);
 
       // B. pull the next pixel of the frame, start the next sample
@@ -267,7 +278,7 @@ wavefront_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfAr
           ray.cone.spread_angle = sh.cone_s[i];
           PreHit ph;
           pc.rays_closest++;
-          const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav);
+          const bool found = bvh_traverse<false, COUNT>(sc, ray, ph, &pc.trav, stk, stale);
           WF_CLK(2);
           const V3 thr = ld3(sh.thr, i);
           if (!found) {
