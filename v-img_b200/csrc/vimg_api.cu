@@ -403,6 +403,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     dt.n_levels = ht.n_levels;
     dt.wrap_u = ht.wrap_u;
     dt.wrap_v = ht.wrap_v;
+    dt.half_log2_wh = (double)0.5f * std::log2((double)(uint32_t)(ht.width * ht.height));
     if (ht.type == VIMG_TEX_IMAGE) {
       if (ht.n_levels == 0 || ht.n_levels > 16) return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture needs 1..16 mip levels");
       for (uint32_t l = 0; l < ht.n_levels; ++l) {

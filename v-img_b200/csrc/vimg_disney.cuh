@@ -326,6 +326,10 @@ VD void principled_eval_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 
   principled_frame_mr(sc, m, dir_in, hit, frame, metallic, roughness);
   V3 base_color = col_at_ray_hit(sc, m.texture, wi, cone, hit);
   V3 half_vector = normalize(dir_in + wo);
+#ifdef VIMG_DEBUG_NEE
+  printf("D   principled: base=%.9g %.9g %.9g metallic=%.9g rough=%.9g uv=%.9g %.9g mruv=%.9g %.9g\n", base_color.x, base_color.y, base_color.z, metallic, roughness,
+         hit.uv.x, hit.uv.y, hit.mr_uv.x, hit.mr_uv.y);
+#endif
 
   constexpr float alpha_min = 0.0001;
   float aspect = sqrtf(1.f - 0.9f * m.anisotropic);
@@ -383,6 +387,11 @@ VD void principled_eval_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 
   float choose_glass = glass_weight / total_w;
   pdf = choose_diff * pdf_diff + choose_clearcoat * pdf_clearcoat + choose_metal * pdf_metal
         + choose_glass * pdf_glass;
+#ifdef VIMG_DEBUG_NEE
+  printf("D   parts: diff=%.9g %.9g %.9g sheen=%.9g %.9g %.9g cc=%.9g %.9g %.9g metal=%.9g %.9g %.9g glass=%.9g %.9g %.9g eval=%.9g %.9g %.9g pdf=%.9g\n", eval_diff.x, eval_diff.y, eval_diff.z,
+         eval_sheen.x, eval_sheen.y, eval_sheen.z, eval_clearcoat.x, eval_clearcoat.y, eval_clearcoat.z, eval_metal.x, eval_metal.y, eval_metal.z,
+         eval_glass.x, eval_glass.y, eval_glass.z, eval.x, eval.y, eval.z, pdf);
+#endif
 }
 
 // Principled::sample_mat (principled.cpp:3-58)

@@ -186,7 +186,10 @@ VD V3 col_at_ray_hit(const DScene& sc, int32_t tex, V3 ray_in_dir, RayCone cone,
   // unqualified log2(width*height) on an unsigned => double
   float lambda = 0.5f * m_log2f(hit.tex_coord_area / hit.primitive_area);
   lambda += m_log2f(fabsf(cone.cone_width) / fabsf(dot(ray_in_dir, hit.hit_n_g)));
-  lambda = (float)((double)lambda + (double)0.5f * d_log2((double)(t.width * t.height)));
+  lambda = (float)((double)lambda + t.half_log2_wh);
+#ifdef VIMG_DEBUG_NEE
+  printf("D   lod: tca=%.9g pa=%.9g cw=%.9g dot=%.9g lambda=%.9g\n", hit.tex_coord_area, hit.primitive_area, cone.cone_width, dot(ray_in_dir, hit.hit_n_g), lambda);
+#endif
   if (is_nan(lambda)) lambda = 0.f;
   return col_mipmap_interpolate(sc, t, lambda - 2.f, hit.uv);
 }
