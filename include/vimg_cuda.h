@@ -135,7 +135,11 @@ typedef struct vimg_texture {
   uint32_t n_levels;     /* image: mipmap.size()                             */
   uint32_t wrap_u, wrap_v;
   const float* const* levels; /* image: n_levels arrays, level l is
-                                 max(W>>l,1) x max(H>>l,1) x 3 floats, row 0 = top */
+                                 max(W>>l,1) x max(H>>l,1) x 3 floats, row 0 = top.
+                                 levels[1 .. n_levels-1] may ALL be NULL: vimg_scene_create then
+                                 builds them on the device from level 0, bit for bit what
+                                 ImageTexture's constructor builds (image_texture.cpp:59-130);
+                                 n_levels must be vimg_mip_chain_levels(width, height)          */
 } vimg_texture;
 
 typedef struct vimg_texture_rg { /* TextureRG include/texture/texture_RG.h:10-57 */
@@ -194,7 +198,9 @@ typedef struct vimg_background {
   uint32_t cdf_width;      /* ArraySampling2D::width / height                */
   uint32_t cdf_height;
   const float* row_cdf;    /* cdf_height + 1 floats  (row_probabilities.cdf) */
-  const float* col_cdfs;   /* cdf_height x (cdf_width + 1) floats            */
+  const float* col_cdfs;   /* cdf_height x (cdf_width + 1) floats.  Both may be NULL: built on
+                              the device from level 0 of `image` (ArraySampling2D's constructor,
+                              include/rng/sampling.h:167-197); cdf_width / cdf_height 0 or the image's */
 } vimg_background;
 
 /* ---- the whole scene ---------------------------------------------------- */

@@ -123,3 +123,27 @@ def test_prep_edge_cases(vimg):
     assert np.array_equal(col, np.tile(np.arange(9, dtype=np.float32) / 8, (4, 1)))
     with pytest.raises(vimg.VimgError):
         vimg.build_envmap_cdf(np.zeros((4, 8, 3), np.float32), device=99)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,key", [("synthetic_small", "mis_64"), ("synthetic_rg", "mis_64")])
+def test_scene_create_builds_missing_levels_and_cdfs(vimg, name, key):
+    """the adapter may hand over level 0 only (levels 1.. NULL) and no env-map CDFs: vimg_scene_create builds
+    them on the device, and the render is the reference's image bit for bit -- as with the host-built ones"""
+    from helpers import golden_ref, manifest
+    v = manifest()[name]["ref"][key]
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    n_tex, cdfs = vimg.strip_prepared(d.ptr)
+    assert n_tex >= 2 and cdfs
+    sc = vimg.Scene(d.ptr)
+    img, st = sc.scene_integrator("mis", v["spp"], v["depth"])
+    assert np.array_equal(img, golden_ref(name)[key])
+    sc.close()
+
+
+def test_stripped_descriptor_cannot_be_saved(tmp_path):
+    vimg = load_product()
+    d = vimg.LoadedDesc(golden_scene_path("synthetic_small"))
+    vimg.strip_prepared(d.ptr)
+    lib = vimg.load_library()
+    assert lib.vimg_scene_desc_save(d.ptr, str(tmp_path / "x.vscene").encode()) != 0

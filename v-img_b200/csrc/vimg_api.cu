@@ -250,6 +250,12 @@ struct vimg_scene {
   }
 };
 
+extern "C" {  // defined next to the C ABI entry points that share them
+static void launch_mip_levels(float* d_all, uint32_t width, uint32_t height, uint32_t n_levels, uint32_t wrap_u,
+                              uint32_t wrap_v);
+static cudaError_t launch_envmap_cdf(const float* d_img, uint32_t width, uint32_t height, float* d_col, float* d_row);
+}
+
 static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   DScene& d = s->d;
   // ---- camera ------------------------------------------------------------
@@ -391,6 +397,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   // ---- textures --------------------------------------------------------------
   std::vector<DTexture> textures(desc->n_textures);
   std::vector<float> texels;
+  std::vector<uint32_t> build_mips;  // image textures whose levels 1.. the device builds
   for (uint32_t t = 0; t < desc->n_textures; ++t) {
     const vimg_texture& ht = desc->textures[t];
     DTexture& dt = textures[t];
@@ -406,10 +413,26 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     dt.half_log2_wh = (double)0.5f * std::log2((double)(uint32_t)(ht.width * ht.height));
     if (ht.type == VIMG_TEX_IMAGE) {
       if (ht.n_levels == 0 || ht.n_levels > 16) return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture needs 1..16 mip levels");
+      if (!ht.levels || !ht.levels[0]) return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture without level 0");
+      // levels 1.. may be left NULL (all of them): the device builds the chain from level 0 with the
+      // kernels of vimg_build_mip_chain once the pool is uploaded (ImageTexture's constructor)
+      uint32_t missing = 0;
+      for (uint32_t l = 1; l < ht.n_levels; ++l) missing += ht.levels[l] == nullptr;
+      if (missing != 0 && missing != ht.n_levels - 1)
+        return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture: pass all mip levels or level 0 only");
+      if (missing) {
+        uint64_t floats = 0;
+        if (vimg_mip_chain_levels(ht.width, ht.height, &floats) != ht.n_levels)
+          return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture: n_levels is not what ImageTexture's constructor builds");
+        build_mips.push_back(t);
+      }
       for (uint32_t l = 0; l < ht.n_levels; ++l) {
         const uint64_t w = std::max(ht.width >> l, 1u), h = std::max(ht.height >> l, 1u);
         dt.level_off[l] = (uint32_t)(texels.size() / 3);
-        texels.insert(texels.end(), ht.levels[l], ht.levels[l] + 3 * w * h);
+        if (ht.levels[l])
+          texels.insert(texels.end(), ht.levels[l], ht.levels[l] + 3 * w * h);
+        else
+          texels.resize(texels.size() + 3 * w * h, 0.f);
       }
     }
   }
@@ -565,12 +588,42 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   UP(s->upload(rg_texels, &d.rg_texels));
   UP(s->upload(desc->lights, desc->n_lights, &d.lights));
   d.n_lights = desc->n_lights;
+  // env-map CDFs left NULL: built on the device from the image's level 0 (ArraySampling2D's constructor)
+  const bool build_cdfs = hb.type == VIMG_BG_ENVMAP && (!hb.row_cdf || !hb.col_cdfs);
+  std::vector<float> zero_cdfs;
   if (hb.type == VIMG_BG_ENVMAP) {
-    UP(s->upload(hb.row_cdf, (size_t)hb.cdf_height + 1, &d.bg.row_cdf));
-    UP(s->upload(hb.col_cdfs, (size_t)hb.cdf_height * (hb.cdf_width + 1), &d.bg.col_cdfs));
+    if (build_cdfs) {
+      const vimg_texture& img = desc->textures[hb.image];
+      if ((hb.cdf_width && hb.cdf_width != img.width) || (hb.cdf_height && hb.cdf_height != img.height))
+        return fail(VIMG_ERR_INVALID_ARGUMENT, "env map: cdf size differs from the image size");
+      d.bg.cdf_w = img.width;
+      d.bg.cdf_h = img.height;
+      zero_cdfs.assign((size_t)img.height * (img.width + 1), 0.f);
+      UP(s->upload(zero_cdfs.data(), (size_t)img.height + 1, &d.bg.row_cdf));
+      UP(s->upload(zero_cdfs.data(), zero_cdfs.size(), &d.bg.col_cdfs));
+    } else {
+      UP(s->upload(hb.row_cdf, (size_t)hb.cdf_height + 1, &d.bg.row_cdf));
+      UP(s->upload(hb.col_cdfs, (size_t)hb.cdf_height * (hb.cdf_width + 1), &d.bg.col_cdfs));
+    }
   }
   UP(s->commit_uploads());
 #undef UP
+  // ---- scene preparation on the device (what the reference's constructors do on the host) ----
+  for (uint32_t t : build_mips) {
+    const DTexture& dt = textures[t];
+    launch_mip_levels(const_cast<float*>(d.texels) + 3 * (size_t)dt.level_off[0], dt.width, dt.height, dt.n_levels,
+                      dt.wrap_u, dt.wrap_v);
+  }
+  if (build_cdfs) {
+    const DTexture& dt = textures[hb.image];
+    const cudaError_t e = launch_envmap_cdf(d.texels + 3 * (size_t)dt.level_off[0], dt.width, dt.height,
+                                            const_cast<float*>(d.bg.col_cdfs), const_cast<float*>(d.bg.row_cdf));
+    if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("env-map CDF build: ") + cudaGetErrorString(e));
+  }
+  if (!build_mips.empty() || build_cdfs) {
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(0));
+  }
   return VIMG_OK;
 }
 
@@ -1412,6 +1465,29 @@ int vimg_build_mip_chain(const float* level0, uint32_t width, uint32_t height, u
   if (e1) cudaEventDestroy(e1);
   if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("vimg_build_mip_chain: ") + cudaGetErrorString(e));
   return VIMG_OK;
+}
+
+// ArraySampling2D on an image that is already in HBM: the H sin(elevation) factors come from the host libm
+// (sampling.h:181-183: v = (y + 0.5f) / height; float sin_elevation = std::sin(std::numbers::pi * v))
+static cudaError_t launch_envmap_cdf(const float* d_img, uint32_t width, uint32_t height, float* d_col, float* d_row) {
+  std::vector<float> sin_elev(height);
+  for (uint32_t y = 0; y < height; ++y) {
+    const float v = (static_cast<float>(y) + 0.5f) / static_cast<float>(height);
+    sin_elev[y] = (float)std::sin(std::numbers::pi * v);
+  }
+  float *d_sin = nullptr, *d_int = nullptr;
+  cudaError_t e = cudaMalloc(&d_sin, height * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_int, height * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_sin, sin_elev.data(), height * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    prep_row_cdf_kernel<<<(height + 127) / 128, 128>>>(d_img, width, height, d_sin, d_col, d_int);
+    prep_row_prob_kernel<<<1, 32>>>(d_int, height, d_row);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (d_sin) cudaFree(d_sin);
+  if (d_int) cudaFree(d_int);
+  return e;
 }
 
 int vimg_build_envmap_cdf(const float* image, uint32_t width, uint32_t height, int device_id, float* out_row_cdf,

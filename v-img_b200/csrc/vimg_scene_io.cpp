@@ -80,6 +80,14 @@ extern "C" {
 
 int vimg_scene_desc_save(const vimg_scene_desc* d, const char* path) {
   if (!d || !path) return VIMG_ERR_INVALID_ARGUMENT;
+  // the file format carries host-built mip levels and CDFs: a descriptor that leaves them to the device
+  // (NULL levels 1.. / NULL CDFs, see vimg_scene_create) cannot be written
+  for (uint32_t t = 0; t < d->n_textures; ++t)
+    if (d->textures[t].type == VIMG_TEX_IMAGE)
+      for (uint32_t l = 0; l < d->textures[t].n_levels; ++l)
+        if (!d->textures[t].levels || !d->textures[t].levels[l]) return VIMG_ERR_INVALID_ARGUMENT;
+  if (d->background.type == VIMG_BG_ENVMAP && (!d->background.row_cdf || !d->background.col_cdfs))
+    return VIMG_ERR_INVALID_ARGUMENT;
   FILE* f = fopen(path, "wb");
   if (!f) return VIMG_ERR_IO;
   Writer w{f};

@@ -491,3 +491,23 @@ def libm_eval(fn, x, y=None, device=0):
     _check(lib, lib.vimg_libm_eval(LIBM_FUNCTIONS[fn], x.ctypes.data, None if y is None else y.ctypes.data, x.size,
                                    device, out.ctypes.data), "vimg_libm_eval")
     return out
+
+
+def strip_prepared(desc_ptr):
+    """Null the host-built mip levels 1.. and env-map CDFs of a descriptor IN PLACE, so that
+    vimg_scene_create builds them on the device (what an adapter that skips ImageTexture's mip loop and
+    ArraySampling2D's constructor hands over).  Returns (textures stripped, cdfs stripped)."""
+    d = C.cast(desc_ptr, C.POINTER(_Desc)).contents
+    n_tex = 0
+    for t in range(d.n_textures):
+        tex = d.textures[t]
+        if tex.type == 2 and tex.n_levels > 1:  # VIMG_TEX_IMAGE
+            for lv in range(1, tex.n_levels):
+                tex.levels[lv] = C.POINTER(C.c_float)()
+            n_tex += 1
+    bg = d.background
+    cdfs = bg.type == 1  # VIMG_BG_ENVMAP
+    if cdfs:
+        bg.row_cdf = C.POINTER(C.c_float)()
+        bg.col_cdfs = C.POINTER(C.c_float)()
+    return n_tex, cdfs
