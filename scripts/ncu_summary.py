@@ -31,7 +31,10 @@ for r in lines[2:]:
     if len(r) < len(h): continue
     m = re.match(r"\s*(@!?U?P\w+\s+)?([A-Z0-9_]+)", r[ci["Source"]])
     op = m.group(2) if m else "?"
-    n = int(r[ci["Instructions Executed"]] or 0); s = int(r[ci["# Samples"]] or 0)
+    try:
+        n = int(r[ci["Instructions Executed"]] or 0); s = int(r[ci["# Samples"]] or 0)
+    except ValueError:  # a report with several launches repeats the header
+        continue
     ops[op] += n; opsamp[op] += s; tot_inst += n; tot_samples += s
 print(f"static SASS instructions {len(lines)-2}, executed warp-instructions {tot_inst}, samples {tot_samples}")
 print("top opcodes by executed count: " + ", ".join(f"{o}:{100*c/tot_inst:.1f}%" for o, c in ops.most_common(14)))
