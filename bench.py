@@ -397,6 +397,25 @@ def cuda_line(w, args):
         post[tm] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
     line["postprocess"] = {"frame": "3840x2160 synthetic, bytes = 15 per pixel (+12 for reinhard's luminance pass)",
                            "per_tonemapper": post}
+    # ---- the step before the path: glTF texture conversion, mip chain, env-map CDFs
+    # on the device, kernel time only (CUDA events inside the calls).  The conversions are HBM bound:
+    # 3 B read + 12 B written per pixel.
+    if rank == 0:
+        tex8 = rng.integers(0, 256, size=(2048, 2048, 3), dtype=np.uint8)
+        conv = {}
+        for name, fn in (("srgb8_to_linear", lambda: vimg.convert_srgb8_to_linear(tex8, device=local_rank)[1]),
+                         ("rgb8_to_normal", lambda: vimg.convert_rgb8_to_normal(tex8, 1.0, device=local_rank)[1])):
+            best = min(fn() for _ in range(5))
+            nbytes = tex8.size * 5
+            conv[name] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
+        tex_ms = min(vimg.build_image_texture(tex8, device=local_rank)[1] for _ in range(3))
+        env = (rng.random((1024, 2048, 3), dtype=np.float32) * 2).astype(np.float32)
+        cdf_ms = min(vimg.build_envmap_cdf(env, device=local_rank)[2] for _ in range(3))
+        line["scene_prep"] = {"texture": "2048x2048 8-bit RGB (12.6 MB in, 50.3 MB out), env map 2048x1024",
+                              "conversions": conv,
+                              "image_texture_ms": tex_ms, "envmap_cdf_ms": cdf_ms,
+                              "note": "image_texture = sRGB8 -> linear + the 10 further mip levels; the CDFs are "
+                                      "sequential float sums per row (one thread per row, the reference's order)"}
     if not args.no_cpu and world == 1:
         r = time_reference(w, 1, 1, budget_s=16.0)
         if r is not None:
