@@ -112,6 +112,23 @@ def test_paths_stay_on_the_reference_rng_trajectory(vimg, man, name, key, min_id
     assert same >= min_identical, same
 
 
+@pytest.mark.parametrize("name", ["glass_in_box", "cornell_box_spheres"])
+def test_full_size_full_spp_mis_against_the_live_reference(vimg, refcpu, man, name):
+    """BASELINE configs C1 (640x480, 200 spp) and C2 (800x800, 100 spp) exactly as the scene files state them,
+    mis, against the compiled reference rendered on this host: every pixel bit-identical.  (C3 at 1800x800,
+    512 spp takes the reference a minute: scripts/full_size_parity.py, profiles/r4_full_size_full_spp_parity.txt
+    -- 0 of 1 440 000 pixels differ.)"""
+    e = man[name]
+    sc = scene(vimg, name)
+    g, st = sc.scene_integrator("mis", e["spp"], e["depth"])
+    d = vimg.LoadedDesc(golden_scene_path(name))
+    rs = refcpu.RefScene.from_desc(d.ptr, e["spp"], e["depth"], "mis")
+    r, _ = rs.render("mis", spp=e["spp"], depth=e["depth"])
+    rs.close()
+    assert st["nan_samples"] == 0 and st["samples"] == e["width"] * e["height"] * e["spp"]
+    assert np.array_equal(g, r), f"{int((g != r).any(-1).sum())} of {e['width'] * e['height']} pixels differ"
+
+
 def test_fresh_stack_flag_stays_within_tolerance(vimg, man):
     """VIMG_FLAG_FRESH_STACK drops the reference's carried-over traversal stack (include/bvh.h:143,165-168):
     on the sky-light scene -- half of its shadow rays are occluded, so stale nodes are common -- a few
