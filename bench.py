@@ -214,7 +214,12 @@ def cuda_line(w, args):
     if vimg.device_count() == 0:
         raise SystemExit("bench.py --impl cuda needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    guard = None
     if world > 1:
+        # NCCL writes its version banner to fd 1 when the first communicator is created; stdout carries
+        # exactly one JSON line, so fd 1 points at stderr until that line is printed
+        guard = StdoutToStderr()
+        guard.__enter__()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -424,7 +429,9 @@ def cuda_line(w, args):
                 "spp_mpix_per_s": r["spp_mpix_per_s"],
                 "sample": f"{w['name']} full frame at {r['spp']} spp (of {w['spp']}), compiled reference "
                           f"(perf flavour, AVX2), rays/sample {r['rays_per_sample']:.3f} (count flavour, 2 spp)"}
-    print(json.dumps(line))
+    if guard is not None:
+        guard.__exit__()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
