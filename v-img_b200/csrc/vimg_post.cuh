@@ -94,8 +94,8 @@ VD uint32_t post_quantise(float v) {  // main.cpp:348-351
 // whose byte is >= b.  They are found once per device by bisection over the float bit patterns
 // WITH the functions above, so the byte of every float is by construction the one the pow path
 // gives (which tests/test_gpu_post.py compares with the CPU's for every float of the pow branch);
-// a pixel then costs three 8-step searches in shared memory instead of three double-precision
-// pow evaluations, and the kernel is bound by its 15 bytes per pixel.
+// a pixel then costs three table look-ups in shared memory (an approximate estimate of the byte,
+// settled by the exact thresholds) instead of three exact pow evaluations.
 __global__ void post_build_thresholds_kernel(uint32_t* __restrict__ thr) {
   const uint32_t b = threadIdx.x;  // 256 threads
   uint32_t lo = 0u, hi = 0x3f800000u;  // bit patterns of 0.0f .. 1.0f order like the values
@@ -116,12 +116,19 @@ __global__ void post_build_thresholds_kernel(uint32_t* __restrict__ thr) {
 }
 VD uint32_t post_byte_from_thresholds(const uint32_t* s_thr, float c) {
   // glm::clamp(c, 0, 1) lets -0.0 through; + 0.0f turns it into +0.0 so that the bits order
-  const uint32_t bits = __float_as_uint(glm_clamp(c, 0.0f, 1.0f) + 0.0f);
-  uint32_t b = 0;
-#pragma unroll
-  for (uint32_t step = 128; step > 0; step >>= 1)
-    if (s_thr[b + step] <= bits) b += step;
-  return b;
+  const float p = glm_clamp(c, 0.0f, 1.0f) + 0.0f;
+  const uint32_t bits = __float_as_uint(p);
+  // The byte is the largest b with T[b] <= bits.  Start from an ESTIMATE -- the same chain with the
+  // hardware's approximate exp2 / log2 (two MUFU operations, ~1e-6 relative) -- and let the exact
+  // table settle it: nearly always two shared-memory reads instead of an 8-step search.  Whatever
+  // the estimate is, the loops end at the same b the search finds (T is non-decreasing, T[0] = 0,
+  // T[256] = 0xffffffff).
+  const float est = p < 0.0031308f ? p * 12.92f : 1.055f * __powf(p, 1.0f / 2.4f) - 0.055f;
+  int b = (int)(255.999f * est);
+  b = b < 0 ? 0 : (b > 255 ? 255 : b);
+  while (s_thr[b] > bits) --b;
+  while (s_thr[b + 1] <= bits) ++b;
+  return (uint32_t)b;
 }
 
 // largest luminance of the frame (reinhard.cpp:3-13): `if (curr > largest)` from 0, so NaN and
