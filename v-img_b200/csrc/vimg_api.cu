@@ -1480,7 +1480,7 @@ static cudaError_t launch_envmap_cdf(const float* d_img, uint32_t width, uint32_
   if (e == cudaSuccess) e = cudaMalloc(&d_int, height * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(d_sin, sin_elev.data(), height * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    prep_row_cdf_kernel<<<(height + 127) / 128, 128>>>(d_img, width, height, d_sin, d_col, d_int);
+    prep_row_cdf_kernel<<<height, 32>>>(d_img, width, height, d_sin, d_col, d_int);
     prep_row_prob_kernel<<<1, 32>>>(d_int, height, d_row);
     e = cudaGetLastError();
   }
@@ -1517,7 +1517,7 @@ int vimg_build_envmap_cdf(const float* image, uint32_t width, uint32_t height, i
   if (e == cudaSuccess) e = cudaMemcpy(d_sin, sin_elev.data(), height * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     cudaEventRecord(e0, 0);
-    prep_row_cdf_kernel<<<(height + 127) / 128, 128>>>(d_img, width, height, d_sin, d_col, d_int);
+    prep_row_cdf_kernel<<<height, 32>>>(d_img, width, height, d_sin, d_col, d_int);
     prep_row_prob_kernel<<<1, 32>>>(d_int, height, d_row);
     cudaEventRecord(e1, 0);
     e = cudaGetLastError();
