@@ -44,8 +44,9 @@ INTEG_NAMES = ["s_normal", "g_normal", "material", "mis"]
 BYTES = {"inner_nodes": 56, "leaf_nodes": 8, "tri_tests": 56, "sphere_tests": 24}
 FLOPS = {"inner_nodes": 50, "tri_tests": 67, "sphere_tests": 40}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an `ncu --set full` capture
-# (profiles/r1s_queue_kernels_disney_8spp.txt, fully loaded iteration of disney_spheres)
-NCU_TRAFFIC = {"qw_trace_kernel": 194.644992e6 + 63.307008e6}
+# (profiles/r4_trace_kernel_fresh_stack.txt: a fully loaded iteration of disney_spheres, 2 M slots, this
+# round's final kernel; mostly path state and queues -- the scene itself is L1 resident)
+NCU_TRAFFIC = {"qw_trace_kernel": 243.432448e6 + 45.497088e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
