@@ -129,6 +129,19 @@ def test_full_size_full_spp_mis_against_the_live_reference(vimg, refcpu, man, na
     assert np.array_equal(g, r), f"{int((g != r).any(-1).sum())} of {e['width'] * e['height']} pixels differ"
 
 
+@pytest.mark.parametrize("name", ["glass_in_box", "cornell_box_spheres", "disney_spheres"])
+def test_baseline_configs_at_full_size_and_spp_match_the_reference_digest(vimg, man, name):
+    """BASELINE configs C1 / C2 / C3 exactly as stated (C3: disney_spheres 1800x800, 512 spp, depth -1,
+    4.2 G rays): the mis image has the digest of the compiled reference's image (rendered in the build
+    container by tests/golden/make_golden_full.py), i.e. every one of its pixels is bit-identical."""
+    from oracle.refcpu import digest
+    v = man[name]["ref"]["mis_full"]
+    img, st = scene(vimg, name).scene_integrator("mis", v["spp"], v["depth"])
+    assert st["nan_samples"] == 0
+    assert np.allclose(img.reshape(-1, 3).mean(0), v["mean"], rtol=1e-6)
+    assert digest(img) == v["hash"]
+
+
 def test_fresh_stack_flag_stays_within_tolerance(vimg, man):
     """VIMG_FLAG_FRESH_STACK drops the reference's carried-over traversal stack (include/bvh.h:143,165-168):
     on the sky-light scene -- half of its shadow rays are occluded, so stale nodes are common -- a few
