@@ -3,6 +3,8 @@ bounce (scripts/build_variant.sh debugnee -DVIMG_DEBUG_NEE).  usage: diag_pixel.
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ.setdefault("VIMG_CUDA_LIB", os.path.join(ROOT, "v-img_b200", "variants", "libvimg_debugnee.so"))
+if not os.path.exists(os.environ["VIMG_CUDA_LIB"]):
+    sys.exit("build the debug variant first: bash scripts/build_variant.sh debugnee -DVIMG_DEBUG_NEE")
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
 from helpers import load_product, golden_scene_path
 vimg = load_product()
