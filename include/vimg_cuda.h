@@ -395,7 +395,8 @@ int vimg_build_image_texture(const uint8_t* srgb8, uint32_t width, uint32_t heig
  * tl_camera.cpp, color_utils.h, agx.cpp, principled BSDF), evaluated on caller-given inputs so that a
  * test can compare them with the host libm bit for bit.
  * fn: 0 sinf, 1 cosf, 2 logf, 3 log2f, 4 powf(x, y), 5 acosf, 6 atan2f(x = y-argument, y = x-argument),
- * 7 atanf.  x, y (y only for fn 4 and 6), out: HOST, n floats. */
+ * 7 atanf; 8 / 9: the low / high 32 bits of the DOUBLE log2((double)x) (std::log2 on doubles:
+ * background.h:100), stored as float bit patterns.  x, y (y only for fn 4 and 6), out: HOST, n floats. */
 int vimg_libm_eval(uint32_t fn, const float* x, const float* y, uint64_t n, int device_id, float* out);
 
 /* ---- post-process chain (the step right after the path: src/main.cpp:304-356) ----------- */

@@ -114,5 +114,45 @@ int main(int argc, char** argv) {
   }
   printf("checked %llu floats: acosf mismatches %llu, atanf mismatches %llu; %llu (y, x) pairs: atan2f mismatches %llu\n",
          n1, bad_acos, bad_atan, n2, bad_atan2);
-  return (bad_sin || bad_cos || bad_sc || bad_log2 || bad_log || bad_pow || bad_pow_r || bad_acos || bad_atan || bad_atan2) ? 1 : 0;
+
+  // double log2: 2^30 pseudo-random doubles (uniform bit patterns of positive doubles incl. subnormals, and
+  // the neighbourhood of 1 that takes the separate polynomial), every float of [2^-20, 2^20] widened
+  auto dbits = [](double v) { uint64_t u; memcpy(&u, &v, 8); return u; };
+  auto dfrom = [](uint64_t u) { double v; memcpy(&v, &u, 8); return v; };
+  unsigned long long bad_log2d = 0, n_log2d = 0;
+  const long long n_rand3 = step == 1 ? (1ll << 30) : (1ll << 20);
+#pragma omp parallel for reduction(+ : bad_log2d, n_log2d) schedule(static)
+  for (long long i = 0; i < n_rand3; ++i) {
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0xabcdefull;
+    h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+    h = (h ^ (h >> 27)) * 0x94D049BB133111EBull;
+    h ^= h >> 31;
+    double x;
+    switch (i & 3) {
+      case 0: x = dfrom(h % 0x7ff0000000000001ull); break;                             // any non-negative double
+      case 1: x = dfrom(0x3fe0000000000000ull + (h % 0x0020000000000000ull)); break;  // [0.5, 2)
+      case 2: x = 1.0 + ((double)(int64_t)(h >> 11) / 9007199254740992.0 - 0.5) * 0.125; break;  // around 1
+      default: x = (double)from_bits((uint32_t)(h % 0x7f800000u)); break;            // floats widened
+    }
+    const double a = vimg_libm::glibc_log2(x), b = log2(x);
+    bad_log2d += !(dbits(a) == dbits(b) || (a != a && b != b));
+    n_log2d++;
+  }
+  const uint32_t f_lo = bits(0x1p-20f), f_hi = bits(0x1p20f);
+#pragma omp parallel for reduction(+ : bad_log2d, n_log2d) schedule(static)
+  for (long long i = f_lo; i <= (long long)f_hi; i += step) {
+    const double x = (double)from_bits((uint32_t)i);
+    bad_log2d += dbits(vimg_libm::glibc_log2(x)) != dbits(log2(x));
+    n_log2d++;
+  }
+  {
+    const double sp[] = {0.0, -0.0, 1.0, -1.0, INFINITY, -INFINITY, NAN, 4096.0, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308};
+    for (double x : sp) {
+      const double a = vimg_libm::glibc_log2(x), b = log2(x);
+      bad_log2d += !(dbits(a) == dbits(b) || (a != a && b != b));
+      n_log2d++;
+    }
+  }
+  printf("checked %llu doubles: log2 mismatches %llu\n", n_log2d, bad_log2d);
+  return (bad_sin || bad_cos || bad_sc || bad_log2 || bad_log || bad_pow || bad_pow_r || bad_acos || bad_atan || bad_atan2 || bad_log2d) ? 1 : 0;
 }

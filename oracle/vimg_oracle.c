@@ -682,7 +682,16 @@ void vimg_oracle_libm(uint32_t fn, const float* x, const float* y, uint64_t n, f
       case 4: out[i] = powf(a, b); break;
       case 5: out[i] = acosf(a); break;
       case 6: out[i] = atan2f(a, b); break;
-      default: out[i] = atanf(a); break;
+      case 7: out[i] = atanf(a); break;
+      default: {  /* 8 / 9: low / high word of the double log2 of the widened input */
+        double r = log2((double)a);
+        uint64_t u;
+        uint32_t w;
+        memcpy(&u, &r, 8);
+        w = fn == 8 ? (uint32_t)u : (uint32_t)(u >> 32);
+        memcpy(&out[i], &w, 4);
+        break;
+      }
     }
   }
 }

@@ -73,6 +73,23 @@ def test_device_libm_equals_the_host_libm(vimg):
 
 
 @pytest.mark.gpu
+def test_device_double_log2_equals_the_host_libm(vimg):
+    """std::log2 on doubles (env-map mip level, background.h:100; log2(width * height), texture_RGB.h:141):
+    the device's restatement of glibc's double log2 on widened floats, both halves of the result's bits"""
+    from oracle import refcpu
+    if not os.path.exists(refcpu.restatement_path()):
+        pytest.skip("oracle/_ref/libvimg_oracle.so not built")
+    rng = np.random.default_rng(7)
+    x = np.concatenate([float_range(1e-45, 3.4e38, 1 << 21, rng), float_range(0.9, 1.1, 1 << 21, rng),
+                        np.array([1.0, 4096.0, 16384.0, 0.5, 3.0, 1e-40, 2048.0 * 1024.0], np.float32)])
+    for fn in ("log2_lo", "log2_hi"):
+        got = vimg.libm_eval(fn, x).view(np.uint32)
+        want = refcpu.host_libm(vimg.LIBM_FUNCTIONS[fn], x).view(np.uint32)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, f"{fn}: {bad.size} of {x.size} differ, first x={x[bad[0]]!r}"
+
+
+@pytest.mark.gpu
 def test_libm_eval_arguments(vimg):
     assert vimg.libm_eval("log2f", np.zeros(0, np.float32)).size == 0
     with pytest.raises(vimg.VimgError):

@@ -410,7 +410,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     dt.n_levels = ht.n_levels;
     dt.wrap_u = ht.wrap_u;
     dt.wrap_v = ht.wrap_v;
-    dt.half_log2_wh = (double)0.5f * std::log2((double)(uint32_t)(ht.width * ht.height));
+    dt.half_log2_wh = (double)0.5f * vimg_libm::glibc_log2((double)(uint32_t)(ht.width * ht.height));
     if (ht.type == VIMG_TEX_IMAGE) {
       if (ht.n_levels == 0 || ht.n_levels > 16) return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture needs 1..16 mip levels");
       if (!ht.levels || !ht.levels[0]) return fail(VIMG_ERR_INVALID_ARGUMENT, "image texture without level 0");
@@ -1407,7 +1407,7 @@ int vimg_build_image_texture(const uint8_t* srgb8, uint32_t width, uint32_t heig
 }
 
 int vimg_libm_eval(uint32_t fn, const float* x, const float* y, uint64_t n, int device_id, float* out) {
-  if (fn > 7) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown function");
+  if (fn > 9) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown function");
   if (n == 0) return VIMG_OK;
   const bool two = fn == 4 || fn == 6;
   if (!x || !out || (two && !y)) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");

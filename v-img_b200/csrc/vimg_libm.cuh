@@ -426,4 +426,105 @@ VLM_FN float glibc_atan2f(float y, float x) {
   }
 }
 
+// ------------------------------------------------------------------ log2 (double) ----
+// glibc 2.39's double log2 (sysdeps/ieee754/dbl-64/e_log2.c, ARM optimized routines), `__log2_fma`
+// variant: 64-entry {1/c, log2(c)} table, r = fma(z, 1/c, -1), r/ln2 split into hi + lo with an fma,
+// degree-6 polynomial; a separate degree-10 path near 1.  Fusions as in the library's disassembly.
+// The reference reaches it through unqualified log2() / std::log2 on doubles: the env map's mip
+// level (background.h:100) and compute_texture_LOD's log2(width * height) (texture_RGB.h:141).
+// oracle/tools/libm_check.cpp compares it with the host libm on 2^30 pseudo-random doubles (all
+// binades, the neighbourhood of 1, subnormals) and on every float in [2^-20, 2^20] widened.
+#define VLM_LOG2D_TABLE(X) \
+  X(0x1.724286bb1acf8p+0, -0x1.1095feecdb000p-1) X(0x1.6e1f766d2cca1p+0, -0x1.08494bd76d000p-1) \
+  X(0x1.6a13d0e30d48ap+0, -0x1.00143aee8f800p-1) X(0x1.661ec32d06c85p+0, -0x1.efec5360b4000p-2) \
+  X(0x1.623fa951198f8p+0, -0x1.dfdd91ab7e000p-2) X(0x1.5e75ba4cf026cp+0, -0x1.cffae0cc79000p-2) \
+  X(0x1.5ac055a214fb8p+0, -0x1.c043811fda000p-2) X(0x1.571ed0f166e1ep+0, -0x1.b0b67323ae000p-2) \
+  X(0x1.53909590bf835p+0, -0x1.a152f5a2db000p-2) X(0x1.5014fed61adddp+0, -0x1.9217f5af86000p-2) \
+  X(0x1.4cab88e487bd0p+0, -0x1.8304db0719000p-2) X(0x1.49539b4334feep+0, -0x1.74189f9a9e000p-2) \
+  X(0x1.460cbdfafd569p+0, -0x1.6552bb5199000p-2) X(0x1.42d664ee4b953p+0, -0x1.56b23a29b1000p-2) \
+  X(0x1.3fb01111dd8a6p+0, -0x1.483650f5fa000p-2) X(0x1.3c995b70c5836p+0, -0x1.39de937f6a000p-2) \
+  X(0x1.3991c4ab6fd4ap+0, -0x1.2baa1538d6000p-2) X(0x1.3698e0ce099b5p+0, -0x1.1d98340ca4000p-2) \
+  X(0x1.33ae48213e7b2p+0, -0x1.0fa853a40e000p-2) X(0x1.30d191985bdb1p+0, -0x1.01d9c32e73000p-2) \
+  X(0x1.2e025cab271d7p+0, -0x1.e857da2fa6000p-3) X(0x1.2b404cf13cd82p+0, -0x1.cd3c8633d8000p-3) \
+  X(0x1.288b02c7ccb50p+0, -0x1.b26034c14a000p-3) X(0x1.25e2263944de5p+0, -0x1.97c1c2f4fe000p-3) \
+  X(0x1.234563d8615b1p+0, -0x1.7d6023f800000p-3) X(0x1.20b46e33eaf38p+0, -0x1.633a71a05e000p-3) \
+  X(0x1.1e2eefdcda3ddp+0, -0x1.494f5e9570000p-3) X(0x1.1bb4a580b3930p+0, -0x1.2f9e424e0a000p-3) \
+  X(0x1.19453847f2200p+0, -0x1.162595afdc000p-3) X(0x1.16e06c0d5d73cp+0, -0x1.f9c9a75bd8000p-4) \
+  X(0x1.1485f47b7e4c2p+0, -0x1.c7b575bf9c000p-4) X(0x1.12358ad0085d1p+0, -0x1.960c60ff48000p-4) \
+  X(0x1.0fef00f532227p+0, -0x1.64ce247b60000p-4) X(0x1.0db2077d03a8fp+0, -0x1.33f78b2014000p-4) \
+  X(0x1.0b7e6d65980d9p+0, -0x1.0387d1a42c000p-4) X(0x1.0953efe7b408dp+0, -0x1.a6f9208b50000p-5) \
+  X(0x1.07325cac53b83p+0, -0x1.47a954f770000p-5) X(0x1.05197e40d1b5cp+0, -0x1.d23a8c50c0000p-6) \
+  X(0x1.03091c1208ea2p+0, -0x1.16a2629780000p-6) X(0x1.0101025b37e21p+0, -0x1.720f8d8e80000p-8) \
+  X(0x1.fc07ef9caa76bp-1, 0x1.6fe53b1500000p-7) X(0x1.f4465d3f6f184p-1, 0x1.11ccce10f8000p-5) \
+  X(0x1.ecc079f84107fp-1, 0x1.c4dfc8c8b8000p-5) X(0x1.e573a99975ae8p-1, 0x1.3aa321e574000p-4) \
+  X(0x1.de5d6f0bd3de6p-1, 0x1.918a0d08b8000p-4) X(0x1.d77b681ff38b3p-1, 0x1.e72e9da044000p-4) \
+  X(0x1.d0cb5724de943p-1, 0x1.1dcd2507f6000p-3) X(0x1.ca4b2dc0e7563p-1, 0x1.476ab03dea000p-3) \
+  X(0x1.c3f8ee8d6cb51p-1, 0x1.7074377e22000p-3) X(0x1.bdd2b4f020c4cp-1, 0x1.98ede8ba94000p-3) \
+  X(0x1.b7d6c006015cap-1, 0x1.c0db86ad2e000p-3) X(0x1.b20366e2e338fp-1, 0x1.e840aafcee000p-3) \
+  X(0x1.ac57026295039p-1, 0x1.0790ab4678000p-2) X(0x1.a6d01bc2731ddp-1, 0x1.1ac056801c000p-2) \
+  X(0x1.a16d3bc3ff18bp-1, 0x1.2db11d4fee000p-2) X(0x1.9c2d14967feadp-1, 0x1.406464ec58000p-2) \
+  X(0x1.970e4f47c9902p-1, 0x1.52dbe093af000p-2) X(0x1.920fb3982bcf2p-1, 0x1.651902050d000p-2) \
+  X(0x1.8d30187f759f1p-1, 0x1.771d2cdeaf000p-2) X(0x1.886e5ebb9f66dp-1, 0x1.88e9c857d9000p-2) \
+  X(0x1.83c97b658b994p-1, 0x1.9a80155e16000p-2) X(0x1.7f405ffc61022p-1, 0x1.abe186ed3d000p-2) \
+  X(0x1.7ad22181415cap-1, 0x1.bd0f2aea0e000p-2) X(0x1.767dcf99eff8cp-1, 0x1.ce0a43dbf4000p-2)
+static const double vlm_host_log2d_tab[128] = {VLM_LOG2D_TABLE(VLM_X_PAIR)};
+#if defined(__CUDACC__)
+__device__ static const double vlm_dev_log2d_tab[128] = {VLM_LOG2D_TABLE(VLM_X_PAIR)};
+#endif
+#if defined(__CUDA_ARCH__)
+#define VLM_LOG2D_TAB vlm_dev_log2d_tab
+#else
+#define VLM_LOG2D_TAB vlm_host_log2d_tab
+#endif
+
+VLM_FN double glibc_log2(double x) {
+  const double InvLn2hi = 0x1.7154765200000p+0, InvLn2lo = 0x1.705fc2eefa200p-33;
+  uint64_t ix = d2u(x);
+  const uint64_t LO = 0x3feea4af00000000ull;  // asuint64(1.0 - 0x1.5b51p-5)
+  if (ix - LO <= 0x210a9ffffffffull) {        // [LO, asuint64(1.0 + 0x1.6ab2p-5)): close to 1
+    if (ix == 0x3ff0000000000000ull) return 0.0;
+    const double r = x - 1.0;
+    const double hi = r * InvLn2hi;
+    double lo = fma(r, InvLn2lo, fma(r, InvLn2hi, -hi));
+    const double r2 = r * r, r4 = r2 * r2;
+    const double q = fma(r, 0x1.ec709dc3a03f7p-2, -0x1.71547652b82fep-1);  // B[0] + r * B[1]
+    const double y = fma(q, r2, hi);                                         // hi + p, p = r2 * q
+    lo = fma(q, r2, hi - y) + lo;                                            // lo += hi - y + p
+    const double b23 = fma(r, 0x1.2776c50f05be4p-2, -0x1.71547652b7c3fp-2);
+    const double b45 = fma(r, 0x1.a61761ec4e736p-3, -0x1.ec709dd768fe5p-3);
+    const double b67 = fma(r, 0x1.484d154f01b4ap-3, -0x1.7153fbc64a79bp-3);
+    const double b89 = fma(r, 0x1.0b32f285aee66p-3, -0x1.289e4a72c383cp-3);
+    const double lowp = fma(b45, r2, b23);
+    const double highp = fma(b89, r2, b67);
+    lo = fma(fma(highp, r4, lowp), r4, lo);
+    return y + lo;
+  }
+  const uint32_t top = (uint32_t)(ix >> 48);
+  if (top - 0x0010u >= 0x7ff0u - 0x0010u) {  // x < 0x1p-1022, inf or nan
+    if (ix * 2 == 0) return u2d(0xfff0000000000000ull);
+    if (ix == 0x7ff0000000000000ull) return x;
+    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return u2d(0x7ff8000000000000ull);
+    ix = d2u(x * 0x1p52);  // subnormal: normalise
+    ix -= 52ull << 52;
+  }
+  const uint64_t tmp = ix - 0x3fe6000000000000ull;  // OFF
+  const uint32_t i = (uint32_t)(tmp >> 46) & 63u;
+  const int k = (int)((int64_t)tmp >> 52);
+  const uint64_t iz = ix - (tmp & 0xfff0000000000000ull);
+  const double invc = VLM_LOG2D_TAB[2 * i], logc = VLM_LOG2D_TAB[2 * i + 1];
+  const double z = u2d(iz), kd = (double)k;
+  const double r = fma(z, invc, -1.0);
+  const double t1 = r * InvLn2hi;
+  const double t2 = fma(r, InvLn2lo, fma(r, InvLn2hi, -t1));
+  const double t3 = kd + logc;
+  const double hi = t3 + t1;
+  const double lo = ((t3 - hi) + t1) + t2;
+  const double r2 = r * r, r4 = r2 * r2;
+  const double a01 = fma(r, 0x1.ec709dc3a04bep-2, -0x1.71547652b8339p-1);
+  const double a23 = fma(r, 0x1.2776c50034c48p-2, -0x1.7154764702ffbp-2);
+  const double a45 = fma(r, 0x1.a6225e117f92ep-3, -0x1.ec7b328ea92bcp-3);
+  const double p = fma(a45, r4, fma(a23, r2, a01));
+  return fma(r2, p, lo) + hi;
+}
+
 }  // namespace vimg_libm

@@ -94,8 +94,8 @@ VD V4 mat4_mul(const float* m, V4 v) {
 // directions, thin-lens primary rays), logf (clearcoat), log2f (texture LOD), acosf / atan2f
 // (env-map uv, ray-cone spread), powf (post-process, sRGB) -- is restated operation by operation
 // in vimg_libm.cuh and checked against the host libm over all float inputs.  Double expressions
-// of the reference call the double functions directly (CUDA's, ~1 ulp in double,
-// rounded to float afterwards).
+// of the reference call the double functions directly: log2 is glibc's, restated
+// too; sin / cos / pow / acos / atan2 are CUDA's (<= 2 ulp in double, rounded to float afterwards).
 // CUDA's double-precision library functions expand to hundreds of instructions each when
 // inlined; the render kernels call them from many places, so they live in ONE out-of-line
 // copy each (instruction-cache footprint, see DESIGN.md "Kernel structure").
@@ -103,7 +103,11 @@ VD V4 mat4_mul(const float* m, V4 v) {
 VNI double d_sin(double x) { return sin(x); }
 VNI double d_cos(double x) { return cos(x); }
 VNI double d_log(double x) { return log(x); }
+#ifndef VIMG_FAST_LIBM
+VNI double d_log2(double x) { return vimg_libm::glibc_log2(x); }  // glibc's double log2, restated exactly
+#else
 VNI double d_log2(double x) { return log2(x); }
+#endif
 VNI double d_pow(double x, double y) { return pow(x, y); }
 VNI double d_acos(double x) { return acos(x); }
 VNI double d_atan2(double y, double x) { return atan2(y, x); }

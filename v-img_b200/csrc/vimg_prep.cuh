@@ -232,7 +232,10 @@ libm_eval_kernel(uint32_t fn, const float* __restrict__ x, const float* __restri
       case 4: r = m_powf(a, b); break;
       case 5: r = m_acosf(a); break;
       case 6: r = m_atan2f(a, b); break;
-      default: r = vimg_libm::glibc_atanf(a); break;
+      case 7: r = vimg_libm::glibc_atanf(a); break;
+      // the DOUBLE log2 of the widened input: low / high word of the result's bit pattern
+      case 8: r = __uint_as_float((uint32_t)vimg_libm::d2u(d_log2((double)a))); break;
+      default: r = __uint_as_float((uint32_t)(vimg_libm::d2u(d_log2((double)a)) >> 32)); break;
     }
     out[i] = r;
   }

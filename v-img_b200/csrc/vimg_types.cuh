@@ -87,9 +87,9 @@ struct DTexture {
   uint32_t width, height, n_levels, wrap_u, wrap_v;
   uint32_t level_off[16];  // texel (float3) offset of each mip level in the texel pool
   // 0.5f * log2(width * height) of compute_texture_LOD (texture_RGB.h:141): the unqualified log2 on
-  // an unsigned is glibc's DOUBLE log2; one value per texture, so the host computes it with the
-  // host libm when the scene is created (CUDA's log2(4096.0) is not exactly 12, which moved the LOD
-  // of a 64x64 texture by one float ulp whenever the sum fell on a rounding tie)
+  // an unsigned is glibc's DOUBLE log2; one value per texture, computed once when the scene is
+  // created with the restatement of vimg_libm.cuh (CUDA's log2(4096.0) is not exactly 12, which moved
+  // the LOD of a 64x64 texture by one float ulp whenever the sum fell on a rounding tie)
   double half_log2_wh;
 };
 

@@ -478,7 +478,8 @@ def build_image_texture(srgb8, wrap_u=0, wrap_v=0, device=0):
     return levels, ms.value
 
 
-LIBM_FUNCTIONS = {"sinf": 0, "cosf": 1, "logf": 2, "log2f": 3, "powf": 4, "acosf": 5, "atan2f": 6, "atanf": 7}
+LIBM_FUNCTIONS = {"sinf": 0, "cosf": 1, "logf": 2, "log2f": 3, "powf": 4, "acosf": 5, "atan2f": 6, "atanf": 7,
+                  "log2_lo": 8, "log2_hi": 9}  # double log2 of the widened input, result bits in two halves
 
 
 def libm_eval(fn, x, y=None, device=0):
