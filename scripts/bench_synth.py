@@ -25,7 +25,8 @@ for rep in range(3):
 rays = st["rays_closest"] + st["rays_shadow"]
 out.update(kernel_ms=st["kernel_ms"], mrays_s=rays / st["kernel_ms"] / 1e3, spp_mpix_s=W * H * spp / st["kernel_ms"] / 1e3,
            rays_per_sample=rays / (W * H * spp))
-_, c = sc.scene_integrator(integ, min(spp, 4), 64, counters=True)
+# counted with the traversal-stack mode of the timed render (streams > 1 => fresh stacks)
+_, c = sc.scene_integrator(integ, min(spp, 4), 64, counters=True, fresh_stack=streams > 1)
 cr = c["rays_closest"] + c["rays_shadow"]
 bpr = sum(BY[k] * c[k] for k in BY) / cr
 out.update(bytes_per_ray=bpr, inner_per_ray=c["inner_nodes"] / cr, leaf_per_ray=c["leaf_nodes"] / cr,
