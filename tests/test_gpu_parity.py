@@ -129,14 +129,17 @@ def test_full_size_full_spp_mis_against_the_live_reference(vimg, refcpu, man, na
     assert np.array_equal(g, r), f"{int((g != r).any(-1).sum())} of {e['width'] * e['height']} pixels differ"
 
 
+@pytest.mark.parametrize("integ", ["mis", "material"])
 @pytest.mark.parametrize("name", ["glass_in_box", "cornell_box_spheres", "disney_spheres"])
-def test_baseline_configs_at_full_size_and_spp_match_the_reference_digest(vimg, man, name):
+def test_baseline_configs_at_full_size_and_spp_match_the_reference_digest(vimg, man, name, integ):
     """BASELINE configs C1 / C2 / C3 exactly as stated (C3: disney_spheres 1800x800, 512 spp, depth -1,
-    4.2 G rays): the mis image has the digest of the compiled reference's image (rendered in the build
-    container by tests/golden/make_golden_full.py), i.e. every one of its pixels is bit-identical."""
+    4.2 G rays under mis): the image has the digest of the compiled reference's image (rendered in the
+    build container by tests/golden/make_golden_full.py), i.e. every one of its pixels is bit-identical."""
     from oracle.refcpu import digest
-    v = man[name]["ref"]["mis_full"]
-    img, st = scene(vimg, name).scene_integrator("mis", v["spp"], v["depth"])
+    if f"{integ}_full" not in man[name]["ref"]:
+        pytest.skip(f"no {integ}_full digest in the manifest (tests/golden/make_golden_full.py)")
+    v = man[name]["ref"][f"{integ}_full"]
+    img, st = scene(vimg, name).scene_integrator(integ, v["spp"], v["depth"])
     assert st["nan_samples"] == 0
     assert np.allclose(img.reshape(-1, 3).mean(0), v["mean"], rtol=1e-6)
     assert digest(img) == v["hash"]
