@@ -266,6 +266,19 @@ typedef struct vimg_render_params {
  * (not bit-identical by construction) implies it. */
 #define VIMG_FLAG_FRESH_STACK 16u
 
+/* material / mis, queue wavefront: the TOLERANCE mode.  The north star's contract for material / mis
+ * images is a relative-MSE tolerance against the CPU renderer (bit-exactness is asked of primary-hit
+ * ids and the normal integrators, which this flag does not touch).  With this flag the device may
+ * (a) evaluate the path arithmetic with the hardware's approximate division / sqrt / sin / cos / log /
+ * pow units, FMA contraction, and float where the reference promotes to double -- the kernels of
+ * vimg_fast.cu, the same sources compiled with -use_fast_math, as the reference's own CMake build
+ * contracts FMAs with -march=native -- and (b) trace through a device-side re-layout of the BVH
+ * instead of the reference's node order: scenes of a few dozen primitives are traced over their
+ * leaf array by a divergence-free kernel (qf_trace_flat_kernel).  Same estimator, same RNG streams
+ * and draw order per path; images agree with the CPU renderer within the stated tolerance
+ * (tests/test_gpu_fast.py), not bit for bit.  Implies VIMG_FLAG_FRESH_STACK. */
+#define VIMG_FLAG_FAST 32u
+
 /* stages of the queue wavefront (vimg_render_stats.stage_ms / stage_launches) */
 typedef enum vimg_stage {
   VIMG_STAGE_TRACE = 0,            /* BVH::hit / BVH::occlude for every queued ray          */

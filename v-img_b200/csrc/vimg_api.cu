@@ -54,6 +54,7 @@ float h_dot(H3 a, H3 b) {
 // shared counter; running two of them lets one pool's TRACE launch (issue bound) overlap the
 // other's SHADE / END launches (latency bound).
 constexpr int QW_MAX_POOLS = 4;
+constexpr uint32_t QF_FLAT_MAX_HOST = 64;  // = QF_FLAT_MAX of the tolerance build (vimg_queues.cuh)
 struct QwPool {
   QwState st{};
   void* mem = nullptr;
@@ -63,7 +64,7 @@ struct QwPool {
   cudaStream_t main = nullptr, side[2] = {nullptr, nullptr};  // shade launches run beside END
   cudaEvent_t snap[2] = {nullptr, nullptr}, fork = nullptr, join[2] = {nullptr, nullptr}, done = nullptr;
   bool finished = false;
-  int trace_grid = 1, item_grid = 1;  // current launch sizes (shrink as the pool drains)
+  int trace_grid = 1, item_grid = 1, flat_grid = 1;  // current launch sizes (shrink as the pool drains)
   // one batch of iterations captured as a CUDA graph (launch sizes it was captured with)
   cudaGraphExec_t batch_exec = nullptr;
   int exec_trace_grid = 0, exec_item_grid = 0;
@@ -318,6 +319,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   const vimg_bvh& b = desc->bvh;
   d.n_nodes = (uint32_t)b.n_nodes;
   d.stack_cap = b.max_depth + 2;
+  d.n_leaf_recs = (uint32_t)b.n_obj_indices;
   if (d.stack_cap > VIMG_STACK_MAX)
     return fail(VIMG_ERR_UNSUPPORTED, "BVH max_depth + 2 exceeds the traversal stack (VIMG_STACK_MAX)");
   std::vector<DPairNode> pairs;
@@ -801,21 +803,50 @@ struct QwLaunchCfg {
   int trace_grid, item_grid;  // full-size grids
   bool concurrent;
   uint32_t class_mask;
+  const QwKernelTable* kt;  // bit-exact or tolerance build of the kernels
+  int integ;                // 0 material, 1 mis
+  bool count;               // traversal counters
+  bool flat;                // tolerance build, small scene: trace + classify in one launch over the leaf array
 };
 
+// the tolerance build of the same kernels (vimg_fast.cu)
+extern "C" void vimg_fast_kernel_table(void* out);
+static const QwKernelTable& kernel_table(bool fast) {
+  static const QwKernelTable exact = qw_kernel_table();
+  static const QwKernelTable fast_t = [] {
+    QwKernelTable t{};
+    vimg_fast_kernel_table(&t);
+    return t;
+  }();
+  return fast ? fast_t : exact;
+}
+
+template <typename... A>
+static cudaError_t launch_k(const void* f, int grid, int block, cudaStream_t st, const A&... a) {
+  void* args[] = {const_cast<void*>(static_cast<const void*>(&a))...};
+  return cudaLaunchKernel(f, dim3((unsigned)grid), dim3((unsigned)block), args, 0, st);
+}
+
 // one iteration of one pool: trace(it) classify(it) {shade(it) | end(it)}; iteration 0 is end only
-template <int INTEGRATOR, bool COUNT>
 static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& w, uint32_t it, const QwLaunchCfg& cfg,
                                      float* out, QwProfile& prof) {
   const QwState& q = pool.st;
   const uint32_t parity = it & 1u;
+  const QwKernelTable& kt = *cfg.kt;
+  DCounters* counters = s->d_counters;
   cudaStream_t st = pool.main;
   uint32_t launches = 0;
   if (it > 0) {
-    qw_trace_kernel<COUNT><<<pool.trace_grid, QW_TRACE_THREADS, 0, st>>>(s->d, q, parity, s->d_counters);
-    prof.mark(1);
-    qw_classify_kernel<<<pool.item_grid, QW_THREADS, 0, st>>>(s->d, q, parity);
-    prof.mark(2);
+    if (cfg.flat) {
+      // thread <-> ray: up to two rays per live slot
+      launch_k(kt.trace_flat[cfg.count], pool.flat_grid, QW_THREADS, st, s->d, q, parity, counters);
+      prof.mark(1);
+    } else {
+      launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
+      prof.mark(1);
+      launch_k(kt.classify, pool.item_grid, QW_THREADS, st, s->d, q, parity);
+      prof.mark(2);
+    }
     // shade launches only feed the next iteration, END only consumes what classify and the
     // previous shade launches queued: fork them onto side streams, join before the next trace
     cudaStream_t sp = st, sl = st;
@@ -827,17 +858,17 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
       cudaStreamWaitEvent(sl, pool.fork, 0);
     }
     if (cfg.class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_PRINCIPLED><<<pool.item_grid, QW_THREADS, 0, sp>>>(s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_PRINCIPLED], pool.item_grid, QW_THREADS, sp, s->d, q, w, parity);
       prof.mark(3);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_LAMBERT)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_LAMBERT><<<pool.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_LAMBERT], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity);
       prof.mark(4);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-      qw_shade_kernel<INTEGRATOR, WF_CLASS_DIELECTRIC><<<pool.item_grid, QW_THREADS, 0, sl>>>(s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_DIELECTRIC], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity);
       prof.mark(5);
       ++launches;
     }
@@ -845,9 +876,9 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
       cudaEventRecord(pool.join[0], sp);
       cudaEventRecord(pool.join[1], sl);
     }
-    launches += 2;
+    launches += cfg.flat ? 1 : 2;
   }
-  qw_end_kernel<INTEGRATOR><<<pool.item_grid, QW_THREADS, 0, st>>>(s->d, q, w, parity, out, s->d_counters);
+  launch_k(kt.end[cfg.integ], pool.item_grid, QW_THREADS, st, s->d, q, w, parity, out, counters);
   prof.mark(6);
   ++launches;
   if (cfg.concurrent && it > 0) {
@@ -860,8 +891,8 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
 // One frame.  Per pool: end(0) | trace(1) classify(1) shade(1) end(1) | ...  until every queue is
 // empty.  The host looks at the queue counters once per batch of iterations and keeps one batch
 // queued ahead of the check, so the device never waits for the host.
-template <int INTEGRATOR, bool COUNT>
-static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t caller, bool stage_times) {
+static int qw_render_t(vimg_scene* s, const WfArgs& w, int integ, bool count, bool fast, float* out, cudaStream_t caller,
+                       bool stage_times) {
   QwProfile prof;
   const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
   prof.on = print_profile || stage_times;
@@ -905,9 +936,16 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
   cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 8) * (256 / QW_THREADS)));
   cfg.concurrent = concurrent;
   cfg.class_mask = s->class_mask;
+  cfg.kt = &kernel_table(fast);
+  cfg.integ = integ;
+  cfg.count = count;
+  // tolerance build: a scene of a few dozen primitives is traced over its leaf array (vimg_queues.cuh)
+  cfg.flat = fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32));
+  const int flat_full = std::max(1, std::min(2 * slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_FLAT_BLOCKS", 8)));
   for (uint32_t p = 0; p < n_pools; ++p) {
     s->ws->qw[p].trace_grid = cfg.trace_grid;
     s->ws->qw[p].item_grid = cfg.item_grid;
+    s->ws->qw[p].flat_grid = flat_full;
   }
   const bool shrink = env_u32("VIMG_QW_SHRINK", 1) != 0;
   // VIMG_QW_GRAPH=1: batches after the first are replayed from a CUDA graph per pool (trace /
@@ -937,7 +975,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
       for (uint32_t k = 0; k < batch; ++k)
         for (uint32_t p = 0; p < n_pools; ++p)
           if (!s->ws->qw[p].finished)
-            launches += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, s->ws->qw[p], w, it + k, cfg, out, prof);
+            launches += qw_enqueue_iteration(s, s->ws->qw[p], w, it + k, cfg, out, prof);
     } else {
       for (uint32_t p = 0; p < n_pools; ++p) {
         QwPool& pool = s->ws->qw[p];
@@ -948,7 +986,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
           uint32_t n = 0;
           CU_TRY(cudaStreamBeginCapture(pool.main, cudaStreamCaptureModeRelaxed));
           for (uint32_t k = 0; k < batch; ++k)
-            n += qw_enqueue_iteration<INTEGRATOR, COUNT>(s, pool, w, batch + k, cfg, out, prof);
+            n += qw_enqueue_iteration(s, pool, w, batch + k, cfg, out, prof);
           CU_TRY(cudaStreamEndCapture(pool.main, &g));
           cudaError_t e = cudaGraphInstantiate(&pool.batch_exec, g, 0);
           cudaGraphDestroy(g);
@@ -1002,6 +1040,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
           }
           pool.item_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.item_grid, ig));
           pool.trace_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.trace_grid, tg));
+          pool.flat_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(flat_full, 2 * ig));
         }
       }
       if (timeline) tl_live.push_back(live);
@@ -1035,10 +1074,9 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, float* out, cudaStream_t 
 }
 
 template <bool COUNT>
-static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, float* out, cudaStream_t st,
+static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, bool fast, float* out, cudaStream_t st,
                      bool stage_times) {
-  if (integrator == VIMG_INTEGRATOR_MIS) return qw_render_t<VIMG_INTEGRATOR_MIS, COUNT>(s, w, out, st, stage_times);
-  return qw_render_t<VIMG_INTEGRATOR_MATERIAL, COUNT>(s, w, out, st, stage_times);
+  return qw_render_t(s, w, integrator == VIMG_INTEGRATOR_MIS ? 1 : 0, COUNT, fast, out, st, stage_times);
 }
 
 template <bool COUNT>
@@ -1067,7 +1105,8 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       return fail(VIMG_ERR_INVALID_ARGUMENT, "spp_streams too large for this frame");
     w.n_local_units = w.n_local_pixels * w.streams;
     w.partial = nullptr;
-    w.fresh_stack = ((flags & VIMG_FLAG_FRESH_STACK) || w.streams > 1) ? 1u : 0u;
+    const bool fast = (flags & VIMG_FLAG_FAST) != 0;
+    w.fresh_stack = ((flags & VIMG_FLAG_FRESH_STACK) || w.streams > 1 || fast) ? 1u : 0u;
     // pipeline: the queue wavefront unless the caller (or VIMG_PIPELINE=block) asks for the
     // block-local kernel
     bool use_block = (flags & VIMG_FLAG_PIPELINE_BLOCK) != 0;
@@ -1075,8 +1114,8 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       const char* e = std::getenv("VIMG_PIPELINE");
       use_block = e && std::strcmp(e, "block") == 0;
     }
-    if (use_block && w.streams > 1)
-      return fail(VIMG_ERR_UNSUPPORTED, "spp_streams > 1 needs the queue wavefront pipeline");
+    if (use_block && (w.streams > 1 || fast))
+      return fail(VIMG_ERR_UNSUPPORTED, "spp_streams > 1 and VIMG_FLAG_FAST need the queue wavefront pipeline");
     if (!use_block && !s->ws) s->ws = ws_acquire(s->device);
     if (w.streams > 1) {
       const size_t need = (size_t)s->W * s->H * w.streams * 3;
@@ -1092,7 +1131,7 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       }
       w.partial = s->ws->d_partial;
     }
-    if (!use_block) return qw_render<COUNT>(s, w, integrator, out, st, (flags & VIMG_FLAG_STAGE_TIMES) != 0);
+    if (!use_block) return qw_render<COUNT>(s, w, integrator, fast, out, st, (flags & VIMG_FLAG_STAGE_TIMES) != 0);
     cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), st);
     if (integrator == VIMG_INTEGRATOR_MIS) {
       const int g = wavefront_grid<VIMG_INTEGRATOR_MIS, COUNT>(s, w.n_local_pixels);

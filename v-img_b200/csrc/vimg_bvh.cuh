@@ -137,9 +137,9 @@ VD bool tri_hit(const float* a, uint32_t flags, Ray& ray, const RayPre& pre, Pre
     // a*b is exact in double; x87 fmal rounds to 64 bits, then to double, then to float.
     // The double fma below rounds the same exact value once to 53 bits (differs from the
     // x87 path only in a double-rounding corner).
-    e0 = (float)fma((double)p1x, (double)p2y, -(double)(p1y * p2x));
-    e1 = (float)fma((double)p2x, (double)p0y, -(double)(p2y * p0x));
-    e2 = (float)fma((double)p0x, (double)p1y, -(double)(p0y * p1x));
+    e0 = (float)fma((vdbl)p1x, (vdbl)p2y, -(vdbl)(p1y * p2x));
+    e1 = (float)fma((vdbl)p2x, (vdbl)p0y, -(vdbl)(p2y * p0x));
+    e2 = (float)fma((vdbl)p0x, (vdbl)p1y, -(vdbl)(p0y * p1x));
   }
   if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
   float det = e0 + e1 + e2;
@@ -164,7 +164,7 @@ VD bool tri_hit(const float* a, uint32_t flags, Ray& ray, const RayPre& pre, Pre
 }
 
 // Sphere::sphere_hit_template + solveQuadratic (sphere.h:13-100).  `q`, x0, x1 run
-// in double because the reference's unqualified sqrt() resolves to ::sqrt(double).
+// in double because the reference's unqualified sqrt() resolves to ::sqrt(vdbl).
 VD bool sphere_hit(const float* a, Ray& r) {
   V3 center = mk3(a[0], a[1], a[2]);
   float radius = a[3];
@@ -179,12 +179,12 @@ VD bool sphere_hit(const float* a, Ray& r) {
   if (discriminant < 0) return false;
   {
     float sign = (b_prime > 0) ? 1.0f : -1.0f;
-    double q = (double)b_prime + (double)sign * sqrt((double)(aa * discriminant));
+    vdbl q = (vdbl)b_prime + (vdbl)sign * sqrt((vdbl)(aa * discriminant));
     if (discriminant == 0) {
-      t0 = t1 = (float)((double)c / q);
+      t0 = t1 = (float)((vdbl)c / q);
     } else {
-      t0 = (float)((double)c / q);
-      t1 = (float)(q / (double)aa);
+      t0 = (float)((vdbl)c / q);
+      t1 = (float)(q / (vdbl)aa);
     }
     if (t0 > t1) {
       float tmp = t0;

@@ -14,8 +14,8 @@ VD float G_w(V3 w, float alphax, float alphay, const ONB& frame) {
   const V3 wl = project_onto_onb(frame, w);
   float vec_alpha
       = ((wl.x * alphax) * (wl.x * alphax) + (wl.y * alphay) * (wl.y * alphay)) / (wl.z * wl.z);
-  float caret = (float)((sqrt(1. + (double)vec_alpha) - 1.) / 2.);
-  return (float)(1. / (1. + (double)caret));
+  float caret = (float)((sqrt(VR(1.) + (vdbl)vec_alpha) - VR(1.)) / VR(2.));
+  return (float)(VR(1.) / (VR(1.) + (vdbl)caret));
 }
 
 // anisotropic_sample_visible_normals (disney_common.h:16-52)
@@ -32,8 +32,8 @@ VD V3 sample_visible_normals(V3 local_dir_in, float alphax, float alphay, Pcg32&
   float phi = (float)(2 * VIMG_PI_D * rand_x);
   float z = fmaf((1.0f - rand_y), (1.0f + hemi_dir_in.z), -hemi_dir_in.z);
   float sinTheta = sqrtf(std_clamp(1.0f - z * z, 0.0f, 1.0f));
-  float x = (float)((double)sinTheta * d_cos((double)phi));
-  float y = (float)((double)sinTheta * d_sin((double)phi));
+  float x = (float)((vdbl)sinTheta * d_cos((vdbl)phi));
+  float y = (float)((vdbl)sinTheta * d_sin((vdbl)phi));
   const V3 hemi_N = mk3(x, y, z) + hemi_dir_in;
   return sign * normalize(mk3(alphax * hemi_N.x, alphay * hemi_N.y, std_max(0.f, hemi_N.z)));
 }
@@ -73,7 +73,7 @@ VD void eval_pdf_disney_diffuse(V3 dir_in, V3 dir_out, const HitInfo& hit, V3 ba
   const float cos_theta_out = std_max(normal_dirout_dot, 0.f);
   const float cos_theta_in = std_max(dot(frame.w, dir_in), 0.f);
   const float dot_h_out = std_max(dot(half_vec, dir_out), 0.f);
-  const float FD_90 = (float)(0.5 + 2.0 * (double)roughness * (double)dot_h_out * (double)dot_h_out);
+  const float FD_90 = (float)(VR(0.5) + VR(2.0) * (vdbl)roughness * (vdbl)dot_h_out * (vdbl)dot_h_out);
   const V3 base_diffuse = base_col * VIMG_INV_PI_F * FD(frame.w, dir_in, FD_90)
                           * FD(frame.w, dir_out, FD_90) * cos_theta_out;
   const float FSS_90 = roughness * dot_h_out * dot_h_out;
@@ -123,13 +123,13 @@ VD void eval_pdf_disney_clearcoat(V3 dir_in, V3 dir_out, const HitInfo& hit, flo
   }
   constexpr float R0 = ((1.5f - 1.f) * (1.5f - 1.f)) / ((1.5f + 1.f) * (1.5f + 1.f));
   float h_dirout_dot = fabsf(dot(half_vec, dir_out));
-  float Fresenl = (float)((double)R0 + (1. - (double)R0) * (double)raise_to_power_5(1.f - h_dirout_dot));
+  float Fresenl = (float)((vdbl)R0 + (VR(1.) - (vdbl)R0) * (vdbl)raise_to_power_5(1.f - h_dirout_dot));
   float G = G_w(dir_in, 0.25f, 0.25f, frame) * G_w(dir_out, 0.25f, 0.25f, frame);
   const float alpha_g_square = alpha_g * alpha_g;
   const V3 local_H = project_onto_onb(frame, half_vec);
-  float D = (float)((double)(alpha_g_square - 1.f)
-                    / (VIMG_PI_D * (double)m_logf(alpha_g_square)
-                       * (1. + ((double)alpha_g_square - 1.) * (double)local_H.z * (double)local_H.z)));
+  float D = (float)((vdbl)(alpha_g_square - 1.f)
+                    / (VIMG_PI_D * (vdbl)m_logf(alpha_g_square)
+                       * (VR(1.) + ((vdbl)alpha_g_square - VR(1.)) * (vdbl)local_H.z * (vdbl)local_H.z)));
   float clearcoat_eval = (Fresenl * D * G) / (4.f * fabsf(dot(frame.w, dir_in)));
   pdf = (D * fabsf(dot(frame.w, half_vec))) / (4.f * h_dirout_dot);
   eval = mk3(clearcoat_eval);
@@ -140,7 +140,7 @@ VD V3 sample_local_h_clearcoat(Pcg32& rng, float alpha) {
   float rand1 = rand_float(rng);
   float rand2 = rand_float(rng);
   float cos_square_elevation
-      = (float)((1.f - d_pow((double)(alpha * alpha), 1. - (double)rand1)) / (double)(1.f - (alpha * alpha)));
+      = (float)((1.f - d_pow((vdbl)(alpha * alpha), VR(1.) - (vdbl)rand1)) / (vdbl)(1.f - (alpha * alpha)));
   float cos_elevation = sqrtf(cos_square_elevation);
   float sin_elevation = sqrtf(1 - cos_square_elevation);
   float h_azimuth = (float)(2.f * VIMG_PI_D * rand2);
@@ -175,7 +175,7 @@ VD bool sample_disney_clearcoat(V3 dir_in, const HitInfo& hit, ONB frame, float 
 VD float ggx_D(V3 local_H, float alphax, float alphay) {
   float h = (local_H.x * local_H.x) / (alphax * alphax) + (local_H.y * local_H.y) / (alphay * alphay)
             + (local_H.z * local_H.z);
-  return (float)(1. / (VIMG_PI_D * (double)alphax * (double)alphay * (double)(h * h)));
+  return (float)(VR(1.) / (VIMG_PI_D * (vdbl)alphax * (vdbl)alphay * (vdbl)(h * h)));
 }
 
 // eval_pdf_disney_metal (disney_metal.h:120-152)
@@ -287,7 +287,7 @@ VD bool sample_disney_rough_glass(V3 dir_in, const HitInfo& hit, float mat_eta, 
   float h_dot_out_sq = 1 - (1 - h_dot_in * h_dot_in) / (eta * eta);
   if (h_dot_out_sq <= 0) return false;
   if (h_dot_in < 0) half_vec = -half_vec;
-  float h_dot_out = (float)sqrt((double)h_dot_out_sq);
+  float h_dot_out = (float)sqrt((vdbl)h_dot_out_sq);
   V3 refracted = -dir_in / eta + (fabsf(h_dot_in) / eta - h_dot_out) * half_vec;
   if (dot(refracted, hit.hit_n_g) * dot(dir_in, hit.hit_n_g) >= 0) return false;
   V3 generalized_h = normalize(dir_in + refracted * eta);

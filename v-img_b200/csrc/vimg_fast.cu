@@ -1,0 +1,19 @@
+// vimg_fast.cu -- the TOLERANCE build of the queue-wavefront kernels (VIMG_FLAG_FAST).
+//
+// The same device sources as the bit-exact build in vimg_api.cu, compiled a second time with
+// -use_fast_math (approximate division / sqrt / transcendental units, FMA contraction, flush to
+// zero) and with VIMG_FAST defined: `vdbl` (the sub-expressions the reference evaluates in double)
+// becomes float, the libm restatements become the hardware's intrinsics, and the kernels the
+// bit-exact contract rules out (qf_trace_flat_kernel) exist.  Everything lives in namespace
+// vimg_fast so that the two builds can sit in one library; vimg_api.cu launches either set through
+// the QwKernelTable below.  The argument structs (DScene, QwState, WfArgs) contain no `vdbl`, so
+// their layout is the same in both builds.
+#define VIMG_FAST 1
+#define VIMG_FAST_LIBM 1
+#define vimg vimg_fast
+#include "vimg_kernels.cuh"
+#undef vimg
+
+extern "C" void vimg_fast_kernel_table(void* out) {
+  *static_cast<vimg_fast::QwKernelTable*>(out) = vimg_fast::qw_kernel_table();
+}

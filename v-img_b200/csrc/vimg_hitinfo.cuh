@@ -34,7 +34,7 @@ VD float float_sign(float in) { return in > 0.f ? 1.f : -1.f; }
 // spread_angle_from_curvature (ray.h:52-61): `1.0e-5` literals are double
 VD float spread_angle_from_curvature(float mean_curvature, float cone_width, V3 ray_dir, V3 normal) {
   float dn = -dot(ray_dir, normal);
-  dn = ((double)fabsf(dn) < 1.0e-5) ? (float)((double)float_sign(dn) * 1.0e-5) : dn;
+  dn = ((vdbl)fabsf(dn) < VR(1.0e-5)) ? (float)((vdbl)float_sign(dn) * VR(1.0e-5)) : dn;
   return mean_curvature * cone_width / dn;
 }
 
@@ -55,8 +55,8 @@ VD bool refract_with_TIR2D(V2 ray_dir, V2 normal, float eta, V2& out) {
 
 // rotate2DPlusMinus (ray.h:81-92): unqualified cos/sin => double, narrowed to float
 VD void rotate2DPlusMinus(V2 vec, float angle, V2& plus, V2& minus) {
-  float c = (float)d_cos((double)angle);
-  float s = (float)d_sin((double)angle);
+  float c = (float)d_cos((vdbl)angle);
+  float s = (float)d_sin((vdbl)angle);
   float cx = c * vec.x, sy = s * vec.y, sx = s * vec.x, cy = c * vec.y;
   plus = mk2(cx - sy, +sx + cy);
   minus = mk2(cx + sy, -sx + cy);
@@ -186,7 +186,7 @@ VD V3 col_at_ray_hit(const DScene& sc, int32_t tex, V3 ray_in_dir, RayCone cone,
   // unqualified log2(width*height) on an unsigned => double
   float lambda = 0.5f * m_log2f(hit.tex_coord_area / hit.primitive_area);
   lambda += m_log2f(fabsf(cone.cone_width) / fabsf(dot(ray_in_dir, hit.hit_n_g)));
-  lambda = (float)((double)lambda + t.half_log2_wh);
+  lambda = (float)((vdbl)lambda + (vdbl)t.half_log2_wh);
 #ifdef VIMG_DEBUG_NEE
   printf("D   lod: tca=%.9g pa=%.9g cw=%.9g dot=%.9g lambda=%.9g\n", hit.tex_coord_area, hit.primitive_area, cone.cone_width, dot(ray_in_dir, hit.hit_n_g), lambda);
 #endif
@@ -447,9 +447,9 @@ VD HitInfo sphere_hit_info(const DLeafPrim& lp, const DShadeRec& sr, const Ray& 
   float u = 0.f, v = 0.f;
   if (needs_uv) {
     float theta = m_acosf(-normal.y);
-    float phi = (float)((double)m_atan2f(-normal.z, normal.x) + VIMG_PI_D);
-    u = (float)((double)phi / (2.f * VIMG_PI_D));
-    v = (float)((double)theta / VIMG_PI_D);
+    float phi = (float)((vdbl)m_atan2f(-normal.z, normal.x) + VIMG_PI_D);
+    u = (float)((vdbl)phi / (2.f * VIMG_PI_D));
+    v = (float)((vdbl)theta / VIMG_PI_D);
   }
   V3 dpdu = mk3(-radius * normal.y, radius * normal.x, 0.f);
   V3 tangent = normalize(dpdu - normal * dot(normal, dpdu));

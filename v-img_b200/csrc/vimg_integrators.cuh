@@ -51,8 +51,8 @@ VD V3 xform_dir(const float* m, V3 d) {
 
 VD void envmap_uv(const DScene& sc, V3 in_dir, float& u, float& v) {
   V3 dir = normalize(xform_dir(sc.bg.world_to_env, in_dir));
-  u = (float)((1.f + (double)m_atan2f(-dir.x, dir.z) * VIMG_INV_PI_D) * 0.5f);
-  v = (float)((double)m_acosf(dir.y) * VIMG_INV_PI_D);
+  u = (float)((1.f + (vdbl)m_atan2f(-dir.x, dir.z) * VIMG_INV_PI_D) * 0.5f);
+  v = (float)((vdbl)m_acosf(dir.y) * VIMG_INV_PI_D);
 }
 
 // ConstBackground / EnvMap::background_emit (background.h:34-36, 88-108)
@@ -61,8 +61,8 @@ VD V3 background_emit(const DScene& sc, V3 in_dir, RayCone cone) {
   float u, v;
   envmap_uv(sc, in_dir, u, v);
   const DTexture& img = sc.textures[sc.bg.image];
-  // std::log2(double): |spread| * (height / pi)
-  float lambda = (float)d_log2((double)fabsf(cone.spread_angle) * ((double)img.height / VIMG_PI_D));
+  // std::log2(vdbl): |spread| * (height / pi)
+  float lambda = (float)d_log2((vdbl)fabsf(cone.spread_angle) * ((vdbl)img.height / VIMG_PI_D));
   lambda = is_nan(lambda) ? 0.f : lambda;
   return col_mipmap_interpolate(sc, img, lambda - 2.f, mk2(u, v)) * sc.bg.radiance_scale;
 }
@@ -81,10 +81,10 @@ VD float background_pdf(const DScene& sc, V3 in_dir) {
   float pdf_y = sc.bg.row_cdf[row_index + 1] - sc.bg.row_cdf[row_index];
   const float* row = sc.bg.col_cdfs + (size_t)row_index * (W + 1);
   float pdf_x = row[column_index + 1] - row[column_index];
-  float sin_elevation = (float)d_sin(VIMG_PI_D * (double)v);
+  float sin_elevation = (float)d_sin(VIMG_PI_D * (vdbl)v);
   (void)H;
-  return (float)((double)(pdf_y * pdf_x * img.width * img.height)
-                 / (2.f * VIMG_PI_D * VIMG_PI_D * (double)sin_elevation));
+  return (float)((vdbl)(pdf_y * pdf_x * img.width * img.height)
+                 / (2.f * VIMG_PI_D * VIMG_PI_D * (vdbl)sin_elevation));
 }
 
 // ------------------------------------------------------------------ lights ----
@@ -152,7 +152,7 @@ VD V3 sphere_light_sample(const DScene& sc, const DLightRec& lr, V3 look_from, P
     V3 point_on_sphere = (point_on_unit_sphere * radius) + center;
     V3 vec_from_lf_to_pos = point_on_sphere - look_from;
     shading_normal = point_on_unit_sphere;
-    const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+    const float sphere_sa = (float)(4.f * VIMG_PI_D * (vdbl)radius * (vdbl)radius);
     V3 dir_to_surf = normalize(vec_from_lf_to_pos);
     float dist2 = length2(vec_from_lf_to_pos);
     float cosine = fabsf(dot(shading_normal, -dir_to_surf));
@@ -164,7 +164,7 @@ VD V3 sphere_light_sample(const DScene& sc, const DLightRec& lr, V3 look_from, P
   } else {
     // unqualified sqrt() on a float => double
     float cos_theta_max
-        = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
+        = (float)sqrt((vdbl)(1.0f - ((radius * radius) / length2(look_from - center))));
     V3 dir_center_to_lf = normalize(look_from - center);
     ONB onb = init_onb(dir_center_to_lf);
     V3 sample_z_dir = sample_sphere_cap(rand1, rand2, cos_theta_max);
@@ -174,7 +174,7 @@ VD V3 sphere_light_sample(const DScene& sc, const DLightRec& lr, V3 look_from, P
     V3 sampled_dir = normalize(sampled_point - look_from);
     float cosine = fabsf(dot(shading_normal, -sampled_dir));
     float G = cosine / dist2;
-    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (vdbl)(1.0f - cos_theta_max)));
     info.wi = sampled_dir;
     info.pdf = pdf_solid_angle * G;
     info.dist = sqrtf(dist2);
@@ -189,11 +189,11 @@ VD float sphere_surf_pdf(const DScene& sc, uint32_t prim, V3 look_from, V3 point
   const V3 center = mk3(s.center[0], s.center[1], s.center[2]);
   const float radius = s.radius;
   if (length2(look_from - center) <= radius * radius) {
-    const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+    const float sphere_sa = (float)(4.f * VIMG_PI_D * (vdbl)radius * (vdbl)radius);
     return 1.f / sphere_sa;
   }
-  float cos_theta_max = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
-  float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+  float cos_theta_max = (float)sqrt((vdbl)(1.0f - ((radius * radius) / length2(look_from - center))));
+  float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (vdbl)(1.0f - cos_theta_max)));
   V3 shading_normal = normalize(point_on_light - center);
   float cosine = fabsf(dot(shading_normal, -dir));
   float dist2 = length2(point_on_light - look_from);
@@ -225,15 +225,15 @@ VD V3 background_light_sample(const DScene& sc, Pcg32& rng, EmitterInfo& info) {
   float choose_sample_pdf = pdf_y * pdf_x;
 
   const DTexture& img = sc.textures[sc.bg.image];
-  float elevation = (float)((double)v_env * VIMG_PI_D);
-  float y = (float)d_cos((double)v_env * VIMG_PI_D);  // std::cos(double)
-  const float azimuth = (float)((double)(u_env * 2.f) * VIMG_PI_D);
+  float elevation = (float)((vdbl)v_env * VIMG_PI_D);
+  float y = (float)d_cos((vdbl)v_env * VIMG_PI_D);  // std::cos(vdbl)
+  const float azimuth = (float)((vdbl)(u_env * 2.f) * VIMG_PI_D);
   float x = m_sinf(azimuth) * m_sinf(elevation);
   float z = -1 * m_cosf(azimuth) * m_sinf(elevation);
   V3 wi = normalize(xform_dir(sc.bg.env_to_world, mk3(x, y, z)));
   float sin_elevation = m_sinf(elevation);
-  float pdf = (float)((double)(choose_sample_pdf * img.width * img.height)
-                      / (2.f * VIMG_PI_D * VIMG_PI_D * (double)sin_elevation));
+  float pdf = (float)((vdbl)(choose_sample_pdf * img.width * img.height)
+                      / (2.f * VIMG_PI_D * VIMG_PI_D * (vdbl)sin_elevation));
   info.wi = wi;
   info.pdf = pdf;
   info.dist = CUDART_INF_F;
@@ -266,11 +266,11 @@ VD float emitter_surf_pdf_leaf(const DLeafPrim& lp, V3 look_from, V3 point_on_li
     const V3 center = mk3(lp.a[0], lp.a[1], lp.a[2]);
     const float radius = lp.a[3];
     if (length2(look_from - center) <= radius * radius) {
-      const float sphere_sa = (float)(4.f * VIMG_PI_D * (double)radius * (double)radius);
+      const float sphere_sa = (float)(4.f * VIMG_PI_D * (vdbl)radius * (vdbl)radius);
       return 1.f / sphere_sa;
     }
-    float cos_theta_max = (float)sqrt((double)(1.0f - ((radius * radius) / length2(look_from - center))));
-    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (double)(1.0f - cos_theta_max)));
+    float cos_theta_max = (float)sqrt((vdbl)(1.0f - ((radius * radius) / length2(look_from - center))));
+    float pdf_solid_angle = (float)(1.0f / (2.f * VIMG_PI_D * (vdbl)(1.0f - cos_theta_max)));
     V3 shading_normal = normalize(point_on_light - center);
     float cosine = fabsf(dot(shading_normal, -dir));
     float dist2 = length2(point_on_light - look_from);
@@ -304,7 +304,7 @@ VD V3 normal_integrator(const DScene& sc, Ray& ray, PathCounters& pc) {
     return (n + 1.0f) / 2.0f;
   }
   V3 unit_dir = normalize(ray.dir);
-  float a = (float)(0.5 * ((double)unit_dir.y + 1.0));  // double arithmetic (normals.cpp:19)
+  float a = (float)(VR(0.5) * ((vdbl)unit_dir.y + VR(1.0)));  // double arithmetic (normals.cpp:19)
   return (1.0f - a) * mk3(1.0f, 1.0f, 1.0f) + a * mk3(0.5f, 0.7f, 1.0f);
 }
 

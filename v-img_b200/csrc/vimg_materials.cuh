@@ -50,7 +50,7 @@ VD bool lambertian_sample(V3 wi, const HitInfo& hit, Pcg32& rng, ScatterInfo& ou
 // Lambertian::eval_pdf_pair (lambertian.cpp:46-54): max(0, wo.n_s) / pi in double, narrowed
 VD void lambertian_eval_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo,
                             const HitInfo& hit, RayCone cone, V3& eval, float& pdf) {
-  float dot_product = (float)((double)std_max(0.0f, dot(wo, hit.hit_n_s)) / VIMG_PI_D);
+  float dot_product = (float)((vdbl)std_max(0.0f, dot(wo, hit.hit_n_s)) / VIMG_PI_D);
   eval = col_at_ray_hit(sc, m.texture, wi, cone, hit) * dot_product;
   pdf = dot_product;
 }

@@ -100,6 +100,9 @@ VD V4 mat4_mul(const float* m, V4 v) {
 // inlined; the render kernels call them from many places, so they live in ONE out-of-line
 // copy each (instruction-cache footprint, see DESIGN.md "Kernel structure").
 #define VNI __device__ __noinline__
+#ifndef VIMG_FAST
+// `vdbl` marks the sub-expressions the reference evaluates in double
+typedef double vdbl;
 VNI double d_sin(double x) { return sin(x); }
 VNI double d_cos(double x) { return cos(x); }
 VNI double d_log(double x) { return log(x); }
@@ -111,6 +114,21 @@ VNI double d_log2(double x) { return log2(x); }
 VNI double d_pow(double x, double y) { return pow(x, y); }
 VNI double d_acos(double x) { return acos(x); }
 VNI double d_atan2(double y, double x) { return atan2(y, x); }
+#else
+// Tolerance build (vimg_fast.cu, -use_fast_math): the same expressions in float with the hardware's
+// approximate division / sqrt / transcendental units.  Images agree with the reference within the
+// stated relMSE tolerance (tests/test_gpu_fast.py), not bit for bit.
+typedef float vdbl;
+VD float d_sin(float x) { return __sinf(x); }
+VD float d_cos(float x) { return __cosf(x); }
+VD float d_log(float x) { return __logf(x); }
+VD float d_log2(float x) { return __log2f(x); }
+VD float d_pow(float x, float y) { return __powf(x, y); }
+VD float d_acos(float x) { return acosf(x); }
+VD float d_atan2(float y, float x) { return atan2f(y, x); }
+#endif
+// a literal of the reference's double arithmetic
+#define VR(x) ((vdbl)(x))
 
 #ifndef VIMG_FAST_LIBM
 // glibc's float functions restated operation by operation (vimg_libm.cuh; every one checked against
@@ -137,8 +155,8 @@ VD float m_atan2f(float y, float x) { return atan2f(y, x); }
 VD float m_powf(float x, float y) { return powf(x, y); }
 #endif
 
-#define VIMG_PI_D 3.141592653589793238462643383279502884  /* std::numbers::pi   */
-#define VIMG_INV_PI_D 0.318309886183790671537767526745028724 /* std::numbers::inv_pi */
+#define VIMG_PI_D VR(3.141592653589793238462643383279502884)  /* std::numbers::pi   */
+#define VIMG_INV_PI_D VR(0.318309886183790671537767526745028724) /* std::numbers::inv_pi */
 #define VIMG_INV_PI_F 0.318309886183790671537767526745028724f /* inv_pi_v<float>  */
 
 VD bool is_inf(float x) { return fabsf(x) == CUDART_INF_F; }

@@ -65,9 +65,9 @@ VD V2 sample_disk(float rand1, float rand2) {
 VD V3 sample_sphere(float rand1, float rand2) {
   float phi = (float)(2 * VIMG_PI_D * rand1);
   float cos_theta = 2 * rand2 - 1;
-  float sin_theta = (float)sqrt((double)(1 - cos_theta * cos_theta));
-  float x = (float)(d_cos((double)phi) * sin_theta);
-  float y = (float)(d_sin((double)phi) * sin_theta);
+  float sin_theta = (float)sqrt((vdbl)(1 - cos_theta * cos_theta));
+  float x = (float)(d_cos((vdbl)phi) * sin_theta);
+  float y = (float)(d_sin((vdbl)phi) * sin_theta);
   return mk3(x, y, cos_theta);
 }
 
@@ -76,8 +76,8 @@ VD V3 sample_sphere_cap(float rand1, float rand2, float cos_theta_max) {
   float phi = (float)(2 * VIMG_PI_D * rand1);
   float cos_theta = std_lerp(cos_theta_max, 1.0f, rand2);
   float sin_theta = sqrtf(1 - cos_theta * cos_theta);
-  float x = (float)(d_cos((double)phi) * sin_theta);
-  float y = (float)(d_sin((double)phi) * sin_theta);
+  float x = (float)(d_cos((vdbl)phi) * sin_theta);
+  float y = (float)(d_sin((vdbl)phi) * sin_theta);
   return mk3(x, y, cos_theta);
 }
 

@@ -136,6 +136,7 @@ struct DScene {
   uint32_t root_first, root_count;  // nodes[0]
   uint32_t n_nodes;
   uint32_t stack_cap;
+  uint32_t n_leaf_recs;  // entries of leaf_prims / leaf_class / shade_recs (= BVH::obj_indices.size())
   // primitives / geometry pools
   const vimg_prim* prims;
   const vimg_sphere* spheres;

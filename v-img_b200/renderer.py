@@ -14,6 +14,7 @@ FLAG_PIPELINE_BLOCK = 2   # persistent block-local wavefront kernel
 FLAG_PIPELINE_QUEUE = 4   # multi-kernel queue wavefront (default)
 FLAG_STAGE_TIMES = 8      # queue wavefront: serial launches, per-stage device times in the stats
 FLAG_FRESH_STACK = 16     # do not reproduce the reference's carried-over traversal stack (faster)
+FLAG_FAST = 32            # tolerance mode: fast-math kernels + device-side BVH re-layout (relMSE contract)
 STAGES = ("trace", "classify", "shade_principled", "shade_lambertian", "shade_dielectric", "end")
 PIPELINES = {None: 0, "block": FLAG_PIPELINE_BLOCK, "queue": FLAG_PIPELINE_QUEUE}
 
@@ -296,14 +297,15 @@ class Scene:
         return int(self._lib.vimg_scene_device_bytes(self._h))
 
     def _params(self, func, samples, depth, rank, n_ranks, counters, pipeline=None, stage_times=False,
-                spp_streams=1, fresh_stack=False):
+                spp_streams=1, fresh_stack=False, fast=False):
         flags = (FLAG_COUNTERS if counters else 0) | PIPELINES[pipeline] | (FLAG_STAGE_TIMES if stage_times else 0)
         flags |= FLAG_FRESH_STACK if fresh_stack else 0
+        flags |= FLAG_FAST if fast else 0
         return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks, flags,
                             int(spp_streams))
 
     def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None,
-                         pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False):
+                         pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False):
         """Mirror of scene_integrator<F>() (include/integrators.h:36-153).
 
         Returns (image float32 [H, W, 3] in HOST memory, row 0 = top; stats dict).
@@ -313,21 +315,25 @@ class Scene:
         (vimg_render_params.spp_streams, include/vimg_cuda.h).
         `fresh_stack` = True drops the reference's carried-over traversal stack (VIMG_FLAG_FRESH_STACK):
         faster, images within the relMSE tolerance instead of bit-identical.
+        `fast` = True selects the tolerance mode (VIMG_FLAG_FAST): fast-math build of the kernels and a
+        device-side re-layout of the BVH; material / mis images within the stated relMSE tolerance.
         """
         if out is None:
             out = np.empty((self.height, self.width, 3), np.float32)
         assert out.dtype == np.float32 and out.size == self.height * self.width * 3
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack,
+                         fast)
         _check(self._lib, self._lib.vimg_render(self._h, C.byref(p), out.ctypes.data, C.byref(st)),
                "vimg_render")
         return out, st.as_dict()
 
     def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None,
-                      pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False):
+                      pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False):
         """Render and leave the frame in HBM.  Returns (device pointer, stats dict)."""
         st = RenderStats()
-        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack)
+        p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack,
+                         fast)
         dev = C.c_void_p()
         _check(self._lib, self._lib.vimg_render_device(self._h, C.byref(p), C.byref(dev), stream,
                                                        C.byref(st)), "vimg_render_device")
