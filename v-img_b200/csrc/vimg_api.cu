@@ -194,6 +194,7 @@ struct vimg_scene {
   // queue wavefront (vimg_queues.cuh): slot pools, class mask of the scene's materials
   uint8_t* d_rgb8 = nullptr;      // vimg_render_srgb8: quantised frame
   uint32_t* d_post_max = nullptr;  // ... and the reinhard tonemapper's largest luminance (float bits)
+  void* d_flat = nullptr;  // tolerance build: flat re-layout of a small scene (vimg_flat.cuh), built at the first fast render
   QwWorkspace* ws = nullptr;  // taken at the first material / mis render
   uint32_t class_mask = 0;
   int sm_count = 0;
@@ -350,6 +351,29 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
       p.r_first = b.nodes[2 * ((uint64_t)first + 1)];
       p.r_count = b.nodes[2 * ((uint64_t)first + 1) + 1];
     }
+    // The device's traversal stacks hold max_depth + 2 entries per traversal and are not bounds checked:
+    // walk the tree once from the root and refuse a descriptor whose nodes are not a tree (a node reached
+    // twice: shared child or cycle) or whose real depth exceeds the stated max_depth.
+    {
+      std::vector<uint8_t> seen(b.n_nodes, 0);
+      std::vector<std::pair<uint32_t, uint32_t>> todo;  // node, depth (root = 0)
+      todo.emplace_back(0u, 0u);
+      seen[0] = 1;
+      uint32_t deepest = 0;
+      while (!todo.empty()) {
+        const auto [n, depth] = todo.back();
+        todo.pop_back();
+        deepest = std::max(deepest, depth);
+        if (b.nodes[2 * (uint64_t)n + 1] != 0) continue;  // leaf
+        const uint32_t first = b.nodes[2 * (uint64_t)n];
+        for (uint32_t ch = first; ch <= first + 1; ++ch) {
+          if (seen[ch]) return fail(VIMG_ERR_INVALID_ARGUMENT, "BVH nodes do not form a tree (node reached twice)");
+          seen[ch] = 1;
+          todo.emplace_back(ch, depth + 1);
+        }
+      }
+      if (deepest > b.max_depth) return fail(VIMG_ERR_INVALID_ARGUMENT, "BVH is deeper than bvh.max_depth");
+    }
   }
   for (uint64_t i = 0; i < b.n_obj_indices; ++i) {
     const uint64_t prim = b.obj_indices[i];
@@ -442,6 +466,7 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   std::vector<float> rg_texels;
   for (uint32_t t = 0; t < desc->n_textures_rg; ++t) {
     const vimg_texture_rg& ht = desc->textures_rg[t];
+    if (ht.width == 0 || ht.height == 0 || !ht.data) return fail(VIMG_ERR_INVALID_ARGUMENT, "RG texture with zero size or no data");
     textures_rg[t] = DTextureRG{ht.width, ht.height, ht.wrap_u, ht.wrap_v, (uint32_t)(rg_texels.size() / 2)};
     // the reference's row-stride quirk (texture_RG.h:47,52) can index up to
     // (w-1) + (h-1)*max(w,h); pad so a non-square texture never reads out of bounds
@@ -807,10 +832,13 @@ struct QwLaunchCfg {
   int integ;                // 0 material, 1 mis
   bool count;               // traversal counters
   bool flat;                // tolerance build, small scene: trace + classify in one launch over the leaf array
+  bool fused;               // tolerance build, small scene: qf_path_kernel + shade launches only (vimg_flat.cuh)
+  const void* d_flat;       // ... and its device-side re-layout of the scene (QfScene)
 };
 
 // the tolerance build of the same kernels (vimg_fast.cu)
 extern "C" void vimg_fast_kernel_table(void* out);
+extern "C" size_t vimg_fast_flat_scene_bytes(void);
 static const QwKernelTable& kernel_table(bool fast) {
   static const QwKernelTable exact = qw_kernel_table();
   static const QwKernelTable fast_t = [] {
@@ -836,10 +864,45 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
   DCounters* counters = s->d_counters;
   cudaStream_t st = pool.main;
   uint32_t launches = 0;
+  if (cfg.fused) {
+    // path(it): shadow ray, closest ray, end-of-path work, next camera ray and its trace, routing;
+    // then the shade launches of the classes side by side.  Nothing else: the next path launch waits for them.
+    launch_k(kt.path_flat[cfg.integ], pool.item_grid, QW_THREADS, st, s->d, q, w, parity, cfg.d_flat, out, counters);
+    prof.mark(1);
+    ++launches;
+    const uint32_t cls_order[3] = {WF_CLASS_LAMBERT, WF_CLASS_PRINCIPLED, WF_CLASS_DIELECTRIC};
+    const int stage_of[3] = {4, 3, 5};
+    cudaStream_t lanes[3] = {st, st, st};
+    if (cfg.concurrent) {
+      lanes[1] = pool.side[0];
+      lanes[2] = pool.side[1];
+      cudaEventRecord(pool.fork, st);
+    }
+    int used = 0;  // the first class present runs on the main stream, the others beside it
+    bool side_used[2] = {false, false};
+    for (int k = 0; k < 3; ++k) {
+      if (!(cfg.class_mask & (1u << cls_order[k]))) continue;
+      cudaStream_t ls = lanes[used];
+      if (cfg.concurrent && used > 0) {
+        cudaStreamWaitEvent(ls, pool.fork, 0);
+        side_used[used - 1] = true;
+      }
+      launch_k(kt.shade[cfg.integ][cls_order[k]], pool.item_grid, QW_THREADS, ls, s->d, q, w, parity);
+      prof.mark(stage_of[k]);
+      ++launches;
+      ++used;
+    }
+    for (int k = 0; k < 2; ++k)
+      if (side_used[k]) {
+        cudaEventRecord(pool.join[k], lanes[k + 1]);
+        cudaStreamWaitEvent(st, pool.join[k], 0);
+      }
+    return launches;
+  }
   if (it > 0) {
     if (cfg.flat) {
       // thread <-> ray: up to two rays per live slot
-      launch_k(kt.trace_flat[cfg.count], pool.flat_grid, QW_THREADS, st, s->d, q, parity, counters);
+      launch_k(kt.trace_flat[cfg.count], pool.flat_grid, QW_THREADS, st, s->d, q, parity, cfg.d_flat, counters);
       prof.mark(1);
     } else {
       launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
@@ -891,8 +954,9 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
 // One frame.  Per pool: end(0) | trace(1) classify(1) shade(1) end(1) | ...  until every queue is
 // empty.  The host looks at the queue counters once per batch of iterations and keeps one batch
 // queued ahead of the check, so the device never waits for the host.
-static int qw_render_t(vimg_scene* s, const WfArgs& w, int integ, bool count, bool fast, float* out, cudaStream_t caller,
+static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count, bool fast, float* out, cudaStream_t caller,
                        bool stage_times) {
+  WfArgs w = w_in;
   QwProfile prof;
   const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
   prof.on = print_profile || stage_times;
@@ -911,6 +975,21 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, int integ, bool count, bo
   for (uint32_t p = 0; p < n_pools; ++p)
     if ((rc = qw_reserve(s, s->ws->qw[p], per_pool)) != VIMG_OK) return rc;
   CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
+  // tolerance build: a scene of a few dozen primitives goes through the flat pipeline (vimg_flat.cuh)
+  QwLaunchCfg cfg{};
+  cfg.kt = &kernel_table(fast);
+  cfg.flat = fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32));
+  cfg.fused = cfg.flat && env_u32("VIMG_FLAT_MODE", 1) == 2 && !count;
+  if (cfg.flat && !s->d_flat) {
+    // device-side re-layout of the BVH: plane-form triangles and spheres as two flat lists
+    CU_TRY(cudaMalloc(&s->d_flat, vimg_fast_flat_scene_bytes()));
+    CU_TRY(launch_k(cfg.kt->build_flat, 1, (int)QF_FLAT_MAX_HOST, caller, s->d, s->d_flat));
+  }
+  if (cfg.fused) {
+    cfg.flat = false;
+    w.fused = 1;
+  }
+  cfg.d_flat = s->d_flat;
   cudaEvent_t start = s->ws->qw[0].done;  // reused as the fork event of the caller's stream
   const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
   for (uint32_t p = 0; p < n_pools; ++p) {
@@ -921,12 +1000,12 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, int integ, bool count, bo
     CU_TRY(cudaStreamWaitEvent(pool.main, start, 0));
     CU_TRY(cudaMemsetAsync(pool.st.slot, 0, (size_t)per_pool * sizeof(QwSlot), pool.main));  // flags = 0: no pixel yet
     QwCounters init{};
-    init.n_end[0] = per_pool;
+    // every slot starts without a pixel: the first launch (END, or the fused path kernel) hands them out
+    (cfg.fused ? init.n_closest[0] : init.n_end[0]) = per_pool;
     *pool.h_cnt = init;
     CU_TRY(cudaMemcpyAsync(pool.st.cnt, pool.h_cnt, sizeof(init), cudaMemcpyHostToDevice, pool.main));
-    qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, pool.main>>>(pool.st.q_end[0], per_pool);
+    qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, pool.main>>>(cfg.fused ? pool.st.q_closest[0] : pool.st.q_end[0], per_pool);
   }
-  QwLaunchCfg cfg;
   // with several pools in flight the persistent trace grid leaves room for the other pool's
   // shade / end blocks on every SM
   const int trace_per_sm = (int)env_u32("VIMG_QW_TRACE_BLOCKS", QW_TRACE_BLOCKS_PER_SM);
@@ -936,11 +1015,8 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w, int integ, bool count, bo
   cfg.item_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 8) * (256 / QW_THREADS)));
   cfg.concurrent = concurrent;
   cfg.class_mask = s->class_mask;
-  cfg.kt = &kernel_table(fast);
   cfg.integ = integ;
   cfg.count = count;
-  // tolerance build: a scene of a few dozen primitives is traced over its leaf array (vimg_queues.cuh)
-  cfg.flat = fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32));
   const int flat_full = std::max(1, std::min(2 * slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_FLAT_BLOCKS", 8)));
   for (uint32_t p = 0; p < n_pools; ++p) {
     s->ws->qw[p].trace_grid = cfg.trace_grid;
@@ -1097,6 +1173,28 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
     w.single_y = a.single_y;
     w.n_local_pixels = a.single_x >= 0 ? 1u : a.n_local_tiles * 64u;
     if (w.n_local_pixels == 0) return VIMG_OK;
+    if (integrator == VIMG_INTEGRATOR_MATERIAL && a.depth == 0) {
+      // material_integrator with depth 0 never traces: every sample is vec3(0) (mat_integrator.cpp:17-21).
+      // Nothing for the pipelines to do -- a slot of the queue wavefront that never gets a live path would
+      // serve one pixel only -- so the frame is written here: zeros for this rank's pixels (the other
+      // ranks' pixels are zero by contract), samples counted.
+      unsigned long long n_samples = a.samples;
+      if (a.single_x < 0) {
+        CU_TRY(cudaMemsetAsync(out, 0, (size_t)s->W * s->H * 3 * sizeof(float), st));
+        unsigned long long pixels = 0;
+        for (uint32_t lt = 0; lt < a.n_local_tiles; ++lt) {
+          const uint32_t tile = a.rank + lt * a.n_ranks, tx = tile / a.tiles_y, ty = tile % a.tiles_y;
+          const uint32_t wx = std::min<uint32_t>(8, (uint32_t)s->W - tx * 8), wy = std::min<uint32_t>(8, (uint32_t)s->H - ty * 8);
+          pixels += (unsigned long long)wx * wy;
+        }
+        n_samples *= pixels;
+      } else {
+        CU_TRY(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
+      }
+      CU_TRY(cudaMemcpyAsync(&s->d_counters->samples, &n_samples, sizeof(n_samples), cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaStreamSynchronize(st));  // n_samples is a local
+      return VIMG_OK;
+    }
     // sample ranges: at least one sample each; trace_pixel and the no-trace corner (material,
     // depth 0) keep the single stream
     w.streams = std::max(1u, std::min(spp_streams, a.samples));
@@ -1199,11 +1297,16 @@ void vimg_release_workspaces(void) {
 void vimg_scene_destroy(vimg_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
+  // the arena and the workspace go back to per-device caches that hand them to the next scene without
+  // the device-wide synchronisation cudaFree would have implied: kernels of a failed render, or a
+  // consumer of vimg_render_device's frame on the caller's stream, may still be in flight
+  cudaDeviceSynchronize();
   for (void* p : s->allocs) arena_release(s->device, p, s->arena_bytes);  // scene arrays, frame, counters
   ws_release(s->device, s->ws);
   s->ws = nullptr;
   if (s->d_rgb8) cudaFree(s->d_rgb8);
   if (s->d_post_max) cudaFree(s->d_post_max);
+  if (s->d_flat) cudaFree(s->d_flat);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;

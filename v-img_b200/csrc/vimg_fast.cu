@@ -12,8 +12,13 @@
 #define VIMG_FAST_LIBM 1
 #define vimg vimg_fast
 #include "vimg_kernels.cuh"
+#include "vimg_flat.cuh"
 #undef vimg
 
 extern "C" void vimg_fast_kernel_table(void* out) {
-  *static_cast<vimg_fast::QwKernelTable*>(out) = vimg_fast::qw_kernel_table();
+  vimg_fast::QwKernelTable t = vimg_fast::qw_kernel_table();
+  vimg_fast::qf_fill_kernel_table(t);
+  *static_cast<vimg_fast::QwKernelTable*>(out) = t;
 }
+
+extern "C" size_t vimg_fast_flat_scene_bytes(void) { return sizeof(vimg_fast::QfScene); }

@@ -118,14 +118,27 @@ VNI double d_atan2(double y, double x) { return atan2(y, x); }
 // Tolerance build (vimg_fast.cu, -use_fast_math): the same expressions in float with the hardware's
 // approximate division / sqrt / transcendental units.  Images agree with the reference within the
 // stated relMSE tolerance (tests/test_gpu_fast.py), not bit for bit.
+// (VIMG_FAST_DBL / VIMG_FAST_NO_INTRIN: bisection knobs of scripts/fast_bias.sh)
+#ifdef VIMG_FAST_DBL
+typedef double vdbl;
+#else
 typedef float vdbl;
-VD float d_sin(float x) { return __sinf(x); }
-VD float d_cos(float x) { return __cosf(x); }
-VD float d_log(float x) { return __logf(x); }
-VD float d_log2(float x) { return __log2f(x); }
-VD float d_pow(float x, float y) { return __powf(x, y); }
-VD float d_acos(float x) { return acosf(x); }
-VD float d_atan2(float y, float x) { return atan2f(y, x); }
+#endif
+#ifdef VIMG_FAST_NO_INTRIN
+VD vdbl d_sin(vdbl x) { return sin(x); }
+VD vdbl d_cos(vdbl x) { return cos(x); }
+VD vdbl d_log(vdbl x) { return log(x); }
+VD vdbl d_log2(vdbl x) { return log2(x); }
+VD vdbl d_pow(vdbl x, vdbl y) { return pow(x, y); }
+#else
+VD vdbl d_sin(vdbl x) { return (vdbl)__sinf((float)x); }
+VD vdbl d_cos(vdbl x) { return (vdbl)__cosf((float)x); }
+VD vdbl d_log(vdbl x) { return (vdbl)__logf((float)x); }
+VD vdbl d_log2(vdbl x) { return (vdbl)__log2f((float)x); }
+VD vdbl d_pow(vdbl x, vdbl y) { return (vdbl)__powf((float)x, (float)y); }
+#endif
+VD vdbl d_acos(vdbl x) { return acos(x); }
+VD vdbl d_atan2(vdbl y, vdbl x) { return atan2(y, x); }
 #endif
 // a literal of the reference's double arithmetic
 #define VR(x) ((vdbl)(x))

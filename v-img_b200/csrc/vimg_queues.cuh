@@ -60,7 +60,8 @@ struct QwCounters {
   uint32_t n_shade[2][WF_NUM_CLASSES];  // by iteration parity: the trace + classify kernel of the tolerance build
                                         // appends while it runs, so the reset happens one iteration ahead
   uint32_t cursor;      // trace kernel's work cursor
-  uint32_t pad_[3];
+  uint32_t blocks_done;  // qf_path_kernel: blocks of the running launch that are done
+  uint32_t pad_[2];
 };
 
 // Path state of one slot: five 32-byte records (one DRAM sector each), grouped by who reads and
@@ -760,7 +761,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       d4 = ldg4(&st.slot[j].ray.d_s);
       h0 = ldg4(&st.slot[j].hit.h0);
       hb = ldg4u(&st.slot[j].hit.h1);
-      if (MIS) {
+      if (MIS && !args.fused) {  // pending shadow ray: resolved by qf_path_kernel in the fused pipeline
         cp4 = ldg4(&st.slot[j].nee.c_pdf);
         L4 = ldg4(&st.slot[j].pix.L_s);
       }
@@ -955,6 +956,12 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     // traversal inherits the stack its occlusion traversal left behind (see bvh_traverse)
     const bool pair = want_closest && want_shadow && !args.fresh_stack;
     if (pair) want_shadow = false;
+    if (args.fused) {
+      // tolerance build, flat scene: ONE queue.  qf_path_kernel reads from the slot's flags what is
+      // pending -- shadow ray (WF_NEE), end of path (WF_END), closest ray -- and does all of it.
+      want_closest = want_closest || want_shadow || want_end;
+      want_shadow = want_end = false;
+    }
     const bool want[3] = {want_closest, want_shadow, want_end};
     QwAppend<3> ap;
     ap.count(s_cnt, want, lane, lane_lt);
@@ -969,140 +976,6 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   }
 }
 
-#ifdef VIMG_FAST
-// ====================================================== TRACE + CLASSIFY, flat (tolerance build) ====
-// Scenes of a few dozen primitives (the reference's own scenes: 18 - 40) in the tolerance mode
-// (VIMG_FLAG_FAST): every ray tests every leaf record in leaf order -- the device-side re-layout of
-// such a BVH is its leaf array.  All 32 lanes of a warp run the same primitive at the same time,
-// so the loop has no divergence, no stack and no box tests (the binary traversal of the same
-// scene runs with 16 of 32 lanes); the records sit in shared memory and are read as broadcasts.
-// Same primitive tests, same tie rule (the last successful primitive in leaf order wins); what
-// differs from BVH::hit is that primitives the box tests would have culled are tested too, which
-// changes a result only where the float slab test is not conservative -- inside the tolerance
-// mode's contract, not the bit-identical mode's.  thread <-> queued ray; the material class of
-// what a closest ray hit routes its path straight into the shade / END queues, so this launch
-// also does qw_classify_kernel's work.
-#ifndef QF_FLAT_MAX
-#define QF_FLAT_MAX 64  // leaf records (3 KB of shared memory)
-#endif
-template <bool COUNT>
-__global__ void __launch_bounds__(QW_THREADS)
-qf_trace_flat_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
-                     const uint32_t parity, DCounters* __restrict__ counters) {
-  __shared__ float4 s_prim[QF_FLAT_MAX * 3];
-  __shared__ uint8_t s_class[QF_FLAT_MAX];
-  __shared__ uint32_t s_cnt[WF_NUM_CLASSES + 1], s_base[WF_NUM_CLASSES + 1];
-  QwCounters* c = st.cnt;
-  const int tid = threadIdx.x;
-  const uint32_t lane = tid & 31u;
-  const uint32_t lane_lt = (1u << lane) - 1u;
-  const uint32_t n_prims = sc.n_leaf_recs;
-  if (blockIdx.x == 0 && tid == 0) {
-    // queues of the NEXT iteration (their last consumers ran before this launch)
-    c->n_closest[parity ^ 1u] = 0;
-    c->n_shadow[parity ^ 1u] = 0;
-    c->n_end[parity ^ 1u] = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) c->n_shade[parity ^ 1u][k] = 0;
-  }
-  for (uint32_t i = tid; i < n_prims * 3; i += QW_THREADS)
-    s_prim[i] = __ldg(reinterpret_cast<const float4*>(sc.leaf_prims) + i);
-  for (uint32_t i = tid; i < n_prims; i += QW_THREADS) s_class[i] = sc.leaf_class[i];
-  const uint32_t n_c = c->n_closest[parity], total = n_c + c->n_shadow[parity];
-  const uint32_t* __restrict__ qc = st.q_closest[parity];
-  const uint32_t* __restrict__ qs = st.q_shadow[parity];
-  PathCounters pc = {};
-
-  for (uint32_t base = blockIdx.x * QW_THREADS; base < total; base += gridDim.x * QW_THREADS) {
-    if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
-    __syncthreads();  // also: the staged records are visible
-    const uint32_t item = base + tid;
-    const bool valid = item < total;
-    const bool any_hit = item >= n_c;
-    uint32_t slot = 0;
-    Ray ray;
-    ray.minT = 0.0001f;
-    ray.maxT = CUDART_INF_F;
-    ray.o = mk3(0.f);
-    ray.dir = mk3(0.f, 0.f, 1.f);
-    if (valid) {
-      slot = any_hit ? qs[item - n_c] : qc[item];
-      const float4 o4 = ldg4(&st.slot[slot].ray.o_w);
-      float4 d4;
-      if (any_hit) {  // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
-        d4 = ldg4(&st.slot[slot].nee.wi_dist);
-        ray.maxT = d4.w - 0.0001f;
-        pc.rays_shadow++;
-      } else {
-        d4 = ldg4(&st.slot[slot].ray.d_s);
-        pc.rays_closest++;
-      }
-      ray.o = xyz(o4);
-      ray.dir = xyz(d4);
-    }
-    const RayPre pre = ray_precompute(ray);
-    PreHit ph;
-    ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
-    ph.leaf_slot = -1;
-    bool live = valid;  // a shadow ray stops at its first hit
-    for (uint32_t i = 0; i < n_prims; ++i) {
-      const float4 r0 = s_prim[3 * i], r1 = s_prim[3 * i + 1], r2 = s_prim[3 * i + 2];
-      const float a[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-      const uint32_t flags = __float_as_uint(r2.z);  // the same word for every lane: no divergence
-      if (live) {
-        bool hit;
-        if (flags & VIMG_LEAF_SPHERE) {
-          if (COUNT) pc.trav.sph++;
-          hit = sphere_hit(a, ray);
-          if (hit) ph.e0 = ph.e1 = ph.e2 = ph.inv_det = 0.f;
-        } else {
-          if (COUNT) pc.trav.tri++;
-          hit = tri_hit(a, flags, ray, pre, ph);
-        }
-        if (hit) {
-          ph.leaf_slot = (int32_t)i;
-          live = !any_hit;
-        }
-      }
-    }
-    uint32_t cls = WF_CLASS_NONE + 1;  // NONE + 1: nothing to route (shadow ray, or no item)
-    if (valid) {
-      QwHit* h = &st.slot[slot].hit;
-      if (any_hit) {
-        h->occl = ph.leaf_slot >= 0 ? 1u : 0u;
-      } else {
-        stg4(&h->h0, make_float4(__int_as_float(ph.leaf_slot), ray.maxT, ph.e0, ph.e1));
-        h->h1 = make_float2(ph.e2, ph.inv_det);
-        cls = WF_CLASS_NONE;
-        if (ph.leaf_slot >= 0) {
-          const uint32_t lc = s_class[ph.leaf_slot];
-          cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
-        }
-      }
-    }
-    bool want[WF_NUM_CLASSES + 1];
-#pragma unroll
-    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
-    QwAppend<WF_NUM_CLASSES + 1> ap;
-    ap.count(s_cnt, want, lane, lane_lt);
-    __syncthreads();
-    if (tid < (int)WF_NUM_CLASSES) {
-      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[parity][tid], s_cnt[tid]);
-    } else if (tid == (int)WF_NUM_CLASSES) {
-      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
-    }
-    __syncthreads();
-    if (cls < WF_NUM_CLASSES) st.q_shade[cls][s_base[cls] + ap.off[cls]] = make_uint2(slot, (uint32_t)ph.leaf_slot);
-    else if (cls == WF_CLASS_NONE) st.q_end[parity][s_base[WF_NUM_CLASSES] + ap.off[WF_NUM_CLASSES]] = slot;
-  }
-  warp_add_counter(&counters->rays_closest, pc.rays_closest);
-  warp_add_counter(&counters->rays_shadow, pc.rays_shadow);
-  if (COUNT) {
-    warp_add_counter(&counters->tri_tests, pc.trav.tri);
-    warp_add_counter(&counters->sphere_tests, pc.trav.sph);
-  }
-}
-#endif  // VIMG_FAST
 
 // The kernels of one build of this header.  The library holds two: the bit-exact build (vimg_api.cu:
 // -fmad=false, IEEE division / sqrt, glibc's libm restated) and the tolerance build (vimg_fast.cu: the
@@ -1110,19 +983,17 @@ qf_trace_flat_kernel(const __grid_constant__ DScene sc, const __grid_constant__ 
 // above that the bit-exact contract rules out).  Launches go through cudaLaunchKernel on these entries.
 struct QwKernelTable {
   const void* trace[2];       // [COUNT]
-  const void* trace_flat[2];  // [COUNT]; tolerance build only (else NULL)
+  const void* trace_flat[2];  // [COUNT]; tolerance build only (else NULL): trace + classify over a flat scene
   const void* classify;
   const void* shade[2][WF_NUM_CLASSES];  // [material = 0, mis = 1][class]
   const void* end[2];                    // [material = 0, mis = 1]
+  const void* path_flat[2];              // [material = 0, mis = 1]; tolerance build only
+  const void* build_flat;                // tolerance build only
 };
 inline QwKernelTable qw_kernel_table() {
   QwKernelTable t{};
   t.trace[0] = (const void*)&qw_trace_kernel<false>;
   t.trace[1] = (const void*)&qw_trace_kernel<true>;
-#ifdef VIMG_FAST
-  t.trace_flat[0] = (const void*)&qf_trace_flat_kernel<false>;
-  t.trace_flat[1] = (const void*)&qf_trace_flat_kernel<true>;
-#endif
   t.classify = (const void*)&qw_classify_kernel;
   t.shade[0][WF_CLASS_LAMBERT] = (const void*)&qw_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_LAMBERT>;
   t.shade[0][WF_CLASS_PRINCIPLED] = (const void*)&qw_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_PRINCIPLED>;

@@ -241,6 +241,39 @@ int vimg_scene_desc_load(const char* path, vimg_scene_desc** out) {
   fclose(f);
   if (!r.ok) return VIMG_ERR_IO;
 
+  // A truncated or hand-edited file must not reach vimg_scene_create, which sizes its reads from the
+  // dimensions (3*w*h floats per mip level, 2*n_verts per uv set, (h+1) and h*(w+1) CDF entries, ...):
+  // every array's stated length has to be what the dimensions next to it imply.
+  {
+    bool ok = L->nodes.size() % 2 == 0 && L->bb.size() % 3 == 0;
+    const uint64_t n_nodes = L->nodes.size() / 2;
+    if (n_nodes && L->bb.size() / 3 < 2 * n_nodes + 2) ok = false;
+    for (uint32_t m = 0; m < n_meshes && ok; ++m) {
+      const size_t nv3 = L->mesh_vertices[m].size();
+      ok = L->mesh_indices[m].size() % 3 == 0 && nv3 % 3 == 0
+           && (L->mesh_normals[m].empty() || L->mesh_normals[m].size() == nv3);
+      for (const auto& set : L->mesh_uvs[m]) ok = ok && set.size() == nv3 / 3 * 2;
+    }
+    for (uint32_t t = 0; t < n_tex && ok; ++t) {
+      const vimg_texture& ht = L->textures[t];
+      if (ht.type != VIMG_TEX_IMAGE) continue;
+      ok = ht.n_levels >= 1 && ht.width > 0 && ht.height > 0;
+      for (uint32_t l = 0; l < ht.n_levels && ok; ++l) {
+        const uint64_t lw = (ht.width >> l) ? (ht.width >> l) : 1, lh = (ht.height >> l) ? (ht.height >> l) : 1;
+        ok = L->tex_levels[t][l].size() == 3 * lw * lh;
+      }
+    }
+    for (uint32_t t = 0; t < n_rg && ok; ++t) {
+      const vimg_texture_rg& ht = L->textures_rg[t];
+      ok = ht.width > 0 && ht.height > 0 && L->rg_data[t].size() == 2ull * ht.width * ht.height;
+    }
+    if (ok && d.background.type == VIMG_BG_ENVMAP) {
+      const uint64_t w = d.background.cdf_width, h = d.background.cdf_height;
+      ok = (L->row_cdf.empty() && L->col_cdfs.empty()) || (L->row_cdf.size() == h + 1 && L->col_cdfs.size() == h * (w + 1));
+    }
+    if (!ok) return VIMG_ERR_IO;
+  }
+
   // wire pointers
   d.bvh.nodes = L->nodes.data();
   d.bvh.n_nodes = L->nodes.size() / 2;
