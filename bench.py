@@ -2,29 +2,42 @@
 """bench.py -- throughput of the v-img render hot path on B200 (and the reference beside it).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference]
-                    [--workload disney_spheres] [--spp S]
+                    [--mode fast|exact] [--scenes default|none|C1,C2,C4,C5] [--spp S]
 
-One "step" = one pass of the hot path over one frame: every pixel of the workload's scene,
-all its samples, through the integrator the scene file names (the reference's
-scene_integrator<F>() call, include/integrators.h:36-153).
+One "step" = one pass of the hot path over one frame: every pixel of the workload's scene, all its
+samples, through the integrator the scene file names (the reference's scene_integrator<F>() call,
+include/integrators.h:36-153).
 
-Workload (BASELINE.json): configs[2] `scenes/disney_spheres.json` -- 1800x800, 512 spp, `mis`,
+Headline workload (BASELINE.json configs[2]): `scenes/disney_spheres.json` -- 1800x800, 512 spp, `mis`,
 "depth": -1, sweep-SAH BVH -- the scene the north star's ">= 100x" target and the README's only
-published number are quoted on.  The scene comes from tests/golden/scenes/*.vscene (the
-reference-loaded scene + host-built BVH, flattened by the adapter); /root/reference is not read.
+published number are quoted on.  The other configs ride along in the same JSON line as `scenes`:
+C1 glass_in_box, C2 cornell_box_spheres (normal + mis), C4 the 2 M-triangle synthetic mesh (1 GPU,
+full spp) and C5 the 10 M-triangle 4K 1024 spp scene, tile-partitioned over the N ranks of this run
+with the NCCL reduce inside the timed region.  Small scenes come from tests/golden/scenes/*.vscene (the
+reference-loaded scene + host-built BVH, flattened by the adapter); C4 / C5 are built on this host by
+the compiled reference's own classes (oracle.refcpu.RefScene.synthetic: mesh, textures, env map,
+sweep-SAH BVH -- scene construction, outside every timed region); /root/reference is not read.
 
 metric `Mrays/s`: a ray is one BVH::hit<closest> or BVH::occlude call (SURVEY.md section 8(d)); rays are
-counted by the kernel itself.  `spp_mpix_per_s` (W*H*spp / s / 1e6) is reported beside it.
-With --gpus N (torchrun, one rank per GPU) the frame's 8x8 tiles are dealt round-robin to the
-ranks and the partial frames are summed with an NCCL reduce to rank 0 inside the timed region
-(strong scaling: the frame is fixed).
+counted by the kernels themselves.  `spp_mpix_per_s` (W*H*spp / s / 1e6) is reported beside it.
 
-`--impl reference` times the compiled, unmodified reference (oracle/_ref, perf flavour = what
-its CMake builds: -O3, AVX2 sibling-pair path) on the host cores, on a bounded sample of the
-same workload (fewer spp; throughput is spp-invariant).  The same measurement is attached to
+Modes.  `value` / `e2e` are measured in the mode --mode names, default `fast`: the TOLERANCE mode
+(VIMG_FLAG_FAST + sample-range streams) -- the north star's contract for material / mis images is a
+relative-MSE tolerance -- with `value_bit_identical` / `e2e_bit_identical` beside them: the same frame
+in the library's default mode (one PCG stream per pixel, the reference's traversal stack, image
+bit-identical to the CPU renderer in every pixel).  `--mode exact` makes the bit-identical mode the value.
+
+With --gpus N (torchrun, one rank per GPU) the frame's 8x8 tiles are dealt round-robin to the ranks and
+the partial frames are summed with an NCCL reduce to rank 0 inside the timed region (strong scaling:
+the frame is fixed); `e2e` ends with the whole frame in rank 0's pinned host memory.
+
+`--impl reference` times the compiled, unmodified reference (oracle/_ref, perf flavour = what its CMake
+builds: -O3, AVX2 sibling-pair path, FMA contraction) on all host threads, each step a bounded sample
+of the same frame (>= 32 spp; throughput is spp-invariant).  The same measurement is attached to
 the cuda arm's line as `cpu_baseline`.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -37,17 +50,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import golden_scene_path, load_product, manifest, rel_mse  # noqa: E402
+from helpers import golden_scene_path, load_product, manifest  # noqa: E402
 
 INTEG_NAMES = ["s_normal", "g_normal", "material", "mis"]
 # algorithmic cost model of SURVEY.md section 8(d), in the REFERENCE's data layout
 BYTES = {"inner_nodes": 56, "leaf_nodes": 8, "tri_tests": 56, "sphere_tests": 24}
 FLOPS = {"inner_nodes": 50, "tri_tests": 67, "sphere_tests": 40}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an `ncu --set full` capture
-# (profiles/r4_trace_kernel_fresh_stack.txt: a fully loaded iteration of disney_spheres, 2 M slots, this
-# round's final kernel; mostly path state and queues -- the scene itself is L1 resident)
-NCU_TRAFFIC = {"qw_trace_kernel": 243.432448e6 + 45.497088e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+DEPTH_RR = 0xFFFFFFFF
+
+# BASELINE.json configs.  golden: tests/golden/scenes/<name>.vscene; synthetic: oracle.refcpu.RefScene.synthetic
+WORKLOADS = {
+    "C1": {"golden": "glass_in_box", "config": "configs[0]"},
+    "C2": {"golden": "cornell_box_spheres", "config": "configs[1]", "also": ["s_normal"]},
+    "C3": {"golden": "disney_spheres", "config": "configs[2]"},
+    "C4": {"synthetic": {"G": 1000, "width": 1366, "height": 768}, "spp": 512, "depth": 64, "integrator": "mis",
+           "config": "configs[3]"},
+    "C5": {"synthetic": {"G": 2236, "width": 3840, "height": 2160}, "spp": 1024, "depth": 64, "integrator": "mis",
+           "config": "configs[4]"},
+}
 
 
 def measured_peaks():
@@ -56,6 +77,33 @@ def measured_peaks():
         with open(p) as f:
             return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash():
+    """Hash of the device sources: an ncu traffic figure is only quoted for the kernels it was captured on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "v-img_b200", "csrc")
+    for n in sorted(os.listdir(d)):
+        if n.endswith((".cuh", ".cu")):
+            with open(os.path.join(d, n), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from this round's committed `ncu --set full`
+    capture (profiles/ncu_traffic.json), or None when the capture is of other kernel sources."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    with open(p) as f:
+        t = json.load(f)
+    if t.get("source_hash") != kernel_source_hash():
+        return None, f"capture {t.get('capture')} is of kernel sources {t.get('source_hash')}, not of this build"
+    e = t.get("kernels", {}).get(f"{workload}:{kernel}")
+    if not e:
+        return None, "kernel not in the capture"
+    return e["dram_bytes_per_launch"], t.get("capture")
 
 
 class ClockSampler:
@@ -103,28 +151,9 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def workload_info(name, spp_override):
-    e = manifest()[name]
-    spp = spp_override or e["spp"]
-    return {"name": name, "scene": golden_scene_path(name), "width": e["width"], "height": e["height"],
-            "spp": spp, "depth": e["depth"], "integrator": INTEG_NAMES[e["integrator"]],
-            "n_prims": e["n_prims"], "n_nodes": e["n_nodes"]}
-
-
-def config_of(w, n_gpus, extra=None):
-    c = {"workload": f"{w['name']} {w['width']}x{w['height']} {w['spp']}spp {w['integrator']} "
-                     f"depth={'-1 (RR only)' if w['depth'] == 0xFFFFFFFF else w['depth']}",
-         "scene": os.path.relpath(w["scene"], ROOT), "prims": w["n_prims"], "bvh_nodes": w["n_nodes"],
-         "partition": f"8x8 tiles round-robin over {n_gpus} rank(s)" + (" + NCCL reduce(sum) to rank 0" if n_gpus > 1 else ""),
-         "l2": "flushed between timed steps (256 MiB memset); scene itself is < 8 KiB"}
-    if extra:
-        c.update(extra)
-    return c
-
-
 class StdoutToStderr:
-    """The reference's scene_integrator prints its progress with std::cout (integrators.h:48,142);
-    bench.py's stdout carries exactly one JSON line, so fd 1 points at stderr while it runs."""
+    """The reference's scene_integrator prints its progress with std::cout (integrators.h:48,142) and NCCL
+    prints a banner; bench.py's stdout carries exactly one JSON line, so fd 1 points at stderr meanwhile."""
 
     def __enter__(self):
         import ctypes
@@ -133,6 +162,7 @@ class StdoutToStderr:
         self.libc.fflush(None)
         self.saved = os.dup(1)
         os.dup2(2, 1)
+        return self
 
     def __exit__(self, *exc):
         self.libc.fflush(None)  # the reference's text sits in C stdio's buffer when fd 1 is a file
@@ -140,301 +170,448 @@ class StdoutToStderr:
         os.close(self.saved)
 
 
-# --------------------------------------------------------------------------- reference arm
-def time_reference(w, steps, warmup, budget_s=25.0):
-    """Times the compiled reference (perf flavour) on the host cores.  Returns a dict."""
-    with StdoutToStderr():
-        return _time_reference(w, steps, warmup, budget_s)
+# ------------------------------------------------------------------------------------- workloads
+class Workload:
+    """One BASELINE config: the flattened scene (vimg_scene_desc) and how to get the reference for it."""
+
+    def __init__(self, key, vimg, spp_override=0):
+        w = WORKLOADS[key]
+        self.key, self.vimg = key, vimg
+        self._ref = {}
+        if "golden" in w:
+            e = manifest()[w["golden"]]
+            self.name = w["golden"]
+            self.scene_path = golden_scene_path(self.name)
+            self.desc = vimg.LoadedDesc(self.scene_path)
+            self.desc_ptr = self.desc.ptr
+            self.width, self.height, self.spp, self.depth = e["width"], e["height"], e["spp"], e["depth"]
+            self.integrator = INTEG_NAMES[e["integrator"]]
+            self.n_prims, self.n_nodes = e["n_prims"], e["n_nodes"]
+            self.build = "tests/golden/scenes/%s.vscene (reference-loaded scene, host-built BVH)" % self.name
+            self.rs = None
+        else:
+            from oracle import refcpu  # scene construction by the compiled reference's own classes (untimed)
+            s = w["synthetic"]
+            self.name = f"synthetic_{s['G']}"
+            t0 = time.time()
+            self.rs = refcpu.RefScene.synthetic(G=s["G"], width=s["width"], height=s["height"], tex_size=2048, env_w=2048,
+                                                env_h=1024, spp=w["spp"], depth=w["depth"], bvh="sweep", aperture=0.02,
+                                                flavour="perf")
+            self.desc_ptr = self.rs.desc_ptr()
+            self.width, self.height, self.spp, self.depth = s["width"], s["height"], w["spp"], w["depth"]
+            self.integrator = w["integrator"]
+            self.n_prims, self.n_nodes = self.rs.n_prims, self.rs.n_nodes
+            self.build = (f"procedural height-field mesh G={s['G']} ({self.n_prims} triangles), 2048^2 mip-mapped colour texture + "
+                          f"normal map, 2048x1024 HDR env map, thin lens, sweep-SAH BVH ({self.n_nodes} nodes, depth "
+                          f"{self.rs.max_depth}) built by the reference's classes on this host in {time.time() - t0:.1f} s")
+            self._ref["perf"] = self.rs
+        if spp_override:
+            self.spp = spp_override
+        self.also = w.get("also", [])
+        self.config_name = w["config"]
+
+    def label(self, integ=None, spp=None):
+        d = "-1 (RR only)" if self.depth == DEPTH_RR else self.depth
+        return f"{self.name} {self.width}x{self.height} {spp or self.spp}spp {integ or self.integrator} depth={d}"
+
+    def reference(self, flavour):
+        from oracle import refcpu
+        if flavour not in self._ref:
+            if not refcpu.available(flavour):
+                return None
+            if self.rs is not None:  # the synthetic scene exists in the perf flavour only (minutes to rebuild)
+                return None
+            self._ref[flavour] = refcpu.RefScene.from_desc(self.desc_ptr, 1, self.depth, self.integrator, flavour=flavour)
+        return self._ref[flavour]
+
+    def close(self):
+        for r in self._ref.values():
+            r.close()
+        self._ref = {}
+        self.rs = None
 
 
-def _time_reference(w, steps, warmup, budget_s):
+# --------------------------------------------------------------------------- reference (CPU) arm
+def time_reference(w, integ, steps, warmup, budget_s, min_spp=32):
+    """Times the compiled reference (perf flavour) on all host threads: one warm call, then `steps` timed
+    calls of a bounded sample of the frame (>= min_spp spp each unless the frame has fewer)."""
     from oracle import refcpu
-    vimg = load_product()  # only for vimg_scene_desc_load (host-side file parsing, no GPU work)
-    if not refcpu.available("perf"):
-        return None
-    d = vimg.LoadedDesc(w["scene"])
-    cores = refcpu.hardware_threads("perf")
-    rs = refcpu.RefScene.from_desc(d.ptr, 1, w["depth"], w["integrator"], flavour="perf")
-    # bounded sample: pick spp so that one step takes ~budget/(steps+warmup) seconds
-    _, t1 = rs.render(w["integrator"], spp=1, threads=cores)  # also warms the thread pool / caches
-    _, t2 = rs.render(w["integrator"], spp=2, threads=cores)
-    per_spp = max(t2 - t1, t2 / 2, 1e-3)
-    spp = int(max(1, min(w["spp"], budget_s / (steps + warmup) / per_spp)))
-    for _ in range(warmup):
-        rs.render(w["integrator"], spp=spp, threads=cores)
-    t_total = 0.0
-    for _ in range(steps):
-        _, sec = rs.render(w["integrator"], spp=spp, threads=cores)
-        t_total += sec
-    samples = w["width"] * w["height"] * spp * steps
-    # rays per sample from the instrumented (count) flavour of the same reference, 2 spp
-    rays_per_sample = None
-    if refcpu.available("count"):
-        rc = refcpu.RefScene.from_desc(d.ptr, 2, w["depth"], w["integrator"], flavour="count")
-        rc.counters(reset=True)
-        rc.render(w["integrator"], spp=2, threads=cores)
-        c = rc.counters()
-        rays_per_sample = (c["rays_closest"] + c["rays_shadow"]) / (w["width"] * w["height"] * 2)
+    with StdoutToStderr():
+        rs = w.reference("perf")
+        if rs is None:
+            return None
+        cores = refcpu.hardware_threads("perf")
+        _, t1 = rs.render(integ, spp=1, threads=cores)  # warms the thread pool / caches; also the cost probe
+        _, t2 = rs.render(integ, spp=2, threads=cores)
+        per_spp = max(t2 - t1, t2 / 2, 1e-4)
+        spp = int(max(min(min_spp, w.spp), min(w.spp, budget_s / (steps + warmup) / per_spp)))
+        for _ in range(warmup):
+            rs.render(integ, spp=spp, threads=cores)
+        t_total = 0.0
+        for _ in range(steps):
+            _, sec = rs.render(integ, spp=spp, threads=cores)
+            t_total += sec
+        samples = w.width * w.height * spp * steps
+        rays_per_sample, rps_src = None, None
+        rc = w.reference("count")  # instrumented flavour of the same reference (small scenes)
+        if rc is not None:
+            rc.counters(reset=True)
+            rc.render(integ, spp=2, threads=cores)
+            c = rc.counters()
+            rays_per_sample = (c["rays_closest"] + c["rays_shadow"]) / (w.width * w.height * 2)
+            rps_src = "count flavour of the reference at 2 spp"
     return {"seconds": t_total, "steps": steps, "spp": spp, "samples": samples, "cores": cores,
-            "spp_mpix_per_s": samples / t_total / 1e6, "rays_per_sample": rays_per_sample,
-            "mrays_per_s": (samples * rays_per_sample / t_total / 1e6) if rays_per_sample else None}
+            "spp_mpix_per_s": samples / t_total / 1e6, "rays_per_sample": rays_per_sample, "rays_per_sample_source": rps_src}
 
 
-def reference_line(w, args):
-    r = time_reference(w, args.steps, args.warmup)
+def cpu_baseline_of(w, integ, r, gpu_rays_per_sample=None):
+    rps, src = r["rays_per_sample"], r["rays_per_sample_source"]
+    if rps is None and gpu_rays_per_sample:
+        # the instrumented reference is not built for this scene: rays per sample as the device counts them in the
+        # bit-identical mode, which equal the instrumented reference's wherever both exist (tests/test_gpu_parity.py)
+        rps, src = gpu_rays_per_sample, "device counters, bit-identical mode"
+    return {"value": r["spp_mpix_per_s"] * rps if rps else None, "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+            "spp_mpix_per_s": r["spp_mpix_per_s"],
+            "sample": f"{w.label(integ, r['spp'])}: full frame at {r['spp']} spp (of {w.spp}), {r['steps']} call(s) after one warm "
+                      f"call; compiled reference, perf flavour (-O3 -march=x86-64-v3: AVX2 sibling-pair path + FMA, what the "
+                      f"reference's CMake builds with -march=native on an AVX2 host); rays/sample {rps and round(rps, 3)} ({src})"}
+
+
+def reference_line(args):
+    vimg = load_product()  # only for vimg_scene_desc_load (host-side file parsing, no GPU work)
+    w = Workload(args.workload, vimg, args.spp)
+    r = time_reference(w, w.integrator, args.steps, args.warmup, budget_s=args.ref_budget)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvimg_ref_perf.so not built"}))
         return
-    sample = (f"{w['name']} full frame at {r['spp']} spp (of {w['spp']}), {r['steps']} step(s); "
-              f"rays/sample {r['rays_per_sample']:.3f} from the count flavour at 2 spp")
-    line = {"metric": "Mrays/s", "value": r["mrays_per_s"], "unit": "Mrays/s", "impl": "reference",
+    cb = cpu_baseline_of(w, w.integrator, r)
+    line = {"metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "spp_mpix_per_s": r["spp_mpix_per_s"],
-            "config": config_of(w, 1, {"partition": f"reference scene_integrator, {r['cores']} host threads",
-                                       "l2": "n/a (CPU)"}),
-            "cpu_baseline": {"value": r["mrays_per_s"], "unit": "Mrays/s", "cores": r["cores"],
-                             "kind": "reference", "sample": sample,
-                             "spp_mpix_per_s": r["spp_mpix_per_s"]},
-            "e2e": {"value": r["mrays_per_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0},
+            "config": {"workload": w.label(), "scene": w.build, "prims": w.n_prims, "bvh_nodes": w.n_nodes,
+                       "partition": f"reference scene_integrator, {r['cores']} host threads", "l2": "n/a (CPU)",
+                       "sample_spp_per_step": r["spp"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------- cuda arm
-def cuda_line(w, args):
-    import torch
-    import torch.distributed as dist
+class Gpu:
+    """torch plumbing of one rank: device, process group, barrier, max / sum over ranks."""
 
-    vimg = load_product()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if vimg.device_count() == 0:
-        raise SystemExit("bench.py --impl cuda needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    guard = None
-    if world > 1:
-        # NCCL writes its version banner to fd 1 when the first communicator is created; stdout carries
-        # exactly one JSON line, so fd 1 points at stderr until that line is printed
-        guard = StdoutToStderr()
-        guard.__enter__()
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
 
-    desc = vimg.LoadedDesc(w["scene"])
-    scene = vimg.Scene(desc.ptr, device=local_rank)
-    integ, spp, depth = w["integrator"], w["spp"], w["depth"]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    streams = 1 if args.pipeline == "block" else max(1, args.spp_streams)
+    def reduce_stats(self, values):
+        """-> (max over ranks, sum over ranks) of a list of floats"""
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return t.tolist(), t.tolist()
+        tmax = t.clone()
+        self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return tmax.tolist(), t.tolist()
+
+
+def mode_kwargs(mode, streams):
+    """render options of a mode.  fast: tolerance mode; exact: the library default, bit-identical images"""
+    if mode == "fast":
+        return {"fast": True, "spp_streams": streams}
+    return {"spp_streams": 1}
+
+
+def time_frames(gpu, scene, integ, spp, depth, kw, steps, warmup):
+    """W untimed + K timed steps of this rank's tiles (+ NCCL reduce to rank 0); frame stays in HBM.
+    -> dict(ms_per_step = max over ranks, rays = all ranks, launches, kernel_ms_max)"""
+    torch, dist = gpu.torch, gpu.dist
 
     def step():
-        """kernel(s) on this rank's tiles (+ NCCL reduce to rank 0); frame stays in HBM"""
-        ptr, st = scene.render_device(integ, spp, depth, rank=rank, n_ranks=world, pipeline=args.pipeline,
-                                      spp_streams=streams)
-        if world > 1:
+        ptr, st = scene.render_device(integ, spp, depth, rank=gpu.rank, n_ranks=gpu.world, **kw)
+        if gpu.world > 1:
             dist.reduce(scene.frame_tensor(ptr), dst=0, op=dist.ReduceOp.SUM)
-        return ptr, st
+        return st
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-        flush.zero_()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+        gpu.flush.zero_()
+    gpu.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = kernel_ms = 0.0
     launches = 0
     ev0.record()
-    for i in range(args.steps):
-        ptr, st = step()
+    for i in range(steps):
+        st = step()
         rays += st["rays_closest"] + st["rays_shadow"]
         kernel_ms += st["kernel_ms"]
         launches += st["kernel_launches"]
-        if i + 1 < args.steps:
-            flush.zero_()
+        if i + 1 < steps:
+            gpu.flush.zero_()
     ev1.record()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms, rays, launches, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        elapsed_ms, kernel_ms_max = float(tmax[0]), float(tmax[3])
-        rays, launches = float(t[1]), int(t[2])
-    else:
-        kernel_ms_max = kernel_ms
+    gpu.barrier()
+    mx, sm = gpu.reduce_stats([ev0.elapsed_time(ev1), rays, launches, kernel_ms])
+    return {"ms_per_step": mx[0] / steps, "seconds": mx[0] / 1e3, "rays": sm[1], "launches": int(sm[2]),
+            "kernel_ms_max": mx[3], "steps": steps, "nan_samples": st["nan_samples"]}
 
-    # ---- end-to-end through the public C-ABI call with HOST buffers (rank-local tiles) ----------
-    # every step: scene upload H2D (vimg_scene_create), render, frame D2H into pinned memory
-    # the resident scene gives its render workspace back to the per-device cache, so the scenes the
-    # loop creates take it over instead of allocating ~1 GB inside the first timed step
-    scene.close()
-    host = torch.empty((w["height"], w["width"], 3), dtype=torch.float32).pin_memory()
+
+def time_e2e(gpu, vimg, w, integ, spp, kw, steps):
+    """End to end through the public C-ABI calls with HOST buffers, every step: scene upload H2D
+    (vimg_scene_create), render, and the WHOLE frame in rank 0's pinned host memory at the end -- N = 1:
+    vimg_render's own D2H; N > 1: partial frames reduced over NCCL to rank 0, then D2H there."""
+    torch, dist = gpu.torch, gpu.dist
+    host = torch.empty((w.height, w.width, 3), dtype=torch.float32).pin_memory()
     host_np = host.numpy()
-    e2e_steps = max(1, min(args.steps, 2))
-    barrier()
+    gpu.barrier()
     t0 = time.perf_counter()
-    e2e_rays = 0
-    e2e_step_ms = []
-    for _ in range(e2e_steps):
-        ts = time.perf_counter()
-        sc2 = vimg.Scene(desc.ptr, device=local_rank)
-        _, st2 = sc2.scene_integrator(integ, spp, depth, rank=rank, n_ranks=world, out=host_np,
-                                      pipeline=args.pipeline, spp_streams=streams)
-        h2d = sc2.device_bytes
-        sc2.close()
-        e2e_rays += st2["rays_closest"] + st2["rays_shadow"]
-        e2e_step_ms.append((1e3 * (time.perf_counter() - ts), st2["kernel_ms"], st2["total_ms"]))
-    t_loop = time.perf_counter() - t0
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    print(f"[bench e2e] rank {rank}: steps (wall, kernel, kernel + D2H) {[tuple(round(v, 1) for v in m) for m in e2e_step_ms]} ms, loop {1e3 * t_loop:.1f} ms, "
-          f"with barrier {1e3 * e2e_s:.1f} ms", file=sys.stderr)
-    te = torch.tensor([e2e_s, e2e_rays], dtype=torch.float64, device=dev)
-    if world > 1:
-        tem = te.clone()
-        dist.all_reduce(tem, op=dist.ReduceOp.MAX)
-        dist.all_reduce(te, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_rays = float(tem[0]), float(te[1])
+    rays, h2d = 0, 0
+    for _ in range(steps):
+        sc = vimg.Scene(w.desc_ptr, device=gpu.local_rank)
+        h2d = sc.device_bytes
+        if gpu.world == 1:
+            _, st = sc.scene_integrator(integ, spp, w.depth, out=host_np, **kw)
+        else:
+            ptr, st = sc.render_device(integ, spp, w.depth, rank=gpu.rank, n_ranks=gpu.world, **kw)
+            frame = sc.frame_tensor(ptr)
+            dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+            if gpu.rank == 0:
+                host.copy_(frame)
+            torch.cuda.synchronize()
+        rays += st["rays_closest"] + st["rays_shadow"]
+        sc.close()
+    gpu.barrier()
+    mx, sm = gpu.reduce_stats([time.perf_counter() - t0, rays])
+    return {"seconds": mx[0], "rays": sm[1], "steps": steps, "h2d": int(h2d)}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    scene = vimg.Scene(desc.ptr, device=local_rank)
-    # ---- roofline of the dominant kernel -----------------------------------------------------
-    # counted pass (untimed): per-ray algorithmic cost, in the reference's layout
-    c_spp = min(spp, 16)
-    _, cst = scene.render_device(integ, c_spp, depth, rank=0, n_ranks=1, counters=True, pipeline=args.pipeline,
-                                 spp_streams=min(streams, c_spp))
+def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
+    """Trace-kernel roofline of one workload on this rank's GPU (rank 0 calls this, whole frame):
+    per-ray algorithmic cost from a counted pass of the bit-exact kernels (the reference's traversal),
+    launch duration from a stage-timed pass in the measured mode."""
+    c_spp = min(spp, 4 if w.n_prims > 100000 else 16)
+    _, cst = scene.render_device(integ, c_spp, w.depth, counters=True, spp_streams=1, fresh_stack=bool(kw.get("fast") or kw.get("spp_streams", 1) > 1))
     c_rays = cst["rays_closest"] + cst["rays_shadow"]
     bytes_per_ray = sum(BYTES[k] * cst[k] for k in BYTES) / c_rays
     flops_per_ray = sum(FLOPS[k] * cst[k] for k in FLOPS) / c_rays
-    hbm_peak, peak_src = measured_peaks()
-    samples_per_step = w["width"] * w["height"] * spp
-    secs = elapsed_ms / 1e3
-    stages = None
-    if args.pipeline != "block" and integ in ("material", "mis"):
-        # queue wavefront: the TRACE kernel (BVH::hit / BVH::occlude of every queued ray) is the
-        # dominant kernel.  Its launches are timed with one CUDA event after every launch of a
-        # serial pass over the same frame (VIMG_FLAG_STAGE_TIMES): in the timed region above the
-        # shade / end launches of a pool overlap on side streams, so per-kernel events there would
-        # measure the overlap, not the kernel.
-        t_spp = min(spp, 64)
-        flush.zero_()
-        _, tst = scene.render_device(integ, t_spp, depth, rank=0, n_ranks=1, pipeline="queue", stage_times=True,
-                                     spp_streams=min(streams, t_spp))
-        t_rays = tst["rays_closest"] + tst["rays_shadow"]
-        n_launch = max(tst["stage_launches"]["trace"], 1)
-        launch_s = tst["stage_ms"]["trace"] / 1e3 / n_launch
-        rays_per_launch_rank = t_rays / n_launch
-        kernel_name = "qw_trace_kernel"
-        stage_total = sum(tst["stage_ms"].values())
-        stages = {"spp": t_spp, "ms": tst["stage_ms"], "launches": tst["stage_launches"],
-                  "trace_share_of_step": tst["stage_ms"]["trace"] / stage_total,
-                  "note": "serial pass, one CUDA event per launch (VIMG_FLAG_STAGE_TIMES)"}
-        timing_note = (f"trace launches timed in a serial stage-timed pass at {t_spp} spp "
-                       f"({n_launch} launches, average duration)")
-    else:
-        rays_per_launch_rank = rays / max(launches, 1)
-        launch_s = kernel_ms_max / 1e3 / max(args.steps, 1)  # one launch per step per rank
-        kernel_name = f"wavefront_kernel<{integ}>"
-        timing_note = "one launch per step, CUDA events around it in the timed region"
-    achieved = bytes_per_ray * rays_per_launch_rank / launch_s / 1e9
+    t_spp = min(spp, 8 if w.n_prims > 100000 else 64)
+    kw_t = dict(kw)
+    kw_t["spp_streams"] = min(kw.get("spp_streams", 1), t_spp)
+    gpu.flush.zero_()
+    _, tst = scene.render_device(integ, t_spp, w.depth, stage_times=True, **kw_t)
+    t_rays = tst["rays_closest"] + tst["rays_shadow"]
+    n_launch = max(tst["stage_launches"]["trace"], 1)
+    launch_s = tst["stage_ms"]["trace"] / 1e3 / n_launch
+    rays_per_launch = t_rays / n_launch
+    achieved = bytes_per_ray * rays_per_launch / launch_s / 1e9
+    total = sum(tst["stage_ms"].values())
+    flat = bool(kw.get("fast")) and w.n_prims <= 32
+    kernel = "qf_trace_flat_kernel" if flat else "qw_trace_kernel"
+    traffic, traffic_src = ncu_traffic(kernel, w.key)
+    shares = {k: v / total for k, v in tst["stage_ms"].items() if tst["stage_launches"][k]}
+    return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
+            "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "rays_per_launch": rays_per_launch,
+            "algorithmic_bytes_per_ray": bytes_per_ray, "algorithmic_flops_per_ray": flops_per_ray,
+            "fp32_tflops_achieved": flops_per_ray * rays_per_launch / launch_s / 1e12,
+            "stage_share_of_step": shares,
+            "note": "algorithmic bytes in the reference's layout (56/inner node, 8/leaf, 56/triangle test, 24/sphere test; "
+                    f"SURVEY.md 8(d)), per-ray averages of a counted pass at {c_spp} spp; every trace launch of a serial pass at "
+                    f"{t_spp} spp timed with CUDA events on its stream (VIMG_FLAG_STAGE_TIMES), average duration; shares = "
+                    "stage time / sum of stages in that pass"
+                    + ("; this scene (< 8 KiB) sits in shared memory: the fraction only normalises throughput" if flat else "")}
 
+
+def run_scene(gpu, vimg, key, args, hbm_peak, peak_src, want_cpu):
+    """One entry of the line's `scenes` map."""
+    w = Workload(key, vimg)
+    big = w.n_prims > 100000
+    streams = 16 if big else args.spp_streams
+    out = {"config": w.config_name, "workload": w.label(), "scene": w.build, "prims": w.n_prims, "bvh_nodes": w.n_nodes,
+           "n_gpus": gpu.world}
+    scene = vimg.Scene(w.desc_ptr, device=gpu.local_rank)
+    out["scene_device_bytes"] = scene.device_bytes
+    samples = w.width * w.height * w.spp
+    kw = mode_kwargs("fast", min(streams, w.spp))
+    warm_spp = max(1, min(w.spp, 8 if big else w.spp))
+    time_frames(gpu, scene, w.integrator, warm_spp, w.depth, mode_kwargs("fast", min(streams, warm_spp)), 1, 1)
+    r = time_frames(gpu, scene, w.integrator, w.spp, w.depth, kw, args.scene_steps, 0)
+    out["fast"] = {"mrays_per_s": r["rays"] / r["seconds"] / 1e6, "spp_mpix_per_s": samples * r["steps"] / r["seconds"] / 1e6,
+                   "ms_per_step": r["ms_per_step"], "steps": r["steps"], "spp_streams": kw["spp_streams"],
+                   "rays_per_sample": r["rays"] / (samples * r["steps"]), "gpu_launches": r["launches"], "nan_samples": r["nan_samples"]}
+    gpu_rps = None
+    if not (big and w.spp > 512):
+        # bit-identical mode (C5 at 1024 spp is left out: one stream per pixel at 4K is minutes of tail)
+        re = time_frames(gpu, scene, w.integrator, w.spp, w.depth, mode_kwargs("exact", 1), 1, 0)
+        gpu_rps = re["rays"] / samples
+        out["bit_identical"] = {"mrays_per_s": re["rays"] / re["seconds"] / 1e6, "spp_mpix_per_s": samples / re["seconds"] / 1e6,
+                                "ms_per_step": re["ms_per_step"], "rays_per_sample": gpu_rps}
+    for integ in w.also:  # the normal integrators: bit-exact by contract, one mode
+        rn = time_frames(gpu, scene, integ, w.spp, w.depth, {}, 2, 1)
+        out[integ] = {"mrays_per_s": rn["rays"] / rn["seconds"] / 1e6, "spp_mpix_per_s": samples * 2 / rn["seconds"] / 1e6,
+                      "ms_per_step": rn["ms_per_step"]}
+    if gpu.rank == 0:
+        out["roofline"] = roofline_of(gpu, scene, w, w.integrator, w.spp, kw, hbm_peak, peak_src)
+        if gpu_rps is None:
+            _, c1 = scene.render_device(w.integrator, 1, w.depth, spp_streams=1)
+            gpu_rps = (c1["rays_closest"] + c1["rays_shadow"]) / (w.width * w.height)
+    gpu.barrier()
+    scene.close()
+    if want_cpu and gpu.rank == 0:
+        rr = time_reference(w, w.integrator, 1, 0, budget_s=args.scene_cpu_budget, min_spp=1 if big else 16)
+        if rr is not None:
+            out["cpu_baseline"] = cpu_baseline_of(w, w.integrator, rr, gpu_rps)
+            if out["cpu_baseline"]["value"]:
+                out["fast"]["vs_cpu_baseline"] = out["fast"]["mrays_per_s"] / out["cpu_baseline"]["value"]
+    gpu.barrier()
+    w.close()
+    vimg.release_workspaces()
+    return out
+
+
+def cuda_line(args):
+    vimg = load_product()
+    if vimg.device_count() == 0:
+        raise SystemExit("bench.py --impl cuda needs a CUDA device (no CPU fallback)")
+    guard = StdoutToStderr().__enter__()  # NCCL's banner, the reference's progress prints
+    gpu = Gpu()
+    torch = gpu.torch
+    hbm_peak, peak_src = measured_peaks()
+
+    w = Workload(args.workload, vimg, args.spp)
+    integ, spp, depth = w.integrator, w.spp, w.depth
+    streams = max(1, args.spp_streams)
+    kw = mode_kwargs(args.mode, streams)
+    other = "exact" if args.mode == "fast" else "fast"
+    kw_other = mode_kwargs(other, streams)
+    samples = w.width * w.height * spp
+
+    # ---- the timed region of record: W warm-up + K steps, frame resident, CUDA events, max over ranks
+    scene = vimg.Scene(w.desc_ptr, device=gpu.local_rank)
+    sampler = ClockSampler(gpu.local_rank) if gpu.rank == 0 else None
+    main = time_frames(gpu, scene, integ, spp, depth, kw, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    # ---- the same frame in the other mode (fewer steps: it is a companion number)
+    o_steps = max(1, min(args.steps, 3))
+    side = time_frames(gpu, scene, integ, spp, depth, kw_other, o_steps, 1)
+    scene.close()  # gives its workspace back to the per-device cache: the e2e scenes take it over
+    # ---- end to end with host buffers
+    e_steps = max(1, min(args.steps, 3))
+    time_e2e(gpu, vimg, w, integ, spp, kw, 1)  # untimed: first-touch of the pinned buffer
+    e2e = time_e2e(gpu, vimg, w, integ, spp, kw, e_steps)
+    e2e_o = time_e2e(gpu, vimg, w, integ, spp, kw_other, max(1, min(e_steps, 2)))
+
+    roof = None
+    scene = vimg.Scene(w.desc_ptr, device=gpu.local_rank)
+    if gpu.rank == 0:
+        roof = roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src)
+    gpu.barrier()
+    scene.close()
+
+    # ---- the other BASELINE configs
+    if args.scenes == "default":
+        keys = ["C1", "C2", "C4", "C5"] if gpu.world == 1 else ["C5"]
+    elif args.scenes == "none":
+        keys = []
+    else:
+        keys = [k for k in args.scenes.split(",") if k in WORKLOADS and k != args.workload]
+    scenes = {}
+    for k in keys:
+        scenes[k] = run_scene(gpu, vimg, k, args, hbm_peak, peak_src, want_cpu=not args.no_cpu)
+
+    if gpu.rank != 0:
+        if gpu.world > 1:
+            gpu.dist.destroy_process_group()
+        return
+
+    def mode_note(m):
+        return ("one PCG stream per pixel and the reference's carried-over traversal stack (library default): image "
+                "bit-identical to the CPU renderer in every pixel" if m == "exact" else
+                f"tolerance mode (VIMG_FLAG_FAST): fast-math build of the kernels, flat-list trace for scenes of <= 32 primitives, "
+                f"{streams} sample ranges per pixel with their own PCG streams; image within the stated relMSE tolerance of the CPU "
+                "renderer (tests/test_gpu_fast.py)")
+
+    secs = main["seconds"]
+    value = main["rays"] / secs / 1e6
+    side_value = side["rays"] / side["seconds"] / 1e6
     line = {
-        "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": gpu.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "cuda",
-        "spp_mpix_per_s": samples_per_step * args.steps / secs / 1e6,
-        "rays_per_sample": rays / (samples_per_step * args.steps),
-        "config": config_of(w, world, {
-            "pipeline": args.pipeline or "queue (library default)",
-            "spp_streams": streams,
-            "rng": ("the reference's one PCG stream per pixel: image bit-identical to the CPU renderer"
-                    if streams == 1 else
-                    f"{streams} sample ranges per pixel, each with its own PCG stream (initseq = range), "
-                    "reference R2 jitter index: image within the stated relMSE tolerance of the CPU "
-                    "renderer (tests/test_gpu_streams.py); --spp-streams 1 gives the bit-identical image")}),
+        "spp_mpix_per_s": samples * args.steps / secs / 1e6,
+        "rays_per_sample": main["rays"] / (samples * args.steps),
+        "value_mode": args.mode,
+        ("value_bit_identical" if other == "exact" else "value_fast"): side_value,
+        "companion": {"mode": other, "mrays_per_s": side_value, "ms_per_step": side["ms_per_step"], "steps": side["steps"],
+                      "spp_mpix_per_s": samples * side["steps"] / side["seconds"] / 1e6, "note": mode_note(other)},
+        "config": {"workload": w.label(), "baseline_config": w.config_name, "scene": w.build, "prims": w.n_prims,
+                   "bvh_nodes": w.n_nodes, "mode": args.mode, "mode_note": mode_note(args.mode), "spp_streams": kw["spp_streams"],
+                   "partition": f"8x8 tiles round-robin over {gpu.world} rank(s)"
+                                + (" + NCCL reduce(sum) to rank 0" if gpu.world > 1 else ""),
+                   "l2": "flushed between timed steps (256 MiB memset); path state (> 300 MB) streams through L2 every launch"},
         "clocks": clocks,
-        "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": w["width"] * w["height"] * 12,
-                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-                "spp_mpix_per_s": samples_per_step * e2e_steps / e2e_s / 1e6,
-                "path": "vimg_scene_create (H2D) + vimg_render into pinned host memory (kernel + D2H)"},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(kernel_name),
-                     "peak_source": peak_src,
-                     "kernel": kernel_name, "launch_ms": 1e3 * launch_s,
-                     "algorithmic_bytes_per_ray": bytes_per_ray,
-                     "algorithmic_flops_per_ray": flops_per_ray,
-                     "rays_per_launch": rays_per_launch_rank,
-                     "fp32_tflops_achieved": flops_per_ray * rays_per_launch_rank / launch_s / 1e12,
-                     "note": "bytes in the reference's layout (56/inner, 8/leaf, 56/tri test, 24/sphere "
-                             "test, SURVEY.md section 8(d)); per-ray averages from a counted pass at "
-                             f"{c_spp} spp; {timing_note}; traffic = dram bytes of one fully loaded "
-                             "launch under ncu --set full (profiles/), mostly path state and queues: "
-                             "this scene's BVH (< 8 KiB) is L1 resident"},
+        "e2e": {"value": e2e["rays"] / e2e["seconds"] / 1e6, "unit": "Mrays/s",
+                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": w.width * w.height * 12,
+                "ms_per_step": 1e3 * e2e["seconds"] / e2e["steps"], "steps": e2e["steps"],
+                "spp_mpix_per_s": samples * e2e["steps"] / e2e["seconds"] / 1e6,
+                "path": ("vimg_scene_create (H2D) + vimg_render into pinned host memory (kernels + D2H)" if gpu.world == 1 else
+                         "per rank vimg_scene_create (H2D) + vimg_render_device, NCCL reduce of the partial frames to rank 0, "
+                         "D2H of the whole frame into rank 0's pinned host memory")},
+        ("e2e_bit_identical" if other == "exact" else "e2e_fast"): e2e_o["rays"] / e2e_o["seconds"] / 1e6,
+        "gpu_launches": main["launches"],
+        "roofline": roof,
+        "scenes": scenes,
     }
-    if stages:
-        line["stages"] = stages
-    # ---- the step after the path (SURVEY.md 8(f) rank 1): tonemapper + sRGB OETF + 8-bit quantisation
-    # on the device.  HBM bound: 12 B read + 3 B written per pixel; timed on a 4K frame (the 1800x800
-    # frame of this workload is 22 MB: one launch of ~10 us, launch-latency bound)
-    post = {}
+    # ---- the step after the path (SURVEY.md 8(f) rank 1): tonemapper + sRGB OETF + 8-bit quantisation on the
+    # device.  HBM bound: 12 B read + 3 B written per pixel; timed on a 4K frame
     rng = np.random.default_rng(0)
-    big = (rng.random((2160, 3840, 3), dtype=np.float32) * 4).astype(np.float32)
-    for tm in ("clamp", "aces", "reinhard", "agx"):
-        best = min(vimg.postprocess(big, tm, device=local_rank, want_srgb=False)[2] for _ in range(5))
-        nbytes = big.size // 3 * 15 + (big.size // 3 * 12 if tm == "reinhard" else 0)
-        post[tm] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
-    line["postprocess"] = {"frame": "3840x2160 synthetic, bytes = 15 per pixel (+12 for reinhard's luminance pass)",
-                           "per_tonemapper": post}
-    # ---- the step before the path (SURVEY.md 8(f) rank 3): glTF texture conversion, mip chain, env-map CDFs
-    # on the device, kernel time only (CUDA events inside the calls).  The conversions are HBM bound:
-    # 3 B read + 12 B written per pixel.
-    if rank == 0:
+    if not args.no_extras:
+        post = {}
+        big = (rng.random((2160, 3840, 3), dtype=np.float32) * 4).astype(np.float32)
+        for tm in ("clamp", "aces", "reinhard", "agx"):
+            best = min(vimg.postprocess(big, tm, device=gpu.local_rank, want_srgb=False)[2] for _ in range(5))
+            nbytes = big.size // 3 * 15 + (big.size // 3 * 12 if tm == "reinhard" else 0)
+            post[tm] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
+        line["postprocess"] = {"frame": "3840x2160 synthetic, bytes = 15 per pixel (+12 for reinhard's luminance pass)",
+                               "per_tonemapper": post}
+        # ---- the step before the path (SURVEY.md 8(f) rank 3): glTF texture conversion, mip chain, env-map CDFs
         tex8 = rng.integers(0, 256, size=(2048, 2048, 3), dtype=np.uint8)
         conv = {}
-        for name, fn in (("srgb8_to_linear", lambda: vimg.convert_srgb8_to_linear(tex8, device=local_rank)[1]),
-                         ("rgb8_to_normal", lambda: vimg.convert_rgb8_to_normal(tex8, 1.0, device=local_rank)[1])):
+        for name, fn in (("srgb8_to_linear", lambda: vimg.convert_srgb8_to_linear(tex8, device=gpu.local_rank)[1]),
+                         ("rgb8_to_normal", lambda: vimg.convert_rgb8_to_normal(tex8, 1.0, device=gpu.local_rank)[1])):
             best = min(fn() for _ in range(5))
             nbytes = tex8.size * 5
             conv[name] = {"kernel_ms": best, "achieved_gbs": nbytes / best / 1e6, "frac_of_hbm": nbytes / best / 1e6 / hbm_peak}
-        tex_ms = min(vimg.build_image_texture(tex8, device=local_rank)[1] for _ in range(3))
+        tex_ms = min(vimg.build_image_texture(tex8, device=gpu.local_rank)[1] for _ in range(3))
         env = (rng.random((1024, 2048, 3), dtype=np.float32) * 2).astype(np.float32)
-        cdf_ms = min(vimg.build_envmap_cdf(env, device=local_rank)[2] for _ in range(3))
+        cdf_ms = min(vimg.build_envmap_cdf(env, device=gpu.local_rank)[2] for _ in range(3))
         line["scene_prep"] = {"texture": "2048x2048 8-bit RGB (12.6 MB in, 50.3 MB out), env map 2048x1024",
-                              "conversions": conv,
-                              "image_texture_ms": tex_ms, "envmap_cdf_ms": cdf_ms,
-                              "note": "image_texture = sRGB8 -> linear + the 10 further mip levels; the CDFs are "
-                                      "sequential float sums per row (one thread per row, the reference's order)"}
-    if not args.no_cpu and world == 1:
-        r = time_reference(w, 1, 1, budget_s=16.0)
+                              "conversions": conv, "image_texture_ms": tex_ms, "envmap_cdf_ms": cdf_ms}
+    if not args.no_cpu and gpu.world == 1:
+        r = time_reference(w, integ, 1, 0, budget_s=args.cpu_budget)
         if r is not None:
-            line["cpu_baseline"] = {
-                "value": r["mrays_per_s"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
-                "spp_mpix_per_s": r["spp_mpix_per_s"],
-                "sample": f"{w['name']} full frame at {r['spp']} spp (of {w['spp']}), compiled reference "
-                          f"(perf flavour, AVX2), rays/sample {r['rays_per_sample']:.3f} (count flavour, 2 spp)"}
-    if guard is not None:
-        guard.__exit__()
+            line["cpu_baseline"] = cpu_baseline_of(w, integ, r)
+    guard.__exit__()
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if gpu.world > 1:
+        gpu.dist.destroy_process_group()
 
 
 def main():
@@ -443,21 +620,27 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="disney_spheres")
-    ap.add_argument("--pipeline", default=None, choices=["queue", "block"],
-                    help="material / mis pipeline (default: the library's, the queue wavefront)")
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS), help="headline workload (BASELINE config)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
+                    help="mode of `value` / `e2e`: fast = tolerance mode (VIMG_FLAG_FAST + sample-range streams), "
+                         "exact = library default, bit-identical images; the other mode is reported beside it")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's spp (invalidates the number)")
     ap.add_argument("--spp-streams", type=int, default=64,
-                    help="sample ranges per pixel with their own RNG streams (vimg_render_params.spp_streams); "
-                         "1 = the reference's single stream per pixel, bit-identical image")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+                    help="fast mode: sample ranges per pixel with their own RNG streams (vimg_render_params.spp_streams)")
+    ap.add_argument("--scenes", default="default",
+                    help="other BASELINE configs measured into `scenes`: default (N = 1: C1,C2,C4,C5; N > 1: C5), none, or a list")
+    ap.add_argument("--scene-steps", type=int, default=1, help="timed steps per entry of `scenes`")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the postprocess / scene_prep timings")
+    ap.add_argument("--cpu-budget", type=float, default=14.0, help="seconds of CPU work for the headline cpu_baseline")
+    ap.add_argument("--scene-cpu-budget", type=float, default=5.0, help="seconds of CPU work per `scenes` cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds for all steps together")
     args = ap.parse_args()
-    w = workload_info(args.workload, args.spp)
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:
-            reference_line(w, args)
+            reference_line(args)
         return
-    cuda_line(w, args)
+    cuda_line(args)
 
 
 if __name__ == "__main__":

@@ -221,8 +221,13 @@ typedef struct vimg_scene_desc {
 
 /* ---- render call -------------------------------------------------------- */
 typedef enum vimg_partition {
-  VIMG_PARTITION_TILE = 0 /* interleaved 8x8 tiles: tile i -> rank i % n_ranks
-                             (mirrors include/integrators.h:57-65,101)       */
+  VIMG_PARTITION_TILE = 0, /* interleaved 8x8 tiles: tile i -> rank i % n_ranks
+                              (mirrors include/integrators.h:57-65,101).  A rank writes its own pixels
+                              and leaves the others 0: the sum over ranks is the one-GPU frame, bit for bit */
+  VIMG_PARTITION_SPP = 1   /* sample ranges (material / mis, spp_streams >= n_ranks): every rank renders EVERY
+                              pixel, the sample ranges rank, rank + n_ranks, ... of it (see spp_streams), and
+                              writes (sum of its ranges) / spp.  The sum over ranks is the spp_streams image up
+                              to the association of K float additions (ranks' sums are added instead of ranges) */
 } vimg_partition;
 
 typedef struct vimg_render_params {
@@ -242,6 +247,7 @@ typedef struct vimg_render_params {
                             different random numbers: the image agrees with the reference within the
                             stated relMSE tolerance, not bit for bit.  Partial sums are combined in
                             range order (deterministic, independent of n_ranks).               */
+  uint32_t partition;    /* vimg_partition: what rank / n_ranks divide                        */
 } vimg_render_params;
 
 #define VIMG_FLAG_COUNTERS 1u /* also gather traversal counters (slower)     */
@@ -336,6 +342,22 @@ uint64_t vimg_scene_device_bytes(const vimg_scene* scene);
  * device->host copy of the frame. */
 int vimg_render(vimg_scene* scene, const vimg_render_params* params, float* out_rgb,
                 vimg_render_stats* stats /* nullable */);
+
+/* The whole frame on several GPUs of one box, behind one call (what a maintainer's `--device cuda:0,1,...`
+ * would call from the seam at src/main.cpp:219-248).  The scene is replicated (one host thread per device
+ * uploads it), the work divided as `partition` says, and the image assembled in the memory of the FIRST device:
+ *   VIMG_PARTITION_TILE: the other devices' kernels store their finished pixels straight into the first
+ *     device's frame through peer-mapped memory (NVLink / NVSwitch); no reduce, no staging -- the stores ARE
+ *     the gather.  Bit-identical to the one-device frame.
+ *   VIMG_PARTITION_SPP: every device renders its sample ranges of every pixel into its own frame; the first
+ *     device then adds the peers' frames in device order with one kernel that reads them over NVLink.
+ * Without peer access between two of the devices the partial frames go through host memory instead.
+ * params->rank / n_ranks / partition are ignored (n_ranks = n_devices).  out_rgb: HOST buffer, W*H*3 floats.
+ * stats (nullable): counters summed over devices, kernel_ms = the slowest device, total_ms = wall time of the
+ * call from after the scene uploads (render + assembly + D2H). */
+int vimg_render_multi(const vimg_scene_desc* desc, const int* device_ids, uint32_t n_devices,
+                      const vimg_render_params* params, uint32_t partition, float* out_rgb,
+                      vimg_render_stats* stats /* nullable */);
 
 /* Same, but the frame stays in device memory (for NCCL / peer stores and for
  * timing without the D2H copy).  *out_dev_rgb is owned by the scene and valid

@@ -134,7 +134,7 @@ void* vref_scene_from_json(const char* path, int bvh_type) {
 }
 
 // G x G quads; tex_size^2 colour texture (mips) and normal map; env_w x env_h env map.
-// with_rg != 0 adds a square metallic-roughness TextureRG (a30) for coverage.
+// with_rg != 0 adds a metallic-roughness TextureRG (a30) for coverage: 1 square, 2 wide (64 x 48).
 void* vref_scene_synthetic(int G, int width, int height, int tex_size, int env_w, int env_h,
                            uint32_t spp, uint32_t depth, int bvh_type, int with_rg,
                            float aperture_radius) {
@@ -190,14 +190,17 @@ void* vref_scene_synthetic(int G, int width, int height, int tex_size, int env_w
 
   TextureRG* rg = nullptr;
   if (with_rg) {
-    const int R = 64;
-    std::vector<glm::vec2> rgimg(size_t(R) * R);
-    for (int y = 0; y < R; ++y)
+    // with_rg = 2: a WIDE texture (64 x 48), where the row-stride slip of TextureRG::get_at_uv
+    // (texture_RG.h:47,52: `next_x + y * height`) reads other texels than `next_x + y * width` would;
+    // width > height keeps the reference's own indexing inside its vector
+    const int R = 64, RH = with_rg == 2 ? 48 : 64;
+    std::vector<glm::vec2> rgimg(size_t(R) * RH);
+    for (int y = 0; y < RH; ++y)
       for (int x = 0; x < R; ++x)
         rgimg[size_t(y) * R + x] = glm::vec2(0.5f + 0.5f * std::sin(0.37f * x) * std::cos(0.21f * y),
                                              0.6f + 0.4f * std::cos(0.11f * (x + y)));
     sc->textureRG_list.push_back(std::make_unique<TextureRG>(
-        R, R, rgimg, TextureWrappingMode::MirroredRepeat, TextureWrappingMode::Repeat));
+        R, RH, rgimg, TextureWrappingMode::MirroredRepeat, TextureWrappingMode::Repeat));
     rg = sc->textureRG_list.back().get();
   }
 
@@ -434,6 +437,40 @@ double vref_render(void* h, int integrator, uint32_t spp, uint32_t depth, int th
   if (out_rgb) std::memcpy(out_rgb, img.data(), img.size() * sizeof(glm::vec3));
   return sec;
 }
+
+#ifdef VREF_WITH_CUDA_BINDING
+// The binding flavour (oracle/Makefile `binding`): the adapter TU compiled WITH scene_integrator_cuda and
+// linked against libvimg_cuda.so -- what a v-img maintainer's build contains.  Same
+// arguments as vref_render; the image comes from the cuda device(s) through the reference-side call that
+// replaces scene_integrator<F>() at the seam of src/main.cpp:219-248.  n_devices > 1: vimg_render_multi.
+// Returns 0, or -1 with the message in err (nullable).
+int vref_render_cuda(void* h, int integrator, uint32_t spp, uint32_t depth, const int* devices, int n_devices,
+                     float* out_rgb, char* err, int err_len) {
+  auto* sc = static_cast<RefScene*>(h);
+  integrator_data& s = sc->settings;
+  uint32_t keep_spp = s.samples, keep_depth = s.depth;
+  if (spp) s.samples = spp;
+  if (depth) s.depth = depth;
+  int rc = 0;
+  try {
+    std::vector<glm::vec3> img
+        = n_devices > 1 ? scene_integrator_cuda_multi(s, sc->bvh, sc->list_objects, sc->list_lights, static_cast<integrator_func>(integrator),
+                                                      std::vector<int>(devices, devices + n_devices))
+                        : scene_integrator_cuda(s, sc->bvh, sc->list_objects, sc->list_lights, static_cast<integrator_func>(integrator),
+                                                n_devices == 1 ? devices[0] : 0);
+    if (out_rgb) std::memcpy(out_rgb, img.data(), img.size() * sizeof(glm::vec3));
+  } catch (const std::exception& e) {
+    if (err && err_len > 0) {
+      std::strncpy(err, e.what(), err_len - 1);
+      err[err_len - 1] = 0;
+    }
+    rc = -1;
+  }
+  s.samples = keep_spp;
+  s.depth = keep_depth;
+  return rc;
+}
+#endif
 
 // The post-process chain of src/main.cpp:304-356 on a W*H linear image: the reference's OWN
 // tonemapper (color_utils.h:21-25 simple_clamp, src/tonemap/{agx,reinhard,aces}.cpp), its sRGB

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-FLAVOURS = ("parity", "perf", "count")
+FLAVOURS = ("parity", "perf", "count", "binding")
 INTEGRATORS = {"s_normal": 0, "g_normal": 1, "material": 2, "mis": 3}
 
 
@@ -56,6 +56,10 @@ def _load(flavour):
     lib.vref_heatmap.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p]
     lib.vref_postprocess.restype = None
     lib.vref_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    if flavour == "binding":
+        lib.vref_render_cuda.restype = C.c_int
+        lib.vref_render_cuda.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_int,
+                                         C.c_void_p, C.c_char_p, C.c_int]
     lib.vref_flavour.restype = C.c_int
     lib.vref_hardware_threads.restype = C.c_int
     _libs[flavour] = lib
@@ -129,6 +133,18 @@ class RefScene:
         sec = self._lib.vref_render(self._h, INTEGRATORS[integrator], spp, depth, threads,
                                     out.ctypes.data)
         return out, sec
+
+    def render_cuda(self, integrator, spp=0, depth=0, devices=(0,)):
+        """binding flavour only: the adapter's scene_integrator_cuda (one device) or
+        scene_integrator_cuda_multi (several) on this scene's reference objects -> image [H, W, 3]"""
+        out = np.empty((self.height, self.width, 3), np.float32)
+        err = C.create_string_buffer(512)
+        ids = (C.c_int * len(devices))(*devices)
+        rc = self._lib.vref_render_cuda(self._h, INTEGRATORS[integrator], spp, depth, ids, len(devices),
+                                        out.ctypes.data, err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return out
 
     def trace_pixel(self, integrator, x, y, spp=0, depth=0):
         out = np.empty(3, np.float32)

@@ -117,3 +117,16 @@ def test_c_restatement_full_size_c2(vimg, man):
     ids, t, sn, gn, _ = refcpu.restatement_primary(d.ptr, e["width"], e["height"], 4)
     assert refcpu.digest(ids) == e["ref"]["ids_hash"] and refcpu.digest(t) == e["ref"]["t_hash"]
     assert refcpu.digest(sn) == e["ref"]["s_normal_hash"] and refcpu.digest(gn) == e["ref"]["g_normal_hash"]
+
+
+def test_binding_flavour_links_the_adapter_and_the_product_library():
+    """oracle/_ref/libvimg_ref_binding.so = reference sources + the adapter WITH scene_integrator_cuda +
+    libvimg_cuda.so (INTEGRATION.md's build): it loads and exports the call; running it needs a GPU
+    (tests/test_gpu_binding.py)"""
+    from oracle import refcpu
+    if not refcpu.available("binding"):
+        pytest.skip("binding flavour not built")
+    import ctypes
+    lib = ctypes.CDLL(refcpu.lib_path("binding"))
+    assert hasattr(lib, "vref_render_cuda") and hasattr(lib, "vref_render")
+    assert not hasattr(ctypes.CDLL(refcpu.lib_path("parity")), "vref_render_cuda")

@@ -294,4 +294,22 @@ std::vector<glm::vec3> scene_integrator_cuda(const integrator_data& settings, co
   if (rc != VIMG_OK) throw std::runtime_error(std::string("vimg_render: ") + vimg_last_error());
   return image;
 }
+
+std::vector<glm::vec3> scene_integrator_cuda_multi(const integrator_data& settings, const BVH& bvh,
+                                                   const std::vector<std::unique_ptr<Surface>>& prims,
+                                                   const std::vector<Emitter*>& lights, integrator_func func,
+                                                   const std::vector<int>& device_ids) {
+  auto fs = vimg_flatten_scene(settings, bvh, prims, lights);
+  vimg_render_params rp{};
+  rp.integrator = static_cast<uint32_t>(func);
+  rp.samples = settings.samples;
+  rp.depth = settings.depth;
+  std::vector<glm::vec3> image(size_t(settings.resolution[0]) * settings.resolution[1]);
+  // 8x8 tiles dealt round-robin, like the reference's own work list (include/integrators.h:57-65,101):
+  // the image is the one-device image bit for bit
+  int rc = vimg_render_multi(&fs->desc, device_ids.data(), static_cast<uint32_t>(device_ids.size()), &rp,
+                             VIMG_PARTITION_TILE, reinterpret_cast<float*>(image.data()), nullptr);
+  if (rc != VIMG_OK) throw std::runtime_error(std::string("vimg_render_multi: ") + vimg_last_error());
+  return image;
+}
 #endif  // VIMG_ADAPTER_FLATTEN_ONLY

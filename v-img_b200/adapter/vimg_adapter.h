@@ -60,3 +60,9 @@ std::vector<glm::vec3> scene_integrator_cuda(const integrator_data& settings, co
                                              const std::vector<std::unique_ptr<Surface>>& prims,
                                              const std::vector<Emitter*>& lights,
                                              integrator_func func, int device_id = 0);
+
+// The same on several GPUs of the box (vimg_render_multi, tile partition: bit-identical to one device).
+std::vector<glm::vec3> scene_integrator_cuda_multi(const integrator_data& settings, const BVH& bvh,
+                                                   const std::vector<std::unique_ptr<Surface>>& prims,
+                                                   const std::vector<Emitter*>& lights, integrator_func func,
+                                                   const std::vector<int>& device_ids);

@@ -11,7 +11,9 @@
 #include <map>
 #include <mutex>
 #include <numbers>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vimg_kernels.cuh"
@@ -816,8 +818,10 @@ __global__ void qw_combine_kernel(const __grid_constant__ DScene sc, const __gri
   if (p >= args.n_local_pixels || !wf_pixel_xy(args, sc.cam, p, px, py)) return;
   const size_t image_index = px + ((size_t)(sc.cam.res[1] - 1 - py) * sc.cam.res[0]);
   const float* part = args.partial + 3 * image_index * args.streams;
-  V3 acc = mk3(part[0], part[1], part[2]);
-  for (uint32_t k = 1; k < args.streams; ++k) acc = acc + mk3(part[3 * k], part[3 * k + 1], part[3 * k + 2]);
+  // this rank's ranges (all of them unless the samples are partitioned over ranks), in range order
+  uint32_t k = args.s_rank;
+  V3 acc = mk3(part[3 * k], part[3 * k + 1], part[3 * k + 2]);
+  for (k += args.s_n_ranks; k < args.streams; k += args.s_n_ranks) acc = acc + mk3(part[3 * k], part[3 * k + 1], part[3 * k + 2]);
   acc = acc / (float)args.samples;
   out[3 * image_index] = acc.x;
   out[3 * image_index + 1] = acc.y;
@@ -1129,6 +1133,7 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
     CU_TRY(cudaStreamWaitEvent(caller, s->ws->qw[p].done, 0));
   }
   if (w.streams > 1) {
+    // (a rank that renders a single range of a sample-range partition still divides its sum by spp here)
     qw_combine_kernel<<<(w.n_local_pixels + QW_THREADS - 1) / QW_THREADS, QW_THREADS, 0, caller>>>(s->d, w, out);
     ++launches;
   }
@@ -1157,7 +1162,7 @@ static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, bool f
 
 template <bool COUNT>
 static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator, float* out, cudaStream_t st,
-                         uint32_t flags = 0, uint32_t spp_streams = 1) {
+                         uint32_t flags = 0, uint32_t spp_streams = 1, uint32_t s_rank = 0, uint32_t s_n_ranks = 1) {
   s->last_launches = 1;
   std::memset(s->stage_ms, 0, sizeof(s->stage_ms));
   std::memset(s->stage_launches, 0, sizeof(s->stage_launches));
@@ -1201,7 +1206,13 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
     if (a.single_x >= 0 || (integrator == VIMG_INTEGRATOR_MATERIAL && a.depth == 0)) w.streams = 1;
     if ((uint64_t)w.n_local_pixels * w.streams > 0xffffffffull || w.streams > 0xffffu)
       return fail(VIMG_ERR_INVALID_ARGUMENT, "spp_streams too large for this frame");
-    w.n_local_units = w.n_local_pixels * w.streams;
+    // sample-range partition over ranks: this rank's share of every pixel's ranges
+    w.s_rank = s_rank;
+    w.s_n_ranks = std::max(1u, s_n_ranks);
+    if (w.s_n_ranks > 1 && w.streams < w.s_n_ranks)
+      return fail(VIMG_ERR_INVALID_ARGUMENT, "VIMG_PARTITION_SPP needs spp_streams (and samples) >= n_ranks");
+    w.my_streams = (w.streams - w.s_rank + w.s_n_ranks - 1) / w.s_n_ranks;
+    w.n_local_units = w.n_local_pixels * w.my_streams;
     w.partial = nullptr;
     const bool fast = (flags & VIMG_FLAG_FAST) != 0;
     w.fresh_stack = ((flags & VIMG_FLAG_FRESH_STACK) || w.streams > 1 || fast) ? 1u : 0u;
@@ -1351,26 +1362,33 @@ int vimg_scene_create(const vimg_scene_desc* desc, int device_id, vimg_scene** o
   return VIMG_OK;
 }
 
-int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_dev_rgb, void* stream,
+}  // extern "C"
+
+// Render this rank's share of the frame into `frame` (W*H*3 floats in memory the device can write: the scene's own
+// frame, or -- vimg_render_multi -- the frame of device 0 mapped through peer access, so that the kernels'
+// pixel stores assemble the image over NVLink).  Returns after the stream is synchronised.
+static int render_into(vimg_scene* s, const vimg_render_params* p, float* frame, bool zero_fill, cudaStream_t st,
                        vimg_render_stats* stats) {
   int rc = check_params(s, p);
   if (rc != VIMG_OK) return rc;
-  if (!out_dev_rgb) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU_TRY(cudaSetDevice(s->device));
-  const RenderArgs a = make_args(s, p->samples, p->depth, p->n_ranks > 1 ? p->rank : 0, p->n_ranks);
+  const bool by_spp = p->partition == VIMG_PARTITION_SPP && p->n_ranks > 1;
+  if (by_spp && p->integrator != VIMG_INTEGRATOR_MATERIAL && p->integrator != VIMG_INTEGRATOR_MIS)
+    return fail(VIMG_ERR_INVALID_ARGUMENT, "VIMG_PARTITION_SPP is for the material / mis integrators");
+  // sample-range partition: every rank renders all tiles, a share of every pixel's sample ranges
+  const RenderArgs a = make_args(s, p->samples, p->depth, (p->n_ranks > 1 && !by_spp) ? p->rank : 0, by_spp ? 1 : p->n_ranks);
+  const uint32_t s_rank = by_spp ? p->rank : 0, s_n = by_spp ? p->n_ranks : 1;
   CU_TRY(cudaMemsetAsync(s->d_counters, 0, sizeof(DCounters), st));
-  if (a.n_ranks > 1) CU_TRY(cudaMemsetAsync(s->d_frame, 0, (size_t)s->W * s->H * 3 * sizeof(float), st));
+  if (a.n_ranks > 1 && zero_fill) CU_TRY(cudaMemsetAsync(frame, 0, (size_t)s->W * s->H * 3 * sizeof(float), st));
   CU_TRY(cudaEventRecord(s->ev0, st));
   if (p->flags & VIMG_FLAG_COUNTERS)
-    rc = launch_render<true>(s, a, p->integrator, s->d_frame, st, p->flags, p->spp_streams);
+    rc = launch_render<true>(s, a, p->integrator, frame, st, p->flags, p->spp_streams, s_rank, s_n);
   else
-    rc = launch_render<false>(s, a, p->integrator, s->d_frame, st, p->flags, p->spp_streams);
+    rc = launch_render<false>(s, a, p->integrator, frame, st, p->flags, p->spp_streams, s_rank, s_n);
   if (rc != VIMG_OK) return rc;
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(s->ev1, st));
   CU_TRY(cudaStreamSynchronize(st));
-  *out_dev_rgb = s->d_frame;
   if (stats) {
     DCounters c;
     CU_TRY(cudaMemcpy(&c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -1396,6 +1414,165 @@ int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_d
             c.stage_clk[3], c.stage_clk[4], c.stage_clk[5], c.stage_clk[6]);
 #endif
   }
+  return VIMG_OK;
+}
+
+extern "C" {
+
+int vimg_render_device(vimg_scene* s, const vimg_render_params* p, float** out_dev_rgb, void* stream,
+                       vimg_render_stats* stats) {
+  if (!s || !out_dev_rgb) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  const int rc = render_into(s, p, s->d_frame, true, static_cast<cudaStream_t>(stream), stats);
+  if (rc == VIMG_OK) *out_dev_rgb = s->d_frame;
+  return rc;
+}
+
+}  // extern "C"
+
+// dst += src, element by element (device 0 pulling a peer's frame over NVLink)
+__global__ void multi_add_frame_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(dst)[i];
+  const float4 b = reinterpret_cast<const float4*>(src)[i];
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+  reinterpret_cast<float4*>(dst)[i] = a;
+}
+
+extern "C" {
+
+int vimg_render_multi(const vimg_scene_desc* desc, const int* device_ids, uint32_t n_devices,
+                      const vimg_render_params* params, uint32_t partition, float* out_rgb, vimg_render_stats* stats) {
+  if (!desc || !device_ids || !params || !out_rgb || n_devices == 0) return fail(VIMG_ERR_INVALID_ARGUMENT, "null argument");
+  if (partition > VIMG_PARTITION_SPP) return fail(VIMG_ERR_INVALID_ARGUMENT, "unknown partition");
+  const int n_visible = vimg_cuda_device_count();
+  if (n_visible == 0) return fail(VIMG_ERR_NO_DEVICE, "no CUDA device visible: the cuda render device has no CPU fallback");
+  for (uint32_t i = 0; i < n_devices; ++i) {
+    if (device_ids[i] < 0 || device_ids[i] >= n_visible) return fail(VIMG_ERR_INVALID_ARGUMENT, "device id out of range");
+    for (uint32_t j = 0; j < i; ++j)
+      if (device_ids[j] == device_ids[i]) return fail(VIMG_ERR_INVALID_ARGUMENT, "device listed twice");
+  }
+  const uint32_t n = n_devices;
+  const int dev0 = device_ids[0];
+  std::vector<vimg_scene*> scenes(n, nullptr);
+  std::vector<int> rcs(n, VIMG_OK);
+  std::vector<std::string> errs(n);
+  // every worker keeps its thread-local error text for the caller
+  auto run_all = [&](auto&& fn) {
+    std::vector<std::thread> th;
+    for (uint32_t i = 1; i < n; ++i)
+      th.emplace_back([&, i] {
+        rcs[i] = fn(i);
+        if (rcs[i] != VIMG_OK) errs[i] = g_last_error;
+      });
+    rcs[0] = fn(0);
+    if (rcs[0] != VIMG_OK) errs[0] = g_last_error;
+    for (auto& t : th) t.join();
+    for (uint32_t i = 0; i < n; ++i)
+      if (rcs[i] != VIMG_OK) return fail(rcs[i], "device " + std::to_string(device_ids[i]) + ": " + errs[i]);
+    return (int)VIMG_OK;
+  };
+  auto destroy_all = [&] {
+    run_all([&](uint32_t i) {
+      vimg_scene_destroy(scenes[i]);
+      scenes[i] = nullptr;
+      return (int)VIMG_OK;
+    });
+  };
+  // ---- the scene on every device (one host thread each: flattening to the GPU layout is host work)
+  int rc = run_all([&](uint32_t i) { return vimg_scene_create(desc, device_ids[i], &scenes[i]); });
+  if (rc != VIMG_OK) {
+    const std::string keep = g_last_error;
+    destroy_all();
+    return fail(rc, keep);
+  }
+  const size_t n_floats = (size_t)scenes[0]->W * scenes[0]->H * 3;
+  // ---- peer access: TILE: device i stores into device 0's frame; SPP: device 0 loads device i's frame
+  bool peer = n > 1;
+  for (uint32_t i = 1; i < n && peer; ++i) {
+    int can = 0;
+    const int from = partition == VIMG_PARTITION_TILE ? device_ids[i] : dev0;
+    const int to = partition == VIMG_PARTITION_TILE ? dev0 : device_ids[i];
+    if (cudaDeviceCanAccessPeer(&can, from, to) != cudaSuccess || !can) {
+      cudaGetLastError();
+      peer = false;
+      break;
+    }
+    cudaSetDevice(from);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer = false;
+    cudaGetLastError();
+  }
+  if (const char* e = std::getenv("VIMG_MULTI_NO_PEER")) peer = peer && std::atoi(e) == 0;
+
+  std::vector<vimg_render_stats> st(n);
+  std::vector<std::vector<float>> staged(peer ? 0 : n);
+  const auto t0 = std::chrono::steady_clock::now();
+  rc = run_all([&](uint32_t i) -> int {
+    vimg_render_params p = *params;
+    p.rank = i;
+    p.n_ranks = n;
+    p.partition = partition;
+    const bool to_dev0 = peer && partition == VIMG_PARTITION_TILE;
+    float* frame = to_dev0 ? scenes[0]->d_frame : scenes[i]->d_frame;
+    // TILE through peer memory: every pixel has exactly one writer, nothing to zero
+    int r = render_into(scenes[i], &p, frame, !to_dev0, nullptr, &st[i]);
+    if (r != VIMG_OK) return r;
+    if (!peer && n > 1) {
+      staged[i].resize(n_floats);
+      cudaError_t e = cudaMemcpy(staged[i].data(), scenes[i]->d_frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return fail(VIMG_ERR_CUDA, std::string("partial frame D2H: ") + cudaGetErrorString(e));
+    }
+    return VIMG_OK;
+  });
+  if (rc == VIMG_OK) {
+    cudaSetDevice(dev0);
+    if (n == 1 || peer) {
+      if (n > 1 && partition == VIMG_PARTITION_SPP) {
+        const size_t n4 = n_floats / 4;  // W * H * 3 floats: a multiple of 4 whenever W * H is; the tail below
+        for (uint32_t i = 1; i < n; ++i) {
+          if (n4) multi_add_frame_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(scenes[0]->d_frame, scenes[i]->d_frame, n4);
+          for (size_t k = 4 * n4; k < n_floats; ++k) {  // at most 3 floats
+            float a = 0, b = 0;
+            cudaMemcpy(&a, scenes[0]->d_frame + k, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&b, scenes[i]->d_frame + k, 4, cudaMemcpyDeviceToHost);
+            a += b;
+            cudaMemcpy(scenes[0]->d_frame + k, &a, 4, cudaMemcpyHostToDevice);
+          }
+        }
+      }
+      const cudaError_t e = cudaMemcpy(out_rgb, scenes[0]->d_frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = fail(VIMG_ERR_CUDA, std::string("frame D2H: ") + cudaGetErrorString(e));
+    } else {
+      // no peer access: the partial frames meet in host memory, added in device order
+      std::memcpy(out_rgb, staged[0].data(), n_floats * sizeof(float));
+      for (uint32_t i = 1; i < n; ++i)
+        for (size_t k = 0; k < n_floats; ++k) out_rgb[k] += staged[i][k];
+    }
+  }
+  const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (rc == VIMG_OK && stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    for (uint32_t i = 0; i < n; ++i) {
+      stats->rays_closest += st[i].rays_closest;
+      stats->rays_shadow += st[i].rays_shadow;
+      stats->inner_nodes += st[i].inner_nodes;
+      stats->leaf_nodes += st[i].leaf_nodes;
+      stats->tri_tests += st[i].tri_tests;
+      stats->sphere_tests += st[i].sphere_tests;
+      stats->nan_samples += st[i].nan_samples;
+      stats->samples += st[i].samples;
+      stats->kernel_launches += st[i].kernel_launches;
+      stats->kernel_ms = std::max(stats->kernel_ms, st[i].kernel_ms);
+    }
+    stats->total_ms = wall_ms;
+  }
+  const std::string keep = g_last_error;
+  destroy_all();
+  if (rc != VIMG_OK) return fail(rc, keep);
   return VIMG_OK;
 }
 

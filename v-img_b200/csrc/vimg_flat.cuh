@@ -525,10 +525,10 @@ qf_path_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwStat
             uint32_t u = pbase + __popc(m & lane_lt), p = 0;
             uint32_t px = 0, py = 0;
             bool got = false;
-            while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.streams, px, py)))
+            while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.my_streams, px, py)))
               u = atomicAdd(st.next_pixel, 1u);
             if (got) {
-              range = u - p * args.streams;
+              range = args.s_rank + (u - p * args.my_streams) * args.s_n_ranks;
               pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), range);
               acc = mk3(0.f);
               s = (uint32_t)(((uint64_t)range * args.samples) / args.streams);

@@ -620,10 +620,10 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
           uint32_t u = pbase + __popc(m & lane_lt), p = 0;
           uint32_t px = 0, py = 0;
           bool got = false;
-          while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.streams, px, py)))
+          while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.my_streams, px, py)))
             u = atomicAdd(st.next_pixel, 1u);
           if (got) {
-            range = u - p * args.streams;
+            range = args.s_rank + (u - p * args.my_streams) * args.s_n_ranks;
             if (!MIS && args.depth == 0) {
               // material_integrator with depth 0 never traces: every sample is vec3(0)
               const size_t image_index = px + ((size_t)(H - 1 - py) * W);

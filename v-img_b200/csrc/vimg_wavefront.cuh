@@ -71,6 +71,10 @@ struct WfArgs {
   // u / streams) and, for streams > 1, the partial sums [image_index][range] x rgb
   uint32_t streams, n_local_units;
   float* partial;
+  // sample-range partition over ranks (VIMG_PARTITION_SPP): this rank renders the ranges s_rank, s_rank +
+  // s_n_ranks, ... of EVERY pixel -- my_streams of them; unit u = range s_rank + (u % my_streams) * s_n_ranks
+  // of local pixel u / my_streams.  Tile partition: s_rank 0, s_n_ranks 1, my_streams = streams.
+  uint32_t s_rank, s_n_ranks, my_streams;
   // 1: every traversal starts from an empty stack (VIMG_FLAG_FRESH_STACK, or streams > 1); 0: a path's
   // closest-hit traversal inherits what its shadow ray's traversal left (the reference's thread_stack)
   uint32_t fresh_stack;

@@ -16,6 +16,7 @@ FLAG_STAGE_TIMES = 8      # queue wavefront: serial launches, per-stage device t
 FLAG_FRESH_STACK = 16     # do not reproduce the reference's carried-over traversal stack (faster)
 FLAG_FAST = 32            # tolerance mode: fast-math kernels + device-side BVH re-layout (relMSE contract)
 STAGES = ("trace", "classify", "shade_principled", "shade_lambertian", "shade_dielectric", "end")
+PARTITIONS = {"tile": 0, "spp": 1}  # vimg_partition
 PIPELINES = {None: 0, "block": FLAG_PIPELINE_BLOCK, "queue": FLAG_PIPELINE_QUEUE}
 
 
@@ -71,7 +72,7 @@ TONEMAPPERS = {"clamp": 0, "agx": 1, "reinhard": 2, "aces": 3, "none": 4}
 class RenderParams(C.Structure):
     _fields_ = [("integrator", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32),
                 ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("flags", C.c_uint32),
-                ("spp_streams", C.c_uint32)]
+                ("spp_streams", C.c_uint32), ("partition", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
@@ -92,7 +93,7 @@ class RenderStats(C.Structure):
 
 EXPORTS = ("vimg_cuda_device_count", "vimg_last_error", "vimg_scene_create", "vimg_scene_destroy",
            "vimg_scene_device_bytes", "vimg_render", "vimg_render_device", "vimg_trace_pixel",
-           "vimg_trace_ids", "vimg_release_workspaces", "vimg_postprocess", "vimg_render_srgb8", "vimg_heatmap",
+           "vimg_trace_ids", "vimg_release_workspaces", "vimg_render_multi", "vimg_postprocess", "vimg_render_srgb8", "vimg_heatmap",
            "vimg_mip_chain_levels", "vimg_build_mip_chain", "vimg_build_envmap_cdf",
            "vimg_convert_srgb8_to_linear", "vimg_convert_rgb8_to_normal", "vimg_build_image_texture", "vimg_libm_eval",
            "vimg_scene_desc_save", "vimg_scene_desc_load", "vimg_scene_desc_free")
@@ -126,6 +127,8 @@ def load_library():
                                 C.POINTER(RenderStats)]
     lib.vimg_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(C.c_void_p),
                                        C.c_void_p, C.POINTER(RenderStats)]
+    lib.vimg_render_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.POINTER(RenderParams), C.c_uint32,
+                                      C.c_void_p, C.POINTER(RenderStats)]
     lib.vimg_postprocess.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_double)]
     lib.vimg_render_srgb8.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.c_void_p,
@@ -151,6 +154,11 @@ def load_library():
     lib.vimg_scene_desc_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
+
+
+def release_workspaces():
+    """Free the idle per-device render workspaces and scene arenas (vimg_release_workspaces)."""
+    load_library().vimg_release_workspaces()
 
 
 def device_count():
@@ -297,15 +305,15 @@ class Scene:
         return int(self._lib.vimg_scene_device_bytes(self._h))
 
     def _params(self, func, samples, depth, rank, n_ranks, counters, pipeline=None, stage_times=False,
-                spp_streams=1, fresh_stack=False, fast=False):
+                spp_streams=1, fresh_stack=False, fast=False, partition="tile"):
         flags = (FLAG_COUNTERS if counters else 0) | PIPELINES[pipeline] | (FLAG_STAGE_TIMES if stage_times else 0)
         flags |= FLAG_FRESH_STACK if fresh_stack else 0
         flags |= FLAG_FAST if fast else 0
         return RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, rank, n_ranks, flags,
-                            int(spp_streams))
+                            int(spp_streams), PARTITIONS[partition])
 
     def scene_integrator(self, func, samples, depth, rank=0, n_ranks=1, counters=False, out=None,
-                         pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False):
+                         pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False, partition="tile"):
         """Mirror of scene_integrator<F>() (include/integrators.h:36-153).
 
         Returns (image float32 [H, W, 3] in HOST memory, row 0 = top; stats dict).
@@ -323,17 +331,17 @@ class Scene:
         assert out.dtype == np.float32 and out.size == self.height * self.width * 3
         st = RenderStats()
         p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack,
-                         fast)
+                         fast, partition)
         _check(self._lib, self._lib.vimg_render(self._h, C.byref(p), out.ctypes.data, C.byref(st)),
                "vimg_render")
         return out, st.as_dict()
 
     def render_device(self, func, samples, depth, rank=0, n_ranks=1, counters=False, stream=None,
-                      pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False):
+                      pipeline=None, stage_times=False, spp_streams=1, fresh_stack=False, fast=False, partition="tile"):
         """Render and leave the frame in HBM.  Returns (device pointer, stats dict)."""
         st = RenderStats()
         p = self._params(func, samples, depth, rank, n_ranks, counters, pipeline, stage_times, spp_streams, fresh_stack,
-                         fast)
+                         fast, partition)
         dev = C.c_void_p()
         _check(self._lib, self._lib.vimg_render_device(self._h, C.byref(p), C.byref(dev), stream,
                                                        C.byref(st)), "vimg_render_device")
@@ -386,6 +394,24 @@ class Scene:
                                                    t.ctypes.data if want_t else None),
                "vimg_trace_ids")
         return ids, t
+
+
+def render_multi(desc_ptr, devices, func, samples, depth, partition="tile", spp_streams=1, fast=False, fresh_stack=False,
+                 out=None):
+    """vimg_render_multi: the whole frame on several GPUs of this box behind one call.
+    desc_ptr: address of a vimg_scene_desc (LoadedDesc.ptr, or the adapter's).  -> (image [H, W, 3], stats dict)"""
+    lib = load_library()
+    head = _DescHead.from_address(desc_ptr)
+    w, h = head.camera.resolution[0], head.camera.resolution[1]
+    if out is None:
+        out = np.empty((h, w, 3), np.float32)
+    flags = (FLAG_FAST if fast else 0) | (FLAG_FRESH_STACK if fresh_stack else 0)
+    p = RenderParams(INTEGRATORS[func], int(samples), int(depth) & UINT32_MAX, 0, 1, flags, int(spp_streams), 0)
+    ids = (C.c_int * len(devices))(*devices)
+    st = RenderStats()
+    _check(lib, lib.vimg_render_multi(desc_ptr, ids, len(devices), C.byref(p), PARTITIONS[partition], out.ctypes.data,
+                                      C.byref(st)), "vimg_render_multi")
+    return out, st.as_dict()
 
 
 def postprocess(img, tonemapper="clamp", device=0, want_srgb=True):
