@@ -449,9 +449,10 @@ def run_scene(gpu, vimg, key, args, hbm_peak, peak_src, want_cpu):
     out["scene_device_bytes"] = scene.device_bytes
     samples = w.width * w.height * w.spp
     kw = mode_kwargs("fast", min(streams, w.spp))
-    warm_spp = max(1, min(w.spp, 8 if big else w.spp))
+    warm_spp = max(1, min(w.spp, 16 if big else w.spp))
     time_frames(gpu, scene, w.integrator, warm_spp, w.depth, mode_kwargs("fast", min(streams, warm_spp)), 1, 1)
-    r = time_frames(gpu, scene, w.integrator, w.spp, w.depth, kw, args.scene_steps, 0)
+    n_steps = args.scene_steps if args.scene_steps else (1 if samples > 4e9 else 2)
+    r = time_frames(gpu, scene, w.integrator, w.spp, w.depth, kw, n_steps, 0)
     out["fast"] = {"mrays_per_s": r["rays"] / r["seconds"] / 1e6, "spp_mpix_per_s": samples * r["steps"] / r["seconds"] / 1e6,
                    "ms_per_step": r["ms_per_step"], "steps": r["steps"], "spp_streams": kw["spp_streams"],
                    "rays_per_sample": r["rays"] / (samples * r["steps"]), "gpu_launches": r["launches"], "nan_samples": r["nan_samples"]}
@@ -629,7 +630,7 @@ def main():
                     help="fast mode: sample ranges per pixel with their own RNG streams (vimg_render_params.spp_streams)")
     ap.add_argument("--scenes", default="default",
                     help="other BASELINE configs measured into `scenes`: default (N = 1: C1,C2,C4,C5; N > 1: C5), none, or a list")
-    ap.add_argument("--scene-steps", type=int, default=1, help="timed steps per entry of `scenes`")
+    ap.add_argument("--scene-steps", type=int, default=0, help="timed steps per entry of `scenes` (0: 2, or 1 for frames of > 4 G samples)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the postprocess / scene_prep timings")
     ap.add_argument("--cpu-budget", type=float, default=14.0, help="seconds of CPU work for the headline cpu_baseline")

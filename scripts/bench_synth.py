@@ -9,6 +9,7 @@ from oracle import refcpu
 G, W, H, spp = [int(a) for a in sys.argv[1:5]]
 integ = sys.argv[5] if len(sys.argv) > 5 and not sys.argv[5].startswith("-") else "mis"
 streams = int(os.environ.get("SPP_STREAMS", "1"))
+fast = os.environ.get("FAST", "0") == "1"
 vimg = load_product()
 t0 = time.time()
 rs = refcpu.RefScene.synthetic(G=G, width=W, height=H, tex_size=2048, env_w=2048, env_h=1024, spp=spp, depth=64,
@@ -18,10 +19,10 @@ sc = vimg.Scene(rs.desc_ptr())
 t2 = time.time()
 BY = {"inner_nodes": 56, "leaf_nodes": 8, "tri_tests": 56, "sphere_tests": 24}
 out = {"G": G, "tris": rs.n_prims, "nodes": rs.n_nodes, "bvh_depth": rs.max_depth, "res": [W, H], "spp": spp,
-       "integrator": integ, "spp_streams": streams, "host_build_s": t1 - t0, "bvh_build_s": rs.bvh_build_s, "upload_s": t2 - t1,
+       "integrator": integ, "spp_streams": streams, "fast": fast, "host_build_s": t1 - t0, "bvh_build_s": rs.bvh_build_s, "upload_s": t2 - t1,
        "scene_bytes": sc.device_bytes}
 for rep in range(3):
-    img, st = sc.scene_integrator(integ, spp, 64, spp_streams=streams)
+    img, st = sc.scene_integrator(integ, spp, 64, spp_streams=streams, fast=fast)
 rays = st["rays_closest"] + st["rays_shadow"]
 out.update(kernel_ms=st["kernel_ms"], mrays_s=rays / st["kernel_ms"] / 1e3, spp_mpix_s=W * H * spp / st["kernel_ms"] / 1e3,
            rays_per_sample=rays / (W * H * spp))

@@ -387,7 +387,10 @@ qf_path_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwStat
 
     // finish the current sample of this slot's pixel (include/integrators.h:128-137)
     auto finish = [&](V3 result) {
-      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) nan_samples++;
+      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) {
+        nan_samples++;
+        result = mk3(0.f);  // counted and dropped (the reference adds it: the pixel turns NaN)
+      }
       acc = acc + result;
       n_samples++;
       f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
