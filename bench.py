@@ -422,7 +422,7 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
     achieved = bytes_per_ray * rays_per_launch / launch_s / 1e9
     total = sum(tst["stage_ms"].values())
     flat = bool(kw.get("fast")) and w.n_prims <= 32
-    kernel = "qf_trace_flat_kernel" if flat else "qw_trace_kernel"
+    kernel = "qv_trace_flat_kernel" if flat else "qw_trace_kernel"
     traffic, traffic_src = ncu_traffic(kernel, w.key)
     shares = {k: v / total for k, v in tst["stage_ms"].items() if tst["stage_launches"][k]}
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -14,7 +14,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     res = {}
     streams = int(os.environ.get("STREAMS", "1"))
     for label, kw, env, mode in (("exact", {}, None, "2"), ("fast_bvh", {"fast": True}, "0", "2"), ("fast_flat", {"fast": True}, "32", "1"),
-                                 ("fast_fused", {"fast": True}, "32", "2")):
+                                 ("fast_fused", {"fast": True}, "32", "2"), ("fast_stream", {"fast": True}, "32", "3")):
         if label != "exact":
             kw["spp_streams"] = streams
         os.environ["VIMG_FLAT_MODE"] = mode
@@ -43,7 +43,7 @@ for lib in sys.argv[3:]:
         base = ex
     assert np.array_equal(ex, base), "bit-exact image moved between libraries"
     m0 = np.array(r["exact"]["mean"])
-    for k in ("fast_bvh", "fast_flat", "fast_fused"):
+    for k in ("fast_bvh", "fast_flat", "fast_fused", "fast_stream"):
         img = np.load(out + "." + k + ".npy")
         print(f"{tag:24s} {k:10s} {r[k]['ms']:8.2f} ms (exact {r['exact']['ms']:.2f})  mean/exact {np.array(r[k]['mean']) / m0}  "
               f"relMSE {rel_mse(img, ex):.3e}  nan {r[k]['nan']}  rays/exact {r[k]['rays'] / r['exact']['rays']:.5f}", flush=True)

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "vimg_kernels.cuh"
+#include "vimg_stream.cuh"
 #include "vimg_post.cuh"
 #include "vimg_prep.cuh"
 
@@ -98,13 +99,28 @@ struct QwPool {
 // its device from a process-wide cache at its first render and gives it back when it is
 // destroyed: a caller that creates a scene per frame (bench.py's end-to-end step, the
 // reference's main.cpp) does not pay cudaMalloc / cudaFree of ~1 GB inside every render.
+// slot lines and queues of one pool of the streamed pipeline (vimg_stream.cuh); streams and events are the QwPool's
+struct QvPool {
+  QvState st{};
+  void* mem = nullptr;
+  uint32_t capacity = 0;
+  QvCounters* h_cnt = nullptr;  // pinned snapshots
+  void destroy() {
+    if (mem) cudaFree(mem);
+    if (h_cnt) cudaFreeHost(h_cnt);
+    *this = QvPool{};
+  }
+};
+
 struct QwWorkspace {
   QwPool qw[QW_MAX_POOLS];
+  QvPool qv[2];
   uint32_t* d_next_pixel = nullptr;
   float* d_partial = nullptr;  // spp_streams > 1: per-range partial sums, W*H*streams*3 floats
   size_t partial_floats = 0;
   void destroy() {
     for (QwPool& p : qw) p.destroy();
+    for (QvPool& p : qv) p.destroy();
     if (d_next_pixel) cudaFree(d_next_pixel);
     if (d_partial) cudaFree(d_partial);
     d_next_pixel = nullptr;
@@ -1154,9 +1170,217 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
   return VIMG_OK;
 }
 
+// ---- the streamed pipeline (vimg_stream.cuh): tolerance build, flat scenes ---------------------------------
+static int qv_reserve(vimg_scene* s, QwPool& streams, QvPool& pool, uint32_t n) {
+  if (!streams.main) {  // streams and events of the pool (shared with the slot-record pipeline)
+    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&streams.h_cnt), 2 * sizeof(QwCounters)));
+    CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&streams.h_next_pixel), 2 * sizeof(uint32_t)));
+    CU_TRY(cudaStreamCreateWithFlags(&streams.main, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CU_TRY(cudaStreamCreateWithFlags(&streams.side[k], cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreateWithFlags(&streams.snap[k], cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&streams.join[k], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&streams.fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&streams.done, cudaEventDisableTiming));
+  }
+  if (!pool.h_cnt) CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&pool.h_cnt), 2 * sizeof(QvCounters)));
+  if (!s->ws->d_next_pixel) CU_TRY(cudaMalloc(&s->ws->d_next_pixel, sizeof(uint32_t)));
+  pool.st.next_pixel = s->ws->d_next_pixel;
+  if (pool.mem && pool.capacity >= n) {
+    pool.st.n_slots = n;
+    return VIMG_OK;
+  }
+  if (pool.mem) {
+    cudaFree(pool.mem);
+    pool.mem = nullptr;
+    pool.capacity = 0;
+  }
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t N = n;
+  const size_t o_line = carve(N * sizeof(QvLine));
+  size_t o_t[2][3], o_h[WF_NUM_CLASSES][2], o_e[2][2];
+  for (int k = 0; k < 2; ++k)
+    for (int a = 0; a < 3; ++a) o_t[k][a] = carve(N * 16);
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k)
+    for (int a = 0; a < 2; ++a) o_h[k][a] = carve(N * 16);
+  for (int k = 0; k < 2; ++k)
+    for (int a = 0; a < 2; ++a) o_e[k][a] = carve(N * 16);
+  const size_t o_cnt = carve(sizeof(QvCounters));
+  CU_TRY(cudaMalloc(&pool.mem, off));
+  pool.capacity = n;
+  char* b = static_cast<char*>(pool.mem);
+  QvState& q = pool.st;
+  q.n_slots = n;
+  q.line = reinterpret_cast<QvLine*>(b + o_line);
+  for (int k = 0; k < 2; ++k) {
+    q.ta[k] = reinterpret_cast<float4*>(b + o_t[k][0]);
+    q.tb[k] = reinterpret_cast<float4*>(b + o_t[k][1]);
+    q.tc[k] = reinterpret_cast<float4*>(b + o_t[k][2]);
+    q.ea[k] = reinterpret_cast<float4*>(b + o_e[k][0]);
+    q.eb[k] = reinterpret_cast<float4*>(b + o_e[k][1]);
+  }
+  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) {
+    q.ha[k] = reinterpret_cast<float4*>(b + o_h[k][0]);
+    q.hb[k] = reinterpret_cast<float4*>(b + o_h[k][1]);
+  }
+  q.cnt = reinterpret_cast<QvCounters*>(b + o_cnt);
+  return VIMG_OK;
+}
+
+// One frame: per pool  end(0) | trace(1) {shade(1) | end(1)} | trace(2) ...  until the ray and END queues are
+// empty; the host looks at the counters once per batch of iterations, one batch behind what it has queued.
+static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, float* out, cudaStream_t caller, bool stage_times) {
+  QwProfile prof;
+  const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
+  prof.on = print_profile || stage_times;
+  const bool concurrent = !prof.on && env_u32("VIMG_QW_SERIAL", 0) == 0;
+  const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
+  const uint32_t total_slots = std::max(1u, std::min(w.n_local_units, cap));
+  uint32_t n_pools = std::min<uint32_t>(2, std::max(1u, env_u32("VIMG_QW_POOLS", 2)));
+  if (!concurrent || total_slots < 65536u) n_pools = 1;
+  const uint32_t per_pool = (total_slots + n_pools - 1) / n_pools;
+  if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+  const QwKernelTable& kt = kernel_table(true);
+  int rc;
+  for (uint32_t p = 0; p < n_pools; ++p)
+    if ((rc = qv_reserve(s, s->ws->qw[p], s->ws->qv[p], per_pool)) != VIMG_OK) return rc;
+  CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
+  if (!s->d_flat) {
+    CU_TRY(cudaMalloc(&s->d_flat, vimg_fast_flat_scene_bytes()));
+    CU_TRY(launch_k(kt.build_flat, 1, (int)QF_FLAT_MAX_HOST, caller, s->d, s->d_flat));
+  }
+  const void* d_flat = s->d_flat;
+  DCounters* counters = s->d_counters;
+  cudaEvent_t start = s->ws->qw[0].done;
+  const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
+  const int full_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 8)));
+  std::vector<int> grid(n_pools, full_grid);
+  std::vector<bool> finished(n_pools, false);
+  for (uint32_t p = 0; p < n_pools; ++p) {
+    QwPool& st = s->ws->qw[p];
+    QvPool& pool = s->ws->qv[p];
+    if (p == 0) CU_TRY(cudaEventRecord(start, caller));
+    CU_TRY(cudaStreamWaitEvent(st.main, start, 0));
+    CU_TRY(cudaMemsetAsync(pool.st.line, 0, (size_t)per_pool * sizeof(QvLine), st.main));  // flags = 0: no pixel yet
+    QvCounters init{};
+    init.n_end[0] = per_pool;  // every slot starts in the END queue, without a pixel
+    pool.h_cnt[0] = init;
+    CU_TRY(cudaMemcpyAsync(pool.st.cnt, &pool.h_cnt[0], sizeof(init), cudaMemcpyHostToDevice, st.main));
+    CU_TRY(launch_k(kt.sv_init, slot_blocks, QW_THREADS, st.main, pool.st.ea[0], pool.st.eb[0], per_pool));
+  }
+  auto enqueue = [&](uint32_t p, uint32_t it) -> uint32_t {
+    QwPool& st = s->ws->qw[p];
+    const QvState& q = s->ws->qv[p].st;
+    const uint32_t parity = it & 1u;
+    uint32_t launches = 0;
+    cudaStream_t m = st.main;
+    if (it > 0) {
+      launch_k(kt.sv_trace_flat[count], grid[p], QW_THREADS, m, q, parity, d_flat, counters);
+      prof.mark(1);
+      ++launches;
+      // the shade launches only feed the next iteration; END consumes what trace (and the last shade launches) queued
+      cudaStream_t sp = m, sl = m;
+      if (concurrent) {
+        sp = st.side[0];
+        sl = st.side[1];
+        cudaEventRecord(st.fork, m);
+        cudaStreamWaitEvent(sp, st.fork, 0);
+        cudaStreamWaitEvent(sl, st.fork, 0);
+      }
+      if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
+        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], grid[p], QW_THREADS, sp, s->d, q, w, parity);
+        prof.mark(3);
+        ++launches;
+      }
+      if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
+        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], grid[p], QW_THREADS, sl, s->d, q, w, parity);
+        prof.mark(4);
+        ++launches;
+      }
+      if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
+        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], grid[p], QW_THREADS, sl, s->d, q, w, parity);
+        prof.mark(5);
+        ++launches;
+      }
+      if (concurrent) {
+        cudaEventRecord(st.join[0], sp);
+        cudaEventRecord(st.join[1], sl);
+      }
+    }
+    launch_k(kt.sv_end[integ], grid[p], QW_THREADS, m, s->d, q, w, parity, out, counters);
+    prof.mark(6);
+    ++launches;
+    if (concurrent && it > 0) {
+      cudaStreamWaitEvent(m, st.join[0], 0);
+      cudaStreamWaitEvent(m, st.join[1], 0);
+    }
+    return launches;
+  };
+  const uint32_t batch = std::max(1u, env_u32("VIMG_QW_BATCH", 8));
+  const bool shrink = env_u32("VIMG_QW_SHRINK", 1) != 0;
+  uint32_t launches = n_pools, it = 0;
+  prof.st = s->ws->qw[0].main;
+  prof.mark(0);
+  for (uint32_t b = 0;; ++b) {
+    for (uint32_t k = 0; k < batch; ++k)
+      for (uint32_t p = 0; p < n_pools; ++p)
+        if (!finished[p]) launches += enqueue(p, it + k);
+    it += batch;
+    CU_TRY(cudaGetLastError());
+    for (uint32_t p = 0; p < n_pools; ++p) {
+      if (finished[p]) continue;
+      QwPool& st = s->ws->qw[p];
+      QvPool& pool = s->ws->qv[p];
+      CU_TRY(cudaMemcpyAsync(&pool.h_cnt[b & 1], pool.st.cnt, sizeof(QvCounters), cudaMemcpyDeviceToHost, st.main));
+      CU_TRY(cudaMemcpyAsync(&st.h_next_pixel[b & 1], s->ws->d_next_pixel, sizeof(uint32_t), cudaMemcpyDeviceToHost, st.main));
+      CU_TRY(cudaEventRecord(st.snap[b & 1], st.main));
+    }
+    if (b > 0) {
+      bool all_done = true;
+      for (uint32_t p = 0; p < n_pools; ++p) {
+        if (finished[p]) continue;
+        QwPool& st = s->ws->qw[p];
+        CU_TRY(cudaEventSynchronize(st.snap[(b - 1) & 1]));
+        const QvCounters& hc = s->ws->qv[p].h_cnt[(b - 1) & 1];
+        const uint32_t par = (b * batch) & 1u;  // parity of the first iteration after batch b - 1
+        if (hc.n_trace[par] == 0 && hc.n_end[par] == 0)
+          finished[p] = true;  // batch b only ran empty iterations for this pool
+        else
+          all_done = false;
+        if (shrink && st.h_next_pixel[(b - 1) & 1] >= w.n_local_units) {
+          const uint64_t bound = (uint64_t)hc.n_trace[par] + hc.n_end[par];
+          grid[p] = (int)std::max<uint64_t>(1, std::min<uint64_t>(full_grid, (bound + QW_THREADS - 1) / QW_THREADS));
+        }
+      }
+      if (all_done) break;
+    }
+  }
+  for (uint32_t p = 0; p < n_pools; ++p) {
+    CU_TRY(cudaEventRecord(s->ws->qw[p].done, s->ws->qw[p].main));
+    CU_TRY(cudaStreamWaitEvent(caller, s->ws->qw[p].done, 0));
+  }
+  if (w.streams > 1) {
+    qw_combine_kernel<<<(w.n_local_pixels + QW_THREADS - 1) / QW_THREADS, QW_THREADS, 0, caller>>>(s->d, w, out);
+    ++launches;
+  }
+  prof.report(print_profile, s->stage_ms, s->stage_launches);
+  s->last_launches = launches;
+  return VIMG_OK;
+}
+
 template <bool COUNT>
 static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, bool fast, float* out, cudaStream_t st,
                      bool stage_times) {
+  // tolerance build, a scene of a few dozen primitives: the streamed pipeline over the flat lists (vimg_stream.cuh)
+  if (fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32))
+      && env_u32("VIMG_FLAT_MODE", 3) == 3)
+    return qv_render(s, w, integrator == VIMG_INTEGRATOR_MIS ? 1 : 0, COUNT, out, st, stage_times);
   return qw_render_t(s, w, integrator == VIMG_INTEGRATOR_MIS ? 1 : 0, COUNT, fast, out, st, stage_times);
 }
 

@@ -437,6 +437,218 @@ qw_classify_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Qw
 // thread <-> slot whose path ended (miss, emitter hit, Russian roulette, depth, no scattering)
 // or that has no pixel yet.  Finishes the sample (include/integrators.h:128-137), hands out
 // the next pixel of this rank's tile list and generates the next camera ray (:116-123).
+// What END reads for one slot and what it leaves behind (layout: the kernel's business, see ShadeIO)
+struct EndIO {
+  // in
+  float4 thr4, o4, d4, h0, cp4, L4, ap4;  // throughput | ray origin | ray direction | leaf, t, e0, e1 | pending contribution,
+                                          // last_pdf | L, sample counter | pixel accumulator, local pixel number
+  uint4 pa1, hb;                          // rng lo, rng hi, flags, depth counter | e2, inv_det, shadow ray occluded, -
+  // out: rng / flags of the slot, its sample counter and accumulator, and the camera ray of its next sample
+  uint4 rng_fd;
+  float4 L_s, acc_pixel, cam_o, cam_d;
+  bool new_ray;
+};
+
+// Finishes the sample of a path that ended (miss, emitter hit, Russian roulette, depth, no scattering;
+// include/integrators.h:128-137), hands out the next pixel of this rank's tile list and generates the next camera
+// ray (:116-123).  Called by EVERY thread of the warp (`valid`: this thread has a slot): the pixel hand-out votes.
+template <int INTEGRATOR>
+VD void end_item(const DScene& sc, const WfArgs& args, uint32_t* next_pixel, float* __restrict__ out, const bool valid,
+                 bool& exhausted, const uint32_t lane, const uint32_t lane_lt, uint32_t& nan_samples, uint32_t& n_samples,
+                 EndIO& io) {
+  constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
+  const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
+  const float4 thr4 = io.thr4, o4 = io.o4, d4 = io.d4, h0 = io.h0, cp4 = io.cp4, L4 = io.L4, ap4 = io.ap4;
+  const uint4 pa1 = io.pa1, hb = io.hb;
+  uint32_t f = pa1.z;
+  const uint32_t d = pa1.w;
+  Pcg32 rng;
+  rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
+  uint32_t range = f >> WF_RANGE_SHIFT;  // sample range of the pixel this slot works on
+  rng.inc = ((uint64_t)range << 1) | 1u;
+  V3 acc = xyz(ap4);
+  uint32_t s = __float_as_uint(L4.w), pixel = __float_as_uint(ap4.w);
+  const bool occl = hb.z != 0;
+  bool new_ray = false;
+
+  // finish the current sample of this slot's pixel (include/integrators.h:128-137)
+  auto finish = [&](V3 result) {
+    if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) {
+      nan_samples++;
+#ifdef VIMG_FAST
+      result = mk3(0.f);  // tolerance build: a NaN sample is counted and dropped (the reference adds it: the pixel turns NaN)
+#endif
+    }
+    acc = acc + result;
+    n_samples++;
+    f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
+    s = s + 1;
+    if (args.streams == 1) {
+      if (s == args.samples) {
+        const V3 px_col = acc / (float)args.samples;
+        uint32_t px, py;
+        wf_pixel_xy(args, sc.cam, pixel, px, py);
+        const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+        float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+        o[0] = px_col.x;
+        o[1] = px_col.y;
+        o[2] = px_col.z;
+        f &= ~WF_ALIVE;
+      }
+    } else if (s == (uint32_t)(((uint64_t)(range + 1) * args.samples) / args.streams)) {
+      // end of this sample range: its partial sum; qw_combine_kernel adds the ranges in order
+      uint32_t px, py;
+      wf_pixel_xy(args, sc.cam, pixel, px, py);
+      const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+      float* o = args.partial + 3 * (image_index * args.streams + range);
+      o[0] = acc.x;
+      o[1] = acc.y;
+      o[2] = acc.z;
+      f &= ~WF_ALIVE;
+    }
+  };
+
+  if (valid && (f & WF_IN_PATH)) {
+    // pending shadow ray of the last bounce (mis_integrator.cpp:64-78)
+    V3 L = xyz(L4);
+#ifdef VIMG_DEBUG_NEE
+    if (MIS) printf("D end: s=%u nee=%d valid=%d occl=%d c=%.9g %.9g %.9g L=%.9g %.9g %.9g END=%d leaf=%d lastpdf=%.9g\n", s, (f & WF_NEE) != 0, (f & WF_NEE_VALID) != 0, (int)occl,
+                    cp4.x, cp4.y, cp4.z, L4.x, L4.y, L4.z, (f & WF_END) != 0, __float_as_int(h0.x), cp4.w);
+#endif
+    if (MIS && (f & WF_NEE) && (f & WF_NEE_VALID) && !occl) L = L + xyz(cp4);
+    if (f & WF_END) {
+      finish(MIS ? L : xyz(cp4));
+    } else {
+      Ray ray;
+      ray.o = xyz(o4);
+      ray.dir = xyz(d4);
+      ray.minT = 0.0001f;
+      ray.maxT = h0.y;
+      ray.cone.cone_width = o4.w;
+      ray.cone.spread_angle = d4.w;
+      PreHit ph;
+      ph.leaf_slot = __float_as_int(h0.x);
+      const V3 thr = xyz(thr4);
+      const float last_pdf = cp4.w;
+      if (ph.leaf_slot < 0) {
+        // miss (mis_integrator.cpp:36-38,173-185; mat_integrator.cpp:24-27)
+        V3 bg = background_emit(sc, ray.dir, ray.cone);
+        if (!MIS) {
+          finish(thr * bg);
+        } else if (f & WF_FIRST) {
+          finish(bg);
+        } else {
+          if (last_pdf != 0 && sc.bg.emissive) {
+            float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
+            float mis_weight = balance_heuristic(last_pdf, light_pdf);
+#ifdef VIMG_DEBUG_NEE
+            printf("D miss: thr=%.9g %.9g %.9g bg=%.9g %.9g %.9g light_pdf=%.9g w=%.9g dir=%.9g %.9g %.9g cone=%.9g %.9g\n", thr.x, thr.y, thr.z, bg.x, bg.y, bg.z,
+                   light_pdf, mis_weight, ray.dir.x, ray.dir.y, ray.dir.z, ray.cone.cone_width, ray.cone.spread_angle);
+#endif
+            L = L + thr * mis_weight * bg;
+          }
+          finish(L);
+        }
+      } else {
+        const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
+        if (mat_is_emissive(nmat)) {
+          ph.e0 = h0.z;
+          ph.e1 = h0.w;
+          ph.e2 = __uint_as_float(hb.x);
+          ph.inv_det = __uint_as_float(hb.y);
+          const DLeafPrim nlp = sc.leaf_prims[ph.leaf_slot];
+          // an emitter's hit: position and normals only
+          const HitInfo next = wf_hit_info<false>(sc, nlp, load_shade_rec(sc, ph.leaf_slot), ph, ray);
+          V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
+          if (!MIS) {
+            finish(thr * emit);  // sample_mat -> nullopt: throughput * emitted
+          } else if (f & WF_FIRST) {
+            finish(emit);
+          } else {
+            if (last_pdf != 0) {
+              // ray.o is the previous hit point, ray.dir the sampled direction
+              float light_pdf = emitter_surf_pdf_leaf(nlp, ray.o, next.hit_p, ray.dir) / sc.n_lights;
+              float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
+              float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
+              L = L + thr * mis_weight * emit;
+            } else {
+              L = L + thr * emit;
+            }
+            finish(L);
+          }
+        } else if (!MIS) {
+          finish(mk3(0.f));  // base Material: sample_mat -> nullopt, emitted = 0
+        } else {
+          // base Material under mis: the Russian-roulette draw still happens before
+          // sample_mat -> nullopt ends the path (mis_integrator.cpp:154-167, 83-88)
+          if (!(f & WF_FIRST) && d > 5) {
+            V3 t = thr;
+            russian_roulette(rng, thr4.w, t);
+          }
+          finish(L);
+        }
+      }
+    }
+  }
+
+  // the next pixel of the frame for a slot without one
+  {
+    const bool want = valid && !(f & WF_ALIVE);
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    if (m) {
+      uint32_t pbase = 0;
+      if (lane == (uint32_t)(__ffs(m) - 1)) {
+        // no atomic once the frame is handed out (the counter was looked at when the launch
+        // started; a warp that sees it run out remembers)
+        pbase = exhausted ? args.n_local_units : atomicAdd(next_pixel, (uint32_t)__popc(m));
+      }
+      pbase = __shfl_sync(0xffffffffu, pbase, __ffs(m) - 1);
+      exhausted = exhausted || pbase >= args.n_local_units;
+      if (want) {
+        // tiles overhanging the frame contain pixel numbers without a pixel: take the next
+        uint32_t u = pbase + __popc(m & lane_lt), p = 0;
+        uint32_t px = 0, py = 0;
+        bool got = false;
+        while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.my_streams, px, py)))
+          u = atomicAdd(next_pixel, 1u);
+        if (got) {
+          range = args.s_rank + (u - p * args.my_streams) * args.s_n_ranks;
+          if (!MIS && args.depth == 0) {
+            // material_integrator with depth 0 never traces: every sample is vec3(0)
+            const size_t image_index = px + ((size_t)(H - 1 - py) * W);
+            float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
+            o[0] = o[1] = o[2] = 0.f;
+            n_samples += args.samples;
+          } else {
+            pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), range);
+            acc = mk3(0.f);
+            s = (uint32_t)(((uint64_t)range * args.samples) / args.streams);
+            pixel = p;
+            f = WF_ALIVE | (range << WF_RANGE_SHIFT);
+          }
+        }
+      }
+    }
+  }
+  // camera ray of the next sample (include/integrators.h:119-123); rand2 gets the first draw
+  if (f & WF_ALIVE) {
+    uint32_t px, py;
+    wf_pixel_xy(args, sc.cam, pixel, px, py);
+    V2 off = random_x_y_r2(px + py + s);
+    float rand2 = rand_float(rng);
+    float rand1 = rand_float(rng);
+    Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
+    io.cam_o = f4(cam.o, cam.cone.cone_width);
+    io.cam_d = f4(cam.dir, cam.cone.spread_angle);
+    f = WF_ALIVE | WF_IN_PATH | WF_FIRST | (range << WF_RANGE_SHIFT);
+    new_ray = true;
+  }
+  io.rng_fd = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), f, 0u);
+  io.L_s = make_float4(0.f, 0.f, 0.f, __uint_as_float(s));
+  io.acc_pixel = f4(acc, __uint_as_float(pixel));
+  io.new_ray = new_ray;
+}
+
 template <int INTEGRATOR>
 __global__ void __launch_bounds__(QW_THREADS, QW_END_MIN_BLOCKS)
 qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
@@ -476,197 +688,29 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
       L4 = ldg4(&st.slot[i].pix.L_s);
       ap4 = ldg4(&st.slot[i].pix.acc_pixel);
     }
-    uint32_t f = pa1.z;
-    const uint32_t d = pa1.w;
-    Pcg32 rng;
-    rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
-    uint32_t range = f >> WF_RANGE_SHIFT;  // sample range of the pixel this slot works on
-    rng.inc = ((uint64_t)range << 1) | 1u;
-    V3 acc = xyz(ap4);
-    uint32_t s = __float_as_uint(L4.w), pixel = __float_as_uint(ap4.w);
-    const bool occl = hb.z != 0;
-    bool new_ray = false;
-
-    // finish the current sample of this slot's pixel (include/integrators.h:128-137)
-    auto finish = [&](V3 result) {
-      if (is_nan(result.x) || is_nan(result.y) || is_nan(result.z)) {
-        nan_samples++;
-#ifdef VIMG_FAST
-        result = mk3(0.f);  // tolerance build: a NaN sample is counted and dropped (the reference adds it: the pixel turns NaN)
-#endif
-      }
-      acc = acc + result;
-      n_samples++;
-      f &= ~(WF_IN_PATH | WF_END | WF_NEE | WF_NEE_VALID);
-      s = s + 1;
-      if (args.streams == 1) {
-        if (s == args.samples) {
-          const V3 px_col = acc / (float)args.samples;
-          uint32_t px, py;
-          wf_pixel_xy(args, sc.cam, pixel, px, py);
-          const size_t image_index = px + ((size_t)(H - 1 - py) * W);
-          float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
-          o[0] = px_col.x;
-          o[1] = px_col.y;
-          o[2] = px_col.z;
-          f &= ~WF_ALIVE;
-        }
-      } else if (s == (uint32_t)(((uint64_t)(range + 1) * args.samples) / args.streams)) {
-        // end of this sample range: its partial sum; qw_combine_kernel adds the ranges in order
-        uint32_t px, py;
-        wf_pixel_xy(args, sc.cam, pixel, px, py);
-        const size_t image_index = px + ((size_t)(H - 1 - py) * W);
-        float* o = args.partial + 3 * (image_index * args.streams + range);
-        o[0] = acc.x;
-        o[1] = acc.y;
-        o[2] = acc.z;
-        f &= ~WF_ALIVE;
-      }
-    };
-
-    if (valid && (f & WF_IN_PATH)) {
-      // pending shadow ray of the last bounce (mis_integrator.cpp:64-78)
-      V3 L = xyz(L4);
-#ifdef VIMG_DEBUG_NEE
-      if (MIS) printf("D end: s=%u nee=%d valid=%d occl=%d c=%.9g %.9g %.9g L=%.9g %.9g %.9g END=%d leaf=%d lastpdf=%.9g\n", s, (f & WF_NEE) != 0, (f & WF_NEE_VALID) != 0, (int)occl,
-                      cp4.x, cp4.y, cp4.z, L4.x, L4.y, L4.z, (f & WF_END) != 0, __float_as_int(h0.x), cp4.w);
-#endif
-      if (MIS && (f & WF_NEE) && (f & WF_NEE_VALID) && !occl) L = L + xyz(cp4);
-      if (f & WF_END) {
-        finish(MIS ? L : xyz(cp4));
-      } else {
-        Ray ray;
-        ray.o = xyz(o4);
-        ray.dir = xyz(d4);
-        ray.minT = 0.0001f;
-        ray.maxT = h0.y;
-        ray.cone.cone_width = o4.w;
-        ray.cone.spread_angle = d4.w;
-        PreHit ph;
-        ph.leaf_slot = __float_as_int(h0.x);
-        const V3 thr = xyz(thr4);
-        const float last_pdf = cp4.w;
-        if (ph.leaf_slot < 0) {
-          // miss (mis_integrator.cpp:36-38,173-185; mat_integrator.cpp:24-27)
-          V3 bg = background_emit(sc, ray.dir, ray.cone);
-          if (!MIS) {
-            finish(thr * bg);
-          } else if (f & WF_FIRST) {
-            finish(bg);
-          } else {
-            if (last_pdf != 0 && sc.bg.emissive) {
-              float light_pdf = background_pdf(sc, ray.dir) / sc.n_lights;
-              float mis_weight = balance_heuristic(last_pdf, light_pdf);
-#ifdef VIMG_DEBUG_NEE
-              printf("D miss: thr=%.9g %.9g %.9g bg=%.9g %.9g %.9g light_pdf=%.9g w=%.9g dir=%.9g %.9g %.9g cone=%.9g %.9g\n", thr.x, thr.y, thr.z, bg.x, bg.y, bg.z,
-                     light_pdf, mis_weight, ray.dir.x, ray.dir.y, ray.dir.z, ray.cone.cone_width, ray.cone.spread_angle);
-#endif
-              L = L + thr * mis_weight * bg;
-            }
-            finish(L);
-          }
-        } else {
-          const vimg_material& nmat = sc.materials[wf_leaf_material(sc, ph.leaf_slot)];
-          if (mat_is_emissive(nmat)) {
-            ph.e0 = h0.z;
-            ph.e1 = h0.w;
-            ph.e2 = __uint_as_float(hb.x);
-            ph.inv_det = __uint_as_float(hb.y);
-            const DLeafPrim nlp = sc.leaf_prims[ph.leaf_slot];
-            // an emitter's hit: position and normals only
-            const HitInfo next = wf_hit_info<false>(sc, nlp, load_shade_rec(sc, ph.leaf_slot), ph, ray);
-            V3 emit = mat_emitted(nmat, ray.dir, next.hit_n_s);
-            if (!MIS) {
-              finish(thr * emit);  // sample_mat -> nullopt: throughput * emitted
-            } else if (f & WF_FIRST) {
-              finish(emit);
-            } else {
-              if (last_pdf != 0) {
-                // ray.o is the previous hit point, ray.dir the sampled direction
-                float light_pdf = emitter_surf_pdf_leaf(nlp, ray.o, next.hit_p, ray.dir) / sc.n_lights;
-                float G = geometric_term(ray.o, next.hit_p, next.hit_n_g);
-                float mis_weight = balance_heuristic(last_pdf * G, light_pdf);
-                L = L + thr * mis_weight * emit;
-              } else {
-                L = L + thr * emit;
-              }
-              finish(L);
-            }
-          } else if (!MIS) {
-            finish(mk3(0.f));  // base Material: sample_mat -> nullopt, emitted = 0
-          } else {
-            // base Material under mis: the Russian-roulette draw still happens before
-            // sample_mat -> nullopt ends the path (mis_integrator.cpp:154-167, 83-88)
-            if (!(f & WF_FIRST) && d > 5) {
-              V3 t = thr;
-              russian_roulette(rng, thr4.w, t);
-            }
-            finish(L);
-          }
-        }
-      }
-    }
-
-    // the next pixel of the frame for a slot without one
-    {
-      const bool want = valid && !(f & WF_ALIVE);
-      const uint32_t m = __ballot_sync(0xffffffffu, want);
-      if (m) {
-        uint32_t pbase = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) {
-          // no atomic once the frame is handed out (the counter was looked at when the launch
-          // started; a warp that sees it run out remembers)
-          pbase = exhausted ? args.n_local_units : atomicAdd(st.next_pixel, (uint32_t)__popc(m));
-        }
-        pbase = __shfl_sync(0xffffffffu, pbase, __ffs(m) - 1);
-        exhausted = exhausted || pbase >= args.n_local_units;
-        if (want) {
-          // tiles overhanging the frame contain pixel numbers without a pixel: take the next
-          uint32_t u = pbase + __popc(m & lane_lt), p = 0;
-          uint32_t px = 0, py = 0;
-          bool got = false;
-          while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.my_streams, px, py)))
-            u = atomicAdd(st.next_pixel, 1u);
-          if (got) {
-            range = args.s_rank + (u - p * args.my_streams) * args.s_n_ranks;
-            if (!MIS && args.depth == 0) {
-              // material_integrator with depth 0 never traces: every sample is vec3(0)
-              const size_t image_index = px + ((size_t)(H - 1 - py) * W);
-              float* o = out + (args.single_x >= 0 ? 0 : 3 * image_index);
-              o[0] = o[1] = o[2] = 0.f;
-              n_samples += args.samples;
-            } else {
-              pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), range);
-              acc = mk3(0.f);
-              s = (uint32_t)(((uint64_t)range * args.samples) / args.streams);
-              pixel = p;
-              f = WF_ALIVE | (range << WF_RANGE_SHIFT);
-            }
-          }
-        }
-      }
-    }
-    // camera ray of the next sample (include/integrators.h:119-123); rand2 gets the first draw
-    if (f & WF_ALIVE) {
-      uint32_t px, py;
-      wf_pixel_xy(args, sc.cam, pixel, px, py);
-      V2 off = random_x_y_r2(px + py + s);
-      float rand2 = rand_float(rng);
-      float rand1 = rand_float(rng);
-      Ray cam = generate_ray(sc.cam, (float)px + off.x, (float)py + off.y, rand1, rand2);
-      stg4(&st.slot[i].ray.o_w, f4(cam.o, cam.cone.cone_width));
-      stg4(&st.slot[i].ray.d_s, f4(cam.dir, cam.cone.spread_angle));
-      f = WF_ALIVE | WF_IN_PATH | WF_FIRST | (range << WF_RANGE_SHIFT);
-      new_ray = true;
+    EndIO io;
+    io.thr4 = thr4;
+    io.o4 = o4;
+    io.d4 = d4;
+    io.h0 = h0;
+    io.cp4 = cp4;
+    io.L4 = L4;
+    io.ap4 = ap4;
+    io.pa1 = pa1;
+    io.hb = hb;
+    end_item<INTEGRATOR>(sc, args, st.next_pixel, out, valid, exhausted, lane, lane_lt, nan_samples, n_samples, io);
+    const bool new_ray = io.new_ray;
+    if (new_ray) {
+      stg4(&st.slot[i].ray.o_w, io.cam_o);
+      stg4(&st.slot[i].ray.d_s, io.cam_d);
     }
     if (valid) {
       // path: throughput 1, eta_scale 1, d 0; nee: last_pdf 0; pix: L 0, s, acc, pixel
       stg4(&st.slot[i].path.thr_eta, make_float4(1.f, 1.f, 1.f, 1.f));
-      __stcg(reinterpret_cast<uint4*>(&st.slot[i].path.rng),
-             make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), f, 0u));
+      __stcg(reinterpret_cast<uint4*>(&st.slot[i].path.rng), io.rng_fd);
       stg4(&st.slot[i].nee.c_pdf, make_float4(0.f, 0.f, 0.f, 0.f));
-      stg4(&st.slot[i].pix.L_s, make_float4(0.f, 0.f, 0.f, __uint_as_float(s)));
-      stg4(&st.slot[i].pix.acc_pixel, f4(acc, __uint_as_float(pixel)));
+      stg4(&st.slot[i].pix.L_s, io.L_s);
+      stg4(&st.slot[i].pix.acc_pixel, io.acc_pixel);
     }
 
     const bool want[1] = {new_ray};
@@ -723,6 +767,222 @@ VD V3 cls_eval_div_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, c
 #define QW_SHADE_MIN_BLOCKS_L 2  // Lambertian, Dielectric
 #endif
 
+// What the shade kernels read for one item and what they leave behind; the memory layout of both is the
+// kernel's business (slot records here, queue-ordered records in the streamed pipeline of vimg_stream.cuh).
+struct ShadeIO {
+  // in: path state, ray, hit, pending NEE contribution, bounce_result so far (the records of the hit primitive are
+  // separate arguments of shade_bounce: they hold arrays and live in local memory)
+  float4 t4, o4, d4, h0, cp4, L4;  // throughput + eta_scale | origin + cone width | direction + spread | leaf, t, e0, e1 |
+                                   // pending contribution + last_pdf | L + sample counter
+  uint4 pa1, hb;                   // rng lo, rng hi, flags, depth counter | e2, inv_det, shadow ray occluded, -
+  // out
+  bool L_changed;    // L4 was updated (pending shadow ray of the last bounce was unoccluded)
+  bool ended_early;  // Russian roulette / depth ended the path before shading: only rng_fd changed
+  bool shaded;       // thr_eta, rng_fd, new_o, new_d, nee_wi, nee_c are the path's new state
+  uint4 rng_fd;
+  float4 thr_eta, new_o, new_d, nee_wi, nee_c;
+  bool want_closest, want_shadow, want_end;
+};
+
+// the body of the bounce loop at one hit (mis_integrator.cpp:45-122, mat_integrator.cpp:21-83)
+template <int INTEGRATOR, uint32_t CLASS>
+VD void shade_bounce(const DScene& sc, const WfArgs& args, const DLeafPrim& lp, const DShadeRec& sr, ShadeIO& io) {
+  constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
+  float4 t4 = io.t4, L4 = io.L4;
+  const float4 o4 = io.o4, d4 = io.d4, h0 = io.h0, cp4 = io.cp4;
+  const uint4 pa1 = io.pa1, hb = io.hb;
+  bool want_closest = false, want_shadow = false, want_end = false;
+  bool go = true;
+  io.L_changed = io.ended_early = io.shaded = false;
+  uint32_t fj = pa1.z, d = pa1.w;
+  Pcg32 rng;
+  rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
+  rng.inc = ((uint64_t)(fj >> WF_RANGE_SHIFT) << 1) | 1u;
+  if (go) {
+    if (MIS) {
+      // what mis_integrator does between the BVH::hit that found this surface and the next
+      // loop body: the shadow ray of the previous bounce (mis_integrator.cpp:64-78), Russian
+      // roulette (:154-167) and the loop condition d < depth
+#ifdef VIMG_DEBUG_NEE
+      if (fj & WF_NEE) printf("D shade: pending nee valid=%d occl=%u c=%.9g %.9g %.9g\n", (fj & WF_NEE_VALID) != 0, hb.z, cp4.x, cp4.y, cp4.z);
+#endif
+      if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && hb.z == 0) {
+        L4.x += cp4.x;
+        L4.y += cp4.y;
+        L4.z += cp4.z;
+        io.L_changed = true;
+      }
+      fj &= ~(WF_NEE | WF_NEE_VALID);
+      bool go_on = true;
+      if (!(fj & WF_FIRST)) {
+        if (d > 5) {
+          V3 t = xyz(t4);
+          go_on = russian_roulette(rng, t4.w, t);
+          if (go_on) t4 = f4(t, t4.w);
+        }
+        d = d + 1;
+      }
+      fj &= ~WF_FIRST;
+      if (!go_on || d >= args.depth) {
+        // the path returns bounce_result: the next END launch finishes the sample
+        fj |= WF_END;
+        io.rng_fd = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d);
+        io.ended_early = true;
+        want_end = true;
+        go = false;
+      }
+    } else {
+      fj &= ~WF_FIRST;
+    }
+  }
+  if (go) {
+    Ray ray;
+    ray.o = xyz(o4);
+    ray.dir = xyz(d4);
+    ray.minT = 0.0001f;
+    ray.maxT = h0.y;
+    ray.cone.cone_width = o4.w;
+    ray.cone.spread_angle = d4.w;
+    PreHit ph;
+    ph.leaf_slot = __float_as_int(h0.x);
+    ph.e0 = h0.z;
+    ph.e1 = h0.w;
+    ph.e2 = __uint_as_float(hb.x);
+    ph.inv_det = __uint_as_float(hb.y);
+    // the tangent frame is read by the Principled BSDF only
+    const HitInfo hit = wf_hit_info<CLASS == WF_CLASS_PRINCIPLED>(sc, lp, sr, ph, ray);
+    const vimg_material& mat = sc.materials[hit.mat];
+    V3 thr = xyz(t4);
+    float eta_scale = t4.w;
+    bool nsb = (fj & WF_NSB) != 0;
+    // ray cones: skipped when nothing in the scene reads them (DScene::uses_cones)
+    const bool cones = sc.uses_cones != 0;
+    float hit_dist = cones ? length(ray.o - hit.hit_p) : 0.f;
+    float surface_spread_angle
+        = cones ? spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s) : 0.f;
+    // records written back at the end (whole sectors)
+    float4 nee_wi = make_float4(0.f, 0.f, 0.f, 0.f), nee_c = nee_wi;
+    float4 new_o = f4(hit.hit_p, o4.w), new_d = d4;  // origin of the shadow ray and of the next ray
+
+    if (MIS) {
+      // ---- mis_integrator.cpp:45-117 at `hit` ----
+      bool nee = false, nee_valid = false;
+      EmitterInfo li;
+      V3 light_col = mk3(0.f);
+      if (CLASS != WF_CLASS_DIELECTRIC) {  // !mat->is_delta()
+        light_col = lights_sample(sc, hit.hit_p, rng, li);
+        nee = li.pdf != 0.f;
+      }
+      const RayCone nee_cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
+      const bool nee_regularize = nsb;
+      ScatterInfo sm;
+      const bool scattered = cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sm);
+      RayCone cone = ray.cone;
+      if (scattered) {
+        if (!sm.is_specular) nsb = true;
+        if (sm.eta != 0.f) {
+          eta_scale /= (sm.eta * sm.eta);
+          if (cones) cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
+        } else {
+          cone = nee_cone;
+        }
+      }
+      // ONE inlined eval_pdf_pair site serves both calls of the loop body:
+      //   q = 0 light direction (mis_integrator.cpp:68-71), q = 1 sampled direction (:104-106)
+      V3 contrib = mk3(0.f), mat_sample_eval = mk3(0.f);
+      float mat_sample_pdf = 0.f;
+#pragma unroll 1
+      for (int qq = 0; qq < 2; ++qq) {
+        if (!(qq == 0 ? nee : scattered)) continue;
+        V3 e;
+        float p;
+        cls_eval_pdf_pair<CLASS>(sc, mat, ray.dir, qq == 0 ? li.wi : sm.wo, hit, qq == 0 ? nee_cone : cone,
+                                 qq == 0 ? nee_regularize : nsb, e, p);
+        if (qq == 0) {
+          if (p != 0 && !is_nan(p)) {
+            float G = li.G;
+            float mis_weight = balance_heuristic(li.pdf, p * G);
+            contrib = thr * e * mis_weight * G * light_col / li.pdf;
+            nee_valid = true;
+          }
+        } else {
+          mat_sample_eval = e;
+          mat_sample_pdf = p;
+        }
+      }
+#ifdef VIMG_DEBUG_NEE
+      printf("D bounce d=%u class=%u hp=%.9g %.9g %.9g n=%.9g %.9g %.9g nee=%d wi=%.9g %.9g %.9g lpdf=%.9g dist=%g valid=%d c=%.9g %.9g %.9g scat=%d wo=%.9g %.9g %.9g mpdf=%.9g thr=%.9g %.9g %.9g\n",
+             d, CLASS, hit.hit_p.x, hit.hit_p.y, hit.hit_p.z, hit.hit_n_s.x, hit.hit_n_s.y, hit.hit_n_s.z, (int)nee, li.wi.x, li.wi.y, li.wi.z, li.pdf, li.dist, (int)nee_valid,
+             contrib.x, contrib.y, contrib.z, (int)scattered, sm.wo.x, sm.wo.y, sm.wo.z, mat_sample_pdf, thr.x, thr.y, thr.z);
+#endif
+      fj &= ~(WF_NSB | WF_NEE | WF_NEE_VALID | WF_END);
+      if (nsb) fj |= WF_NSB;
+      if (nee) {
+        fj |= WF_NEE | (nee_valid ? WF_NEE_VALID : 0u);
+        nee_wi = f4(li.wi, li.dist);
+        nee_c = f4(contrib, 0.f);
+        want_shadow = true;
+      }
+      if (!scattered || is_nan(mat_sample_pdf)) {
+        fj |= WF_END;  // return bounce_result (after the pending shadow ray)
+        want_end = true;
+      } else {
+        thr = thr * (mat_sample_eval / mat_sample_pdf);
+        nee_c.w = mat_sample_pdf;  // last_pdf
+        new_o.w = cone.cone_width;
+        new_d = f4(sm.wo, cone.spread_angle);
+        want_closest = true;
+      }
+    } else {
+      // ---- material_integrator, mat_integrator.cpp:21-83 at `hit` ----
+      V3 emitted_col = mat_emitted(mat, ray.dir, hit.hit_n_s);
+      ScatterInfo sr;
+      fj &= ~(WF_NSB | WF_END);
+      if (!cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sr)) {
+        nee_c = f4(thr * emitted_col, 0.f);
+        fj |= WF_END;
+        want_end = true;
+      } else {
+        if (!sr.is_specular) nsb = true;
+        RayCone cone;
+        if (sr.eta != 0.f) {
+          eta_scale /= (sr.eta * sr.eta);
+          cone = cones ? propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo) : ray.cone;
+        } else {
+          cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
+        }
+        thr = thr * (emitted_col + cls_eval_div_pdf<CLASS>(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
+        bool go_on = true;
+        if (d > 5) go_on = russian_roulette(rng, eta_scale, thr);
+        if (!go_on || d + 1 >= args.depth) {
+          // `break`, or the for loop runs out before the next BVH::hit: return vec3(0)
+          nee_c = make_float4(0.f, 0.f, 0.f, 0.f);
+          fj |= WF_END;
+          want_end = true;
+        } else {
+          new_o.w = cone.cone_width;
+          new_d = f4(sr.wo, cone.spread_angle);
+          d = d + 1;
+          want_closest = true;
+        }
+      }
+      if (nsb) fj |= WF_NSB;
+    }
+    io.thr_eta = f4(thr, eta_scale);
+    io.rng_fd = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d);
+    io.new_o = new_o;
+    io.new_d = new_d;
+    io.nee_wi = nee_wi;
+    io.nee_c = nee_c;
+    io.shaded = true;
+  }
+
+  io.L4 = L4;
+  io.want_closest = want_closest;
+  io.want_shadow = want_shadow;
+  io.want_end = want_end;
+}
+
 // thread <-> item of the class's shade queue: the body of the bounce loop at one hit
 // (mis_integrator.cpp:45-122, mat_integrator.cpp:21-83)
 template <int INTEGRATOR, uint32_t CLASS>
@@ -771,188 +1031,32 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
         L4 = ldg4(&st.slot[j].pix.L_s);
       }
     }
-    uint32_t fj = pa1.z, d = pa1.w;
-    Pcg32 rng;
-    rng.state = ((unsigned long long)pa1.y << 32) | pa1.x;
-    rng.inc = ((uint64_t)(fj >> WF_RANGE_SHIFT) << 1) | 1u;
+    ShadeIO io;
+    io.t4 = t4;
+    io.o4 = o4;
+    io.d4 = d4;
+    io.h0 = h0;
+    io.cp4 = cp4;
+    io.L4 = L4;
+    io.pa1 = pa1;
+    io.hb = hb;
+    io.want_closest = io.want_shadow = io.want_end = false;
     if (go) {
-      if (MIS) {
-        // what mis_integrator does between the BVH::hit that found this surface and the next
-        // loop body: the shadow ray of the previous bounce (mis_integrator.cpp:64-78), Russian
-        // roulette (:154-167) and the loop condition d < depth
-#ifdef VIMG_DEBUG_NEE
-        if (fj & WF_NEE) printf("D shade: pending nee valid=%d occl=%u c=%.9g %.9g %.9g\n", (fj & WF_NEE_VALID) != 0, hb.z, cp4.x, cp4.y, cp4.z);
-#endif
-        if ((fj & WF_NEE) && (fj & WF_NEE_VALID) && hb.z == 0) {
-          L4.x += cp4.x;
-          L4.y += cp4.y;
-          L4.z += cp4.z;
-          stg4(&st.slot[j].pix.L_s, L4);
-        }
-        fj &= ~(WF_NEE | WF_NEE_VALID);
-        bool go_on = true;
-        if (!(fj & WF_FIRST)) {
-          if (d > 5) {
-            V3 t = xyz(t4);
-            go_on = russian_roulette(rng, t4.w, t);
-            if (go_on) t4 = f4(t, t4.w);
-          }
-          d = d + 1;
-        }
-        fj &= ~WF_FIRST;
-        if (!go_on || d >= args.depth) {
-          // the path returns bounce_result: the next END launch finishes the sample
-          fj |= WF_END;
-          __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng),
-                 make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
-          want_end = true;
-          go = false;
-        }
-      } else {
-        fj &= ~WF_FIRST;
+      shade_bounce<INTEGRATOR, CLASS>(sc, args, lp, sr, io);
+      if (io.L_changed) stg4(&st.slot[j].pix.L_s, io.L4);
+      if (io.ended_early) __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng), io.rng_fd);
+      if (io.shaded) {
+        stg4(&st.slot[j].path.thr_eta, io.thr_eta);
+        __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng), io.rng_fd);
+        stg4(&st.slot[j].ray.o_w, io.new_o);
+        stg4(&st.slot[j].ray.d_s, io.new_d);
+        stg4(&st.slot[j].nee.wi_dist, io.nee_wi);
+        stg4(&st.slot[j].nee.c_pdf, io.nee_c);
       }
     }
-    if (go) {
-      Ray ray;
-      ray.o = xyz(o4);
-      ray.dir = xyz(d4);
-      ray.minT = 0.0001f;
-      ray.maxT = h0.y;
-      ray.cone.cone_width = o4.w;
-      ray.cone.spread_angle = d4.w;
-      PreHit ph;
-      ph.leaf_slot = __float_as_int(h0.x);
-      ph.e0 = h0.z;
-      ph.e1 = h0.w;
-      ph.e2 = __uint_as_float(hb.x);
-      ph.inv_det = __uint_as_float(hb.y);
-      // the tangent frame is read by the Principled BSDF only
-      const HitInfo hit = wf_hit_info<CLASS == WF_CLASS_PRINCIPLED>(sc, lp, sr, ph, ray);
-      const vimg_material& mat = sc.materials[hit.mat];
-      V3 thr = xyz(t4);
-      float eta_scale = t4.w;
-      bool nsb = (fj & WF_NSB) != 0;
-      // ray cones: skipped when nothing in the scene reads them (DScene::uses_cones)
-      const bool cones = sc.uses_cones != 0;
-      float hit_dist = cones ? length(ray.o - hit.hit_p) : 0.f;
-      float surface_spread_angle
-          = cones ? spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s) : 0.f;
-      // records written back at the end (whole sectors)
-      float4 nee_wi = make_float4(0.f, 0.f, 0.f, 0.f), nee_c = nee_wi;
-      float4 new_o = f4(hit.hit_p, o4.w), new_d = d4;  // origin of the shadow ray and of the next ray
-
-      if (MIS) {
-        // ---- mis_integrator.cpp:45-117 at `hit` ----
-        bool nee = false, nee_valid = false;
-        EmitterInfo li;
-        V3 light_col = mk3(0.f);
-        if (CLASS != WF_CLASS_DIELECTRIC) {  // !mat->is_delta()
-          light_col = lights_sample(sc, hit.hit_p, rng, li);
-          nee = li.pdf != 0.f;
-        }
-        const RayCone nee_cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
-        const bool nee_regularize = nsb;
-        ScatterInfo sm;
-        const bool scattered = cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sm);
-        RayCone cone = ray.cone;
-        if (scattered) {
-          if (!sm.is_specular) nsb = true;
-          if (sm.eta != 0.f) {
-            eta_scale /= (sm.eta * sm.eta);
-            if (cones) cone = propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sm.eta, sm.wo);
-          } else {
-            cone = nee_cone;
-          }
-        }
-        // ONE inlined eval_pdf_pair site serves both calls of the loop body:
-        //   q = 0 light direction (mis_integrator.cpp:68-71), q = 1 sampled direction (:104-106)
-        V3 contrib = mk3(0.f), mat_sample_eval = mk3(0.f);
-        float mat_sample_pdf = 0.f;
-#pragma unroll 1
-        for (int qq = 0; qq < 2; ++qq) {
-          if (!(qq == 0 ? nee : scattered)) continue;
-          V3 e;
-          float p;
-          cls_eval_pdf_pair<CLASS>(sc, mat, ray.dir, qq == 0 ? li.wi : sm.wo, hit, qq == 0 ? nee_cone : cone,
-                                   qq == 0 ? nee_regularize : nsb, e, p);
-          if (qq == 0) {
-            if (p != 0 && !is_nan(p)) {
-              float G = li.G;
-              float mis_weight = balance_heuristic(li.pdf, p * G);
-              contrib = thr * e * mis_weight * G * light_col / li.pdf;
-              nee_valid = true;
-            }
-          } else {
-            mat_sample_eval = e;
-            mat_sample_pdf = p;
-          }
-        }
-#ifdef VIMG_DEBUG_NEE
-        printf("D bounce d=%u class=%u hp=%.9g %.9g %.9g n=%.9g %.9g %.9g nee=%d wi=%.9g %.9g %.9g lpdf=%.9g dist=%g valid=%d c=%.9g %.9g %.9g scat=%d wo=%.9g %.9g %.9g mpdf=%.9g thr=%.9g %.9g %.9g\n",
-               d, CLASS, hit.hit_p.x, hit.hit_p.y, hit.hit_p.z, hit.hit_n_s.x, hit.hit_n_s.y, hit.hit_n_s.z, (int)nee, li.wi.x, li.wi.y, li.wi.z, li.pdf, li.dist, (int)nee_valid,
-               contrib.x, contrib.y, contrib.z, (int)scattered, sm.wo.x, sm.wo.y, sm.wo.z, mat_sample_pdf, thr.x, thr.y, thr.z);
-#endif
-        fj &= ~(WF_NSB | WF_NEE | WF_NEE_VALID | WF_END);
-        if (nsb) fj |= WF_NSB;
-        if (nee) {
-          fj |= WF_NEE | (nee_valid ? WF_NEE_VALID : 0u);
-          nee_wi = f4(li.wi, li.dist);
-          nee_c = f4(contrib, 0.f);
-          want_shadow = true;
-        }
-        if (!scattered || is_nan(mat_sample_pdf)) {
-          fj |= WF_END;  // return bounce_result (after the pending shadow ray)
-          want_end = true;
-        } else {
-          thr = thr * (mat_sample_eval / mat_sample_pdf);
-          nee_c.w = mat_sample_pdf;  // last_pdf
-          new_o.w = cone.cone_width;
-          new_d = f4(sm.wo, cone.spread_angle);
-          want_closest = true;
-        }
-      } else {
-        // ---- material_integrator, mat_integrator.cpp:21-83 at `hit` ----
-        V3 emitted_col = mat_emitted(mat, ray.dir, hit.hit_n_s);
-        ScatterInfo sr;
-        fj &= ~(WF_NSB | WF_END);
-        if (!cls_sample<CLASS>(sc, mat, ray.dir, hit, rng, nsb, sr)) {
-          nee_c = f4(thr * emitted_col, 0.f);
-          fj |= WF_END;
-          want_end = true;
-        } else {
-          if (!sr.is_specular) nsb = true;
-          RayCone cone;
-          if (sr.eta != 0.f) {
-            eta_scale /= (sr.eta * sr.eta);
-            cone = cones ? propagate_refract_cone(ray.cone, ray.dir, surface_spread_angle, sr.eta, sr.wo) : ray.cone;
-          } else {
-            cone = cones ? propagate_reflect_cone(ray.cone, surface_spread_angle * 2.f, hit_dist) : ray.cone;
-          }
-          thr = thr * (emitted_col + cls_eval_div_pdf<CLASS>(sc, mat, ray.dir, sr.wo, hit, cone, nsb));
-          bool go_on = true;
-          if (d > 5) go_on = russian_roulette(rng, eta_scale, thr);
-          if (!go_on || d + 1 >= args.depth) {
-            // `break`, or the for loop runs out before the next BVH::hit: return vec3(0)
-            nee_c = make_float4(0.f, 0.f, 0.f, 0.f);
-            fj |= WF_END;
-            want_end = true;
-          } else {
-            new_o.w = cone.cone_width;
-            new_d = f4(sr.wo, cone.spread_angle);
-            d = d + 1;
-            want_closest = true;
-          }
-        }
-        if (nsb) fj |= WF_NSB;
-      }
-      stg4(&st.slot[j].path.thr_eta, f4(thr, eta_scale));
-      __stcg(reinterpret_cast<uint4*>(&st.slot[j].path.rng),
-             make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), fj, d));
-      stg4(&st.slot[j].ray.o_w, new_o);
-      stg4(&st.slot[j].ray.d_s, new_d);
-      stg4(&st.slot[j].nee.wi_dist, nee_wi);
-      stg4(&st.slot[j].nee.c_pdf, nee_c);
-    }
+    want_closest = io.want_closest;
+    want_shadow = io.want_shadow;
+    want_end = io.want_end;
 
     // every queue written here belongs to the NEXT iteration, so this launch is independent of
     // the END launch of the same iteration and the two run concurrently
@@ -994,6 +1098,11 @@ struct QwKernelTable {
   const void* end[2];                    // [material = 0, mis = 1]
   const void* path_flat[2];              // [material = 0, mis = 1]; tolerance build only
   const void* build_flat;                // tolerance build only
+  // the streamed pipeline of vimg_stream.cuh (tolerance build only)
+  const void* sv_trace_flat[2];          // [COUNT]
+  const void* sv_shade[2][WF_NUM_CLASSES];
+  const void* sv_end[2];
+  const void* sv_init;
 };
 inline QwKernelTable qw_kernel_table() {
   QwKernelTable t{};

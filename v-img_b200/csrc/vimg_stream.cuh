@@ -1,0 +1,371 @@
+// vimg_stream.cuh -- the STREAMED queue wavefront (tolerance build, flat scenes): SoA ray / hit queues.
+//
+// What ncu showed about the slot-record pipeline of vimg_queues.cuh (profiles/r5_*): its kernels gather path
+// state by slot number -- 32-byte sectors at random places of a 335 MB array -- and the memory system fetches
+// them at 128-byte granularity.  qf_trace_flat_kernel needs 32 - 48 bytes per ray and moved 218
+// (dram__bytes_read 524 MB for 2.4 M rays); the shade / END kernels moved 2.2 - 2.6x their sector bytes and every
+// item costs two dependent DRAM round trips (queue entry -> slot).  With the traversal itself reduced to a
+// divergence-free loop, that traffic is the frame time.
+//
+// Here everything that flows from one kernel to the next flows through QUEUE-ORDERED records, written with
+// block-aggregated appends and read back fully coalesced, 16 bytes per lane and array:
+//   ray queue   (shade / END -> trace):  ta = origin, shadow-ray length | tb = direction, slot + what to trace |
+//                                        tc = shadow-ray direction                         (32 or 48 B per path segment)
+//   hit queues  (trace -> shade per material class, trace / shade -> END):
+//                                        ha = slot, leaf record, t, occluded | hb = e0, e1, e2, inv_det   (32 B)
+// and what stays with the path lives in ONE 128-byte, 128-byte-aligned line per slot (QvLine): throughput, RNG,
+// flags, bounce_result, accumulator, the ray (hit-info needs it), pending NEE contribution.  One line fetch per
+// shade / END item instead of two; full-sector writes only.  A path segment's shadow ray and closest ray are one
+// ray-queue item traced by one lane (both loops are divergence free), so the occlusion result travels in the hit
+// record instead of a 4-byte scatter.
+//
+// Per path, the estimator, the RNG stream and its draw order are those of vimg_queues.cuh (the shade and END
+// bodies are the same functions: shade_bounce, end_item).
+#pragma once
+#include "vimg_queues.cuh"
+#ifdef VIMG_FAST
+#include "vimg_flat.cuh"
+#endif
+
+namespace vimg {
+
+struct __align__(128) QvLine {
+  float4 thr_eta;    // sector 0: throughput rgb, eta_scale
+  uint4 rng_fd;      //           rng lo, rng hi, flags | sample range << 16, depth counter
+  float4 L_s;        // sector 1: bounce_result rgb, sample counter
+  float4 acc_pixel;  //           pixel accumulator rgb, local pixel number
+  float4 o_w;        // sector 2: ray origin, cone width
+  float4 d_s;        //           ray direction, cone spread
+  float4 c_pdf;      // sector 3: pending NEE contribution rgb, last_pdf
+  float4 spare;
+};
+static_assert(sizeof(QvLine) == 128, "one line per slot");
+
+struct QvCounters {
+  uint32_t n_trace[2];                  // ray queue, by iteration parity
+  uint32_t n_end[2];                    // END queue, by iteration parity
+  uint32_t n_shade[2][WF_NUM_CLASSES];  // hit queues
+  uint32_t pad_[6];
+};
+
+#define QV_HAS_CLOSEST 0x40000000u
+#define QV_HAS_SHADOW 0x80000000u
+#define QV_SLOT_MASK 0x3fffffffu
+
+struct QvState {
+  uint32_t n_slots;
+  QvLine* line;
+  float4 *ta[2], *tb[2], *tc[2];                    // ray queue
+  float4 *ha[WF_NUM_CLASSES], *hb[WF_NUM_CLASSES];  // hit queues of the material classes
+  float4 *ea[2], *eb[2];                            // END queue
+  QvCounters* cnt;
+  uint32_t* next_pixel;
+};
+
+#ifdef VIMG_FAST
+VD float4 ldq(const float4* p) { return __ldcs(p); }  // queue records are read once: evict first
+VD void stq(float4* p, float4 v) { __stcs(p, v); }
+
+// ====================================================== TRACE over the flat lists, streamed ====
+// thread <-> item of the ray queue: the shadow ray and / or the closest ray of one path segment.
+template <bool COUNT>
+__global__ void __launch_bounds__(QW_THREADS, 4)
+qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, const QfScene* __restrict__ flat,
+                     DCounters* __restrict__ counters) {
+  __shared__ QfScene fs;
+  __shared__ uint32_t s_cnt[WF_NUM_CLASSES + 1], s_base[WF_NUM_CLASSES + 1];
+  QvCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  if (blockIdx.x == 0 && tid == 0) {
+    // queues the NEXT iteration fills (their last consumers ran before this launch)
+    c->n_trace[parity ^ 1u] = 0;
+    c->n_end[parity ^ 1u] = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) c->n_shade[parity ^ 1u][k] = 0;
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(flat);
+    uint4* dst = reinterpret_cast<uint4*>(&fs);
+    for (uint32_t i = tid; i < sizeof(QfScene) / 16; i += QW_THREADS) dst[i] = __ldg(src + i);
+  }
+  const uint32_t n = c->n_trace[parity];
+  const float4* __restrict__ ta = st.ta[parity];
+  const float4* __restrict__ tb = st.tb[parity];
+  const float4* __restrict__ tc = st.tc[parity];
+  uint32_t rays_closest = 0, rays_shadow = 0;
+
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
+    __syncthreads();  // also: the staged lists are visible
+    const uint32_t item = base + tid;
+    const bool valid = item < n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f), w = b;
+    if (valid) {
+      a = ldq(ta + item);
+      b = ldq(tb + item);
+    }
+    const uint32_t bits = __float_as_uint(b.w);
+    const bool has_c = valid && (bits & QV_HAS_CLOSEST), has_s = valid && (bits & QV_HAS_SHADOW);
+    if (has_s) w = ldq(tc + item);
+    const V3 o = xyz(a);
+    bool occl = false;
+    if (__any_sync(0xffffffffu, has_s)) {
+      // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
+      QfBest sh;
+      sh.t = has_s ? a.w - 0.0001f : 0.f;
+      sh.k = -1;
+      sh.u = sh.v = 0.f;
+      qf_trace(fs, o, xyz(w), 0.0001f, sh);
+      occl = sh.k >= 0;
+      rays_shadow += has_s;
+    }
+    QfBest best;
+    best.t = has_c ? CUDART_INF_F : 0.f;
+    best.k = -1;
+    best.u = best.v = 0.f;
+    if (__any_sync(0xffffffffu, has_c)) {
+      qf_trace(fs, o, xyz(b), 0.0001f, best);
+      rays_closest += has_c;
+    }
+    uint32_t cls = WF_CLASS_NONE + 1;  // NONE + 1: no item
+    int32_t leaf = -1;
+    float4 hb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      cls = WF_CLASS_NONE;  // END: miss, emitter, base material, or a path that only had its last shadow ray left
+      if (best.k >= 0) {
+        const bool is_tri = (uint32_t)best.k < fs.n_tri;
+        const uint32_t e = is_tri ? (uint32_t)best.k : (uint32_t)best.k - fs.n_tri;
+        leaf = is_tri ? fs.tri_leaf[e] : fs.sph_leaf[e];
+        const uint32_t lc = is_tri ? fs.tri_class[e] : fs.sph_class[e];
+        cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
+        if (is_tri) hb4 = make_float4(1.f - best.u - best.v, best.u, best.v, 1.f);  // weights of p0, p1, p2 (e_i * inv_det)
+      }
+    }
+    bool want[WF_NUM_CLASSES + 1];
+#pragma unroll
+    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
+    QwAppend<WF_NUM_CLASSES + 1> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid < (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[parity][tid], s_cnt[tid]);
+    } else if (tid == (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
+    }
+    __syncthreads();
+    if (valid) {
+      const float4 ha4 = make_float4(__uint_as_float(bits & QV_SLOT_MASK), __int_as_float(leaf),
+                                     best.k >= 0 ? best.t : CUDART_INF_F, __uint_as_float(occl ? 1u : 0u));
+      const uint32_t pos = s_base[cls] + ap.off[cls];
+      float4* qa = cls < WF_NUM_CLASSES ? st.ha[cls] : st.ea[parity];
+      float4* qb = cls < WF_NUM_CLASSES ? st.hb[cls] : st.eb[parity];
+      stq(qa + pos, ha4);
+      stq(qb + pos, hb4);
+    }
+  }
+  warp_add_counter(&counters->rays_closest, rays_closest);
+  warp_add_counter(&counters->rays_shadow, rays_shadow);
+  if (COUNT) {
+    warp_add_counter(&counters->tri_tests, (rays_closest + rays_shadow) * fs.n_tri);
+    warp_add_counter(&counters->sphere_tests, (rays_closest + rays_shadow) * fs.n_sph);
+  }
+}
+
+// ====================================================================== SHADE, streamed ====
+// thread <-> item of the class's hit queue
+template <int INTEGRATOR, uint32_t CLASS>
+__global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_SHADE_MIN_BLOCKS_P : QW_SHADE_MIN_BLOCKS_L)
+qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
+                const __grid_constant__ WfArgs args, const uint32_t parity) {
+  __shared__ uint32_t s_cnt[2], s_base[2];
+  QvCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint32_t n = c->n_shade[parity][CLASS];
+  const float4* __restrict__ qa = st.ha[CLASS];
+  const float4* __restrict__ qb = st.hb[CLASS];
+
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t item = base + tid;
+    const bool go = item < n;
+    float4 ha4 = make_float4(0.f, 0.f, 0.f, 0.f), hb4 = ha4;
+    if (go) {
+      ha4 = ldq(qa + item);
+      hb4 = ldq(qb + item);
+    }
+    const uint32_t j = __float_as_uint(ha4.x);
+    const int32_t leaf = __float_as_int(ha4.y);
+    QvLine* ln = st.line + j;
+    ShadeIO io;
+    io.t4 = io.o4 = io.d4 = io.cp4 = io.L4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    io.pa1 = make_uint4(0, 0, 0, 0);
+    float4 ap4 = io.t4;
+    DLeafPrim lp;
+    DShadeRec sr;
+    if (go) {
+      {
+        const float4* rec = reinterpret_cast<const float4*>(sc.leaf_prims + leaf);
+        float4* dst = reinterpret_cast<float4*>(&lp);
+        dst[0] = __ldg(rec);
+        dst[1] = __ldg(rec + 1);
+        dst[2] = __ldg(rec + 2);
+      }
+      sr = load_shade_rec(sc, leaf);
+      io.t4 = ldg4(&ln->thr_eta);
+      io.pa1 = ldg4u(&ln->rng_fd);
+      io.L4 = ldg4(&ln->L_s);
+      ap4 = ldg4(&ln->acc_pixel);
+      io.o4 = ldg4(&ln->o_w);
+      io.d4 = ldg4(&ln->d_s);
+      io.cp4 = ldg4(&ln->c_pdf);
+    }
+    io.h0 = make_float4(ha4.y, ha4.z, hb4.x, hb4.y);  // leaf, t, e0, e1
+    io.hb = make_uint4(__float_as_uint(hb4.z), __float_as_uint(hb4.w), __float_as_uint(ha4.w), 0u);  // e2, inv_det, occluded
+    io.want_closest = io.want_shadow = io.want_end = false;
+    io.shaded = io.ended_early = io.L_changed = false;
+    if (go) {
+      shade_bounce<INTEGRATOR, CLASS>(sc, args, lp, sr, io);
+      if (io.L_changed) {  // the whole sector: no partial writes
+        stg4(&ln->L_s, io.L4);
+        stg4(&ln->acc_pixel, ap4);
+      }
+      if (io.ended_early) {
+        stg4(&ln->thr_eta, io.t4);
+        __stcg(&ln->rng_fd, io.rng_fd);
+      }
+      if (io.shaded) {
+        stg4(&ln->thr_eta, io.thr_eta);
+        __stcg(&ln->rng_fd, io.rng_fd);
+        stg4(&ln->o_w, io.new_o);
+        stg4(&ln->d_s, io.new_d);
+        stg4(&ln->c_pdf, io.nee_c);
+        stg4(&ln->spare, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    // a path segment to trace (closest ray and / or shadow ray), or straight to END (ended, nothing pending)
+    const bool to_trace = io.want_closest || io.want_shadow;
+    const bool to_end = io.want_end && !io.want_shadow;
+    const bool want[2] = {to_trace, to_end};
+    QwAppend<2> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
+    if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[1]);
+    __syncthreads();
+    if (to_trace) {
+      const uint32_t pos = s_base[0] + ap.off[0];
+      const uint32_t bits = j | (io.want_closest ? QV_HAS_CLOSEST : 0u) | (io.want_shadow ? QV_HAS_SHADOW : 0u);
+      stq(st.ta[parity ^ 1u] + pos, make_float4(io.new_o.x, io.new_o.y, io.new_o.z, io.nee_wi.w));
+      stq(st.tb[parity ^ 1u] + pos, make_float4(io.new_d.x, io.new_d.y, io.new_d.z, __uint_as_float(bits)));
+      if (io.want_shadow) stq(st.tc[parity ^ 1u] + pos, io.nee_wi);
+    } else if (to_end) {
+      const uint32_t pos = s_base[1] + ap.off[1];
+      stq(st.ea[parity ^ 1u] + pos, make_float4(__uint_as_float(j), __int_as_float(-1), CUDART_INF_F, __uint_as_float(0u)));
+      stq(st.eb[parity ^ 1u] + pos, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+}
+
+// ======================================================================== END, streamed ====
+// thread <-> item of the END queue: a path that ended (or a slot that has no pixel yet)
+template <int INTEGRATOR>
+__global__ void __launch_bounds__(QW_THREADS, QW_END_MIN_BLOCKS)
+qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
+              const __grid_constant__ WfArgs args, const uint32_t parity, float* __restrict__ out,
+              DCounters* __restrict__ counters) {
+  __shared__ uint32_t s_cnt[1], s_base[1];
+  QvCounters* c = st.cnt;
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint32_t n = c->n_end[parity];
+  const float4* __restrict__ qa = st.ea[parity];
+  const float4* __restrict__ qb = st.eb[parity];
+  uint32_t nan_samples = 0, n_samples = 0;
+  bool exhausted = *reinterpret_cast<volatile uint32_t*>(st.next_pixel) >= args.n_local_units;
+
+  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
+    const uint32_t item = base + tid;
+    const bool valid = item < n;
+    float4 ha4 = make_float4(0.f, 0.f, 0.f, 0.f), hb4 = ha4;
+    if (valid) {
+      ha4 = ldq(qa + item);
+      hb4 = ldq(qb + item);
+    }
+    const uint32_t i = __float_as_uint(ha4.x);
+    QvLine* ln = st.line + i;
+    EndIO io;
+    io.thr4 = io.o4 = io.d4 = io.cp4 = io.L4 = io.ap4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    io.pa1 = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      io.thr4 = ldg4(&ln->thr_eta);
+      io.pa1 = ldg4u(&ln->rng_fd);
+      io.L4 = ldg4(&ln->L_s);
+      io.ap4 = ldg4(&ln->acc_pixel);
+      io.o4 = ldg4(&ln->o_w);
+      io.d4 = ldg4(&ln->d_s);
+      io.cp4 = ldg4(&ln->c_pdf);
+    }
+    io.h0 = make_float4(ha4.y, ha4.z, hb4.x, hb4.y);
+    io.hb = make_uint4(__float_as_uint(hb4.z), __float_as_uint(hb4.w), __float_as_uint(ha4.w), 0u);
+    end_item<INTEGRATOR>(sc, args, st.next_pixel, out, valid, exhausted, lane, lane_lt, nan_samples, n_samples, io);
+    if (valid) {
+      // path: throughput 1, eta_scale 1, d 0; nee: last_pdf 0; pix: L 0, s, acc, pixel
+      stg4(&ln->thr_eta, make_float4(1.f, 1.f, 1.f, 1.f));
+      __stcg(&ln->rng_fd, io.rng_fd);
+      stg4(&ln->L_s, io.L_s);
+      stg4(&ln->acc_pixel, io.acc_pixel);
+      stg4(&ln->c_pdf, make_float4(0.f, 0.f, 0.f, 0.f));
+      stg4(&ln->spare, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (io.new_ray) {
+        stg4(&ln->o_w, io.cam_o);
+        stg4(&ln->d_s, io.cam_d);
+      }
+    }
+    const bool want[1] = {io.new_ray};
+    QwAppend<1> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
+    __syncthreads();
+    if (io.new_ray) {
+      const uint32_t pos = s_base[0] + ap.off[0];
+      stq(st.ta[parity ^ 1u] + pos, make_float4(io.cam_o.x, io.cam_o.y, io.cam_o.z, 0.f));
+      stq(st.tb[parity ^ 1u] + pos, make_float4(io.cam_d.x, io.cam_d.y, io.cam_d.z, __uint_as_float(i | QV_HAS_CLOSEST)));
+    }
+  }
+  warp_add_counter(&counters->nan_samples, nan_samples);
+  warp_add_counter(&counters->samples, n_samples);
+}
+
+// the first END queue: every slot, none with a pixel yet
+__global__ void qv_init_kernel(float4* __restrict__ ea, float4* __restrict__ eb, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ea[i] = make_float4(__uint_as_float(i), __int_as_float(-1), CUDART_INF_F, __uint_as_float(0u));
+  eb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+inline void qv_fill_kernel_table(QwKernelTable& t) {
+  t.sv_trace_flat[0] = (const void*)&qv_trace_flat_kernel<false>;
+  t.sv_trace_flat[1] = (const void*)&qv_trace_flat_kernel<true>;
+  t.sv_shade[0][WF_CLASS_LAMBERT] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_LAMBERT>;
+  t.sv_shade[0][WF_CLASS_PRINCIPLED] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_PRINCIPLED>;
+  t.sv_shade[0][WF_CLASS_DIELECTRIC] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_DIELECTRIC>;
+  t.sv_shade[1][WF_CLASS_LAMBERT] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MIS, WF_CLASS_LAMBERT>;
+  t.sv_shade[1][WF_CLASS_PRINCIPLED] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MIS, WF_CLASS_PRINCIPLED>;
+  t.sv_shade[1][WF_CLASS_DIELECTRIC] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MIS, WF_CLASS_DIELECTRIC>;
+  t.sv_end[0] = (const void*)&qv_end_kernel<VIMG_INTEGRATOR_MATERIAL>;
+  t.sv_end[1] = (const void*)&qv_end_kernel<VIMG_INTEGRATOR_MIS>;
+  t.sv_init = (const void*)&qv_init_kernel;
+}
+#endif  // VIMG_FAST
+
+}  // namespace vimg
