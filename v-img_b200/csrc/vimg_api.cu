@@ -67,7 +67,7 @@ struct QwPool {
   cudaStream_t main = nullptr, side[2] = {nullptr, nullptr};  // shade launches run beside END
   cudaEvent_t snap[2] = {nullptr, nullptr}, fork = nullptr, join[2] = {nullptr, nullptr}, done = nullptr;
   bool finished = false;
-  int trace_grid = 1, item_grid = 1, flat_grid = 1;  // current launch sizes (shrink as the pool drains)
+  int trace_grid = 1, item_grid = 1;  // current launch sizes (shrink as the pool drains)
   // one batch of iterations captured as a CUDA graph (launch sizes it was captured with)
   cudaGraphExec_t batch_exec = nullptr;
   int exec_trace_grid = 0, exec_item_grid = 0;
@@ -851,9 +851,6 @@ struct QwLaunchCfg {
   const QwKernelTable* kt;  // bit-exact or tolerance build of the kernels
   int integ;                // 0 material, 1 mis
   bool count;               // traversal counters
-  bool flat;                // tolerance build, small scene: trace + classify in one launch over the leaf array
-  bool fused;               // tolerance build, small scene: qf_path_kernel + shade launches only (vimg_flat.cuh)
-  const void* d_flat;       // ... and its device-side re-layout of the scene (QfScene)
 };
 
 // the tolerance build of the same kernels (vimg_fast.cu)
@@ -884,52 +881,11 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
   DCounters* counters = s->d_counters;
   cudaStream_t st = pool.main;
   uint32_t launches = 0;
-  if (cfg.fused) {
-    // path(it): shadow ray, closest ray, end-of-path work, next camera ray and its trace, routing;
-    // then the shade launches of the classes side by side.  Nothing else: the next path launch waits for them.
-    launch_k(kt.path_flat[cfg.integ], pool.item_grid, QW_THREADS, st, s->d, q, w, parity, cfg.d_flat, out, counters);
-    prof.mark(1);
-    ++launches;
-    const uint32_t cls_order[3] = {WF_CLASS_LAMBERT, WF_CLASS_PRINCIPLED, WF_CLASS_DIELECTRIC};
-    const int stage_of[3] = {4, 3, 5};
-    cudaStream_t lanes[3] = {st, st, st};
-    if (cfg.concurrent) {
-      lanes[1] = pool.side[0];
-      lanes[2] = pool.side[1];
-      cudaEventRecord(pool.fork, st);
-    }
-    int used = 0;  // the first class present runs on the main stream, the others beside it
-    bool side_used[2] = {false, false};
-    for (int k = 0; k < 3; ++k) {
-      if (!(cfg.class_mask & (1u << cls_order[k]))) continue;
-      cudaStream_t ls = lanes[used];
-      if (cfg.concurrent && used > 0) {
-        cudaStreamWaitEvent(ls, pool.fork, 0);
-        side_used[used - 1] = true;
-      }
-      launch_k(kt.shade[cfg.integ][cls_order[k]], pool.item_grid, QW_THREADS, ls, s->d, q, w, parity);
-      prof.mark(stage_of[k]);
-      ++launches;
-      ++used;
-    }
-    for (int k = 0; k < 2; ++k)
-      if (side_used[k]) {
-        cudaEventRecord(pool.join[k], lanes[k + 1]);
-        cudaStreamWaitEvent(st, pool.join[k], 0);
-      }
-    return launches;
-  }
   if (it > 0) {
-    if (cfg.flat) {
-      // thread <-> ray: up to two rays per live slot
-      launch_k(kt.trace_flat[cfg.count], pool.flat_grid, QW_THREADS, st, s->d, q, parity, cfg.d_flat, counters);
-      prof.mark(1);
-    } else {
-      launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
-      prof.mark(1);
-      launch_k(kt.classify, pool.item_grid, QW_THREADS, st, s->d, q, parity);
-      prof.mark(2);
-    }
+    launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
+    prof.mark(1);
+    launch_k(kt.classify, pool.item_grid, QW_THREADS, st, s->d, q, parity);
+    prof.mark(2);
     // shade launches only feed the next iteration, END only consumes what classify and the
     // previous shade launches queued: fork them onto side streams, join before the next trace
     cudaStream_t sp = st, sl = st;
@@ -959,7 +915,7 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
       cudaEventRecord(pool.join[0], sp);
       cudaEventRecord(pool.join[1], sl);
     }
-    launches += cfg.flat ? 1 : 2;
+    launches += 2;
   }
   launch_k(kt.end[cfg.integ], pool.item_grid, QW_THREADS, st, s->d, q, w, parity, out, counters);
   prof.mark(6);
@@ -976,7 +932,7 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
 // queued ahead of the check, so the device never waits for the host.
 static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count, bool fast, float* out, cudaStream_t caller,
                        bool stage_times) {
-  WfArgs w = w_in;
+  const WfArgs& w = w_in;
   QwProfile prof;
   const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
   prof.on = print_profile || stage_times;
@@ -995,21 +951,8 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
   for (uint32_t p = 0; p < n_pools; ++p)
     if ((rc = qw_reserve(s, s->ws->qw[p], per_pool)) != VIMG_OK) return rc;
   CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
-  // tolerance build: a scene of a few dozen primitives goes through the flat pipeline (vimg_flat.cuh)
   QwLaunchCfg cfg{};
   cfg.kt = &kernel_table(fast);
-  cfg.flat = fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32));
-  cfg.fused = cfg.flat && env_u32("VIMG_FLAT_MODE", 1) == 2 && !count;
-  if (cfg.flat && !s->d_flat) {
-    // device-side re-layout of the BVH: plane-form triangles and spheres as two flat lists
-    CU_TRY(cudaMalloc(&s->d_flat, vimg_fast_flat_scene_bytes()));
-    CU_TRY(launch_k(cfg.kt->build_flat, 1, (int)QF_FLAT_MAX_HOST, caller, s->d, s->d_flat));
-  }
-  if (cfg.fused) {
-    cfg.flat = false;
-    w.fused = 1;
-  }
-  cfg.d_flat = s->d_flat;
   cudaEvent_t start = s->ws->qw[0].done;  // reused as the fork event of the caller's stream
   const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
   for (uint32_t p = 0; p < n_pools; ++p) {
@@ -1020,11 +963,10 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
     CU_TRY(cudaStreamWaitEvent(pool.main, start, 0));
     CU_TRY(cudaMemsetAsync(pool.st.slot, 0, (size_t)per_pool * sizeof(QwSlot), pool.main));  // flags = 0: no pixel yet
     QwCounters init{};
-    // every slot starts without a pixel: the first launch (END, or the fused path kernel) hands them out
-    (cfg.fused ? init.n_closest[0] : init.n_end[0]) = per_pool;
+    init.n_end[0] = per_pool;  // every slot starts without a pixel: the first launch (END) hands them out
     *pool.h_cnt = init;
     CU_TRY(cudaMemcpyAsync(pool.st.cnt, pool.h_cnt, sizeof(init), cudaMemcpyHostToDevice, pool.main));
-    qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, pool.main>>>(cfg.fused ? pool.st.q_closest[0] : pool.st.q_end[0], per_pool);
+    qw_iota_kernel<<<slot_blocks, QW_THREADS, 0, pool.main>>>(pool.st.q_end[0], per_pool);
   }
   // with several pools in flight the persistent trace grid leaves room for the other pool's
   // shade / end blocks on every SM
@@ -1037,11 +979,9 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
   cfg.class_mask = s->class_mask;
   cfg.integ = integ;
   cfg.count = count;
-  const int flat_full = std::max(1, std::min(2 * slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_FLAT_BLOCKS", 8)));
   for (uint32_t p = 0; p < n_pools; ++p) {
     s->ws->qw[p].trace_grid = cfg.trace_grid;
     s->ws->qw[p].item_grid = cfg.item_grid;
-    s->ws->qw[p].flat_grid = flat_full;
   }
   const bool shrink = env_u32("VIMG_QW_SHRINK", 1) != 0;
   // VIMG_QW_GRAPH=1: batches after the first are replayed from a CUDA graph per pool (trace /
@@ -1136,7 +1076,6 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
           }
           pool.item_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.item_grid, ig));
           pool.trace_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(cfg.trace_grid, tg));
-          pool.flat_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(flat_full, 2 * ig));
         }
       }
       if (timeline) tl_live.push_back(live);
@@ -1259,7 +1198,8 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
   DCounters* counters = s->d_counters;
   cudaEvent_t start = s->ws->qw[0].done;
   const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
-  const int full_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 8)));
+  // 4 blocks per SM: every thread works through several items, so the next item's line is on its way while this one is shaded
+  const int full_grid = std::max(1, std::min(slot_blocks, s->sm_count * (int)env_u32("VIMG_QW_ITEM_BLOCKS", 4)));
   std::vector<int> grid(n_pools, full_grid);
   std::vector<bool> finished(n_pools, false);
   for (uint32_t p = 0; p < n_pools; ++p) {
@@ -1379,7 +1319,7 @@ static int qw_render(vimg_scene* s, const WfArgs& w, uint32_t integrator, bool f
                      bool stage_times) {
   // tolerance build, a scene of a few dozen primitives: the streamed pipeline over the flat lists (vimg_stream.cuh)
   if (fast && s->d.n_leaf_recs > 0 && s->d.n_leaf_recs <= std::min<uint32_t>(QF_FLAT_MAX_HOST, env_u32("VIMG_FLAT_MAX", 32))
-      && env_u32("VIMG_FLAT_MODE", 3) == 3)
+      && env_u32("VIMG_FLAT", 1) != 0)
     return qv_render(s, w, integrator == VIMG_INTEGRATOR_MIS ? 1 : 0, COUNT, out, st, stage_times);
   return qw_render_t(s, w, integrator == VIMG_INTEGRATOR_MIS ? 1 : 0, COUNT, fast, out, st, stage_times);
 }

@@ -57,11 +57,9 @@ namespace vimg {
 struct QwCounters {
   uint32_t n_closest[2], n_shadow[2];  // queue lengths, double buffered by iteration parity
   uint32_t n_end[2];
-  uint32_t n_shade[2][WF_NUM_CLASSES];  // by iteration parity: the trace + classify kernel of the tolerance build
-                                        // appends while it runs, so the reset happens one iteration ahead
+  uint32_t n_shade[2][WF_NUM_CLASSES];  // by iteration parity
   uint32_t cursor;      // trace kernel's work cursor
-  uint32_t blocks_done;  // qf_path_kernel: blocks of the running launch that are done
-  uint32_t pad_[2];
+  uint32_t pad_[3];
 };
 
 // Path state of one slot: five 32-byte records (one DRAM sector each), grouped by who reads and
@@ -1026,7 +1024,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
       d4 = ldg4(&st.slot[j].ray.d_s);
       h0 = ldg4(&st.slot[j].hit.h0);
       hb = ldg4u(&st.slot[j].hit.h1);
-      if (MIS && !args.fused) {  // pending shadow ray: resolved by qf_path_kernel in the fused pipeline
+      if (MIS) {
         cp4 = ldg4(&st.slot[j].nee.c_pdf);
         L4 = ldg4(&st.slot[j].pix.L_s);
       }
@@ -1065,12 +1063,6 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     // traversal inherits the stack its occlusion traversal left behind (see bvh_traverse)
     const bool pair = want_closest && want_shadow && !args.fresh_stack;
     if (pair) want_shadow = false;
-    if (args.fused) {
-      // tolerance build, flat scene: ONE queue.  qf_path_kernel reads from the slot's flags what is
-      // pending -- shadow ray (WF_NEE), end of path (WF_END), closest ray -- and does all of it.
-      want_closest = want_closest || want_shadow || want_end;
-      want_shadow = want_end = false;
-    }
     const bool want[3] = {want_closest, want_shadow, want_end};
     QwAppend<3> ap;
     ap.count(s_cnt, want, lane, lane_lt);
@@ -1092,13 +1084,11 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
 // above that the bit-exact contract rules out).  Launches go through cudaLaunchKernel on these entries.
 struct QwKernelTable {
   const void* trace[2];       // [COUNT]
-  const void* trace_flat[2];  // [COUNT]; tolerance build only (else NULL): trace + classify over a flat scene
   const void* classify;
   const void* shade[2][WF_NUM_CLASSES];  // [material = 0, mis = 1][class]
   const void* end[2];                    // [material = 0, mis = 1]
-  const void* path_flat[2];              // [material = 0, mis = 1]; tolerance build only
-  const void* build_flat;                // tolerance build only
-  // the streamed pipeline of vimg_stream.cuh (tolerance build only)
+  // tolerance build only: flat re-layout of a small scene (vimg_flat.cuh) and the streamed pipeline (vimg_stream.cuh)
+  const void* build_flat;
   const void* sv_trace_flat[2];          // [COUNT]
   const void* sv_shade[2][WF_NUM_CLASSES];
   const void* sv_end[2];

@@ -63,6 +63,10 @@ struct QvState {
 };
 
 #ifdef VIMG_FAST
+#ifndef QV_PREFETCH
+#define QV_PREFETCH 1  // 1: shade / END start the fetch of their NEXT item's line into L2 while they work on this one
+#endif
+VD void qv_prefetch_line(const QvLine* ln) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ln)); }
 VD float4 ldq(const float4* p) { return __ldcs(p); }  // queue records are read once: evict first
 VD void stq(float4* p, float4 v) { __stcs(p, v); }
 
@@ -135,12 +139,9 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
     if (valid) {
       cls = WF_CLASS_NONE;  // END: miss, emitter, base material, or a path that only had its last shadow ray left
       if (best.k >= 0) {
-        const bool is_tri = (uint32_t)best.k < fs.n_tri;
-        const uint32_t e = is_tri ? (uint32_t)best.k : (uint32_t)best.k - fs.n_tri;
-        leaf = is_tri ? fs.tri_leaf[e] : fs.sph_leaf[e];
-        const uint32_t lc = is_tri ? fs.tri_class[e] : fs.sph_class[e];
+        uint32_t lc;
+        qf_decode(fs, best, leaf, lc, hb4);
         cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
-        if (is_tri) hb4 = make_float4(1.f - best.u - best.v, best.u, best.v, 1.f);  // weights of p0, p1, p2 (e_i * inv_det)
       }
     }
     bool want[WF_NUM_CLASSES + 1];
@@ -201,6 +202,10 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
     const uint32_t j = __float_as_uint(ha4.x);
     const int32_t leaf = __float_as_int(ha4.y);
     QvLine* ln = st.line + j;
+    if (QV_PREFETCH) {
+      const uint32_t next = item + gridDim.x * QW_THREADS;
+      if (next < n) qv_prefetch_line(st.line + __float_as_uint(__ldg(reinterpret_cast<const float*>(qa + next))));
+    }
     ShadeIO io;
     io.t4 = io.o4 = io.d4 = io.cp4 = io.L4 = make_float4(0.f, 0.f, 0.f, 0.f);
     io.pa1 = make_uint4(0, 0, 0, 0);
@@ -301,6 +306,10 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
     }
     const uint32_t i = __float_as_uint(ha4.x);
     QvLine* ln = st.line + i;
+    if (QV_PREFETCH) {
+      const uint32_t next = item + gridDim.x * QW_THREADS;
+      if (next < n) qv_prefetch_line(st.line + __float_as_uint(__ldg(reinterpret_cast<const float*>(qa + next))));
+    }
     EndIO io;
     io.thr4 = io.o4 = io.d4 = io.cp4 = io.L4 = io.ap4 = make_float4(0.f, 0.f, 0.f, 0.f);
     io.pa1 = make_uint4(0, 0, 0, 0);

@@ -78,9 +78,6 @@ struct WfArgs {
   // 1: every traversal starts from an empty stack (VIMG_FLAG_FRESH_STACK, or streams > 1); 0: a path's
   // closest-hit traversal inherits what its shadow ray's traversal left (the reference's thread_stack)
   uint32_t fresh_stack;
-  // 1: the fused small-scene pipeline of the tolerance build (vimg_flat.cuh): the shade kernels queue every
-  // slot that goes on in ONE queue and leave the pending shadow ray to qf_path_kernel
-  uint32_t fused;
 };
 // a slot's sample range number lives in the upper half of its flag word
 #define WF_RANGE_SHIFT 16
