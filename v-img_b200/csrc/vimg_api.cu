@@ -114,7 +114,7 @@ struct QvPool {
 
 struct QwWorkspace {
   QwPool qw[QW_MAX_POOLS];
-  QvPool qv[2];
+  QvPool qv[QW_MAX_POOLS];
   uint32_t* d_next_pixel = nullptr;
   float* d_partial = nullptr;  // spp_streams > 1: per-range partial sums, W*H*streams*3 floats
   size_t partial_floats = 0;
@@ -1181,11 +1181,13 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
   const bool concurrent = !prof.on && env_u32("VIMG_QW_SERIAL", 0) == 0;
   const uint32_t cap = env_u32("VIMG_QW_SLOTS", 1u << 21);
   const uint32_t total_slots = std::max(1u, std::min(w.n_local_units, cap));
-  uint32_t n_pools = std::min<uint32_t>(2, std::max(1u, env_u32("VIMG_QW_POOLS", 2)));
+  uint32_t n_pools = std::min<uint32_t>(QW_MAX_POOLS, std::max(1u, env_u32("VIMG_QW_POOLS", 2)));
   if (!concurrent || total_slots < 65536u) n_pools = 1;
   const uint32_t per_pool = (total_slots + n_pools - 1) / n_pools;
   if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
   const QwKernelTable& kt = kernel_table(true);
+  // blocks per SM of the trace launches: fewer than the 4 that fit leave registers for the other pool's shade / END blocks
+  const int trace_per_sm = (int)std::max(1u, env_u32("VIMG_QV_TRACE_BLOCKS", 4));
   int rc;
   for (uint32_t p = 0; p < n_pools; ++p)
     if ((rc = qv_reserve(s, s->ws->qw[p], s->ws->qv[p], per_pool)) != VIMG_OK) return rc;
@@ -1221,7 +1223,7 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
     uint32_t launches = 0;
     cudaStream_t m = st.main;
     if (it > 0) {
-      launch_k(kt.sv_trace_flat[count], grid[p], QW_THREADS, m, q, parity, d_flat, counters);
+      launch_k(kt.sv_trace_flat[count], std::min(grid[p], s->sm_count * trace_per_sm), QW_THREADS, m, q, parity, d_flat, counters);
       prof.mark(1);
       ++launches;
       // the shade launches only feed the next iteration; END consumes what trace (and the last shade launches) queued
