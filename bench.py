@@ -401,12 +401,30 @@ def time_e2e(gpu, vimg, w, integ, spp, kw, steps):
     return {"seconds": mx[0], "rays": sm[1], "steps": steps, "h2d": int(h2d)}
 
 
+# ALGORITHMIC bytes per item of the path-state kernels: what an item must move through HBM in
+# the layout of its pipeline -- records read + sectors written + queue records -- not counting scene tables
+# (leaf / shade / light records), which are cache resident for small scenes.
+STATE_BYTES = {
+    # streamed pipeline (vimg_stream.cuh): hit record 32 + slot line 128 read; sectors 0, 2, 3 (96) + ray record 48 written
+    "stream": {"shade": 32 + 128 + 96 + 48, "end": 32 + 128 + 96 + 32 + 32},
+    # slot-record pipeline (vimg_queues.cuh): queue entry 8 + 160-byte slot read; 112 + queue entry written (END: + ray 32)
+    "slot": {"shade": 8 + 160 + 112 + 8, "end": 4 + 160 + 112 + 32 + 4},
+}
+STAGE_KERNEL = {"trace": None, "classify": "qw_classify_kernel", "shade_principled": "shade_kernel<mis, Principled>",
+                "shade_lambertian": "shade_kernel<mis, Lambertian>", "shade_dielectric": "shade_kernel<mis, Dielectric>",
+                "end": "end_kernel<mis>"}
+
+
 def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
-    """Trace-kernel roofline of one workload on this rank's GPU (rank 0 calls this, whole frame):
-    per-ray algorithmic cost from a counted pass of the bit-exact kernels (the reference's traversal),
-    launch duration from a stage-timed pass in the measured mode."""
+    """Roofline of the DOMINANT kernel of one workload on this rank's GPU (rank 0 calls this, whole frame): every
+    launch of a serial pass in the measured mode is timed with CUDA events on its stream (VIMG_FLAG_STAGE_TIMES),
+    the stage with the largest share is the dominant kernel.  TRACE: algorithmic bytes per ray in the REFERENCE's
+    layout, per-ray averages from a counted pass of the bit-exact kernels (the reference's
+    traversal).  SHADE / END: path-state bytes per item (STATE_BYTES)."""
+    flat = bool(kw.get("fast")) and w.n_prims <= 32
     c_spp = min(spp, 4 if w.n_prims > 100000 else 16)
-    _, cst = scene.render_device(integ, c_spp, w.depth, counters=True, spp_streams=1, fresh_stack=bool(kw.get("fast") or kw.get("spp_streams", 1) > 1))
+    _, cst = scene.render_device(integ, c_spp, w.depth, counters=True, spp_streams=1,
+                                 fresh_stack=bool(kw.get("fast") or kw.get("spp_streams", 1) > 1))
     c_rays = cst["rays_closest"] + cst["rays_shadow"]
     bytes_per_ray = sum(BYTES[k] * cst[k] for k in BYTES) / c_rays
     flops_per_ray = sum(FLOPS[k] * cst[k] for k in FLOPS) / c_rays
@@ -415,27 +433,43 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
     kw_t["spp_streams"] = min(kw.get("spp_streams", 1), t_spp)
     gpu.flush.zero_()
     _, tst = scene.render_device(integ, t_spp, w.depth, stage_times=True, **kw_t)
-    t_rays = tst["rays_closest"] + tst["rays_shadow"]
-    n_launch = max(tst["stage_launches"]["trace"], 1)
-    launch_s = tst["stage_ms"]["trace"] / 1e3 / n_launch
-    rays_per_launch = t_rays / n_launch
-    achieved = bytes_per_ray * rays_per_launch / launch_s / 1e9
     total = sum(tst["stage_ms"].values())
-    flat = bool(kw.get("fast")) and w.n_prims <= 32
-    kernel = "qv_trace_flat_kernel" if flat else "qw_trace_kernel"
-    traffic, traffic_src = ncu_traffic(kernel, w.key)
     shares = {k: v / total for k, v in tst["stage_ms"].items() if tst["stage_launches"][k]}
+    top = max(shares, key=shares.get)
+    n_launch = max(tst["stage_launches"][top], 1)
+    launch_s = tst["stage_ms"][top] / 1e3 / n_launch
+    items_per_launch = tst["stage_items"][top] / n_launch
+    layout = "stream" if flat else "slot"
+    prefix = "qv_" if flat else "qw_"
+    if top == "trace":
+        kernel = "qv_trace_flat_kernel" if flat else "qw_trace_kernel"
+        per_item, unit_note = bytes_per_ray, ("bytes per ray in the reference's layout (56/inner node, 8/leaf, 56/triangle test, "
+                                             f"24/sphere test; SURVEY.md 8(d)), per-ray averages of a counted pass at {c_spp} spp")
+    else:
+        kernel = prefix + STAGE_KERNEL[top].replace("mis", integ)
+        per_item = STATE_BYTES[layout]["end" if top == "end" else "shade"]
+        unit_note = (f"path-state bytes per item of the {layout} layout (records read + sectors written + queue records; "
+                     "DESIGN.md 5.2), scene tables not counted")
+    achieved = per_item * items_per_launch / launch_s / 1e9
+    traffic, traffic_src = ncu_traffic(kernel, w.key)
+    trace_launch_s = tst["stage_ms"]["trace"] / 1e3 / max(tst["stage_launches"]["trace"], 1)
+    t_rays = tst["rays_closest"] + tst["rays_shadow"]
+    rays_per_trace_launch = t_rays / max(tst["stage_launches"]["trace"], 1)
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
-            "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "rays_per_launch": rays_per_launch,
-            "algorithmic_bytes_per_ray": bytes_per_ray, "algorithmic_flops_per_ray": flops_per_ray,
-            "fp32_tflops_achieved": flops_per_ray * rays_per_launch / launch_s / 1e12,
+            "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "items_per_launch": items_per_launch,
+            "algorithmic_bytes_per_item": per_item,
             "stage_share_of_step": shares,
-            "note": "algorithmic bytes in the reference's layout (56/inner node, 8/leaf, 56/triangle test, 24/sphere test; "
-                    f"SURVEY.md 8(d)), per-ray averages of a counted pass at {c_spp} spp; every trace launch of a serial pass at "
-                    f"{t_spp} spp timed with CUDA events on its stream (VIMG_FLAG_STAGE_TIMES), average duration; shares = "
-                    "stage time / sum of stages in that pass"
-                    + ("; this scene (< 8 KiB) sits in shared memory: the fraction only normalises throughput" if flat else "")}
+            "trace": {"kernel": "qv_trace_flat_kernel" if flat else "qw_trace_kernel", "launch_ms": 1e3 * trace_launch_s,
+                      "rays_per_launch": rays_per_trace_launch, "algorithmic_bytes_per_ray": bytes_per_ray,
+                      "algorithmic_flops_per_ray": flops_per_ray,
+                      "reference_layout_gbs": bytes_per_ray * rays_per_trace_launch / trace_launch_s / 1e9,
+                      "fp32_tflops_achieved": flops_per_ray * rays_per_trace_launch / trace_launch_s / 1e12,
+                      "note": "the reference-layout figure normalises throughput across scenes; "
+                              + ("this scene (< 8 KiB) is traced from shared memory, the kernel's bound is instruction issue"
+                                 if flat else "node and primitive records come from L2 / HBM")},
+            "note": f"dominant kernel = largest stage share of a serial pass at {t_spp} spp, every launch timed with CUDA events "
+                    f"on its stream (VIMG_FLAG_STAGE_TIMES), average duration; {unit_note}"}
 
 
 def run_scene(gpu, vimg, key, args, hbm_peak, peak_src, want_cpu):

@@ -310,6 +310,8 @@ typedef struct vimg_render_stats {
   uint32_t kernel_launches;
   uint32_t stage_launches[VIMG_STAGE_COUNT]; /* VIMG_FLAG_STAGE_TIMES only                */
   double stage_ms[VIMG_STAGE_COUNT];         /* VIMG_FLAG_STAGE_TIMES only                */
+  uint64_t stage_items[VIMG_STAGE_COUNT];    /* queue wavefront: items the stage's launches processed (rays for
+                                                TRACE, path segments for SHADE_*, ended paths for END)   */
 } vimg_render_stats;
 
 typedef struct vimg_scene vimg_scene; /* opaque device-resident scene */

@@ -897,17 +897,17 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
       cudaStreamWaitEvent(sl, pool.fork, 0);
     }
     if (cfg.class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-      launch_k(kt.shade[cfg.integ][WF_CLASS_PRINCIPLED], pool.item_grid, QW_THREADS, sp, s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_PRINCIPLED], pool.item_grid, QW_THREADS, sp, s->d, q, w, parity, counters);
       prof.mark(3);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_LAMBERT)) {
-      launch_k(kt.shade[cfg.integ][WF_CLASS_LAMBERT], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_LAMBERT], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity, counters);
       prof.mark(4);
       ++launches;
     }
     if (cfg.class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-      launch_k(kt.shade[cfg.integ][WF_CLASS_DIELECTRIC], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity);
+      launch_k(kt.shade[cfg.integ][WF_CLASS_DIELECTRIC], pool.item_grid, QW_THREADS, sl, s->d, q, w, parity, counters);
       prof.mark(5);
       ++launches;
     }
@@ -1236,17 +1236,17 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         cudaStreamWaitEvent(sl, st.fork, 0);
       }
       if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], grid[p], QW_THREADS, sp, s->d, q, w, parity);
+        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], grid[p], QW_THREADS, sp, s->d, q, w, parity, counters);
         prof.mark(3);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], grid[p], QW_THREADS, sl, s->d, q, w, parity);
+        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], grid[p], QW_THREADS, sl, s->d, q, w, parity, counters);
         prof.mark(4);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], grid[p], QW_THREADS, sl, s->d, q, w, parity);
+        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], grid[p], QW_THREADS, sl, s->d, q, w, parity, counters);
         prof.mark(5);
         ++launches;
       }
@@ -1574,6 +1574,7 @@ static int render_into(vimg_scene* s, const vimg_render_params* p, float* frame,
     stats->kernel_launches = s->last_launches;
     std::memcpy(stats->stage_ms, s->stage_ms, sizeof(s->stage_ms));
     std::memcpy(stats->stage_launches, s->stage_launches, sizeof(s->stage_launches));
+    for (int k = 0; k < VIMG_STAGE_COUNT; ++k) stats->stage_items[k] = c.stage_items[k];
 #ifdef WF_STAGE_CLOCKS
     fprintf(stderr, "[wf stage cycles, summed over warps] shadow %llu regen %llu closest %llu resolve+bucket %llu "
             "barrier1 %llu shade %llu barrier2 %llu\n", c.stage_clk[0], c.stage_clk[1], c.stage_clk[2],
@@ -1732,6 +1733,7 @@ int vimg_render_multi(const vimg_scene_desc* desc, const int* device_ids, uint32
       stats->nan_samples += st[i].nan_samples;
       stats->samples += st[i].samples;
       stats->kernel_launches += st[i].kernel_launches;
+      for (int k = 0; k < VIMG_STAGE_COUNT; ++k) stats->stage_items[k] += st[i].stage_items[k];
       stats->kernel_ms = std::max(stats->kernel_ms, st[i].kernel_ms);
     }
     stats->total_ms = wall_ms;

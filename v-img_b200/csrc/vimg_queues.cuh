@@ -156,6 +156,7 @@ qw_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) c->n_shade[parity ^ 1u][k] = 0;
   }
   const uint32_t n_c = c->n_closest[parity], total = n_c + c->n_shadow[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_TRACE], (unsigned long long)total);
   const uint32_t* __restrict__ qc = st.q_closest[parity];
   const uint32_t* __restrict__ qs = st.q_shadow[parity];
   const uint32_t lane = threadIdx.x & 31u;
@@ -660,6 +661,7 @@ qw_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t W = sc.cam.res[0], H = sc.cam.res[1];
   const uint32_t n = c->n_end[parity];
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_END], (unsigned long long)n);
   const uint32_t* __restrict__ q = st.q_end[parity];
   uint32_t nan_samples = 0, n_samples = 0;
   // one look at the unit counter per warp and launch, in flight together with the first gathers
@@ -756,6 +758,12 @@ VD V3 cls_eval_div_pdf(const DScene& sc, const vimg_material& m, V3 wi, V3 wo, c
     principled_eval_pdf(sc, m, wi, wo, hit, cone, regularize, e, p);
     return e / p;
   }
+}
+
+// vimg_stage of a material class's shade launches
+VD constexpr uint32_t wf_class_stage(uint32_t cls) {
+  return cls == WF_CLASS_PRINCIPLED ? VIMG_STAGE_SHADE_PRINCIPLED
+                                    : (cls == WF_CLASS_LAMBERT ? VIMG_STAGE_SHADE_LAMBERTIAN : VIMG_STAGE_SHADE_DIELECTRIC);
 }
 
 #ifndef QW_SHADE_MIN_BLOCKS_P
@@ -986,7 +994,7 @@ VD void shade_bounce(const DScene& sc, const WfArgs& args, const DLeafPrim& lp, 
 template <int INTEGRATOR, uint32_t CLASS>
 __global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_SHADE_MIN_BLOCKS_P : QW_SHADE_MIN_BLOCKS_L)
 qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwState st,
-                const __grid_constant__ WfArgs args, const uint32_t parity) {
+                const __grid_constant__ WfArgs args, const uint32_t parity, DCounters* __restrict__ counters) {
   constexpr bool MIS = INTEGRATOR == VIMG_INTEGRATOR_MIS;
   __shared__ uint32_t s_cnt[3], s_base[3];
   QwCounters* c = st.cnt;
@@ -994,6 +1002,7 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t n = c->n_shade[parity][CLASS];
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[wf_class_stage(CLASS)], (unsigned long long)n);
   const uint2* __restrict__ q = st.q_shade[CLASS];
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {

@@ -95,6 +95,7 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
     for (uint32_t i = tid; i < sizeof(QfScene) / 16; i += QW_THREADS) dst[i] = __ldg(src + i);
   }
   const uint32_t n = c->n_trace[parity];
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_TRACE], (unsigned long long)n);
   const float4* __restrict__ ta = st.ta[parity];
   const float4* __restrict__ tb = st.tb[parity];
   const float4* __restrict__ tc = st.tc[parity];
@@ -179,13 +180,14 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
 template <int INTEGRATOR, uint32_t CLASS>
 __global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_SHADE_MIN_BLOCKS_P : QW_SHADE_MIN_BLOCKS_L)
 qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
-                const __grid_constant__ WfArgs args, const uint32_t parity) {
+                const __grid_constant__ WfArgs args, const uint32_t parity, DCounters* __restrict__ counters) {
   __shared__ uint32_t s_cnt[2], s_base[2];
   QvCounters* c = st.cnt;
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t n = c->n_shade[parity][CLASS];
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[wf_class_stage(CLASS)], (unsigned long long)n);
   const float4* __restrict__ qa = st.ha[CLASS];
   const float4* __restrict__ qb = st.hb[CLASS];
 
@@ -289,6 +291,7 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t n = c->n_end[parity];
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_END], (unsigned long long)n);
   const float4* __restrict__ qa = st.ea[parity];
   const float4* __restrict__ qb = st.eb[parity];
   uint32_t nan_samples = 0, n_samples = 0;

@@ -122,6 +122,7 @@ struct DCounters {  // matches the tail of vimg_render_stats
   unsigned long long rays_closest, rays_shadow, inner_nodes, leaf_nodes, tri_tests, sphere_tests,
       nan_samples, samples;
   unsigned long long stage_clk[8];  // WF_STAGE_CLOCKS builds only: per-stage SM cycles summed over warps
+  unsigned long long stage_items[8];  // queue wavefront: items each stage's launches processed (index = vimg_stage)
 };
 
 struct DScene {

@@ -82,12 +82,13 @@ class RenderStats(C.Structure):
                 ("nan_samples", C.c_uint64), ("samples", C.c_uint64),
                 ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("stage_launches", C.c_uint32 * 6),
-                ("stage_ms", C.c_double * 6)]
+                ("stage_ms", C.c_double * 6), ("stage_items", C.c_uint64 * 6)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["stage_ms"] = dict(zip(STAGES, self.stage_ms))
         d["stage_launches"] = dict(zip(STAGES, self.stage_launches))
+        d["stage_items"] = dict(zip(STAGES, self.stage_items))
         return d
 
 
