@@ -335,7 +335,7 @@ class Gpu:
 def mode_kwargs(mode, streams):
     """render options of a mode.  fast: tolerance mode; exact: the library default, bit-identical images"""
     if mode == "fast":
-        return {"fast": True, "spp_streams": streams}
+        return {"fast": True, "spp_streams": streams}  # flat lists + streamed queues (<= 32 primitives) or the 4-wide BVH
     return {"spp_streams": 1}
 
 
@@ -441,8 +441,9 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
     items_per_launch = tst["stage_items"][top] / n_launch
     layout = "stream" if flat else "slot"
     prefix = "qv_" if flat else "qw_"
+    trace_kernel = "qv_trace_flat_kernel" if flat else ("qw_trace_wide_kernel" if kw.get("fast") else "qw_trace_kernel")
     if top == "trace":
-        kernel = "qv_trace_flat_kernel" if flat else "qw_trace_kernel"
+        kernel = trace_kernel
         per_item, unit_note = bytes_per_ray, ("bytes per ray in the reference's layout (56/inner node, 8/leaf, 56/triangle test, "
                                              f"24/sphere test; SURVEY.md 8(d)), per-ray averages of a counted pass at {c_spp} spp")
     else:
@@ -460,7 +461,7 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
             "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "items_per_launch": items_per_launch,
             "algorithmic_bytes_per_item": per_item,
             "stage_share_of_step": shares,
-            "trace": {"kernel": "qv_trace_flat_kernel" if flat else "qw_trace_kernel", "launch_ms": 1e3 * trace_launch_s,
+            "trace": {"kernel": trace_kernel, "launch_ms": 1e3 * trace_launch_s,
                       "rays_per_launch": rays_per_trace_launch, "algorithmic_bytes_per_ray": bytes_per_ray,
                       "algorithmic_flops_per_ray": flops_per_ray,
                       "reference_layout_gbs": bytes_per_ray * rays_per_trace_launch / trace_launch_s / 1e9,

@@ -77,3 +77,38 @@ def test_golden_files_present(man):
     for name, e in man.items():
         assert os.path.exists(os.path.join(GOLDEN, e["scene"])), name
         assert os.path.exists(os.path.join(GOLDEN, "ref", name + ".npz")), name
+
+
+def test_vscene_load_rejects_arrays_that_contradict_their_dimensions(vimg, tmp_path):
+    """A hand-edited file whose array lengths disagree with the dimensions next to them must not reach
+    vimg_scene_create, which sizes its reads from the dimensions: here a mesh's normal array loses one
+    vertex, everything else stays parseable."""
+    import struct
+    raw = open(golden_scene_path("synthetic_small"), "rb").read()
+    off = 8 + 4 + 92  # magic, abi version, vimg_camera
+
+    def skip_arr(o, elem):
+        n, = struct.unpack_from("<Q", raw, o)
+        return o + 8 + n * elem, n
+
+    off, _ = skip_arr(off, 4)    # nodes (u32)
+    off, _ = skip_arr(off, 4)    # bb_mins_maxes (f32)
+    off, _ = skip_arr(off, 8)    # obj_indices (u64)
+    off += 4                     # max_depth
+    off, _ = skip_arr(off, 12)   # prims
+    off, _ = skip_arr(off, 20)   # spheres
+    n_meshes, = struct.unpack_from("<I", raw, off)
+    assert n_meshes >= 1
+    off += 4
+    off, _ = skip_arr(off, 4)    # mesh 0: indices
+    off, n_vert_floats = skip_arr(off, 4)  # vertices
+    n_norm, = struct.unpack_from("<Q", raw, off)
+    assert n_norm == n_vert_floats and n_norm >= 6
+    bad = raw[:off] + struct.pack("<Q", n_norm - 3) + raw[off + 8:off + 8 + 4 * (n_norm - 3)] + raw[off + 8 + 4 * n_norm:]
+    p = tmp_path / "edited.vscene"
+    p.write_bytes(bad)
+    with pytest.raises(vimg.VimgError):
+        vimg.LoadedDesc(str(p))
+    ok = tmp_path / "same.vscene"
+    ok.write_bytes(raw)
+    vimg.LoadedDesc(str(ok)).close()

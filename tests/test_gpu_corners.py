@@ -188,3 +188,45 @@ def test_non_square_texture_rg(vimg, refcpu):
     sc.close()
     rs.close()
     rs2.close()
+
+
+def test_scene_create_rejects_a_bvh_that_is_not_a_tree_of_the_stated_depth(vimg):
+    """The device's traversal stacks hold max_depth + 2 entries and are not bounds checked: vimg_scene_create walks
+    the tree once and refuses an understated depth, a shared child and a cycle."""
+    d = vimg.LoadedDesc(golden_scene_path("cornell_skylight"))
+    keep = _chain_bvh(vimg, d, 12)
+    desc = _desc(vimg, d)
+    vimg.Scene(d.ptr).close()  # the chain itself is fine
+    desc.bvh.max_depth = 5     # 12 levels deep
+    with pytest.raises(vimg.VimgError) as e:
+        vimg.Scene(d.ptr)
+    assert "deeper" in str(e.value)
+    desc.bvh.max_depth = 12
+    nodes = keep[0]
+    saved = nodes[4].copy()
+    nodes[4] = (1, 0)          # inner node 4 now points back at children (1, 2): node 2 is its own ancestor
+    with pytest.raises(vimg.VimgError) as e:
+        vimg.Scene(d.ptr)
+    assert "tree" in str(e.value)
+    nodes[4] = saved
+    vimg.Scene(d.ptr).close()
+    d.close()
+
+
+def test_scene_create_rejects_an_empty_rg_texture(vimg, refcpu):
+    rs = refcpu.RefScene.synthetic(G=8, width=32, height=32, tex_size=16, env_w=16, env_h=8, spp=1, depth=4,
+                                   bvh="binned", with_rg=1, aperture=0.0)
+    desc = vimg.renderer._Desc.from_address(rs.desc_ptr())
+
+    class _TexRG(C.Structure):  # vimg_texture_rg
+        _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32),
+                    ("data", C.c_void_p)]
+    rg = C.cast(desc.textures_rg, C.POINTER(_TexRG))
+    assert desc.n_textures_rg == 1
+    vimg.Scene(rs.desc_ptr()).close()
+    w = rg[0].width
+    rg[0].width = 0
+    with pytest.raises(vimg.VimgError):
+        vimg.Scene(rs.desc_ptr())
+    rg[0].width = w
+    rs.close()

@@ -18,6 +18,7 @@
 
 #include "vimg_kernels.cuh"
 #include "vimg_stream.cuh"
+#include "vimg_wide.cuh"
 #include "vimg_post.cuh"
 #include "vimg_prep.cuh"
 
@@ -213,6 +214,9 @@ struct vimg_scene {
   uint8_t* d_rgb8 = nullptr;      // vimg_render_srgb8: quantised frame
   uint32_t* d_post_max = nullptr;  // ... and the reinhard tonemapper's largest luminance (float bits)
   void* d_flat = nullptr;  // tolerance build: flat re-layout of a small scene (vimg_flat.cuh), built at the first fast render
+  DWideNode* d_wide = nullptr;  // tolerance build: 4-wide BVH of a large scene (vimg_wide.cuh), built at the first fast render
+  bool wide_ok = false;         // every leaf fits a wide leaf reference
+  uint32_t n_pairs = 0;
   QwWorkspace* ws = nullptr;  // taken at the first material / mis render
   uint32_t class_mask = 0;
   int sm_count = 0;
@@ -339,6 +343,10 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
   d.n_nodes = (uint32_t)b.n_nodes;
   d.stack_cap = b.max_depth + 2;
   d.n_leaf_recs = (uint32_t)b.n_obj_indices;
+  s->n_pairs = b.n_nodes ? (uint32_t)((b.n_nodes - 1) / 2) : 0;
+  s->wide_ok = s->n_pairs > 0 && b.n_obj_indices < WIDE_MAX_LEAF_FIRST;
+  for (uint64_t n = 0; n < b.n_nodes && s->wide_ok; ++n)
+    if (b.nodes[2 * n + 1] > WIDE_MAX_LEAF_COUNT) s->wide_ok = false;
   if (d.stack_cap > VIMG_STACK_MAX)
     return fail(VIMG_ERR_UNSUPPORTED, "BVH max_depth + 2 exceeds the traversal stack (VIMG_STACK_MAX)");
   std::vector<DPairNode> pairs;
@@ -851,6 +859,7 @@ struct QwLaunchCfg {
   const QwKernelTable* kt;  // bit-exact or tolerance build of the kernels
   int integ;                // 0 material, 1 mis
   bool count;               // traversal counters
+  const DWideNode* wide;    // tolerance build, large scene: trace through the 4-wide BVH (else NULL)
 };
 
 // the tolerance build of the same kernels (vimg_fast.cu)
@@ -882,7 +891,10 @@ static uint32_t qw_enqueue_iteration(vimg_scene* s, QwPool& pool, const WfArgs& 
   cudaStream_t st = pool.main;
   uint32_t launches = 0;
   if (it > 0) {
-    launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
+    if (cfg.wide)
+      launch_k(kt.trace_wide[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, cfg.wide, counters);
+    else
+      launch_k(kt.trace[cfg.count], pool.trace_grid, QW_TRACE_THREADS, st, s->d, q, parity, counters);
     prof.mark(1);
     launch_k(kt.classify, pool.item_grid, QW_THREADS, st, s->d, q, parity);
     prof.mark(2);
@@ -953,6 +965,17 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
   CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
   QwLaunchCfg cfg{};
   cfg.kt = &kernel_table(fast);
+  if (fast && s->wide_ok && env_u32("VIMG_WIDE", 1) != 0) {
+    if (!s->d_wide) {
+      // device-side re-layout of a large BVH: every binary inner node's grandchildren as one 128-byte record
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&s->d_wide), (size_t)s->n_pairs * sizeof(DWideNode)));
+      CU_TRY(launch_k(cfg.kt->wide_build, (int)((s->n_pairs + 255) / 256), 256, caller, s->d.pairs, s->n_pairs, s->d_wide));
+    }
+    cfg.wide = s->d_wide;
+  }
+  if (env_u32("VIMG_VERBOSE", 0))
+    fprintf(stderr, "[vimg] slot-record pipeline: %s build, %s traversal (%u pair records, wide_ok %d)\n", fast ? "tolerance" : "bit-exact",
+            cfg.wide ? "4-wide" : "binary", s->n_pairs, (int)s->wide_ok);
   cudaEvent_t start = s->ws->qw[0].done;  // reused as the fork event of the caller's stream
   const int slot_blocks = (int)((per_pool + QW_THREADS - 1) / QW_THREADS);
   for (uint32_t p = 0; p < n_pools; ++p) {
@@ -1484,6 +1507,7 @@ void vimg_scene_destroy(vimg_scene* s) {
   if (s->d_rgb8) cudaFree(s->d_rgb8);
   if (s->d_post_max) cudaFree(s->d_post_max);
   if (s->d_flat) cudaFree(s->d_flat);
+  if (s->d_wide) cudaFree(s->d_wide);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;

@@ -14,12 +14,14 @@
 #include "vimg_kernels.cuh"
 #include "vimg_flat.cuh"
 #include "vimg_stream.cuh"
+#include "vimg_wide.cuh"
 #undef vimg
 
 extern "C" void vimg_fast_kernel_table(void* out) {
   vimg_fast::QwKernelTable t = vimg_fast::qw_kernel_table();
   vimg_fast::qf_fill_kernel_table(t);
   vimg_fast::qv_fill_kernel_table(t);
+  vimg_fast::qw_wide_fill_kernel_table(t);
   *static_cast<vimg_fast::QwKernelTable*>(out) = t;
 }
 

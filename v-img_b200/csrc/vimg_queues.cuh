@@ -1102,6 +1102,9 @@ struct QwKernelTable {
   const void* sv_shade[2][WF_NUM_CLASSES];
   const void* sv_end[2];
   const void* sv_init;
+  // 4-wide BVH for large scenes (vimg_wide.cuh)
+  const void* wide_build;
+  const void* trace_wide[2];  // [COUNT]
 };
 inline QwKernelTable qw_kernel_table() {
   QwKernelTable t{};
