@@ -11,4 +11,4 @@ raises VimgError when the CUDA extension or a CUDA device is missing.
 from .renderer import (INTEGRATORS, TONEMAPPERS, LoadedDesc, Scene, VimgError, device_count,  # noqa: F401
                        lib_path, load_library, postprocess, tile_owner, build_mip_chain, build_envmap_cdf,
                        desc_envmap, desc_image_textures, convert_srgb8_to_linear, convert_rgb8_to_normal,
-                       build_image_texture, libm_eval, LIBM_FUNCTIONS, strip_prepared, release_workspaces, render_multi)
+                       build_image_texture, libm_eval, LIBM_FUNCTIONS, strip_prepared, release_workspaces, render_multi, spp_ranges)

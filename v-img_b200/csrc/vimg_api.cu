@@ -1239,6 +1239,7 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
     CU_TRY(cudaMemcpyAsync(pool.st.cnt, &pool.h_cnt[0], sizeof(init), cudaMemcpyHostToDevice, st.main));
     CU_TRY(launch_k(kt.sv_init, slot_blocks, QW_THREADS, st.main, pool.st.ea[0], pool.st.eb[0], per_pool));
   }
+  auto item_grid = [&](uint32_t p) { return grid[p] * (256 / QV_THREADS); };  // shade / END blocks of QV_THREADS threads
   auto enqueue = [&](uint32_t p, uint32_t it) -> uint32_t {
     QwPool& st = s->ws->qw[p];
     const QvState& q = s->ws->qv[p].st;
@@ -1259,17 +1260,17 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         cudaStreamWaitEvent(sl, st.fork, 0);
       }
       if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], grid[p], QW_THREADS, sp, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], item_grid(p), QV_THREADS, sp, s->d, q, w, parity, counters);
         prof.mark(3);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], grid[p], QW_THREADS, sl, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, counters);
         prof.mark(4);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], grid[p], QW_THREADS, sl, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, counters);
         prof.mark(5);
         ++launches;
       }
@@ -1278,7 +1279,7 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         cudaEventRecord(st.join[1], sl);
       }
     }
-    launch_k(kt.sv_end[integ], grid[p], QW_THREADS, m, s->d, q, w, parity, out, counters);
+    launch_k(kt.sv_end[integ], item_grid(p), QV_THREADS, m, s->d, q, w, parity, out, counters);
     prof.mark(6);
     ++launches;
     if (concurrent && it > 0) {

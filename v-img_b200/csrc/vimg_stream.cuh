@@ -48,6 +48,22 @@ struct QvCounters {
   uint32_t pad_[6];
 };
 
+// Streamed shade / END launches: 128-thread blocks pack the register file in finer steps than 256-thread ones
+// (measured, disney_spheres 256 spp: 231.9 -> 226.4 ms at the same registers per thread); the Principled kernel
+// gets 168 registers (3 blocks per SM: no spills, 224.3 ms).  More warps at fewer registers lose: Lambertian at 96
+// registers (5 blocks, 178 B of spills) 235.8 ms, at 80 registers 242.4 ms.
+#ifndef QV_THREADS
+#define QV_THREADS 128
+#endif
+#ifndef QV_SHADE_MIN_BLOCKS_L
+#define QV_SHADE_MIN_BLOCKS_L 4  // Lambertian, Dielectric: 128 registers
+#endif
+#ifndef QV_SHADE_MIN_BLOCKS_P
+#define QV_SHADE_MIN_BLOCKS_P 3  // Principled: 168 registers
+#endif
+#ifndef QV_END_MIN_BLOCKS
+#define QV_END_MIN_BLOCKS 6      // 80 registers
+#endif
 #define QV_HAS_CLOSEST 0x40000000u
 #define QV_HAS_SHADOW 0x80000000u
 #define QV_SLOT_MASK 0x3fffffffu
@@ -178,7 +194,7 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
 // ====================================================================== SHADE, streamed ====
 // thread <-> item of the class's hit queue
 template <int INTEGRATOR, uint32_t CLASS>
-__global__ void __launch_bounds__(QW_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QW_SHADE_MIN_BLOCKS_P : QW_SHADE_MIN_BLOCKS_L)
+__global__ void __launch_bounds__(QV_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QV_SHADE_MIN_BLOCKS_P : QV_SHADE_MIN_BLOCKS_L)
 qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
                 const __grid_constant__ WfArgs args, const uint32_t parity, DCounters* __restrict__ counters) {
   __shared__ uint32_t s_cnt[2], s_base[2];
@@ -191,7 +207,7 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
   const float4* __restrict__ qa = st.ha[CLASS];
   const float4* __restrict__ qb = st.hb[CLASS];
 
-  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+  for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
     if (tid < 2) s_cnt[tid] = 0;
     __syncthreads();
     const uint32_t item = base + tid;
@@ -205,7 +221,7 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
     const int32_t leaf = __float_as_int(ha4.y);
     QvLine* ln = st.line + j;
     if (QV_PREFETCH) {
-      const uint32_t next = item + gridDim.x * QW_THREADS;
+      const uint32_t next = item + gridDim.x * QV_THREADS;
       if (next < n) qv_prefetch_line(st.line + __float_as_uint(__ldg(reinterpret_cast<const float*>(qa + next))));
     }
     ShadeIO io;
@@ -281,7 +297,7 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
 // ======================================================================== END, streamed ====
 // thread <-> item of the END queue: a path that ended (or a slot that has no pixel yet)
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(QW_THREADS, QW_END_MIN_BLOCKS)
+__global__ void __launch_bounds__(QV_THREADS, QV_END_MIN_BLOCKS)
 qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
               const __grid_constant__ WfArgs args, const uint32_t parity, float* __restrict__ out,
               DCounters* __restrict__ counters) {
@@ -297,7 +313,7 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
   uint32_t nan_samples = 0, n_samples = 0;
   bool exhausted = *reinterpret_cast<volatile uint32_t*>(st.next_pixel) >= args.n_local_units;
 
-  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
+  for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
     if (tid == 0) s_cnt[0] = 0;
     __syncthreads();
     const uint32_t item = base + tid;
@@ -310,7 +326,7 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
     const uint32_t i = __float_as_uint(ha4.x);
     QvLine* ln = st.line + i;
     if (QV_PREFETCH) {
-      const uint32_t next = item + gridDim.x * QW_THREADS;
+      const uint32_t next = item + gridDim.x * QV_THREADS;
       if (next < n) qv_prefetch_line(st.line + __float_as_uint(__ldg(reinterpret_cast<const float*>(qa + next))));
     }
     EndIO io;

@@ -192,6 +192,17 @@ def tile_owner(width, height, n_ranks):
     return owner[::-1].copy()                   # image row 0 is y = H - 1
 
 
+def spp_ranges(samples, spp_streams, rank=0, n_ranks=1):
+    """Sample ranges [begin, end) a rank renders of EVERY pixel under VIMG_PARTITION_SPP, in the order its
+    combine pass adds them.  Host-side mirror of the device mapping (vimg_wavefront.cuh WfArgs::s_rank /
+    s_n_ranks / my_streams; include/vimg_cuda.h vimg_render_params.spp_streams): K = min(spp_streams, samples)
+    ranges [k * samples / K, (k + 1) * samples / K), range k belongs to rank k % n_ranks."""
+    k_total = max(1, min(int(spp_streams), int(samples)))
+    if n_ranks > 1 and k_total < n_ranks:
+        raise VimgError("VIMG_PARTITION_SPP needs spp_streams (and samples) >= n_ranks")
+    return [(k * samples // k_total, (k + 1) * samples // k_total) for k in range(rank, k_total, max(n_ranks, 1))]
+
+
 class LoadedDesc:
     """A vimg_scene_desc read from a .vscene file; `.ptr` is its address (host memory)."""
 
