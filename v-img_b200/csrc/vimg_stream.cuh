@@ -82,6 +82,29 @@ struct QvState {
 #ifndef QV_PREFETCH
 #define QV_PREFETCH 1  // 1: shade / END start the fetch of their NEXT item's line into L2 while they work on this one
 #endif
+// Queue appends: block-aggregated (one global atomic per block and queue, two __syncthreads per batch of items) or, 1,
+// per warp (one atomic per warp and queue, no barrier: a block no longer waits for the slowest of its warps and for the
+// round trip of one thread's atomic).  Measured (disney_spheres, 256 spp, per launch): the shade kernels gain (Lambertian
+// 118.6 -> 114.0 us), END loses (86.6 -> 90.0: it also takes pixels from a global counter), trace loses (99 -> 131 us:
+// 4 x as many atomics on the four counters every ray is routed through).
+#ifndef QV_WARP_APPEND
+#define QV_WARP_APPEND 1        // shade
+#endif
+#ifndef QV_WARP_APPEND_END
+#define QV_WARP_APPEND_END 0
+#endif
+#ifndef QV_WARP_APPEND_TRACE
+#define QV_WARP_APPEND_TRACE 0
+#endif
+VD uint32_t qv_warp_append(uint32_t* counter, bool want, uint32_t lane, uint32_t lane_lt) {
+  const uint32_t m = __ballot_sync(0xffffffffu, want);
+  if (m == 0) return 0;
+  const uint32_t leader = (uint32_t)__ffs(m) - 1u;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(m & lane_lt);
+}
 VD void qv_prefetch_line(const QvLine* ln) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ln)); }
 VD float4 ldq(const float4* p) { return __ldcs(p); }  // queue records are read once: evict first
 VD void stq(float4* p, float4 v) { __stcs(p, v); }
@@ -110,6 +133,7 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
     uint4* dst = reinterpret_cast<uint4*>(&fs);
     for (uint32_t i = tid; i < sizeof(QfScene) / 16; i += QW_THREADS) dst[i] = __ldg(src + i);
   }
+  __syncthreads();  // the staged lists are visible
   const uint32_t n = c->n_trace[parity];
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_TRACE], (unsigned long long)n);
   const float4* __restrict__ ta = st.ta[parity];
@@ -118,8 +142,10 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
   uint32_t rays_closest = 0, rays_shadow = 0;
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
-    if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
-    __syncthreads();  // also: the staged lists are visible
+    if (!QV_WARP_APPEND_TRACE) {
+      if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
+      __syncthreads();
+    }
     const uint32_t item = base + tid;
     const bool valid = item < n;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f), w = b;
@@ -161,22 +187,31 @@ qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, 
         cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
       }
     }
-    bool want[WF_NUM_CLASSES + 1];
+    uint32_t pos = 0;
+    if (QV_WARP_APPEND_TRACE) {
 #pragma unroll
-    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
-    QwAppend<WF_NUM_CLASSES + 1> ap;
-    ap.count(s_cnt, want, lane, lane_lt);
-    __syncthreads();
-    if (tid < (int)WF_NUM_CLASSES) {
-      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[parity][tid], s_cnt[tid]);
-    } else if (tid == (int)WF_NUM_CLASSES) {
-      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
+      for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) {
+        const uint32_t at = qv_warp_append(k < WF_NUM_CLASSES ? &c->n_shade[parity][k] : &c->n_end[parity], cls == k, lane, lane_lt);
+        if (cls == k) pos = at;
+      }
+    } else {
+      bool want[WF_NUM_CLASSES + 1];
+#pragma unroll
+      for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
+      QwAppend<WF_NUM_CLASSES + 1> ap;
+      ap.count(s_cnt, want, lane, lane_lt);
+      __syncthreads();
+      if (tid < (int)WF_NUM_CLASSES) {
+        if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[parity][tid], s_cnt[tid]);
+      } else if (tid == (int)WF_NUM_CLASSES) {
+        if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
+      }
+      __syncthreads();
+      if (valid) pos = s_base[cls] + ap.off[cls];
     }
-    __syncthreads();
     if (valid) {
       const float4 ha4 = make_float4(__uint_as_float(bits & QV_SLOT_MASK), __int_as_float(leaf),
                                      best.k >= 0 ? best.t : CUDART_INF_F, __uint_as_float(occl ? 1u : 0u));
-      const uint32_t pos = s_base[cls] + ap.off[cls];
       float4* qa = cls < WF_NUM_CLASSES ? st.ha[cls] : st.ea[parity];
       float4* qb = cls < WF_NUM_CLASSES ? st.hb[cls] : st.eb[parity];
       stq(qa + pos, ha4);
@@ -208,8 +243,10 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
   const float4* __restrict__ qb = st.hb[CLASS];
 
   for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
-    if (tid < 2) s_cnt[tid] = 0;
-    __syncthreads();
+    if (!QV_WARP_APPEND) {
+      if (tid < 2) s_cnt[tid] = 0;
+      __syncthreads();
+    }
     const uint32_t item = base + tid;
     const bool go = item < n;
     float4 ha4 = make_float4(0.f, 0.f, 0.f, 0.f), hb4 = ha4;
@@ -221,6 +258,7 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
     const int32_t leaf = __float_as_int(ha4.y);
     QvLine* ln = st.line + j;
     if (QV_PREFETCH) {
+      // (holding the next slot number in a register and prefetching after the item is shaded measured slower: spills)
       const uint32_t next = item + gridDim.x * QV_THREADS;
       if (next < n) qv_prefetch_line(st.line + __float_as_uint(__ldg(reinterpret_cast<const float*>(qa + next))));
     }
@@ -273,21 +311,29 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
     // a path segment to trace (closest ray and / or shadow ray), or straight to END (ended, nothing pending)
     const bool to_trace = io.want_closest || io.want_shadow;
     const bool to_end = io.want_end && !io.want_shadow;
-    const bool want[2] = {to_trace, to_end};
-    QwAppend<2> ap;
-    ap.count(s_cnt, want, lane, lane_lt);
-    __syncthreads();
-    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
-    if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[1]);
-    __syncthreads();
+    uint32_t pos_t, pos_e;
+    if (QV_WARP_APPEND) {
+      pos_t = qv_warp_append(&c->n_trace[parity ^ 1u], to_trace, lane, lane_lt);
+      pos_e = qv_warp_append(&c->n_end[parity ^ 1u], to_end, lane, lane_lt);
+    } else {
+      const bool want[2] = {to_trace, to_end};
+      QwAppend<2> ap;
+      ap.count(s_cnt, want, lane, lane_lt);
+      __syncthreads();
+      if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
+      if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[1]);
+      __syncthreads();
+      pos_t = s_base[0] + ap.off[0];
+      pos_e = s_base[1] + ap.off[1];
+    }
     if (to_trace) {
-      const uint32_t pos = s_base[0] + ap.off[0];
+      const uint32_t pos = pos_t;
       const uint32_t bits = j | (io.want_closest ? QV_HAS_CLOSEST : 0u) | (io.want_shadow ? QV_HAS_SHADOW : 0u);
       stq(st.ta[parity ^ 1u] + pos, make_float4(io.new_o.x, io.new_o.y, io.new_o.z, io.nee_wi.w));
       stq(st.tb[parity ^ 1u] + pos, make_float4(io.new_d.x, io.new_d.y, io.new_d.z, __uint_as_float(bits)));
       if (io.want_shadow) stq(st.tc[parity ^ 1u] + pos, io.nee_wi);
     } else if (to_end) {
-      const uint32_t pos = s_base[1] + ap.off[1];
+      const uint32_t pos = pos_e;
       stq(st.ea[parity ^ 1u] + pos, make_float4(__uint_as_float(j), __int_as_float(-1), CUDART_INF_F, __uint_as_float(0u)));
       stq(st.eb[parity ^ 1u] + pos, make_float4(0.f, 0.f, 0.f, 0.f));
     }
@@ -314,8 +360,10 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
   bool exhausted = *reinterpret_cast<volatile uint32_t*>(st.next_pixel) >= args.n_local_units;
 
   for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
-    if (tid == 0) s_cnt[0] = 0;
-    __syncthreads();
+    if (!QV_WARP_APPEND_END) {
+      if (tid == 0) s_cnt[0] = 0;
+      __syncthreads();
+    }
     const uint32_t item = base + tid;
     const bool valid = item < n;
     float4 ha4 = make_float4(0.f, 0.f, 0.f, 0.f), hb4 = ha4;
@@ -357,14 +405,19 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
         stg4(&ln->d_s, io.cam_d);
       }
     }
-    const bool want[1] = {io.new_ray};
-    QwAppend<1> ap;
-    ap.count(s_cnt, want, lane, lane_lt);
-    __syncthreads();
-    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
-    __syncthreads();
+    uint32_t pos;
+    if (QV_WARP_APPEND_END) {
+      pos = qv_warp_append(&c->n_trace[parity ^ 1u], io.new_ray, lane, lane_lt);
+    } else {
+      const bool want[1] = {io.new_ray};
+      QwAppend<1> ap;
+      ap.count(s_cnt, want, lane, lane_lt);
+      __syncthreads();
+      if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
+      __syncthreads();
+      pos = s_base[0] + ap.off[0];
+    }
     if (io.new_ray) {
-      const uint32_t pos = s_base[0] + ap.off[0];
       stq(st.ta[parity ^ 1u] + pos, make_float4(io.cam_o.x, io.cam_o.y, io.cam_o.z, 0.f));
       stq(st.tb[parity ^ 1u] + pos, make_float4(io.cam_d.x, io.cam_d.y, io.cam_d.z, __uint_as_float(i | QV_HAS_CLOSEST)));
     }
