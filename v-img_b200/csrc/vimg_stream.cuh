@@ -29,7 +29,10 @@
 
 namespace vimg {
 
-struct __align__(128) QvLine {
+#ifndef QV_LINE_BYTES
+#define QV_LINE_BYTES 128  // 256 / 512: the address-range experiment of DESIGN.md 5.1c (same slots, 2x / 4x the range)
+#endif
+struct __align__(QV_LINE_BYTES) QvLine {
   float4 thr_eta;    // sector 0: throughput rgb, eta_scale
   uint4 rng_fd;      //           rng lo, rng hi, flags | sample range << 16, depth counter
   float4 L_s;        // sector 1: bounce_result rgb, sample counter
@@ -39,7 +42,7 @@ struct __align__(128) QvLine {
   float4 c_pdf;      // sector 3: pending NEE contribution rgb, last_pdf
   float4 spare;
 };
-static_assert(sizeof(QvLine) == 128, "one line per slot");
+static_assert(sizeof(QvLine) == QV_LINE_BYTES, "one line per slot");
 
 struct QvCounters {
   uint32_t n_trace[2];                  // ray queue, by iteration parity
