@@ -38,8 +38,13 @@ struct __align__(16) DLeafPrim {
   uint32_t prim_id;  // index in list_objects
   uint32_t flags;
   uint32_t pad_;
+#ifdef LEAF_PRIM_PAD  // the address-range experiment of DESIGN.md 5.1d
+  uint32_t pad2_[LEAF_PRIM_PAD / 4];
+#endif
 };
+#ifndef LEAF_PRIM_PAD
 static_assert(sizeof(DLeafPrim) == 48, "leaf record must be 48 bytes");
+#endif
 
 // shading record of a leaf entry (same index as leaf_prims)
 #define VIMG_SHADE_HAS_NORMALS 1u      /* n[] valid (Mesh::normals not empty)                        */

@@ -25,12 +25,15 @@ namespace vimg {
 #define WIDE_MAX_LEAF_COUNT 16u
 #define WIDE_MAX_LEAF_FIRST (1u << 27)
 
-struct __align__(128) DWideNode {
+#ifndef WIDE_NODE_BYTES
+#define WIDE_NODE_BYTES 128  // 256: the address-range experiment of DESIGN.md 5.1d
+#endif
+struct __align__(WIDE_NODE_BYTES) DWideNode {
   float4 minx, miny, minz, maxx, maxy, maxz;  // the four children's boxes, one coordinate per vector
   uint4 ref;                                  // WIDE_EMPTY | leaf reference | wide index of an inner child
   uint4 pad_;
 };
-static_assert(sizeof(DWideNode) == 128, "one line per wide node");
+static_assert(sizeof(DWideNode) == WIDE_NODE_BYTES, "one line per wide node");
 
 #ifdef VIMG_FAST
 VD uint32_t wide_ref(uint32_t first, uint32_t count) {
