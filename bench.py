@@ -405,8 +405,9 @@ def time_e2e(gpu, vimg, w, integ, spp, kw, steps):
 # the layout of its pipeline -- records read + sectors written + queue records -- not counting scene tables
 # (leaf / shade / light records), which are cache resident for small scenes.
 STATE_BYTES = {
-    # streamed pipeline (vimg_stream.cuh): hit record 32 + slot line 128 read; sectors 0, 2, 3 (96) + ray record 48 written
-    "stream": {"shade": 32 + 128 + 96 + 48, "end": 32 + 128 + 96 + 32 + 32},
+    # streamed pipeline (vimg_stream.cuh): hit record 32 + slot line 128 read; sectors 0, 2, 3 (96; END: all four) + the hit
+    # record of the traced segment (32) written -- the kernel traces the rays it makes itself, there is no ray queue
+    "stream": {"shade": 32 + 128 + 96 + 32, "end": 32 + 128 + 128 + 32},
     # slot-record pipeline (vimg_queues.cuh): queue entry 8 + 160-byte slot read; 112 + queue entry written (END: + ray 32)
     "slot": {"shade": 8 + 160 + 112 + 8, "end": 4 + 160 + 112 + 32 + 4},
 }
@@ -441,7 +442,7 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
     items_per_launch = tst["stage_items"][top] / n_launch
     layout = "stream" if flat else "slot"
     prefix = "qv_" if flat else "qw_"
-    trace_kernel = "qv_trace_flat_kernel" if flat else ("qw_trace_wide_kernel" if kw.get("fast") else "qw_trace_kernel")
+    trace_kernel = "qw_trace_wide_kernel" if kw.get("fast") else "qw_trace_kernel"
     if top == "trace":
         kernel = trace_kernel
         per_item, unit_note = bytes_per_ray, ("bytes per ray in the reference's layout (56/inner node, 8/leaf, 56/triangle test, "
@@ -453,22 +454,31 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
                      "DESIGN.md 5.2), scene tables not counted")
     achieved = per_item * items_per_launch / launch_s / 1e9
     traffic, traffic_src = ncu_traffic(kernel, w.key)
-    trace_launch_s = tst["stage_ms"]["trace"] / 1e3 / max(tst["stage_launches"]["trace"], 1)
     t_rays = tst["rays_closest"] + tst["rays_shadow"]
-    rays_per_trace_launch = t_rays / max(tst["stage_launches"]["trace"], 1)
+    if tst["stage_launches"].get("trace", 0):
+        trace_launch_s = tst["stage_ms"]["trace"] / 1e3 / tst["stage_launches"]["trace"]
+        rays_per_trace_launch = t_rays / tst["stage_launches"]["trace"]
+        trace = {"kernel": trace_kernel, "launch_ms": 1e3 * trace_launch_s,
+                 "rays_per_launch": rays_per_trace_launch, "algorithmic_bytes_per_ray": bytes_per_ray,
+                 "algorithmic_flops_per_ray": flops_per_ray,
+                 "reference_layout_gbs": bytes_per_ray * rays_per_trace_launch / trace_launch_s / 1e9,
+                 "fp32_tflops_achieved": flops_per_ray * rays_per_trace_launch / trace_launch_s / 1e12,
+                 "note": "the reference-layout figure normalises throughput across scenes; node and primitive records come from L2 / HBM"}
+    else:
+        # streamed pipeline: no trace launch -- shade / END trace the rays they make over the flat lists in shared memory
+        step_s = total / 1e3
+        trace = {"kernel": "qv_trace_route (inside qv_shade_kernel / qv_end_kernel)", "launch_ms": None,
+                 "rays_per_step": t_rays, "algorithmic_bytes_per_ray": bytes_per_ray, "algorithmic_flops_per_ray": flops_per_ray,
+                 "reference_layout_gbs": bytes_per_ray * t_rays / step_s / 1e9,
+                 "fp32_tflops_achieved": flops_per_ray * t_rays / step_s / 1e12,
+                 "note": "this scene (< 8 KiB) is traced from shared memory at the tail of the kernel that made the ray; the "
+                         "reference-layout figures are over the whole serial pass (they normalise throughput across scenes)"}
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
             "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "items_per_launch": items_per_launch,
             "algorithmic_bytes_per_item": per_item,
             "stage_share_of_step": shares,
-            "trace": {"kernel": trace_kernel, "launch_ms": 1e3 * trace_launch_s,
-                      "rays_per_launch": rays_per_trace_launch, "algorithmic_bytes_per_ray": bytes_per_ray,
-                      "algorithmic_flops_per_ray": flops_per_ray,
-                      "reference_layout_gbs": bytes_per_ray * rays_per_trace_launch / trace_launch_s / 1e9,
-                      "fp32_tflops_achieved": flops_per_ray * rays_per_trace_launch / trace_launch_s / 1e12,
-                      "note": "the reference-layout figure normalises throughput across scenes; "
-                              + ("this scene (< 8 KiB) is traced from shared memory, the kernel's bound is instruction issue"
-                                 if flat else "node and primitive records come from L2 / HBM")},
+            "trace": trace,
             "note": f"dominant kernel = largest stage share of a serial pass at {t_spp} spp, every launch timed with CUDA events "
                     f"on its stream (VIMG_FLAG_STAGE_TIMES), average duration; {unit_note}"}
 

@@ -107,6 +107,43 @@ def test_fast_is_deterministic_and_rank_independent(vimg):
     assert np.array_equal(acc, a) and samples == st["samples"]
 
 
+@pytest.mark.parametrize("name,integ", [("disney_small", "mis"), ("cornell_small", "material"), ("glass_small", "mis"),
+                                        ("cornell_checker", "mis"), ("sphere_light_small", "mis")])
+def test_lean_build_is_the_same_estimator(vimg, name, integ, monkeypatch):
+    """scenes without image textures / normal maps / env map are rendered by the build of the streamed kernels that has
+    the code of those features compiled out (vimg_lean.cu; every tolerance test above on such a scene runs it).  The
+    full build on the same scene and the same random numbers: fast-math contracts some float expressions differently
+    in the two, so single paths part ways -- the two images are closer than two renders with unrelated random
+    numbers, and their means agree"""
+    sc = scene(vimg, name)
+    lean8, st1 = sc.scene_integrator(integ, 64, 64, spp_streams=8, fast=True)
+    lean32, _ = sc.scene_integrator(integ, 64, 64, spp_streams=32, fast=True)
+    monkeypatch.setenv("VIMG_LEAN", "0")
+    full8, st0 = sc.scene_integrator(integ, 64, 64, spp_streams=8, fast=True)
+    monkeypatch.delenv("VIMG_LEAN")
+    again, _ = sc.scene_integrator(integ, 64, 64, spp_streams=8, fast=True)
+    assert np.array_equal(again, lean8) and not np.array_equal(full8, lean8)  # the switch does select another build
+    e_builds, e_seeds = rel_mse(full8, lean8), rel_mse(lean32, lean8)
+    print(f"{name}/{integ}: relMSE full-lean {e_builds:.2e}, lean K8-K32 {e_seeds:.2e}, rays {st0['rays_closest']} / {st1['rays_closest']}")
+    assert np.isfinite(full8).all() and st0["samples"] == st1["samples"]
+    assert e_builds <= e_seeds + 1e-6
+    ok, ratio = _means_close(full8, lean8)
+    assert ok, ratio
+
+
+@pytest.mark.parametrize("name,integ", [("disney_small", "mis"), ("cornell_small", "material"), ("glass_small", "mis"),
+                                        ("cornell_checker", "mis"), ("sphere_light_small", "material")])
+def test_lean_bit_exact_build_changes_no_bit(vimg, name, integ, monkeypatch):
+    """the same for the bit-exact build (vimg_exact_lean.cu): no contraction there, so leaving out code that does not
+    run leaves every pixel and every counter as it was"""
+    sc = scene(vimg, name)
+    lean, st1 = sc.scene_integrator(integ, 16, 64)
+    monkeypatch.setenv("VIMG_LEAN", "0")
+    full, st0 = sc.scene_integrator(integ, 16, 64)
+    assert np.array_equal(full, lean)
+    assert st0["rays_closest"] == st1["rays_closest"] and st0["rays_shadow"] == st1["rays_shadow"]
+
+
 def test_fast_needs_the_queue_pipeline(vimg):
     with pytest.raises(vimg.VimgError):
         scene(vimg, "cornell_small").scene_integrator("mis", 8, 64, fast=True, pipeline="block")

@@ -216,6 +216,7 @@ struct vimg_scene {
   void* d_flat = nullptr;  // tolerance build: flat re-layout of a small scene (vimg_flat.cuh), built at the first fast render
   DWideNode* d_wide = nullptr;  // tolerance build: 4-wide BVH of a large scene (vimg_wide.cuh), built at the first fast render
   bool wide_ok = false;         // every leaf fits a wide leaf reference
+  bool lean = false;            // no image texture, normal map, metallic-roughness texture, env map, general uv walk (vimg_lean.cu)
   uint32_t n_pairs = 0;
   QwWorkspace* ws = nullptr;  // taken at the first material / mis render
   uint32_t class_mask = 0;
@@ -618,6 +619,14 @@ static int build_scene(const vimg_scene_desc* desc, vimg_scene* s) {
     if (t >= 0 && desc->textures[t].type == VIMG_TEX_IMAGE) d.uses_cones = 1u;
   }
   if (const char* e = std::getenv("VIMG_FORCE_CONES")) d.uses_cones = std::atoi(e) ? 1u : d.uses_cones;
+  // a scene the lean build of the streamed kernels renders (VIMG_LEAN, vimg_math.cuh): none of the features it leaves out
+  s->lean = d.uses_cones == 0 && hb.type == VIMG_BG_CONST && desc->n_textures_rg == 0;
+  for (uint32_t t = 0; t < desc->n_textures; ++t)
+    if (desc->textures[t].type != VIMG_TEX_CONST && desc->textures[t].type != VIMG_TEX_CHECKER) s->lean = false;
+  for (uint32_t m = 0; m < desc->n_materials; ++m)
+    if (desc->materials[m].normal_map >= 0 || desc->materials[m].texture_rg >= 0) s->lean = false;
+  for (const DShadeRec& sr : shade_recs)
+    if (sr.flags & VIMG_SHADE_GENERAL) s->lean = false;
 
   // ---- upload ------------------------------------------------------------------
   int rc;
@@ -865,14 +874,28 @@ struct QwLaunchCfg {
 // the tolerance build of the same kernels (vimg_fast.cu)
 extern "C" void vimg_fast_kernel_table(void* out);
 extern "C" size_t vimg_fast_flat_scene_bytes(void);
-static const QwKernelTable& kernel_table(bool fast) {
+// ... and its streamed shade / END kernels without the code of the features a lean scene does not use (vimg_lean.cu)
+extern "C" void vimg_lean_kernel_table(void* out);
+// ... and the bit-exact shade / END kernels without that code (vimg_exact_lean.cu)
+extern "C" void vimg_exact_lean_kernel_table(void* out);
+static const QwKernelTable& kernel_table(bool fast, bool lean = false) {
   static const QwKernelTable exact = qw_kernel_table();
+  static const QwKernelTable exact_lean = [] {
+    QwKernelTable t = exact;
+    vimg_exact_lean_kernel_table(&t);
+    return t;
+  }();
   static const QwKernelTable fast_t = [] {
     QwKernelTable t{};
     vimg_fast_kernel_table(&t);
     return t;
   }();
-  return fast ? fast_t : exact;
+  static const QwKernelTable lean_t = [] {
+    QwKernelTable t = fast_t;
+    vimg_lean_kernel_table(&t);
+    return t;
+  }();
+  return fast ? (lean ? lean_t : fast_t) : (lean ? exact_lean : exact);
 }
 
 template <typename... A>
@@ -964,7 +987,8 @@ static int qw_render_t(vimg_scene* s, const WfArgs& w_in, int integ, bool count,
     if ((rc = qw_reserve(s, s->ws->qw[p], per_pool)) != VIMG_OK) return rc;
   CU_TRY(cudaMemsetAsync(s->ws->d_next_pixel, 0, sizeof(uint32_t), caller));
   QwLaunchCfg cfg{};
-  cfg.kt = &kernel_table(fast);
+  // (the tolerance build's lean kernels are the streamed ones: qv_render)
+  cfg.kt = &kernel_table(fast, !fast && s->lean && env_u32("VIMG_LEAN", 1) != 0);
   if (fast && s->wide_ok && env_u32("VIMG_WIDE", 1) != 0) {
     if (!s->d_wide) {
       // device-side re-layout of a large BVH: every binary inner node's grandchildren as one 128-byte record
@@ -1166,13 +1190,12 @@ static int qv_reserve(vimg_scene* s, QwPool& streams, QvPool& pool, uint32_t n) 
   };
   const size_t N = n;
   const size_t o_line = carve(N * sizeof(QvLine));
-  size_t o_t[2][3], o_h[WF_NUM_CLASSES][2], o_e[2][2];
-  for (int k = 0; k < 2; ++k)
-    for (int a = 0; a < 3; ++a) o_t[k][a] = carve(N * 16);
-  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k)
-    for (int a = 0; a < 2; ++a) o_h[k][a] = carve(N * 16);
-  for (int k = 0; k < 2; ++k)
+  size_t o_h[2][WF_NUM_CLASSES][2], o_e[2][2];
+  for (int k = 0; k < 2; ++k) {
+    for (uint32_t cl = 0; cl < WF_NUM_CLASSES; ++cl)
+      for (int a = 0; a < 2; ++a) o_h[k][cl][a] = carve(N * 16);
     for (int a = 0; a < 2; ++a) o_e[k][a] = carve(N * 16);
+  }
   const size_t o_cnt = carve(sizeof(QvCounters));
   CU_TRY(cudaMalloc(&pool.mem, off));
   pool.capacity = n;
@@ -1181,22 +1204,21 @@ static int qv_reserve(vimg_scene* s, QwPool& streams, QvPool& pool, uint32_t n) 
   q.n_slots = n;
   q.line = reinterpret_cast<QvLine*>(b + o_line);
   for (int k = 0; k < 2; ++k) {
-    q.ta[k] = reinterpret_cast<float4*>(b + o_t[k][0]);
-    q.tb[k] = reinterpret_cast<float4*>(b + o_t[k][1]);
-    q.tc[k] = reinterpret_cast<float4*>(b + o_t[k][2]);
     q.ea[k] = reinterpret_cast<float4*>(b + o_e[k][0]);
     q.eb[k] = reinterpret_cast<float4*>(b + o_e[k][1]);
-  }
-  for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) {
-    q.ha[k] = reinterpret_cast<float4*>(b + o_h[k][0]);
-    q.hb[k] = reinterpret_cast<float4*>(b + o_h[k][1]);
+    for (uint32_t cl = 0; cl < WF_NUM_CLASSES; ++cl) {
+      q.ha[k][cl] = reinterpret_cast<float4*>(b + o_h[k][cl][0]);
+      q.hb[k][cl] = reinterpret_cast<float4*>(b + o_h[k][cl][1]);
+    }
   }
   q.cnt = reinterpret_cast<QvCounters*>(b + o_cnt);
   return VIMG_OK;
 }
 
-// One frame: per pool  end(0) | trace(1) {shade(1) | end(1)} | trace(2) ...  until the ray and END queues are
-// empty; the host looks at the counters once per batch of iterations, one batch behind what it has queued.
+// One frame: per pool  end(0) | {shade(1) per class, end(1)} | {shade(2), end(2)} ...  until the hit and END queues
+// are empty -- the launches of an iteration read the queues of its parity and fill those of the other one (each
+// traces the rays it makes itself), so they run side by side; the host clears the drained counters between two
+// iterations and looks at them once per batch of iterations, one batch behind what it has queued.
 static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, float* out, cudaStream_t caller, bool stage_times) {
   QwProfile prof;
   const bool print_profile = env_u32("VIMG_QW_PROFILE", 0) != 0;
@@ -1208,9 +1230,7 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
   if (!concurrent || total_slots < 65536u) n_pools = 1;
   const uint32_t per_pool = (total_slots + n_pools - 1) / n_pools;
   if (s->sm_count == 0) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
-  const QwKernelTable& kt = kernel_table(true);
-  // blocks per SM of the trace launches: fewer than the 4 that fit leave registers for the other pool's shade / END blocks
-  const int trace_per_sm = (int)std::max(1u, env_u32("VIMG_QV_TRACE_BLOCKS", 4));
+  const QwKernelTable& kt = kernel_table(true, s->lean && env_u32("VIMG_LEAN", 1) != 0);
   int rc;
   for (uint32_t p = 0; p < n_pools; ++p)
     if ((rc = qv_reserve(s, s->ws->qw[p], s->ws->qv[p], per_pool)) != VIMG_OK) return rc;
@@ -1219,6 +1239,9 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
     CU_TRY(cudaMalloc(&s->d_flat, vimg_fast_flat_scene_bytes()));
     CU_TRY(launch_k(kt.build_flat, 1, (int)QF_FLAT_MAX_HOST, caller, s->d, s->d_flat));
   }
+  if (env_u32("VIMG_VERBOSE", 0))
+    fprintf(stderr, "[vimg] streamed pipeline: %s shade / END kernels, %u pool(s) of %u slots\n",
+            &kt == &kernel_table(true, true) ? "lean" : "full", n_pools, per_pool);
   const void* d_flat = s->d_flat;
   DCounters* counters = s->d_counters;
   cudaEvent_t start = s->ws->qw[0].done;
@@ -1234,12 +1257,13 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
     CU_TRY(cudaStreamWaitEvent(st.main, start, 0));
     CU_TRY(cudaMemsetAsync(pool.st.line, 0, (size_t)per_pool * sizeof(QvLine), st.main));  // flags = 0: no pixel yet
     QvCounters init{};
-    init.n_end[0] = per_pool;  // every slot starts in the END queue, without a pixel
+    init.q[0].n_end = per_pool;  // every slot starts in the END queue, without a pixel
     pool.h_cnt[0] = init;
     CU_TRY(cudaMemcpyAsync(pool.st.cnt, &pool.h_cnt[0], sizeof(init), cudaMemcpyHostToDevice, st.main));
     CU_TRY(launch_k(kt.sv_init, slot_blocks, QW_THREADS, st.main, pool.st.ea[0], pool.st.eb[0], per_pool));
   }
   auto item_grid = [&](uint32_t p) { return grid[p] * (256 / QV_THREADS); };  // shade / END blocks of QV_THREADS threads
+  const uint32_t count_flag = count ? 1u : 0u;
   auto enqueue = [&](uint32_t p, uint32_t it) -> uint32_t {
     QwPool& st = s->ws->qw[p];
     const QvState& q = s->ws->qv[p].st;
@@ -1247,10 +1271,8 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
     uint32_t launches = 0;
     cudaStream_t m = st.main;
     if (it > 0) {
-      launch_k(kt.sv_trace_flat[count], std::min(grid[p], s->sm_count * trace_per_sm), QW_THREADS, m, q, parity, d_flat, counters);
-      prof.mark(1);
-      ++launches;
-      // the shade launches only feed the next iteration; END consumes what trace (and the last shade launches) queued
+      // the queues this iteration fills were drained by the previous one
+      cudaMemsetAsync(&q.cnt->q[parity ^ 1u], 0, sizeof(QvQueueCounters), m);
       cudaStream_t sp = m, sl = m;
       if (concurrent) {
         sp = st.side[0];
@@ -1260,17 +1282,17 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         cudaStreamWaitEvent(sl, st.fork, 0);
       }
       if (s->class_mask & (1u << WF_CLASS_PRINCIPLED)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], item_grid(p), QV_THREADS, sp, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_PRINCIPLED], item_grid(p), QV_THREADS, sp, s->d, q, w, parity, d_flat, count_flag, counters);
         prof.mark(3);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_LAMBERT)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_LAMBERT], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, d_flat, count_flag, counters);
         prof.mark(4);
         ++launches;
       }
       if (s->class_mask & (1u << WF_CLASS_DIELECTRIC)) {
-        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, counters);
+        launch_k(kt.sv_shade[integ][WF_CLASS_DIELECTRIC], item_grid(p), QV_THREADS, sl, s->d, q, w, parity, d_flat, count_flag, counters);
         prof.mark(5);
         ++launches;
       }
@@ -1279,7 +1301,7 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         cudaEventRecord(st.join[1], sl);
       }
     }
-    launch_k(kt.sv_end[integ], item_grid(p), QV_THREADS, m, s->d, q, w, parity, out, counters);
+    launch_k(kt.sv_end[integ], item_grid(p), QV_THREADS, m, s->d, q, w, parity, out, d_flat, count_flag, counters);
     prof.mark(6);
     ++launches;
     if (concurrent && it > 0) {
@@ -1315,13 +1337,14 @@ static int qv_render(vimg_scene* s, const WfArgs& w, int integ, bool count, floa
         CU_TRY(cudaEventSynchronize(st.snap[(b - 1) & 1]));
         const QvCounters& hc = s->ws->qv[p].h_cnt[(b - 1) & 1];
         const uint32_t par = (b * batch) & 1u;  // parity of the first iteration after batch b - 1
-        if (hc.n_trace[par] == 0 && hc.n_end[par] == 0)
+        uint64_t queued = hc.q[par].n_end;
+        for (uint32_t cl = 0; cl < WF_NUM_CLASSES; ++cl) queued += hc.q[par].n_shade[cl];
+        if (queued == 0)
           finished[p] = true;  // batch b only ran empty iterations for this pool
         else
           all_done = false;
         if (shrink && st.h_next_pixel[(b - 1) & 1] >= w.n_local_units) {
-          const uint64_t bound = (uint64_t)hc.n_trace[par] + hc.n_end[par];
-          grid[p] = (int)std::max<uint64_t>(1, std::min<uint64_t>(full_grid, (bound + QW_THREADS - 1) / QW_THREADS));
+          grid[p] = (int)std::max<uint64_t>(1, std::min<uint64_t>(full_grid, (queued + QW_THREADS - 1) / QW_THREADS));
         }
       }
       if (all_done) break;

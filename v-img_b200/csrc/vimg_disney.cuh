@@ -309,7 +309,7 @@ VD void principled_frame_mr(const DScene& sc, const vimg_material& m, V3 dir_in,
     frame.w = -frame.w;
   }
   V2 m_r = mk2(1.f, 1.f);
-  if (m.texture_rg >= 0) m_r = texrg_get_at_uv(sc, sc.textures_rg[m.texture_rg], hit.mr_uv);
+  if (!VIMG_LEAN && m.texture_rg >= 0) m_r = texrg_get_at_uv(sc, sc.textures_rg[m.texture_rg], hit.mr_uv);
   m_r = m_r * mk2(m.metallic_roughness_factor[0], m.metallic_roughness_factor[1]);
   metallic = m_r.x;
   roughness = m_r.y;

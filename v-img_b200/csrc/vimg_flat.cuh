@@ -203,6 +203,30 @@ VD void qf_trace(const QfScene& fs, V3 o, V3 d, float tmin, QfBest& best) {
   for (int k = 0; k < ns; ++k) qf_test_sphere(fs.sph[k], o, d, tmin, nt + k, best);
 }
 
+// the closest ray and the shadow ray of one path segment (same origin) in ONE pass over the lists: an entry's record is
+// read once and the two tests are independent instruction streams (the fused tail of the shade kernels, vimg_stream.cuh)
+VD void qf_trace2(const QfScene& fs, V3 o, V3 d1, V3 d2, float tmin, QfBest& best1, QfBest& best2) {
+  const int nq = (int)fs.n_quad, nt = (int)fs.n_tri, ns = (int)fs.n_sph;
+#pragma unroll 2
+  for (int k = 0; k < nq; ++k) {
+    const float4 a = fs.tri[3 * k], b = fs.tri[3 * k + 1], c = fs.tri[3 * k + 2];
+    qf_test_tri<true>(a, b, c, o, d1, tmin, k, best1);
+    qf_test_tri<true>(a, b, c, o, d2, tmin, k, best2);
+  }
+#pragma unroll 2
+  for (int k = nq; k < nt; ++k) {
+    const float4 a = fs.tri[3 * k], b = fs.tri[3 * k + 1], c = fs.tri[3 * k + 2];
+    qf_test_tri<false>(a, b, c, o, d1, tmin, k, best1);
+    qf_test_tri<false>(a, b, c, o, d2, tmin, k, best2);
+  }
+#pragma unroll 2
+  for (int k = 0; k < ns; ++k) {
+    const float4 sp = fs.sph[k];
+    qf_test_sphere(sp, o, d1, tmin, nt + k, best1);
+    qf_test_sphere(sp, o, d2, tmin, nt + k, best2);
+  }
+}
+
 // what entry best.k is: leaf record, class byte and the weights of that leaf's p0, p1, p2 (Triangle::hit_info reads
 // them as e_i * inv_det; spheres: zeros)
 VD void qf_decode(const QfScene& fs, const QfBest& best, int32_t& leaf, uint32_t& lc, float4& e) {

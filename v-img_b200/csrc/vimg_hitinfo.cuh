@@ -174,7 +174,7 @@ VD V3 tex_get_normal(const DScene& sc, const DTexture& t, V2 uv) {
 VD V3 col_at_ray_hit(const DScene& sc, int32_t tex, V3 ray_in_dir, RayCone cone, const HitInfo& hit) {
   const DTexture& t = sc.textures[tex];
   if (t.type == VIMG_TEX_CONST) return mk3(t.col_a[0], t.col_a[1], t.col_a[2]);
-  if (t.type == VIMG_TEX_CHECKER) {
+  if (VIMG_LEAN || t.type == VIMG_TEX_CHECKER) {
     // uint32_t u_board = std::floor(uv[0] * width): x86-64 converts float -> uint32 through a
     // 64-bit cvttss2si and truncates (negative values wrap); CUDA's direct cast saturates.
     uint32_t u_board = (uint32_t)(long long)floorf(hit.uv.x * t.width);
@@ -272,7 +272,7 @@ __device__ __noinline__ HitInfo triangle_hit_info_general(const DScene& sc, cons
   }
 
   const vimg_material& mat = sc.materials[mesh.material];
-  if (mat.normal_map >= 0) {
+  if (!VIMG_LEAN && mat.normal_map >= 0) {
     V2 n_uv = mk2(u, v);
     if (mesh.uv_normal >= 0) {
       const float* tc = sc.uvs + 2 * (size_t)mesh.uv_normal;
@@ -341,7 +341,7 @@ VD DLightRec load_light_rec(const DScene& sc, int index) {
 // or the ray cones need them.
 template <bool NEED_FRAME = true>
 VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShadeRec& sr, const PreHit& pre) {
-  if (sr.flags & VIMG_SHADE_GENERAL) return triangle_hit_info_general(sc, lp, pre);
+  if (!VIMG_LEAN && (sr.flags & VIMG_SHADE_GENERAL)) return triangle_hit_info_general(sc, lp, pre);
   V3 p0 = mk3(lp.a[0], lp.a[1], lp.a[2]), p1 = mk3(lp.a[3], lp.a[4], lp.a[5]),
      p2 = mk3(lp.a[6], lp.a[7], lp.a[8]);
   V3 edge1 = p1 - p0, edge2 = p2 - p0;
@@ -367,8 +367,8 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
     uv2 = mk2(sr.uv[4], sr.uv[5]);
     uv = u * uv0 + v * uv1 + w * uv2;
   }
-  const int32_t normal_map = sc.materials[sr.material].normal_map;
-  const bool derivs = NEED_FRAME || sc.uses_cones != 0 || normal_map >= 0;
+  const int32_t normal_map = VIMG_LEAN ? -1 : sc.materials[sr.material].normal_map;
+  const bool derivs = NEED_FRAME || (!VIMG_LEAN && sc.uses_cones != 0) || normal_map >= 0;
   V2 duvds = uv2 - uv0;
   V2 duvdt = uv2 - uv1;
   float det = duvds.x * duvdt.y - duvdt.x * duvds.y;
@@ -401,13 +401,13 @@ VD HitInfo triangle_hit_info(const DScene& sc, const DLeafPrim& lp, const DShade
   }
 
   V3 tangent = mk3(0.f), bitangent = mk3(0.f);
-  if (NEED_FRAME || sc.uses_cones != 0) {
+  if (NEED_FRAME || (!VIMG_LEAN && sc.uses_cones != 0)) {
     tangent = normalize(dpdu - shading_normal * dot(shading_normal, dpdu));
     bitangent = normalize(cross(shading_normal, tangent));
   }
   // curvature and the two areas only feed ray cones / texture LOD (DScene::uses_cones)
   float mean_curvature = 0.f, twice_tri_area = 1.f, uv_area = 1.f;
-  if (sc.uses_cones) {
+  if (!VIMG_LEAN && sc.uses_cones) {
     V3 dnds = n2 - n0;
     V3 dndt = n2 - n1;
     V3 dndu = dnds * dsdu + dndt * dtdu;

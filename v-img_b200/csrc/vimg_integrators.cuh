@@ -57,7 +57,7 @@ VD void envmap_uv(const DScene& sc, V3 in_dir, float& u, float& v) {
 
 // ConstBackground / EnvMap::background_emit (background.h:34-36, 88-108)
 VD V3 background_emit(const DScene& sc, V3 in_dir, RayCone cone) {
-  if (sc.bg.type == VIMG_BG_CONST) return mk3(sc.bg.color[0], sc.bg.color[1], sc.bg.color[2]);
+  if (VIMG_LEAN || sc.bg.type == VIMG_BG_CONST) return mk3(sc.bg.color[0], sc.bg.color[1], sc.bg.color[2]);
   float u, v;
   envmap_uv(sc, in_dir, u, v);
   const DTexture& img = sc.textures[sc.bg.image];
@@ -69,7 +69,7 @@ VD V3 background_emit(const DScene& sc, V3 in_dir, RayCone cone) {
 
 // background_pdf (background.h:56, 141-169)
 VD float background_pdf(const DScene& sc, V3 in_dir) {
-  if (sc.bg.type == VIMG_BG_CONST) return (float)(1.f / (4 * VIMG_PI_D));
+  if (VIMG_LEAN || sc.bg.type == VIMG_BG_CONST) return (float)(1.f / (4 * VIMG_PI_D));
   float u, v;
   envmap_uv(sc, in_dir, u, v);
   const uint32_t W = sc.bg.cdf_w, H = sc.bg.cdf_h;
@@ -204,7 +204,7 @@ VD float sphere_surf_pdf(const DScene& sc, uint32_t prim, V3 look_from, V3 point
 VD V3 background_light_sample(const DScene& sc, Pcg32& rng, EmitterInfo& info) {
   float r1 = rand_float(rng);
   float r2 = rand_float(rng);
-  if (sc.bg.type == VIMG_BG_CONST) {
+  if (VIMG_LEAN || sc.bg.type == VIMG_BG_CONST) {
     info.wi = sample_sphere(r1, r2);
     info.pdf = (float)(1.f / (4 * VIMG_PI_D));
     info.dist = CUDART_INF_F;

@@ -15,6 +15,14 @@
 #include "vimg_libm.cuh"
 
 #define VD __device__ __forceinline__
+// VIMG_LEAN 1 (vimg_lean.cu): a build of the shade / END kernels for scenes WITHOUT image textures, normal maps,
+// metallic-roughness textures, an env map and meshes whose uv sets differ -- the reference's own scenes.  The code of
+// those features is what sets the register need of the kernels (Lambertian shade 167 -> 126, END 117 -> 91 without
+// it), whether a scene uses them or not; vimg_api.cu looks at the scene (vimg_scene::lean) and launches this build
+// when none is there.  Every test below is `VIMG_LEAN ||` / `!VIMG_LEAN &&` in front of the run-time test it replaces.
+#ifndef VIMG_LEAN
+#define VIMG_LEAN 0
+#endif
 
 namespace vimg {
 

@@ -862,7 +862,7 @@ VD void shade_bounce(const DScene& sc, const WfArgs& args, const DLeafPrim& lp, 
     float eta_scale = t4.w;
     bool nsb = (fj & WF_NSB) != 0;
     // ray cones: skipped when nothing in the scene reads them (DScene::uses_cones)
-    const bool cones = sc.uses_cones != 0;
+    const bool cones = !VIMG_LEAN && sc.uses_cones != 0;
     float hit_dist = cones ? length(ray.o - hit.hit_p) : 0.f;
     float surface_spread_angle
         = cones ? spread_angle_from_curvature(hit.mean_curvature, ray.cone.cone_width, ray.dir, hit.hit_n_s) : 0.f;
@@ -1098,7 +1098,6 @@ struct QwKernelTable {
   const void* end[2];                    // [material = 0, mis = 1]
   // tolerance build only: flat re-layout of a small scene (vimg_flat.cuh) and the streamed pipeline (vimg_stream.cuh)
   const void* build_flat;
-  const void* sv_trace_flat[2];          // [COUNT]
   const void* sv_shade[2][WF_NUM_CLASSES];
   const void* sv_end[2];
   const void* sv_init;

@@ -44,11 +44,13 @@ struct __align__(QV_LINE_BYTES) QvLine {
 };
 static_assert(sizeof(QvLine) == QV_LINE_BYTES, "one line per slot");
 
+struct QvQueueCounters {  // the queues one iteration fills (16 bytes: the host clears them with one memset)
+  uint32_t n_end;
+  uint32_t n_shade[WF_NUM_CLASSES];
+};
 struct QvCounters {
-  uint32_t n_trace[2];                  // ray queue, by iteration parity
-  uint32_t n_end[2];                    // END queue, by iteration parity
-  uint32_t n_shade[2][WF_NUM_CLASSES];  // hit queues
-  uint32_t pad_[6];
+  QvQueueCounters q[2];  // by iteration parity
+  uint32_t pad_[8];
 };
 
 // Streamed shade / END launches: 128-thread blocks pack the register file in finer steps than 256-thread ones
@@ -74,9 +76,8 @@ struct QvCounters {
 struct QvState {
   uint32_t n_slots;
   QvLine* line;
-  float4 *ta[2], *tb[2], *tc[2];                    // ray queue
-  float4 *ha[WF_NUM_CLASSES], *hb[WF_NUM_CLASSES];  // hit queues of the material classes
-  float4 *ea[2], *eb[2];                            // END queue
+  float4 *ha[2][WF_NUM_CLASSES], *hb[2][WF_NUM_CLASSES];  // hit queues of the material classes, by iteration parity
+  float4 *ea[2], *eb[2];                                  // END queue
   QvCounters* cnt;
   uint32_t* next_pixel;
 };
@@ -112,142 +113,111 @@ VD void qv_prefetch_line(const QvLine* ln) { asm volatile("prefetch.global.L2 [%
 VD float4 ldq(const float4* p) { return __ldcs(p); }  // queue records are read once: evict first
 VD void stq(float4* p, float4 v) { __stcs(p, v); }
 
-// ====================================================== TRACE over the flat lists, streamed ====
-// thread <-> item of the ray queue: the shadow ray and / or the closest ray of one path segment.
-template <bool COUNT>
-__global__ void __launch_bounds__(QW_THREADS, 4)
-qv_trace_flat_kernel(const __grid_constant__ QvState st, const uint32_t parity, const QfScene* __restrict__ flat,
-                     DCounters* __restrict__ counters) {
+// ============================================== the traces of a path segment, at the tail of its producer ====
+// The kernel that made a path segment's rays -- a shade kernel (closest ray and / or shadow ray) or END (camera ray)
+// -- traces them itself over the flat lists in shared memory and routes the result: the hit record goes straight
+// into the hit queue of the hit material's class, or into the END queue (miss, emitter, base material, a path that
+// only had its last shadow ray left, a path that ended with nothing pending).  There is no ray queue and no trace
+// launch: the divergence-free test loop (issue bound as a kernel of its own, 65 % of the issue slots) fills the slots
+// the shade / END bodies leave idle while they wait for their gathers (23 - 35 %), and a path segment costs one
+// kernel instead of two.
+//   valid: this lane has an item to route;  has_c / has_s: it has a closest / shadow ray to trace first
+//   o: origin of both rays, d: closest-ray direction, w: shadow-ray direction + distance to the light sample
+template <bool WARP_APPEND>
+VD void qv_trace_route(const QfScene& fs, const QvState& st, QvCounters* c, const uint32_t q, uint32_t* s_cnt,
+                       uint32_t* s_base, const bool valid, const bool has_c, const bool has_s, const V3 o, const V3 d,
+                       const float4 w, const uint32_t slot, const int tid, const uint32_t lane, const uint32_t lane_lt,
+                       uint32_t& rays_closest, uint32_t& rays_shadow) {
+  // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
+  QfBest sh, best;
+  sh.t = has_s ? w.w - 0.0001f : 0.f;
+  sh.k = -1;
+  sh.u = sh.v = 0.f;
+  best.t = has_c ? CUDART_INF_F : 0.f;
+  best.k = -1;
+  best.u = best.v = 0.f;
+  const bool any_s = __any_sync(0xffffffffu, has_s), any_c = __any_sync(0xffffffffu, has_c);
+  if (any_s && any_c)
+    qf_trace2(fs, o, d, xyz(w), 0.0001f, best, sh);  // both rays in one pass over the lists
+  else if (any_c)
+    qf_trace(fs, o, d, 0.0001f, best);
+  else if (any_s)
+    qf_trace(fs, o, xyz(w), 0.0001f, sh);
+  const bool occl = sh.k >= 0;
+  rays_shadow += has_s;
+  rays_closest += has_c;
+  uint32_t cls = WF_CLASS_NONE + 1;  // NONE + 1: no item
+  int32_t leaf = -1;
+  float4 hb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    cls = WF_CLASS_NONE;  // END
+    if (best.k >= 0) {
+      uint32_t lc;
+      qf_decode(fs, best, leaf, lc, hb4);
+      cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
+    }
+  }
+  uint32_t pos = 0;
+  if (WARP_APPEND) {
+#pragma unroll
+    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) {
+      const uint32_t at = qv_warp_append(k < WF_NUM_CLASSES ? &c->q[q].n_shade[k] : &c->q[q].n_end, cls == k, lane, lane_lt);
+      if (cls == k) pos = at;
+    }
+  } else {
+    bool want[WF_NUM_CLASSES + 1];
+#pragma unroll
+    for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
+    QwAppend<WF_NUM_CLASSES + 1> ap;
+    ap.count(s_cnt, want, lane, lane_lt);
+    __syncthreads();
+    if (tid < (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->q[q].n_shade[tid], s_cnt[tid]);
+    } else if (tid == (int)WF_NUM_CLASSES) {
+      if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->q[q].n_end, s_cnt[tid]);
+    }
+    __syncthreads();
+    if (valid) pos = s_base[cls] + ap.off[cls];
+  }
+  if (valid) {
+    const float4 ha4 = make_float4(__uint_as_float(slot), __int_as_float(leaf), best.k >= 0 ? best.t : CUDART_INF_F,
+                                   __uint_as_float(occl ? 1u : 0u));
+    float4* qa = cls < WF_NUM_CLASSES ? st.ha[q][cls] : st.ea[q];
+    float4* qb = cls < WF_NUM_CLASSES ? st.hb[q][cls] : st.eb[q];
+    stq(qa + pos, ha4);
+    stq(qb + pos, hb4);
+  }
+}
+VD void qv_stage_flat(QfScene& fs, const QfScene* __restrict__ flat, int tid) {
+  const uint4* src = reinterpret_cast<const uint4*>(flat);
+  uint4* dst = reinterpret_cast<uint4*>(&fs);
+  for (uint32_t i = tid; i < sizeof(QfScene) / 16; i += QV_THREADS) dst[i] = __ldg(src + i);
+  __syncthreads();  // the staged lists are visible
+}
+
+// ====================================================================== SHADE, streamed ====
+// thread <-> item of the class's hit queue; reads the queues of `parity`, fills those of parity ^ 1
+template <int INTEGRATOR, uint32_t CLASS>
+__global__ void __launch_bounds__(QV_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QV_SHADE_MIN_BLOCKS_P : QV_SHADE_MIN_BLOCKS_L)
+qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
+                const __grid_constant__ WfArgs args, const uint32_t parity, const QfScene* __restrict__ flat,
+                const uint32_t count, DCounters* __restrict__ counters) {
   __shared__ QfScene fs;
   __shared__ uint32_t s_cnt[WF_NUM_CLASSES + 1], s_base[WF_NUM_CLASSES + 1];
   QvCounters* c = st.cnt;
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
-  if (blockIdx.x == 0 && tid == 0) {
-    // queues the NEXT iteration fills (their last consumers ran before this launch)
-    c->n_trace[parity ^ 1u] = 0;
-    c->n_end[parity ^ 1u] = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < WF_NUM_CLASSES; ++k) c->n_shade[parity ^ 1u][k] = 0;
-  }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(flat);
-    uint4* dst = reinterpret_cast<uint4*>(&fs);
-    for (uint32_t i = tid; i < sizeof(QfScene) / 16; i += QW_THREADS) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();  // the staged lists are visible
-  const uint32_t n = c->n_trace[parity];
-  if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_TRACE], (unsigned long long)n);
-  const float4* __restrict__ ta = st.ta[parity];
-  const float4* __restrict__ tb = st.tb[parity];
-  const float4* __restrict__ tc = st.tc[parity];
-  uint32_t rays_closest = 0, rays_shadow = 0;
-
-  for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
-    if (!QV_WARP_APPEND_TRACE) {
-      if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
-      __syncthreads();
-    }
-    const uint32_t item = base + tid;
-    const bool valid = item < n;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 1.f, 0.f), w = b;
-    if (valid) {
-      a = ldq(ta + item);
-      b = ldq(tb + item);
-    }
-    const uint32_t bits = __float_as_uint(b.w);
-    const bool has_c = valid && (bits & QV_HAS_CLOSEST), has_s = valid && (bits & QV_HAS_SHADOW);
-    if (has_s) w = ldq(tc + item);
-    const V3 o = xyz(a);
-    bool occl = false;
-    if (__any_sync(0xffffffffu, has_s)) {
-      // shadow ray (mis_integrator.cpp:59-64): origin = hit point, maxT = dist - 1e-4
-      QfBest sh;
-      sh.t = has_s ? a.w - 0.0001f : 0.f;
-      sh.k = -1;
-      sh.u = sh.v = 0.f;
-      qf_trace(fs, o, xyz(w), 0.0001f, sh);
-      occl = sh.k >= 0;
-      rays_shadow += has_s;
-    }
-    QfBest best;
-    best.t = has_c ? CUDART_INF_F : 0.f;
-    best.k = -1;
-    best.u = best.v = 0.f;
-    if (__any_sync(0xffffffffu, has_c)) {
-      qf_trace(fs, o, xyz(b), 0.0001f, best);
-      rays_closest += has_c;
-    }
-    uint32_t cls = WF_CLASS_NONE + 1;  // NONE + 1: no item
-    int32_t leaf = -1;
-    float4 hb4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      cls = WF_CLASS_NONE;  // END: miss, emitter, base material, or a path that only had its last shadow ray left
-      if (best.k >= 0) {
-        uint32_t lc;
-        qf_decode(fs, best, leaf, lc, hb4);
-        cls = (lc & VIMG_LEAF_CLASS_EMISSIVE) ? WF_CLASS_NONE : (lc & 3u);
-      }
-    }
-    uint32_t pos = 0;
-    if (QV_WARP_APPEND_TRACE) {
-#pragma unroll
-      for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) {
-        const uint32_t at = qv_warp_append(k < WF_NUM_CLASSES ? &c->n_shade[parity][k] : &c->n_end[parity], cls == k, lane, lane_lt);
-        if (cls == k) pos = at;
-      }
-    } else {
-      bool want[WF_NUM_CLASSES + 1];
-#pragma unroll
-      for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) want[k] = cls == k;
-      QwAppend<WF_NUM_CLASSES + 1> ap;
-      ap.count(s_cnt, want, lane, lane_lt);
-      __syncthreads();
-      if (tid < (int)WF_NUM_CLASSES) {
-        if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_shade[parity][tid], s_cnt[tid]);
-      } else if (tid == (int)WF_NUM_CLASSES) {
-        if (s_cnt[tid]) s_base[tid] = atomicAdd(&c->n_end[parity], s_cnt[tid]);
-      }
-      __syncthreads();
-      if (valid) pos = s_base[cls] + ap.off[cls];
-    }
-    if (valid) {
-      const float4 ha4 = make_float4(__uint_as_float(bits & QV_SLOT_MASK), __int_as_float(leaf),
-                                     best.k >= 0 ? best.t : CUDART_INF_F, __uint_as_float(occl ? 1u : 0u));
-      float4* qa = cls < WF_NUM_CLASSES ? st.ha[cls] : st.ea[parity];
-      float4* qb = cls < WF_NUM_CLASSES ? st.hb[cls] : st.eb[parity];
-      stq(qa + pos, ha4);
-      stq(qb + pos, hb4);
-    }
-  }
-  warp_add_counter(&counters->rays_closest, rays_closest);
-  warp_add_counter(&counters->rays_shadow, rays_shadow);
-  if (COUNT) {
-    warp_add_counter(&counters->tri_tests, (rays_closest + rays_shadow) * fs.n_tri);
-    warp_add_counter(&counters->sphere_tests, (rays_closest + rays_shadow) * fs.n_sph);
-  }
-}
-
-// ====================================================================== SHADE, streamed ====
-// thread <-> item of the class's hit queue
-template <int INTEGRATOR, uint32_t CLASS>
-__global__ void __launch_bounds__(QV_THREADS, CLASS == WF_CLASS_PRINCIPLED ? QV_SHADE_MIN_BLOCKS_P : QV_SHADE_MIN_BLOCKS_L)
-qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
-                const __grid_constant__ WfArgs args, const uint32_t parity, DCounters* __restrict__ counters) {
-  __shared__ uint32_t s_cnt[2], s_base[2];
-  QvCounters* c = st.cnt;
-  const int tid = threadIdx.x;
-  const uint32_t lane = tid & 31u;
-  const uint32_t lane_lt = (1u << lane) - 1u;
-  const uint32_t n = c->n_shade[parity][CLASS];
+  qv_stage_flat(fs, flat, tid);
+  const uint32_t n = c->q[parity].n_shade[CLASS];
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[wf_class_stage(CLASS)], (unsigned long long)n);
-  const float4* __restrict__ qa = st.ha[CLASS];
-  const float4* __restrict__ qb = st.hb[CLASS];
+  const float4* __restrict__ qa = st.ha[parity][CLASS];
+  const float4* __restrict__ qb = st.hb[parity][CLASS];
+  uint32_t rays_closest = 0, rays_shadow = 0;
 
   for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
     if (!QV_WARP_APPEND) {
-      if (tid < 2) s_cnt[tid] = 0;
+      if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
       __syncthreads();
     }
     const uint32_t item = base + tid;
@@ -268,6 +238,7 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
     ShadeIO io;
     io.t4 = io.o4 = io.d4 = io.cp4 = io.L4 = make_float4(0.f, 0.f, 0.f, 0.f);
     io.pa1 = make_uint4(0, 0, 0, 0);
+    io.new_o = io.new_d = io.nee_wi = make_float4(0.f, 0.f, 1.f, 0.f);
     float4 ap4 = io.t4;
     DLeafPrim lp;
     DShadeRec sr;
@@ -311,35 +282,17 @@ qv_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvSta
         stg4(&ln->spare, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
-    // a path segment to trace (closest ray and / or shadow ray), or straight to END (ended, nothing pending)
+    // the path segment's rays (closest ray and / or shadow ray), or straight to END (ended, nothing pending)
     const bool to_trace = io.want_closest || io.want_shadow;
     const bool to_end = io.want_end && !io.want_shadow;
-    uint32_t pos_t, pos_e;
-    if (QV_WARP_APPEND) {
-      pos_t = qv_warp_append(&c->n_trace[parity ^ 1u], to_trace, lane, lane_lt);
-      pos_e = qv_warp_append(&c->n_end[parity ^ 1u], to_end, lane, lane_lt);
-    } else {
-      const bool want[2] = {to_trace, to_end};
-      QwAppend<2> ap;
-      ap.count(s_cnt, want, lane, lane_lt);
-      __syncthreads();
-      if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
-      if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[1]);
-      __syncthreads();
-      pos_t = s_base[0] + ap.off[0];
-      pos_e = s_base[1] + ap.off[1];
-    }
-    if (to_trace) {
-      const uint32_t pos = pos_t;
-      const uint32_t bits = j | (io.want_closest ? QV_HAS_CLOSEST : 0u) | (io.want_shadow ? QV_HAS_SHADOW : 0u);
-      stq(st.ta[parity ^ 1u] + pos, make_float4(io.new_o.x, io.new_o.y, io.new_o.z, io.nee_wi.w));
-      stq(st.tb[parity ^ 1u] + pos, make_float4(io.new_d.x, io.new_d.y, io.new_d.z, __uint_as_float(bits)));
-      if (io.want_shadow) stq(st.tc[parity ^ 1u] + pos, io.nee_wi);
-    } else if (to_end) {
-      const uint32_t pos = pos_e;
-      stq(st.ea[parity ^ 1u] + pos, make_float4(__uint_as_float(j), __int_as_float(-1), CUDART_INF_F, __uint_as_float(0u)));
-      stq(st.eb[parity ^ 1u] + pos, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
+    qv_trace_route<QV_WARP_APPEND != 0>(fs, st, c, parity ^ 1u, s_cnt, s_base, to_trace || to_end, io.want_closest, io.want_shadow,
+                                        xyz(io.new_o), xyz(io.new_d), io.nee_wi, j, tid, lane, lane_lt, rays_closest, rays_shadow);
+  }
+  warp_add_counter(&counters->rays_closest, rays_closest);
+  warp_add_counter(&counters->rays_shadow, rays_shadow);
+  if (count) {
+    warp_add_counter(&counters->tri_tests, (rays_closest + rays_shadow) * fs.n_tri);
+    warp_add_counter(&counters->sphere_tests, (rays_closest + rays_shadow) * fs.n_sph);
   }
 }
 
@@ -349,22 +302,24 @@ template <int INTEGRATOR>
 __global__ void __launch_bounds__(QV_THREADS, QV_END_MIN_BLOCKS)
 qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState st,
               const __grid_constant__ WfArgs args, const uint32_t parity, float* __restrict__ out,
-              DCounters* __restrict__ counters) {
-  __shared__ uint32_t s_cnt[1], s_base[1];
+              const QfScene* __restrict__ flat, const uint32_t count, DCounters* __restrict__ counters) {
+  __shared__ QfScene fs;
+  __shared__ uint32_t s_cnt[WF_NUM_CLASSES + 1], s_base[WF_NUM_CLASSES + 1];
   QvCounters* c = st.cnt;
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   const uint32_t lane_lt = (1u << lane) - 1u;
-  const uint32_t n = c->n_end[parity];
+  qv_stage_flat(fs, flat, tid);
+  const uint32_t n = c->q[parity].n_end;
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&counters->stage_items[VIMG_STAGE_END], (unsigned long long)n);
   const float4* __restrict__ qa = st.ea[parity];
   const float4* __restrict__ qb = st.eb[parity];
-  uint32_t nan_samples = 0, n_samples = 0;
+  uint32_t nan_samples = 0, n_samples = 0, rays_closest = 0, rays_shadow = 0;
   bool exhausted = *reinterpret_cast<volatile uint32_t*>(st.next_pixel) >= args.n_local_units;
 
   for (uint32_t base = blockIdx.x * QV_THREADS; base < n; base += gridDim.x * QV_THREADS) {
     if (!QV_WARP_APPEND_END) {
-      if (tid == 0) s_cnt[0] = 0;
+      if (tid < (int)WF_NUM_CLASSES + 1) s_cnt[tid] = 0;
       __syncthreads();
     }
     const uint32_t item = base + tid;
@@ -383,6 +338,7 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
     EndIO io;
     io.thr4 = io.o4 = io.d4 = io.cp4 = io.L4 = io.ap4 = make_float4(0.f, 0.f, 0.f, 0.f);
     io.pa1 = make_uint4(0, 0, 0, 0);
+    io.cam_o = io.cam_d = make_float4(0.f, 0.f, 1.f, 0.f);
     if (valid) {
       io.thr4 = ldg4(&ln->thr_eta);
       io.pa1 = ldg4u(&ln->rng_fd);
@@ -408,25 +364,18 @@ qv_end_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QvState
         stg4(&ln->d_s, io.cam_d);
       }
     }
-    uint32_t pos;
-    if (QV_WARP_APPEND_END) {
-      pos = qv_warp_append(&c->n_trace[parity ^ 1u], io.new_ray, lane, lane_lt);
-    } else {
-      const bool want[1] = {io.new_ray};
-      QwAppend<1> ap;
-      ap.count(s_cnt, want, lane, lane_lt);
-      __syncthreads();
-      if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_trace[parity ^ 1u], s_cnt[0]);
-      __syncthreads();
-      pos = s_base[0] + ap.off[0];
-    }
-    if (io.new_ray) {
-      stq(st.ta[parity ^ 1u] + pos, make_float4(io.cam_o.x, io.cam_o.y, io.cam_o.z, 0.f));
-      stq(st.tb[parity ^ 1u] + pos, make_float4(io.cam_d.x, io.cam_d.y, io.cam_d.z, __uint_as_float(i | QV_HAS_CLOSEST)));
-    }
+    // the camera ray of the slot's next sample: traced here, its hit record routed to the queues of parity ^ 1
+    qv_trace_route<QV_WARP_APPEND_END != 0>(fs, st, c, parity ^ 1u, s_cnt, s_base, io.new_ray, io.new_ray, false, xyz(io.cam_o),
+                                            xyz(io.cam_d), make_float4(0.f, 0.f, 1.f, 0.f), i, tid, lane, lane_lt, rays_closest,
+                                            rays_shadow);
   }
   warp_add_counter(&counters->nan_samples, nan_samples);
   warp_add_counter(&counters->samples, n_samples);
+  warp_add_counter(&counters->rays_closest, rays_closest);
+  if (count) {
+    warp_add_counter(&counters->tri_tests, rays_closest * fs.n_tri);
+    warp_add_counter(&counters->sphere_tests, rays_closest * fs.n_sph);
+  }
 }
 
 // the first END queue: every slot, none with a pixel yet
@@ -438,8 +387,6 @@ __global__ void qv_init_kernel(float4* __restrict__ ea, float4* __restrict__ eb,
 }
 
 inline void qv_fill_kernel_table(QwKernelTable& t) {
-  t.sv_trace_flat[0] = (const void*)&qv_trace_flat_kernel<false>;
-  t.sv_trace_flat[1] = (const void*)&qv_trace_flat_kernel<true>;
   t.sv_shade[0][WF_CLASS_LAMBERT] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_LAMBERT>;
   t.sv_shade[0][WF_CLASS_PRINCIPLED] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_PRINCIPLED>;
   t.sv_shade[0][WF_CLASS_DIELECTRIC] = (const void*)&qv_shade_kernel<VIMG_INTEGRATOR_MATERIAL, WF_CLASS_DIELECTRIC>;
