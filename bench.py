@@ -103,7 +103,7 @@ def ncu_traffic(kernel, workload):
     e = t.get("kernels", {}).get(f"{workload}:{kernel}")
     if not e:
         return None, "kernel not in the capture"
-    return e["dram_bytes_per_launch"], t.get("capture")
+    return e, t.get("capture")
 
 
 class ClockSampler:
@@ -453,7 +453,15 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
         unit_note = (f"path-state bytes per item of the {layout} layout (records read + sectors written + queue records; "
                      "DESIGN.md 5.2), scene tables not counted")
     achieved = per_item * items_per_launch / launch_s / 1e9
-    traffic, traffic_src = ncu_traffic(kernel, w.key)
+    cap, traffic_src = ncu_traffic(kernel, w.key)
+    traffic = None
+    if cap:
+        # the captured launch had cap["items"] items (its queue-record loads, counted by ncu); the bench's average launch has
+        # items_per_launch: the DRAM bytes are quoted for the launch size `achieved` is quoted for
+        traffic = cap["dram_bytes_per_launch"] * (items_per_launch / cap["items"] if cap.get("items") else 1.0)
+        traffic_src = {"capture": traffic_src, "dram_bytes_of_the_captured_launch": cap["dram_bytes_per_launch"],
+                       "items_of_the_captured_launch": cap.get("items"),
+                       "scaled_to_items_per_launch": bool(cap.get("items"))}
     t_rays = tst["rays_closest"] + tst["rays_shadow"]
     if tst["stage_launches"].get("trace", 0):
         trace_launch_s = tst["stage_ms"]["trace"] / 1e3 / tst["stage_launches"]["trace"]

@@ -144,6 +144,30 @@ def test_lean_bit_exact_build_changes_no_bit(vimg, name, integ, monkeypatch):
     assert st0["rays_closest"] == st1["rays_closest"] and st0["rays_shadow"] == st1["rays_shadow"]
 
 
+def test_small_textured_scene_takes_the_full_streamed_kernels(vimg, refcpu):
+    """a scene of <= 32 primitives WITH an image texture, a normal map, an env map and a thin lens (the synthetic height
+    field at G = 4: 32 triangles, built through the reference's classes): streamed pipeline, flat-list trace, the full
+    build of the shade / END kernels (not a lean scene) -- against the compiled reference's image"""
+    rs = refcpu.RefScene.synthetic(G=4, width=96, height=64, tex_size=64, env_w=64, env_h=32, spp=64, depth=64, bvh="sweep",
+                                   aperture=0.02)
+    sc = vimg.Scene(rs.desc_ptr())
+    ref, _ = rs.render("mis", spp=64)
+    ref4, _ = rs.render("mis", spp=256)
+    exact, _ = sc.scene_integrator("mis", 64, 64)
+    assert np.array_equal(exact, ref)  # the bit-identical mode, for the record
+    imgs = {}
+    for k in (8, 32):
+        imgs[k], st = sc.scene_integrator("mis", 64, 64, spp_streams=k, fast=True)
+        ok, ratio = _means_close(imgs[k], ref4, 0.03)  # 6144 pixels at 64 spp: the means themselves carry ~1 % of noise
+        assert ok, (k, ratio)
+        assert np.isfinite(imgs[k]).all() and st["samples"] == 64 * 96 * 64
+    e8, e32, e_8_32 = rel_mse(imgs[8], ref), rel_mse(imgs[32], ref), rel_mse(imgs[8], imgs[32])
+    print(f"synthetic G=4 fast: relMSE K8-ref {e8:.3e} K32-ref {e32:.3e} K8-K32 {e_8_32:.3e}")
+    assert max(e8, e32) <= 3.0 * e_8_32 + 1e-5
+    sc.close()
+    rs.close()
+
+
 def test_fast_needs_the_queue_pipeline(vimg):
     with pytest.raises(vimg.VimgError):
         scene(vimg, "cornell_small").scene_integrator("mis", 8, 64, fast=True, pipeline="block")

@@ -4,7 +4,7 @@
 // -use_fast_math (approximate division / sqrt / transcendental units, FMA contraction, flush to
 // zero) and with VIMG_FAST defined: `vdbl` (the sub-expressions the reference evaluates in double)
 // becomes float, the libm restatements become the hardware's intrinsics, and the kernels the
-// bit-exact contract rules out (qf_trace_flat_kernel) exist.  Everything lives in namespace
+// bit-exact contract rules out (the flat-list trace of vimg_flat.cuh, the 4-wide BVH of vimg_wide.cuh) exist.  Everything lives in namespace
 // vimg_fast so that the two builds can sit in one library; vimg_api.cu launches either set through
 // the QwKernelTable below.  The argument structs (DScene, QwState, WfArgs) contain no `vdbl`, so
 // their layout is the same in both builds.

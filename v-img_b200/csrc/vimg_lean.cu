@@ -2,13 +2,14 @@
 // features VIMG_LEAN compiles out (vimg_math.cuh): no image texture, normal map, metallic-roughness texture, env map,
 // ray cones, general uv walk.  Those paths never run on such a scene but they set the kernels' register need;
 // without them the Lambertian / Dielectric shade kernels fit 5 blocks of 128 threads per SM (96 registers, no
-// spills) instead of 4 and Principled 4 instead of 3.  Same sources, namespace vimg_lean; vimg_api.cu picks this
-// table when vimg_scene::lean is set.
+// spills) instead of 4, Principled 4 instead of 3 and END 8 (64 registers) instead of 6.  Same sources, namespace
+// vimg_lean; vimg_api.cu picks this table when vimg_scene::lean is set.
 #define VIMG_FAST 1
 #define VIMG_FAST_LIBM 1
 #define VIMG_LEAN 1
 #define QV_SHADE_MIN_BLOCKS_L 5
 #define QV_SHADE_MIN_BLOCKS_P 4
+#define QV_END_MIN_BLOCKS 8
 #define vimg vimg_lean
 #include "vimg_kernels.cuh"
 #include "vimg_flat.cuh"

@@ -2,22 +2,23 @@
 //
 // What ncu showed about the slot-record pipeline of vimg_queues.cuh (profiles/r5_*): its kernels gather path
 // state by slot number -- 32-byte sectors at random places of a 335 MB array -- and the memory system fetches
-// them at 128-byte granularity.  qf_trace_flat_kernel needs 32 - 48 bytes per ray and moved 218
+// them at 128-byte granularity.  A flat-list trace kernel fed from slots needed 32 - 48 bytes per ray and moved 218
 // (dram__bytes_read 524 MB for 2.4 M rays); the shade / END kernels moved 2.2 - 2.6x their sector bytes and every
 // item costs two dependent DRAM round trips (queue entry -> slot).  With the traversal itself reduced to a
 // divergence-free loop, that traffic is the frame time.
 //
 // Here everything that flows from one kernel to the next flows through QUEUE-ORDERED records, written with
-// block-aggregated appends and read back fully coalesced, 16 bytes per lane and array:
-//   ray queue   (shade / END -> trace):  ta = origin, shadow-ray length | tb = direction, slot + what to trace |
-//                                        tc = shadow-ray direction                         (32 or 48 B per path segment)
-//   hit queues  (trace -> shade per material class, trace / shade -> END):
+// warp- or block-aggregated appends and read back fully coalesced, 16 bytes per lane and array:
+//   hit queues  (-> shade per material class) and the END queue, double buffered by iteration parity:
 //                                        ha = slot, leaf record, t, occluded | hb = e0, e1, e2, inv_det   (32 B)
 // and what stays with the path lives in ONE 128-byte, 128-byte-aligned line per slot (QvLine): throughput, RNG,
 // flags, bounce_result, accumulator, the ray (hit-info needs it), pending NEE contribution.  One line fetch per
-// shade / END item instead of two; full-sector writes only.  A path segment's shadow ray and closest ray are one
-// ray-queue item traced by one lane (both loops are divergence free), so the occlusion result travels in the hit
-// record instead of a 4-byte scatter.
+// shade / END item instead of two; full-sector writes only.
+//
+// There is no ray queue and no trace kernel: the kernel that makes a path segment's rays -- shade: closest ray and / or
+// shadow ray, END: the camera ray of the slot's next sample -- traces them itself over the flat lists in shared memory
+// (qv_trace_route) and appends the hit record to the queue of the hit material's class, or to the END queue.  The
+// launches of an iteration read the queues of its parity and fill those of the other one, so they run side by side.
 //
 // Per path, the estimator, the RNG stream and its draw order are those of vimg_queues.cuh (the shade and END
 // bodies are the same functions: shade_bounce, end_item).
@@ -88,17 +89,14 @@ struct QvState {
 #endif
 // Queue appends: block-aggregated (one global atomic per block and queue, two __syncthreads per batch of items) or, 1,
 // per warp (one atomic per warp and queue, no barrier: a block no longer waits for the slowest of its warps and for the
-// round trip of one thread's atomic).  Measured (disney_spheres, 256 spp, per launch): the shade kernels gain (Lambertian
-// 118.6 -> 114.0 us), END loses (86.6 -> 90.0: it also takes pixels from a global counter), trace loses (99 -> 131 us:
-// 4 x as many atomics on the four counters every ray is routed through).
+// round trip of one thread's atomic).  Measured (disney_spheres, 256 spp): the shade kernels gain with warp appends
+// (Lambertian 118.6 -> 114.0 us per launch), END -- which also takes pixels from a global counter -- does not
+// (86.6 -> 90.0 us; with the four-queue routing of qv_trace_route: frame 188.4 -> 189.9 ms).
 #ifndef QV_WARP_APPEND
 #define QV_WARP_APPEND 1        // shade
 #endif
 #ifndef QV_WARP_APPEND_END
 #define QV_WARP_APPEND_END 0
-#endif
-#ifndef QV_WARP_APPEND_TRACE
-#define QV_WARP_APPEND_TRACE 0
 #endif
 VD uint32_t qv_warp_append(uint32_t* counter, bool want, uint32_t lane, uint32_t lane_lt) {
   const uint32_t m = __ballot_sync(0xffffffffu, want);
@@ -159,11 +157,21 @@ VD void qv_trace_route(const QfScene& fs, const QvState& st, QvCounters* c, cons
   }
   uint32_t pos = 0;
   if (WARP_APPEND) {
+    // one atomic instruction for the warp: lane k reserves the warp's items of queue k (0 = END, 1 + class), so the
+    // four reservations are one round trip instead of four dependent ones
+    static_assert(WF_NUM_CLASSES == 3 && WF_CLASS_NONE == 3, "queue index = (class + 1) & 3");
+    const uint32_t qi = (cls + 1u) & 3u;  // END -> 0, class k -> k + 1 (no item: cls = 4 -> 1, masked out by the ballots)
+    uint32_t mine = 0, m_own = 0;
 #pragma unroll
     for (uint32_t k = 0; k <= WF_NUM_CLASSES; ++k) {
-      const uint32_t at = qv_warp_append(k < WF_NUM_CLASSES ? &c->q[q].n_shade[k] : &c->q[q].n_end, cls == k, lane, lane_lt);
-      if (cls == k) pos = at;
+      const uint32_t m = __ballot_sync(0xffffffffu, valid && qi == k);
+      if (lane == k) mine = m;
+      if (qi == k) m_own = m;
     }
+    uint32_t base = 0;
+    if (lane <= WF_NUM_CLASSES && mine) base = atomicAdd(&c->q[q].n_end + lane, (uint32_t)__popc(mine));
+    base = __shfl_sync(0xffffffffu, base, qi);
+    pos = base + __popc(m_own & lane_lt);
   } else {
     bool want[WF_NUM_CLASSES + 1];
 #pragma unroll
