@@ -12,6 +12,10 @@ nvcc $common -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -f
   -c $src/vimg_api.cu -o $out/obj_$name/vimg_api.o 2> $out/obj_$name/ptxas_api.txt &
 nvcc $common -use_fast_math -Xcompiler -fPIC,-Wno-unknown-pragmas "$@" \
   -c $src/vimg_fast.cu -o $out/obj_$name/vimg_fast.o 2> $out/obj_$name/ptxas_fast.txt &
+nvcc $common -use_fast_math -Xcompiler -fPIC,-Wno-unknown-pragmas "$@" \
+  -c $src/vimg_lean.cu -o $out/obj_$name/vimg_lean.o 2> $out/obj_$name/ptxas_lean.txt &
+nvcc $common -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-ffp-contract=off,-Wno-unknown-pragmas "$@" \
+  -c $src/vimg_exact_lean.cu -o $out/obj_$name/vimg_exact_lean.o 2> $out/obj_$name/ptxas_exact_lean.txt &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libvimg_$name.so $out/obj_$name/vimg_api.o $out/obj_$name/vimg_fast.o $src/vimg_scene_io.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libvimg_$name.so $out/obj_$name/vimg_api.o $out/obj_$name/vimg_fast.o $out/obj_$name/vimg_lean.o $out/obj_$name/vimg_exact_lean.o $src/vimg_scene_io.o
 echo "built $name"

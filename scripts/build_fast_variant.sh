@@ -10,5 +10,5 @@ out=$root/v-img_b200/variants
 mkdir -p $out/obj_$name
 nvcc -std=c++20 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wno-unknown-pragmas -Xptxas -v "$@" \
   -c $src/vimg_fast.cu -o $out/obj_$name/vimg_fast.o 2> $out/obj_$name/ptxas.txt || { cat $out/obj_$name/ptxas.txt; exit 1; }
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libvimg_$name.so $src/vimg_api.o $out/obj_$name/vimg_fast.o $src/vimg_scene_io.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libvimg_$name.so $src/vimg_api.o $out/obj_$name/vimg_fast.o $src/vimg_lean.o $src/vimg_exact_lean.o $src/vimg_scene_io.o
 echo "built $name"

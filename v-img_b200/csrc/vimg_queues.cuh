@@ -56,7 +56,7 @@ namespace vimg {
 
 struct QwCounters {
   uint32_t n_closest[2], n_shadow[2];  // queue lengths, double buffered by iteration parity
-  uint32_t n_end[2];
+  uint32_t n_end[2];                   // (qw_shade_kernel addresses these three pairs as &n_closest[0] + 2 k + parity)
   uint32_t n_shade[2][WF_NUM_CLASSES];  // by iteration parity
   uint32_t cursor;      // trace kernel's work cursor
   uint32_t pad_[3];
@@ -766,6 +766,9 @@ VD constexpr uint32_t wf_class_stage(uint32_t cls) {
                                     : (cls == WF_CLASS_LAMBERT ? VIMG_STAGE_SHADE_LAMBERTIAN : VIMG_STAGE_SHADE_DIELECTRIC);
 }
 
+#ifndef QW_WARP_APPEND_SHADE
+#define QW_WARP_APPEND_SHADE 1  // 0: block-aggregated appends behind two barriers
+#endif
 #ifndef QW_SHADE_MIN_BLOCKS_P
 #define QW_SHADE_MIN_BLOCKS_P 2  // Principled
 #endif
@@ -1006,8 +1009,10 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
   const uint2* __restrict__ q = st.q_shade[CLASS];
 
   for (uint32_t base = blockIdx.x * QW_THREADS; base < n; base += gridDim.x * QW_THREADS) {
-    if (tid < 3) s_cnt[tid] = 0;
-    __syncthreads();
+    if (!QW_WARP_APPEND_SHADE) {
+      if (tid < 3) s_cnt[tid] = 0;
+      __syncthreads();
+    }
     const uint32_t item = base + tid;
     bool want_closest = false, want_shadow = false, want_end = false;
     bool go = item < n;
@@ -1072,17 +1077,34 @@ qw_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ QwSta
     // traversal inherits the stack its occlusion traversal left behind (see bvh_traverse)
     const bool pair = want_closest && want_shadow && !args.fresh_stack;
     if (pair) want_shadow = false;
-    const bool want[3] = {want_closest, want_shadow, want_end};
-    QwAppend<3> ap;
-    ap.count(s_cnt, want, lane, lane_lt);
-    __syncthreads();
-    if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_closest[parity ^ 1u], s_cnt[0]);
-    if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_shadow[parity ^ 1u], s_cnt[1]);
-    if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[2]);
-    __syncthreads();
-    if (want_closest) st.q_closest[parity ^ 1u][s_base[0] + ap.off[0]] = pair ? (j | QW_PAIR_BIT) : j;
-    if (want_shadow) st.q_shadow[parity ^ 1u][s_base[1] + ap.off[1]] = j;
-    if (want_end) st.q_end[parity ^ 1u][s_base[2] + ap.off[2]] = j;
+    uint32_t pos_c, pos_s, pos_e;
+    if (QW_WARP_APPEND_SHADE) {
+      // one atomic instruction per warp: lane k reserves the warp's entries of queue k (closest, shadow, END; their
+      // counters lie 8 bytes apart) -- no block barrier, one round trip (the order of a queue is not part of any result)
+      const uint32_t m0 = __ballot_sync(0xffffffffu, want_closest), m1 = __ballot_sync(0xffffffffu, want_shadow),
+                     m2 = __ballot_sync(0xffffffffu, want_end);
+      const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : (lane == 2 ? m2 : 0u));
+      uint32_t b = 0;
+      if (mine) b = atomicAdd(&c->n_closest[0] + 2u * lane + (parity ^ 1u), (uint32_t)__popc(mine));
+      pos_c = __shfl_sync(0xffffffffu, b, 0) + __popc(m0 & lane_lt);
+      pos_s = __shfl_sync(0xffffffffu, b, 1) + __popc(m1 & lane_lt);
+      pos_e = __shfl_sync(0xffffffffu, b, 2) + __popc(m2 & lane_lt);
+    } else {
+      const bool want[3] = {want_closest, want_shadow, want_end};
+      QwAppend<3> ap;
+      ap.count(s_cnt, want, lane, lane_lt);
+      __syncthreads();
+      if (tid == 0 && s_cnt[0]) s_base[0] = atomicAdd(&c->n_closest[parity ^ 1u], s_cnt[0]);
+      if (tid == 1 && s_cnt[1]) s_base[1] = atomicAdd(&c->n_shadow[parity ^ 1u], s_cnt[1]);
+      if (tid == 2 && s_cnt[2]) s_base[2] = atomicAdd(&c->n_end[parity ^ 1u], s_cnt[2]);
+      __syncthreads();
+      pos_c = s_base[0] + ap.off[0];
+      pos_s = s_base[1] + ap.off[1];
+      pos_e = s_base[2] + ap.off[2];
+    }
+    if (want_closest) st.q_closest[parity ^ 1u][pos_c] = pair ? (j | QW_PAIR_BIT) : j;
+    if (want_shadow) st.q_shadow[parity ^ 1u][pos_s] = j;
+    if (want_end) st.q_end[parity ^ 1u][pos_e] = j;
   }
 }
 

@@ -98,15 +98,6 @@ struct QvState {
 #ifndef QV_WARP_APPEND_END
 #define QV_WARP_APPEND_END 0
 #endif
-VD uint32_t qv_warp_append(uint32_t* counter, bool want, uint32_t lane, uint32_t lane_lt) {
-  const uint32_t m = __ballot_sync(0xffffffffu, want);
-  if (m == 0) return 0;
-  const uint32_t leader = (uint32_t)__ffs(m) - 1u;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return base + __popc(m & lane_lt);
-}
 VD void qv_prefetch_line(const QvLine* ln) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ln)); }
 VD float4 ldq(const float4* p) { return __ldcs(p); }  // queue records are read once: evict first
 VD void stq(float4* p, float4 v) { __stcs(p, v); }
