@@ -1426,6 +1426,10 @@ static int launch_render(vimg_scene* s, const RenderArgs& a, uint32_t integrator
       return fail(VIMG_ERR_INVALID_ARGUMENT, "VIMG_PARTITION_SPP needs spp_streams (and samples) >= n_ranks");
     w.my_streams = (w.streams - w.s_rank + w.s_n_ranks - 1) / w.s_n_ranks;
     w.n_local_units = w.n_local_pixels * w.my_streams;
+    w.div_tiles_y = make_fast_div(std::max(1u, w.tiles_y));
+    w.div_my_streams = make_fast_div(std::max(1u, w.my_streams));
+    w.div_streams = make_fast_div(w.streams);
+    w.samples_small = w.samples < 65536u ? 1u : 0u;
     w.partial = nullptr;
     const bool fast = (flags & VIMG_FLAG_FAST) != 0;
     w.fresh_stack = ((flags & VIMG_FLAG_FRESH_STACK) || w.streams > 1 || fast) ? 1u : 0u;

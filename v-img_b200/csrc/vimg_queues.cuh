@@ -494,7 +494,7 @@ VD void end_item(const DScene& sc, const WfArgs& args, uint32_t* next_pixel, flo
         o[2] = px_col.z;
         f &= ~WF_ALIVE;
       }
-    } else if (s == (uint32_t)(((uint64_t)(range + 1) * args.samples) / args.streams)) {
+    } else if (s == wf_range_begin(args, range + 1)) {
       // end of this sample range: its partial sum; qw_combine_kernel adds the ranges in order
       uint32_t px, py;
       wf_pixel_xy(args, sc.cam, pixel, px, py);
@@ -608,7 +608,7 @@ VD void end_item(const DScene& sc, const WfArgs& args, uint32_t* next_pixel, flo
         uint32_t u = pbase + __popc(m & lane_lt), p = 0;
         uint32_t px = 0, py = 0;
         bool got = false;
-        while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = u / args.my_streams, px, py)))
+        while (u < args.n_local_units && !(got = wf_pixel_xy(args, sc.cam, p = fast_div(u, args.div_my_streams), px, py)))
           u = atomicAdd(next_pixel, 1u);
         if (got) {
           range = args.s_rank + (u - p * args.my_streams) * args.s_n_ranks;
@@ -621,7 +621,7 @@ VD void end_item(const DScene& sc, const WfArgs& args, uint32_t* next_pixel, flo
           } else {
             pcg32_seed(rng, px + ((size_t)(H - 1 - py) * W), range);
             acc = mk3(0.f);
-            s = (uint32_t)(((uint64_t)range * args.samples) / args.streams);
+            s = wf_range_begin(args, range);
             pixel = p;
             f = WF_ALIVE | (range << WF_RANGE_SHIFT);
           }

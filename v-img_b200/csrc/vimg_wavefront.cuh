@@ -60,6 +60,29 @@ struct WfShared {
   uint32_t class_count[2][WF_NUM_CLASSES];
 };
 
+// n / d for a divisor that is fixed for the launch, exact for every 32-bit n (Granlund-Montgomery: multiply-high
+// with a 33-bit reciprocal split into a 32-bit multiplier and two shifts): 4 instructions where the hardware-less
+// integer division is ~25.  The END kernels divide three times per item (pixel -> tile -> x, y; unit -> pixel).
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+};
+#ifdef __CUDACC__
+VD uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+#endif
+inline FastDiv make_fast_div(uint32_t d) {  // d >= 1
+  FastDiv f;
+  uint32_t l = 0;
+  while (l < 32 && (1ull << l) < d) ++l;  // ceil(log2 d)
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 1 ? l - 1 : 0;
+  f.d = d;
+  return f;
+}
+
 struct WfArgs {
   uint32_t samples, depth;
   uint32_t rank, n_ranks;
@@ -78,7 +101,18 @@ struct WfArgs {
   // 1: every traversal starts from an empty stack (VIMG_FLAG_FRESH_STACK, or streams > 1); 0: a path's
   // closest-hit traversal inherits what its shadow ray's traversal left (the reference's thread_stack)
   uint32_t fresh_stack;
+  // the launch's fixed divisors (tiles_y, my_streams, streams) and, when a range boundary fits 32 bits
+  // (samples < 65536: range <= 65535), the switch to divide it that way
+  FastDiv div_tiles_y, div_my_streams, div_streams;
+  uint32_t samples_small;
 };
+// first sample of sample range r: floor(r * samples / streams) (r = streams: one past the last)
+#ifdef __CUDACC__
+VD uint32_t wf_range_begin(const WfArgs& a, uint32_t r) {
+  if (a.samples_small) return fast_div(r * a.samples, a.div_streams);
+  return (uint32_t)(((uint64_t)r * a.samples) / a.streams);
+}
+#endif
 // a slot's sample range number lives in the upper half of its flag word
 #define WF_RANGE_SHIFT 16
 #define WF_FLAG_MASK 0xffffu
@@ -98,7 +132,7 @@ VD bool wf_pixel_xy(const WfArgs& a, const DCamera& cam, uint32_t p, uint32_t& x
     return true;
   }
   const uint32_t tile = a.rank + (p >> 6) * a.n_ranks;
-  const uint32_t tx = tile / a.tiles_y, ty = tile % a.tiles_y;
+  const uint32_t tx = fast_div(tile, a.div_tiles_y), ty = tile - tx * a.tiles_y;
   x = tx * 8 + (p & 7);
   y = ty * 8 + ((p >> 3) & 7);
   return x < (uint32_t)cam.res[0] && y < (uint32_t)cam.res[1];
