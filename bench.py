@@ -416,6 +416,28 @@ STAGE_KERNEL = {"trace": None, "classify": "qw_classify_kernel", "shade_principl
                 "end": "end_kernel<mis>"}
 
 
+def pattern_peak(slots, items):
+    """What the memory system delivers for the streamed shade / END kernels' access pattern with no arithmetic in the
+    way (scripts/gather_peak.cu, built by __graft_entry__.build(): per item a 32-byte queue record in order, a random
+    128-byte slot line read, 96 bytes of it written back, a 32-byte record appended): measured here, on this GPU,
+    outside every timed region.  roofline.frac stays against the copy peak; this says how much of the gap is the
+    pattern's."""
+    exe = os.path.join(ROOT, "scripts", "gather_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        # (rank 0 calls this while the other ranks wait: device 0 of the visible set is its GPU)
+        out = subprocess.run([exe, "--one", str(int(slots)), str(int(items))], capture_output=True, text=True, timeout=120)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # a diagnostic: never fails the bench
+        return {"unavailable": repr(e)[:200]}
+    return {"value": r["pattern_gbs"], "unit": "GB/s", "copy_gbs_same_run": r["copy_gbs"], "slots": r["slots"], "items": r["items"],
+            "bytes_per_item": r["bytes_per_item"],
+            "what": "scripts/gather_peak.cu --one: the access pattern of the streamed shade / END kernels without arithmetic "
+                    "(32-byte record in order, random 128-byte line read, 96 bytes written back, 32-byte record appended), "
+                    "slot numbers in random order over the address range of one serial pool"}
+
+
 def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
     """Roofline of the DOMINANT kernel of one workload on this rank's GPU (rank 0 calls this, whole frame): every
     launch of a serial pass in the measured mode is timed with CUDA events on its stream (VIMG_FLAG_STAGE_TIMES),
@@ -481,7 +503,13 @@ def roofline_of(gpu, scene, w, integ, spp, kw, hbm_peak, peak_src):
                  "fp32_tflops_achieved": flops_per_ray * t_rays / step_s / 1e12,
                  "note": "this scene (< 8 KiB) is traced from shared memory at the tail of the kernel that made the ray; the "
                          "reference-layout figures are over the whole serial pass (they normalise throughput across scenes)"}
+    pp = None
+    if flat and top != "trace":
+        pp = pattern_peak(min(2 << 20, w.width * w.height * kw_t.get("spp_streams", 1)), items_per_launch)
+        if pp and pp.get("value"):
+            pp["achieved_over_it"] = achieved / pp["value"]
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "pattern_peak": pp,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
             "launch_ms": 1e3 * launch_s, "launches_timed": n_launch, "items_per_launch": items_per_launch,
             "algorithmic_bytes_per_item": per_item,

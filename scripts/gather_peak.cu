@@ -4,11 +4,14 @@
 // = 288 algorithmic bytes per item, the figure bench.py's roofline uses for the shade kernels (304 with the shadow ray).
 // Prints GB/s of those bytes for several slot counts (= address ranges) and items per launch, next to a plain copy.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gather_peak gather_peak.cu && ./gather_peak
+//   ./gather_peak --one SLOTS ITEMS : that one case (random order), one JSON line -- what bench.py's roofline.pattern_peak runs
 #include <cstdio>
 #include <cstdint>
 #include <vector>
 #include <algorithm>
 #include <random>
+#include <string>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 struct __align__(128) Line { float4 c[8]; };
@@ -60,7 +63,8 @@ __global__ void copy_kernel(const float4* __restrict__ in, float4* __restrict__ 
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
-int main() {
+int main(int argc, char** argv) {
+  const bool one = argc == 4 && std::string(argv[1]) == "--one";
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const uint32_t max_slots = 8u << 20;
@@ -71,13 +75,38 @@ int main() {
   const size_t flush_n = (512u << 20) / 16;
   CK(cudaMalloc(&flush, flush_n * 16 * 2));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double copy_gbs = 0;
   {  // plain copy, 512 MB in + 512 MB out
     float best = 1e9f;
     for (int r = 0; r < 5; ++r) {
       cudaEventRecord(e0); copy_kernel<<<sms * 8, 256>>>(flush, flush + flush_n, flush_n); cudaEventRecord(e1);
       CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
     }
-    printf("copy 512 MB -> 512 MB: %.1f GB/s\n", 2.0 * flush_n * 16 / best / 1e6);
+    copy_gbs = 2.0 * flush_n * 16 / best / 1e6;
+    if (!one) printf("copy 512 MB -> 512 MB: %.1f GB/s\n", copy_gbs);
+  }
+  if (one) {
+    const uint32_t slots = (uint32_t)std::min<unsigned long long>(std::strtoull(argv[2], nullptr, 10), max_slots);
+    const uint32_t n = (uint32_t)std::min<unsigned long long>(std::strtoull(argv[3], nullptr, 10), slots);
+    std::mt19937 rng1(1);
+    std::vector<uint32_t> perm(slots);
+    for (uint32_t i = 0; i < slots; ++i) perm[i] = i;
+    std::shuffle(perm.begin(), perm.end(), rng1);
+    std::vector<float4> h(n);
+    for (uint32_t i = 0; i < n; ++i) { h[i] = make_float4(0, 0, 0, 0); ((uint32_t*)&h[i])[0] = perm[i]; }
+    CK(cudaMemcpy(qa, h.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    float best = 1e9f;
+    for (int r = 0; r < 8; ++r) {
+      copy_kernel<<<sms * 8, 256>>>(flush, flush + flush_n, flush_n);  // evict the lines from L2
+      cudaEventRecord(e0);
+      gather_kernel<2><<<sms * 8, 256>>>(qa, qb, lines, ta, tb, tc, n);
+      cudaEventRecord(e1);
+      CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (r > 0) best = std::min(best, ms);
+    }
+    printf("{\"slots\": %u, \"items\": %u, \"bytes_per_item\": 288, \"us\": %.2f, \"pattern_gbs\": %.1f, \"copy_gbs\": %.1f}\n", slots, n,
+           best * 1e3, 288.0 * n / best / 1e6, copy_gbs);
+    return 0;
   }
   std::mt19937 rng(1);
   printf("%10s %10s %8s %14s %4s %10s %12s\n", "slots", "items", "range", "order", "mlp", "us", "GB/s(288B)");
